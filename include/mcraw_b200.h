@@ -1,0 +1,113 @@
+/*
+ * mcraw_b200.h -- C-ABI of the B200-native MCRAW frame decoder (libmcraw_b200.so).
+ *
+ * The reference (mirsadm/motioncam-decoder) has no FFI layer: its boundary for this path is two C++ free
+ * functions and one class.  This header is the plain-C surface underneath our drop-in versions of those,
+ * and the batched device entry point the reference does not have:
+ *
+ *   reference interface (file:line under /root/reference)            entry point here
+ *   ---------------------------------------------------------------  -----------------------------------------
+ *   raw::Decode        lib/include/motioncam/RawData.hpp:25-30       mcraw_decode_host(..., MCRAW_COMPRESSION_CURRENT)
+ *                      lib/RawData.cpp:528-612
+ *   raw::DecodeLegacy  lib/include/motioncam/RawData.hpp:32-37       mcraw_decode_host(..., MCRAW_COMPRESSION_LEGACY)
+ *                      lib/RawData_Legacy.cpp:445-495
+ *   Decoder::loadFrame lib/Decoder.cpp:184-235 (one frame per call,  mcraw_decode_batch / mcraw_decode_batch_host
+ *                      host vectors)                                 (many frames per call, device output)
+ *
+ * Conventions (same as the reference): results are counted in uint16 ELEMENTS written; 0 means the frame
+ * failed (RawData.cpp:547-554, Decoder.cpp:225-230).  Nothing here throws; functions returning int give
+ * MCRAW_OK or a negative error and leave text in mcraw_last_error().
+ *
+ * There is no CPU decode path behind this API: every decode runs the sm_100a kernels, and context creation
+ * fails when no CUDA device is usable.
+ *
+ * Threading: a context is not thread-safe; contexts are independent (one per GPU / host thread).
+ */
+#ifndef MCRAW_B200_H
+#define MCRAW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCRAW_COMPRESSION_LEGACY 6  /* Decoder.cpp:20 MOTIONCAM_COMPRESSION_TYPE_LEGACY */
+#define MCRAW_COMPRESSION_CURRENT 7 /* Decoder.cpp:21 MOTIONCAM_COMPRESSION_TYPE */
+
+#define MCRAW_OK 0
+#define MCRAW_ERR_CUDA (-1)     /* a CUDA runtime call failed */
+#define MCRAW_ERR_ARG (-2)      /* bad argument (null, misaligned, unsupported geometry) */
+#define MCRAW_ERR_NO_DEVICE (-3)
+#define MCRAW_ERR_STATE (-4)    /* e.g. results requested with no batch in flight */
+
+/* Per-frame failure reasons reported by mcraw_batch_status() (0 = decoded). */
+#define MCRAW_FRAME_OK 0u
+#define MCRAW_FRAME_BAD_HEADER 1u      /* offsets > len, encodedWidth % 64, encodedWidth < width (RawData.cpp:547-554) */
+#define MCRAW_FRAME_TRUNCATED 2u       /* a block or metadata block runs past len (reference: stale data, RawData.cpp:419) */
+#define MCRAW_FRAME_BAD_BITS 4u        /* bits[] value > 16 (reference: out-of-bounds table read) */
+#define MCRAW_FRAME_BAD_META_COUNT 8u  /* metadata count smaller than the number of blocks */
+#define MCRAW_FRAME_GEOMETRY 16u       /* encoded size larger than width/height in the descriptor allow */
+#define MCRAW_FRAME_BAD_TYPE 32u       /* compression_type not 6 or 7 (Decoder.cpp:233) */
+
+typedef struct mcraw_ctx mcraw_ctx; /* opaque; owns scratch, streams, staging rings on one device */
+
+/* One frame of a batch.  For mcraw_decode_batch src and dst are DEVICE pointers, 16-byte aligned.
+ * For mcraw_decode_batch_host src is HOST memory (pinned for overlap; pageable works but serialises). */
+typedef struct mcraw_frame_desc {
+    const uint8_t* src;          /* compressed frame buffer (what Decoder.cpp:199-201 freads into mTmpBuffer) */
+    uint64_t len;                /* its size in bytes */
+    int32_t width;               /* frame JSON "width"  (Decoder.cpp:216) */
+    int32_t height;              /* frame JSON "height" (Decoder.cpp:217) */
+    int32_t compression_type;    /* frame JSON "compressionType": 7 or 6 (Decoder.cpp:218) */
+    int32_t reserved;
+    uint16_t* dst;               /* DEVICE output, width*height uint16, row-major (Decoder.cpp:221-222) */
+    uint64_t dst_capacity_elems; /* capacity of dst in uint16 elements */
+} mcraw_frame_desc;
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+int mcraw_ctx_create(int device, mcraw_ctx** out);
+void mcraw_ctx_destroy(mcraw_ctx* ctx);
+const char* mcraw_last_error(const mcraw_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+int mcraw_ctx_device(const mcraw_ctx* ctx);
+
+/* ---- batched device entry point -------------------------------------------------------------------- */
+/* Enqueue the decode of n frames on `stream` (a cudaStream_t passed as void*; NULL = the context's own
+ * stream).  Asynchronous: returns once the work is enqueued.  Frames may mix sizes and compression types. */
+int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);
+
+/* Same, but descs[i].src are HOST buffers: the context copies them to device staging on its side streams in
+ * chunks (double-buffered) so transfer overlaps decode, then decodes into descs[i].dst (device). */
+int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);
+
+/* Wait for the most recently enqueued batch and fetch its per-frame results: written_elems[i] is the number
+ * of uint16 elements written for frame i (0 = failed), status[i] the MCRAW_FRAME_* bits.  Either may be NULL. */
+int mcraw_batch_wait(mcraw_ctx* ctx, uint64_t* written_elems, uint32_t* status, uint32_t n);
+
+/* ---- reference-shaped single-frame call (host in, host out, synchronous) ---------------------------- */
+/* Same contract as motioncam::raw::Decode / DecodeLegacy: output holds width*height uint16; returns the
+ * element count written or 0.  H2D, decode and D2H all happen inside the call. */
+size_t mcraw_decode_host(mcraw_ctx* ctx, uint16_t* output, int width, int height, const uint8_t* input, size_t len,
+                         int compression_type);
+
+/* ---- memory helpers (so a C caller needs no CUDA headers) ------------------------------------------- */
+int mcraw_device_alloc(mcraw_ctx* ctx, size_t bytes, void** out);
+int mcraw_device_free(mcraw_ctx* ctx, void* p);
+int mcraw_host_alloc_pinned(mcraw_ctx* ctx, size_t bytes, void** out);
+int mcraw_host_free_pinned(mcraw_ctx* ctx, void* p);
+int mcraw_memcpy_h2d(mcraw_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int mcraw_memcpy_d2h(mcraw_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int mcraw_stream_sync(mcraw_ctx* ctx, void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------------------- */
+/* Kernels of this library launched through ctx since creation (bench.py reports the per-step delta). */
+uint64_t mcraw_kernel_launches(const mcraw_ctx* ctx);
+/* CUDA-event time of the decode kernels of the last waited batch, in milliseconds (0 if unavailable). */
+float mcraw_last_batch_kernel_ms(const mcraw_ctx* ctx);
+const char* mcraw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCRAW_B200_H */

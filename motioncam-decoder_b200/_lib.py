@@ -1,0 +1,19 @@
+"""Locations and loaders of the in-tree shared libraries (built by csrc/Makefile)."""
+import ctypes
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+
+LIB_CAPI = os.path.join(PKG_DIR, "libmcraw_b200.so")           # kernels + C-ABI (needs a GPU to run)
+LIB_TOOLS = os.path.join(PKG_DIR, "libmcraw_tools.so")         # CPU encoder / generators
+LIB_DROPIN = os.path.join(PKG_DIR, "libmotioncam_decoder_b200.so")  # drop-in C++ API + flat wrappers
+
+
+def load(path):
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{os.path.basename(path)} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or `make -C {CSRC}` first (there is no CPU fallback for the decode path)")
+    return ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)

@@ -1,0 +1,227 @@
+"""ctypes binding of the C-ABI in include/mcraw_b200.h (libmcraw_b200.so).
+
+This is what tests/ and bench.py call; it adds nothing to the decode path.  Loading fails loudly when the
+library is not built, and Context() raises when no CUDA device is usable -- there is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+COMPRESSION_LEGACY = 6
+COMPRESSION_CURRENT = 7
+
+FRAME_OK = 0
+FRAME_BAD_HEADER = 1
+FRAME_TRUNCATED = 2
+FRAME_BAD_BITS = 4
+FRAME_BAD_META_COUNT = 8
+FRAME_GEOMETRY = 16
+FRAME_BAD_TYPE = 32
+
+
+class FrameDesc(ctypes.Structure):
+    _fields_ = [
+        ("src", ctypes.c_void_p),
+        ("len", ctypes.c_uint64),
+        ("width", ctypes.c_int32),
+        ("height", ctypes.c_int32),
+        ("compression_type", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("dst", ctypes.c_void_p),
+        ("dst_capacity_elems", ctypes.c_uint64),
+    ]
+
+
+EXPORTED = [
+    "mcraw_version", "mcraw_ctx_create", "mcraw_ctx_destroy", "mcraw_last_error", "mcraw_ctx_device",
+    "mcraw_decode_batch", "mcraw_decode_batch_host", "mcraw_batch_wait", "mcraw_decode_host",
+    "mcraw_device_alloc", "mcraw_device_free", "mcraw_host_alloc_pinned", "mcraw_host_free_pinned",
+    "mcraw_memcpy_h2d", "mcraw_memcpy_d2h", "mcraw_stream_sync", "mcraw_kernel_launches",
+    "mcraw_last_batch_kernel_ms",
+]
+
+_c = None
+
+
+def lib():
+    global _c
+    if _c is None:
+        c = _lib.load(_lib.LIB_CAPI)
+        vp, u64, u32, sz = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_size_t
+        c.mcraw_version.restype = ctypes.c_char_p
+        c.mcraw_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+        c.mcraw_ctx_destroy.argtypes = [vp]
+        c.mcraw_ctx_destroy.restype = None
+        c.mcraw_last_error.argtypes = [vp]
+        c.mcraw_last_error.restype = ctypes.c_char_p
+        c.mcraw_ctx_device.argtypes = [vp]
+        c.mcraw_decode_batch.argtypes = [vp, ctypes.POINTER(FrameDesc), u32, vp]
+        c.mcraw_decode_batch_host.argtypes = [vp, ctypes.POINTER(FrameDesc), u32, vp]
+        c.mcraw_batch_wait.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u32), u32]
+        c.mcraw_decode_host.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, sz, ctypes.c_int]
+        c.mcraw_decode_host.restype = sz
+        c.mcraw_device_alloc.argtypes = [vp, sz, ctypes.POINTER(vp)]
+        c.mcraw_device_free.argtypes = [vp, vp]
+        c.mcraw_host_alloc_pinned.argtypes = [vp, sz, ctypes.POINTER(vp)]
+        c.mcraw_host_free_pinned.argtypes = [vp, vp]
+        c.mcraw_memcpy_h2d.argtypes = [vp, vp, vp, sz, vp]
+        c.mcraw_memcpy_d2h.argtypes = [vp, vp, vp, sz, vp]
+        c.mcraw_stream_sync.argtypes = [vp, vp]
+        c.mcraw_kernel_launches.argtypes = [vp]
+        c.mcraw_kernel_launches.restype = u64
+        c.mcraw_last_batch_kernel_ms.argtypes = [vp]
+        c.mcraw_last_batch_kernel_ms.restype = ctypes.c_float
+        _c = c
+    return _c
+
+
+class McrawError(RuntimeError):
+    pass
+
+
+class Context:
+    """One decoder context on one CUDA device (mcraw_ctx)."""
+
+    def __init__(self, device=0):
+        self._c = lib()
+        h = ctypes.c_void_p()
+        rc = self._c.mcraw_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise McrawError(f"mcraw_ctx_create({device}) failed ({rc}): {self._c.mcraw_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._c.mcraw_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise McrawError(f"{what} failed ({rc}): {self._c.mcraw_last_error(self._h).decode()}")
+
+    # -- memory -------------------------------------------------------------------------------------
+    def device_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(self._c.mcraw_device_alloc(self._h, nbytes, ctypes.byref(p)), "mcraw_device_alloc")
+        return p.value
+
+    def device_free(self, ptr):
+        self._check(self._c.mcraw_device_free(self._h, ptr), "mcraw_device_free")
+
+    def pinned_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(self._c.mcraw_host_alloc_pinned(self._h, nbytes, ctypes.byref(p)), "mcraw_host_alloc_pinned")
+        return p.value
+
+    def pinned_free(self, ptr):
+        self._check(self._c.mcraw_host_free_pinned(self._h, ptr), "mcraw_host_free_pinned")
+
+    def pinned_array(self, nbytes):
+        """A pinned host buffer viewed as a numpy uint8 array (freed with the context owner's pinned_free)."""
+        ptr = self.pinned_alloc(nbytes)
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        return ptr, arr
+
+    def h2d(self, dst_dev, src, stream=None, sync=True):
+        src = np.ascontiguousarray(src)
+        self._check(self._c.mcraw_memcpy_h2d(self._h, dst_dev, src.ctypes.data, src.nbytes, stream), "mcraw_memcpy_h2d")
+        if sync:
+            self.sync(stream)
+
+    def d2h(self, dst, src_dev, nbytes=None, stream=None, sync=True):
+        assert dst.flags["C_CONTIGUOUS"]
+        self._check(self._c.mcraw_memcpy_d2h(self._h, dst.ctypes.data, src_dev, dst.nbytes if nbytes is None else nbytes,
+                                             stream), "mcraw_memcpy_d2h")
+        if sync:
+            self.sync(stream)
+
+    def sync(self, stream=None):
+        self._check(self._c.mcraw_stream_sync(self._h, stream), "mcraw_stream_sync")
+
+    # -- decode -------------------------------------------------------------------------------------
+    @staticmethod
+    def make_descs(frames):
+        """frames: iterable of (src_ptr, len, width, height, compression_type, dst_ptr, dst_capacity_elems)."""
+        frames = list(frames)
+        arr = (FrameDesc * max(1, len(frames)))()
+        for i, (src, ln, w, h, ct, dst, cap) in enumerate(frames):
+            arr[i].src, arr[i].len, arr[i].width, arr[i].height = src, ln, w, h
+            arr[i].compression_type, arr[i].reserved, arr[i].dst, arr[i].dst_capacity_elems = ct, 0, dst, cap
+        return arr, len(frames)
+
+    def decode_batch(self, descs, n, stream=None):
+        self._check(self._c.mcraw_decode_batch(self._h, descs, n, stream), "mcraw_decode_batch")
+
+    def decode_batch_host(self, descs, n, stream=None):
+        self._check(self._c.mcraw_decode_batch_host(self._h, descs, n, stream), "mcraw_decode_batch_host")
+
+    def batch_wait(self, n):
+        written = (ctypes.c_uint64 * max(1, n))()
+        status = (ctypes.c_uint32 * max(1, n))()
+        self._check(self._c.mcraw_batch_wait(self._h, written, status, n), "mcraw_batch_wait")
+        return list(written[:n]), list(status[:n])
+
+    def decode_host(self, stream_bytes, width, height, compression_type, fill=0xA5A5):
+        """Reference-shaped call: host bytes in, host uint16 image out -> (elements_written, image)."""
+        src = np.ascontiguousarray(stream_bytes, dtype=np.uint8)
+        out = np.full(width * height + 64, fill, dtype=np.uint16)
+        n = self._c.mcraw_decode_host(self._h, out.ctypes.data, width, height, src.ctypes.data, src.size, compression_type)
+        assert np.all(out[width * height:] == fill)
+        return int(n), out[:width * height].reshape(height, width)
+
+    @property
+    def kernel_launches(self):
+        return int(self._c.mcraw_kernel_launches(self._h))
+
+    @property
+    def last_batch_kernel_ms(self):
+        return float(self._c.mcraw_last_batch_kernel_ms(self._h))
+
+
+class DeviceBatch:
+    """Test/bench helper: uploads compressed frames to device memory and owns the output buffers."""
+
+    def __init__(self, ctx, frames):
+        """frames: list of (np.uint8 stream, width, height, compression_type)."""
+        self.ctx = ctx
+        self.frames = frames
+        self.src_ptrs, self.dst_ptrs = [], []
+        items = []
+        for stream, w, h, ct in frames:
+            stream = np.ascontiguousarray(stream, dtype=np.uint8)
+            sp = ctx.device_alloc(stream.size + 16)
+            dp = ctx.device_alloc(w * h * 2 + 16)
+            ctx.h2d(sp, stream)
+            self.src_ptrs.append(sp)
+            self.dst_ptrs.append(dp)
+            items.append((sp, stream.size, w, h, ct, dp, w * h))
+        self.descs, self.n = Context.make_descs(items)
+
+    def decode(self, stream=None):
+        self.ctx.decode_batch(self.descs, self.n, stream)
+        return self.ctx.batch_wait(self.n)
+
+    def fetch(self, i, fill=None):
+        _, w, h, _ = self.frames[i]
+        out = np.empty(w * h, dtype=np.uint16)
+        self.ctx.d2h(out, self.dst_ptrs[i])
+        return out.reshape(h, w)
+
+    def fill_outputs(self, value=0xA5A5):
+        for (_, w, h, _), dp in zip(self.frames, self.dst_ptrs):
+            self.ctx.h2d(dp, np.full(w * h, value, dtype=np.uint16))
+
+    def free(self):
+        for p in self.src_ptrs + self.dst_ptrs:
+            self.ctx.device_free(p)
+        self.src_ptrs, self.dst_ptrs = [], []

@@ -1,0 +1,107 @@
+"""GPU parity: the CUDA path (through the C-ABI, ctypes) against the oracle on the shared seeded vectors,
+current frame format (compressionType 7).  Bit-exact or fail."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import vectors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from motioncam_decoder_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _check_batch(ctx, vecs, ctype, oracle_fn):
+    from motioncam_decoder_b200 import capi
+    frames = [(s, w, h, ctype) for (_, s, w, h, _) in vecs]
+    batch = capi.DeviceBatch(ctx, frames)
+    batch.fill_outputs(0xA5A5)
+    written, status = batch.decode()
+    for i, (name, s, w, h, img) in enumerate(vecs):
+        n, want = oracle_fn(s, w, h)
+        got = batch.fetch(i)
+        assert status[i] == 0, (name, status[i])
+        assert written[i] == n, (name, written[i], n)
+        assert np.array_equal(got, want), f"{name}: CUDA output differs from the oracle"
+        if img is not None:
+            assert np.array_equal(got, img), name
+    batch.free()
+
+
+def test_current_vectors_batched(ctx):
+    from motioncam_decoder_b200 import capi
+    _check_batch(ctx, vectors.current_vectors(small=True), capi.COMPRESSION_CURRENT, ol.oracle_decode)
+
+
+def test_current_vectors_one_by_one_host_call(ctx):
+    """mcraw_decode_host = the reference-shaped call (host in / host out)."""
+    from motioncam_decoder_b200 import capi
+    for name, s, w, h, img in vectors.current_vectors(small=True):
+        n, got = ctx.decode_host(s, w, h, capi.COMPRESSION_CURRENT)
+        n_or, want = ol.oracle_decode(s, w, h)
+        assert n == n_or == w * h, name
+        assert np.array_equal(got, want), name
+
+
+def test_current_full_size(ctx):
+    from motioncam_decoder_b200 import capi
+    vecs = [v for v in vectors.current_vectors(small=False) if v[0] in ("photon_1080p", "photon_c1")]
+    _check_batch(ctx, vecs, capi.COMPRESSION_CURRENT, ol.oracle_decode)
+
+
+def test_current_rejects_bad_frames(ctx):
+    """Same 0-means-failure convention as RawData.cpp:547-554, plus the hardened corners."""
+    from motioncam_decoder_b200 import capi, testvec as tv
+    img = tv.gen_photon(128, 8, 1023, seed=1)
+    good = tv.encode_current(img)
+
+    def u32(v):
+        return np.frombuffer(np.uint32(v).tobytes(), dtype=np.uint8)
+
+    cases = {}
+    s = good.copy(); s[0:4] = u32(96); cases["ew_not_64"] = (s, 128, capi.FRAME_BAD_HEADER)
+    s = good.copy(); s[8:12] = u32(len(s) + 1); cases["bits_off"] = (s, 128, capi.FRAME_BAD_HEADER)
+    s = good.copy(); s[12:16] = u32(len(s) + 1); cases["refs_off"] = (s, 128, capi.FRAME_BAD_HEADER)
+    cases["ew_lt_width"] = (good.copy(), 192, capi.FRAME_BAD_HEADER)
+    cases["truncated"] = (good[: len(good) - 7].copy(), 128, capi.FRAME_TRUNCATED)
+    cases["short"] = (good[:8].copy(), 128, capi.FRAME_BAD_HEADER)
+    frames = [(s, w, 8, capi.COMPRESSION_CURRENT) for (s, w, _) in cases.values()]
+    frames.append((good, 128, 8, capi.COMPRESSION_CURRENT))      # a good frame in the same batch still decodes
+    frames.append((good, 128, 8, 5))                             # unknown compression type (Decoder.cpp:233)
+    batch = capi.DeviceBatch(ctx, frames)
+    written, status = batch.decode()
+    for i, (name, (_, _, want_status)) in enumerate(cases.items()):
+        assert written[i] == 0, name
+        assert status[i] & want_status, (name, status[i])
+        n_or, _ = ol.oracle_decode(frames[i][0], frames[i][1], 8)
+        assert n_or == 0, name
+    assert written[len(cases)] == 128 * 8 and status[len(cases)] == 0
+    assert np.array_equal(batch.fetch(len(cases)), img)
+    assert written[len(cases) + 1] == 0 and status[len(cases) + 1] == capi.FRAME_BAD_TYPE
+    batch.free()
+
+
+def test_dst_capacity_crops_rows(ctx):
+    """encodedHeight rows are emitted (RawData.cpp:571,598-608) but never past dst capacity."""
+    from motioncam_decoder_b200 import capi, testvec as tv
+    img = tv.gen_photon(256, 16, 1023, seed=3)
+    s = tv.encode_current(img)
+    sp = ctx.device_alloc(len(s) + 16)
+    dp = ctx.device_alloc(256 * 16 * 2)
+    ctx.h2d(sp, s)
+    ctx.h2d(dp, np.full(256 * 16, 0xA5A5, dtype=np.uint16))
+    descs, n = capi.Context.make_descs([(sp, len(s), 256, 16, capi.COMPRESSION_CURRENT, dp, 256 * 10)])
+    ctx.decode_batch(descs, n)
+    written, status = ctx.batch_wait(n)
+    out = np.empty(256 * 16, dtype=np.uint16)
+    ctx.d2h(out, dp)
+    out = out.reshape(16, 256)
+    assert status[0] == 0 and written[0] == 256 * 10
+    assert np.array_equal(out[:10], img[:10]) and np.all(out[10:] == 0xA5A5)
+    ctx.device_free(sp); ctx.device_free(dp)
