@@ -39,7 +39,7 @@ EXPORTED = [
     "mcraw_decode_batch", "mcraw_decode_batch_host", "mcraw_batch_wait", "mcraw_decode_host",
     "mcraw_device_alloc", "mcraw_device_free", "mcraw_host_alloc_pinned", "mcraw_host_free_pinned",
     "mcraw_memcpy_h2d", "mcraw_memcpy_d2h", "mcraw_stream_sync", "mcraw_kernel_launches",
-    "mcraw_last_batch_kernel_ms",
+    "mcraw_last_batch_kernel_ms", "mcraw_kernel_time_totals",
 ]
 
 _c = None
@@ -73,6 +73,8 @@ def lib():
         c.mcraw_kernel_launches.restype = u64
         c.mcraw_last_batch_kernel_ms.argtypes = [vp]
         c.mcraw_last_batch_kernel_ms.restype = ctypes.c_float
+        c.mcraw_kernel_time_totals.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                               ctypes.POINTER(u64)]
         _c = c
     return _c
 
@@ -182,6 +184,13 @@ class Context:
     @property
     def kernel_launches(self):
         return int(self._c.mcraw_kernel_launches(self._h))
+
+    def kernel_time_totals(self):
+        """(metadata-kernel ms, main-kernel ms, chunks) accumulated since the context was created."""
+        a, b, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
+        self._check(self._c.mcraw_kernel_time_totals(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)),
+                    "mcraw_kernel_time_totals")
+        return a.value, b.value, n.value
 
     @property
     def last_batch_kernel_ms(self):

@@ -17,8 +17,11 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSlots = 4;              // batches that may be in flight per context
+constexpr int kSlots = 6;              // chunks (sub-batches) that may be in flight per context
 constexpr uint32_t kMaxGridY = 32768;  // frames per launch
+constexpr int kStage = 3;              // device staging buffers of the host-input pipeline
+constexpr size_t kStageBytes = 48u << 20;
+constexpr int kCopyStreams = 2;
 
 struct Slot {
     FrameDev* h_frames = nullptr;   // pinned
@@ -28,9 +31,19 @@ struct Slot {
     uint32_t cap_frames = 0;
     uint8_t* d_scratch = nullptr;
     size_t scratch_bytes = 0;
-    cudaEvent_t done = nullptr, k_start = nullptr, k_stop = nullptr;
+    cudaEvent_t done = nullptr, e0 = nullptr, e1 = nullptr, e2 = nullptr;
     bool in_flight = false;
+    bool timed = false;
     uint32_t n = 0;
+    uint32_t result_offset = 0;     // index of this chunk's first frame inside the logical batch
+    uint64_t batch_id = 0;
+};
+
+struct Stage {
+    uint8_t* d_buf = nullptr;
+    cudaEvent_t copied = nullptr;   // H2D of the chunk finished (recorded on a copy stream)
+    cudaEvent_t freed = nullptr;    // decode that read the buffer finished (recorded on the decode stream)
+    bool used = false;
 };
 
 }  // namespace
@@ -38,11 +51,20 @@ struct Slot {
 struct mcraw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    uint32_t* d_tab = nullptr;
+    cudaStream_t copy_streams[kCopyStreams] = {nullptr, nullptr};
     Slot slots[kSlots];
     int cur = -1;
+    Stage stages[kStage];
+    int stage_cur = 0;
     uint64_t launches = 0;
+    uint64_t batch_id = 0;
+    uint32_t batch_n = 0;
+    std::vector<uint64_t> res_written;
+    std::vector<uint32_t> res_status;
+    std::vector<int> res_type;
     float last_kernel_ms = 0.f;
+    double acc_meta_ms = 0, acc_main_ms = 0;
+    uint64_t acc_chunks = 0;
     std::string err;
     // staging for the single-frame host call
     uint8_t* h_in = nullptr; size_t h_in_cap = 0;
@@ -96,32 +118,45 @@ int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t scratch) {
     return MCRAW_OK;
 }
 
-int pick_threads(uint32_t units) {
-    // block size (multiple of 32, 96..256) that wastes the fewest lanes over ceil(units/threads) rounds
-    int best = 256;
-    double best_waste = 1e9;
-    for (int t = 256; t >= 96; t -= 32) {
-        uint32_t rounds = (units + t - 1) / t;
-        double waste = (double)rounds * t / (double)units;
-        if (waste < best_waste - 1e-9) { best_waste = waste; best = t; }
+// Wait for a slot's chunk, fold its results into the logical batch (if it still belongs to the current
+// one) and its kernel times into the context totals.
+int harvest(mcraw_ctx* ctx, Slot& s) {
+    if (!s.in_flight) return MCRAW_OK;
+    CU_TRY(ctx, cudaEventSynchronize(s.done));
+    s.in_flight = false;
+    if (s.timed) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, s.e0, s.e1) == cudaSuccess && cudaEventElapsedTime(&b, s.e1, s.e2) == cudaSuccess) {
+            ctx->acc_meta_ms += a; ctx->acc_main_ms += b; ctx->acc_chunks += 1;
+            ctx->last_kernel_ms = a + b;
+        }
     }
-    return best;
+    if (s.batch_id == ctx->batch_id) {
+        for (uint32_t i = 0; i < s.n; i++) {
+            const uint32_t k = s.result_offset + i;
+            if (k >= ctx->res_written.size()) break;
+            ctx->res_written[k] = s.h_results[i].written;
+            ctx->res_status[k] = s.h_results[i].status;
+        }
+    }
+    return MCRAW_OK;
 }
 
-// Validate descriptors, fill the slot's FrameDev array, return scratch needed.
-int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, std::vector<FrameDev>& out, size_t& scratch,
-            uint32_t& max_tile_rows, uint32_t& max_units, bool& any7, bool& any6) {
+// Validate descriptors and build the device-side frame records; tilemeta holds an OFFSET until rebased.
+int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t first_index, std::vector<FrameDev>& out,
+            size_t& scratch, uint32_t& max_tile_rows, uint32_t& max_units, bool& any7, bool& any6) {
     out.resize(n);
     scratch = 0; max_tile_rows = 0; max_units = 0; any7 = any6 = false;
     for (uint32_t i = 0; i < n; i++) {
         const mcraw_frame_desc& d = descs[i];
+        const std::string who = "frame " + std::to_string(first_index + i);
         FrameDev f;
         std::memset(&f, 0, sizeof f);
-        if (!d.src || !d.dst) return fail_arg(ctx, "frame " + std::to_string(i) + ": null src/dst");
+        if (!d.src || !d.dst) return fail_arg(ctx, who + ": null src/dst");
         if (d.width <= 0 || d.height <= 0 || d.width > 65536 || d.height > 65536)
-            return fail_arg(ctx, "frame " + std::to_string(i) + ": unsupported width/height");
+            return fail_arg(ctx, who + ": unsupported width/height");
         if (((uintptr_t)d.src & 15) || ((uintptr_t)d.dst & 1))
-            return fail_arg(ctx, "frame " + std::to_string(i) + ": src must be 16-byte aligned, dst 2-byte aligned");
+            return fail_arg(ctx, who + ": src must be 16-byte aligned, dst 2-byte aligned");
         f.src = d.src; f.len = d.len; f.dst = d.dst; f.dst_cap = d.dst_capacity_elems;
         f.width = d.width; f.height = d.height; f.type = d.compression_type;
         f.tiles_x = (uint32_t)(d.width + 63) / 64;
@@ -129,10 +164,19 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, std::vect
         f.flags = ((d.width % 8) == 0 && ((uintptr_t)d.dst & 15) == 0) ? FLAG_VEC_STORE : 0;
         if (d.compression_type == MCRAW_COMPRESSION_CURRENT) {
             any7 = true;
-            f.tilemeta = reinterpret_cast<uint4*>(scratch);   // offset for now, rebased below
-            scratch += (size_t)f.tiles_x * f.tile_rows * sizeof(uint4);
+            const uint64_t ntiles = (uint64_t)f.tiles_x * f.tile_rows;
+            f.nunits = (uint32_t)((ntiles + 15) / 16);
+            f.inv_tiles_x = (ntiles * f.tiles_x < (1ull << 32)) ? (uint32_t)(((1ull << 32) + f.tiles_x - 1) / f.tiles_x) : 0u;
+            if (f.tiles_x == 1) f.inv_tiles_x = 0;   // 2^32 does not fit; plain division
+            // scratch layout (offsets for now, rebased on the slot's buffer): unitoff | pairinfo | pairrefs
+            f.unitoff = reinterpret_cast<uint32_t*>(scratch);
+            scratch += (((size_t)f.nunits + 1) * 4 + 15) & ~(size_t)15;
+            f.pairinfo = reinterpret_cast<uint32_t*>(scratch);
+            scratch += (size_t)f.nunits * 32 * 4;
+            f.pairrefs = reinterpret_cast<uint32_t*>(scratch);
+            scratch += (size_t)f.nunits * 32 * 4;
             max_tile_rows = std::max(max_tile_rows, f.tile_rows);
-            max_units = std::max(max_units, f.tiles_x * 16u);
+            max_units = std::max(max_units, f.nunits);
         } else if (d.compression_type == MCRAW_COMPRESSION_LEGACY) {
             any6 = true;
         } else {
@@ -143,44 +187,67 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, std::vect
     return MCRAW_OK;
 }
 
-int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStream_t st) {
-    if (!descs && n) return fail_arg(ctx, "descs is null");
-    int rc = bind(ctx);
-    if (rc) return rc;
+// Start a new logical batch of n frames: earlier batches' unharvested chunks only keep their timing.
+int begin_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n) {
+    ctx->batch_id++;
+    ctx->batch_n = n;
+    ctx->res_written.assign(n, 0);
+    ctx->res_status.assign(n, 0);
+    ctx->res_type.resize(n);
+    for (uint32_t i = 0; i < n; i++) ctx->res_type[i] = descs[i].compression_type;
+    return MCRAW_OK;
+}
+
+// Enqueue one chunk (device-resident sources) of the current logical batch on `st`.
+int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st) {
+    if (n == 0) return MCRAW_OK;
     ctx->cur = (ctx->cur + 1) % kSlots;
     Slot& s = ctx->slots[ctx->cur];
-    if (s.in_flight) { CU_TRY(ctx, cudaEventSynchronize(s.done)); s.in_flight = false; }
-    s.n = n;
-    if (n == 0) { CU_TRY(ctx, cudaEventRecord(s.done, st)); s.in_flight = true; return MCRAW_OK; }
+    int rc = harvest(ctx, s);
+    if (rc) return rc;
 
     std::vector<FrameDev> frames;
     size_t scratch; uint32_t max_tile_rows, max_units; bool any7, any6;
-    rc = prepare(ctx, descs, n, frames, scratch, max_tile_rows, max_units, any7, any6);
+    rc = prepare(ctx, descs, n, result_offset, frames, scratch, max_tile_rows, max_units, any7, any6);
     if (rc) return rc;
     rc = slot_reserve(ctx, s, n, scratch);
     if (rc) return rc;
     for (uint32_t i = 0; i < n; i++) {
-        if (frames[i].type == MCRAW_COMPRESSION_CURRENT)
-            frames[i].tilemeta = reinterpret_cast<uint4*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].tilemeta));
+        if (frames[i].type == MCRAW_COMPRESSION_CURRENT) {
+            frames[i].unitoff = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].unitoff));
+            frames[i].pairinfo = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].pairinfo));
+            frames[i].pairrefs = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].pairrefs));
+        }
         s.h_frames[i] = frames[i];
     }
+    s.n = n; s.result_offset = result_offset; s.batch_id = ctx->batch_id; s.timed = false;
     CU_TRY(ctx, cudaMemcpyAsync(s.d_frames, s.h_frames, sizeof(FrameDev) * n, cudaMemcpyHostToDevice, st));
     CU_TRY(ctx, cudaMemsetAsync(s.d_results, 0, sizeof(Result) * n, st));
-    CU_TRY(ctx, cudaEventRecord(s.k_start, st));
-    for (uint32_t base = 0; base < n; base += kMaxGridY) {
-        const uint32_t cnt = std::min(kMaxGridY, n - base);
-        if (any7) {
-            k_meta<<<2 * cnt, K1_THREADS, 0, st>>>(s.d_frames + base, ctx->d_tab);
-            const int threads = pick_threads(max_units);
-            k_tiles<<<dim3(max_tile_rows, cnt), threads, 0, st>>>(s.d_frames + base, ctx->d_tab, s.d_results + base);
-            ctx->launches += 2;
-        }
+    if (any7) {
+        CU_TRY(ctx, cudaEventRecord(s.e0, st));
+        k_meta<<<2 * n, K1_THREADS, 0, st>>>(s.d_frames);
+        CU_TRY(ctx, cudaEventRecord(s.e1, st));
+        k_units<<<dim3((max_units + KU_WARPS - 1) / KU_WARPS, n), 32 * KU_WARPS, KU_SMEM, st>>>(s.d_frames, s.d_results);
+        CU_TRY(ctx, cudaEventRecord(s.e2, st));
+        ctx->launches += 2;
+        s.timed = true;
     }
     CU_TRY(ctx, cudaGetLastError());
-    CU_TRY(ctx, cudaEventRecord(s.k_stop, st));
     CU_TRY(ctx, cudaMemcpyAsync(s.h_results, s.d_results, sizeof(Result) * n, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaEventRecord(s.done, st));
     s.in_flight = true;
+    return MCRAW_OK;
+}
+
+int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStream_t st) {
+    if (!descs && n) return fail_arg(ctx, "descs is null");
+    int rc = bind(ctx);
+    if (rc) return rc;
+    begin_batch(ctx, descs, n);
+    for (uint32_t base = 0; base < n; base += kMaxGridY) {
+        rc = enqueue_chunk(ctx, descs + base, std::min(kMaxGridY, n - base), base, st);
+        if (rc) return rc;
+    }
     return MCRAW_OK;
 }
 
@@ -224,15 +291,20 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         return bail(MCRAW_ERR_NO_DEVICE);
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
-    std::vector<uint32_t> tab(MCRAW_TAB_ENTRIES * MCRAW_TAB_WORDS);
-    mcraw_build_table(tab.data());
-    if (cudaMalloc(&ctx->d_tab, tab.size() * 4) != cudaSuccess ||
-        cudaMemcpy(ctx->d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
-        ctx->err = "table upload failed"; return bail(MCRAW_ERR_CUDA);
+    for (auto& cs : ctx->copy_streams)
+        if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
+    if (cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess) {
+        ctx->err = "cudaFuncSetAttribute(k_units, smem) failed"; return bail(MCRAW_ERR_CUDA);
     }
     for (auto& s : ctx->slots) {
-        if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&s.k_start) != cudaSuccess ||
-            cudaEventCreate(&s.k_stop) != cudaSuccess) {
+        if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&s.e0) != cudaSuccess ||
+            cudaEventCreate(&s.e1) != cudaSuccess || cudaEventCreate(&s.e2) != cudaSuccess) {
+            ctx->err = "event create failed"; return bail(MCRAW_ERR_CUDA);
+        }
+    }
+    for (auto& g : ctx->stages) {
+        if (cudaEventCreateWithFlags(&g.copied, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g.freed, cudaEventDisableTiming) != cudaSuccess) {
             ctx->err = "event create failed"; return bail(MCRAW_ERR_CUDA);
         }
     }
@@ -243,23 +315,28 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
 void mcraw_ctx_destroy(mcraw_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     for (auto& s : ctx->slots) {
-        if (s.in_flight && s.done) cudaEventSynchronize(s.done);
         if (s.h_frames) cudaFreeHost(s.h_frames);
         if (s.h_results) cudaFreeHost(s.h_results);
         if (s.d_frames) cudaFree(s.d_frames);
         if (s.d_results) cudaFree(s.d_results);
         if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.done) cudaEventDestroy(s.done);
-        if (s.k_start) cudaEventDestroy(s.k_start);
-        if (s.k_stop) cudaEventDestroy(s.k_stop);
+        if (s.e0) cudaEventDestroy(s.e0);
+        if (s.e1) cudaEventDestroy(s.e1);
+        if (s.e2) cudaEventDestroy(s.e2);
+    }
+    for (auto& g : ctx->stages) {
+        if (g.d_buf) cudaFree(g.d_buf);
+        if (g.copied) cudaEventDestroy(g.copied);
+        if (g.freed) cudaEventDestroy(g.freed);
     }
     if (ctx->h_in) cudaFreeHost(ctx->h_in);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
-    if (ctx->d_tab) cudaFree(ctx->d_tab);
+    for (auto& cs : ctx->copy_streams) if (cs) cudaStreamDestroy(cs);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -269,28 +346,89 @@ int mcraw_ctx_device(const mcraw_ctx* ctx) { return ctx ? ctx->device : -1; }
 uint64_t mcraw_kernel_launches(const mcraw_ctx* ctx) { return ctx ? ctx->launches : 0; }
 float mcraw_last_batch_kernel_ms(const mcraw_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
 
+int mcraw_kernel_time_totals(mcraw_ctx* ctx, double* meta_ms, double* main_ms, uint64_t* chunks) {
+    if (!ctx) return MCRAW_ERR_ARG;
+    int rc = bind(ctx);
+    if (rc) return rc;
+    for (auto& s : ctx->slots) { rc = harvest(ctx, s); if (rc) return rc; }
+    if (meta_ms) *meta_ms = ctx->acc_meta_ms;
+    if (main_ms) *main_ms = ctx->acc_main_ms;
+    if (chunks) *chunks = ctx->acc_chunks;
+    return MCRAW_OK;
+}
+
 int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
     return enqueue(ctx, descs, n, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
 }
 
-int mcraw_batch_wait(mcraw_ctx* ctx, uint64_t* written_elems, uint32_t* status, uint32_t n) {
+int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
-    if (ctx->cur < 0 || !ctx->slots[ctx->cur].in_flight) { ctx->err = "no batch in flight"; return MCRAW_ERR_STATE; }
+    if (!descs && n) return fail_arg(ctx, "descs is null");
     int rc = bind(ctx);
     if (rc) return rc;
-    Slot& s = ctx->slots[ctx->cur];
-    CU_TRY(ctx, cudaEventSynchronize(s.done));
-    s.in_flight = false;
-    if (s.n) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, s.k_start, s.k_stop) == cudaSuccess) ctx->last_kernel_ms = ms;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    begin_batch(ctx, descs, n);
+    std::vector<mcraw_frame_desc> chunk;
+    uint32_t i = 0;
+    int copy_rr = 0;
+    while (i < n) {
+        // ---- pick the frames of this chunk: as many as fit one staging buffer (at least one)
+        size_t bytes = 0;
+        uint32_t j = i;
+        while (j < n && j - i < kMaxGridY) {
+            if (!descs[j].src) return fail_arg(ctx, "frame " + std::to_string(j) + ": null src");
+            size_t need = (descs[j].len + 255) & ~(size_t)255;
+            if (j > i && bytes + need > kStageBytes) break;
+            bytes += need;
+            j++;
+        }
+        Stage& g = ctx->stages[ctx->stage_cur];
+        ctx->stage_cur = (ctx->stage_cur + 1) % kStage;
+        cudaStream_t cs = ctx->copy_streams[copy_rr];
+        copy_rr = (copy_rr + 1) % kCopyStreams;
+        uint8_t* buf = g.d_buf;
+        if (bytes > kStageBytes) {   // a single frame larger than a staging buffer: dedicated, synchronous allocation
+            if (g.used) CU_TRY(ctx, cudaEventSynchronize(g.freed));
+            if (g.d_buf) { cudaFree(g.d_buf); g.d_buf = nullptr; }
+            CU_TRY(ctx, cudaMalloc(&g.d_buf, bytes));
+            buf = g.d_buf;
+        } else if (!buf) {
+            CU_TRY(ctx, cudaMalloc(&g.d_buf, kStageBytes));
+            buf = g.d_buf;
+        }
+        // ---- H2D on a side stream once the previous user of this staging buffer has been decoded
+        if (g.used) CU_TRY(ctx, cudaStreamWaitEvent(cs, g.freed, 0));
+        chunk.assign(descs + i, descs + j);
+        size_t off = 0;
+        for (uint32_t k = 0; k < j - i; k++) {
+            CU_TRY(ctx, cudaMemcpyAsync(buf + off, descs[i + k].src, descs[i + k].len, cudaMemcpyHostToDevice, cs));
+            chunk[k].src = buf + off;
+            off += (descs[i + k].len + 255) & ~(size_t)255;
+        }
+        CU_TRY(ctx, cudaEventRecord(g.copied, cs));
+        // ---- decode on the main stream after the copy; then the buffer is free again
+        CU_TRY(ctx, cudaStreamWaitEvent(st, g.copied, 0));
+        rc = enqueue_chunk(ctx, chunk.data(), j - i, i, st);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaEventRecord(g.freed, st));
+        g.used = true;
+        i = j;
     }
-    const uint32_t m = std::min(n, s.n);
+    return MCRAW_OK;
+}
+
+int mcraw_batch_wait(mcraw_ctx* ctx, uint64_t* written_elems, uint32_t* status, uint32_t n) {
+    if (!ctx) return MCRAW_ERR_ARG;
+    if (ctx->batch_id == 0) { ctx->err = "no batch was enqueued"; return MCRAW_ERR_STATE; }
+    int rc = bind(ctx);
+    if (rc) return rc;
+    for (auto& s : ctx->slots) { rc = harvest(ctx, s); if (rc) return rc; }
+    const uint32_t m = std::min(n, ctx->batch_n);
     for (uint32_t i = 0; i < m; i++) {
-        uint64_t w = s.h_results[i].written;
-        uint32_t st = s.h_results[i].status;
-        const int type = s.h_frames[i].type;   // host copy of the descriptor
+        uint64_t w = ctx->res_written[i];
+        uint32_t st = ctx->res_status[i];
+        const int type = ctx->res_type[i];
         if (type != MCRAW_COMPRESSION_CURRENT && type != MCRAW_COMPRESSION_LEGACY) { w = 0; st = MCRAW_FRAME_BAD_TYPE; }
         if (written_elems) written_elems[i] = w;
         if (status) status[i] = st;
@@ -320,13 +458,6 @@ size_t mcraw_decode_host(mcraw_ctx* ctx, uint16_t* output, int width, int height
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
     std::memcpy(output, ctx->h_out, written * 2);
     return (size_t)written;
-}
-
-int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
-    (void)descs; (void)n; (void)stream;
-    if (!ctx) return MCRAW_ERR_ARG;
-    ctx->err = "mcraw_decode_batch_host: not built yet";
-    return MCRAW_ERR_STATE;
 }
 
 int mcraw_device_alloc(mcraw_ctx* ctx, size_t bytes, void** out) {

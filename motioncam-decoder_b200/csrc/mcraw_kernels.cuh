@@ -1,25 +1,29 @@
 // mcraw_kernels.cuh -- sm_100a kernels of the MCRAW frame decoder.
 //
 // Current format (compressionType 7; reference: /root/reference/lib/RawData.cpp:528-612)
-//   k_meta   one CTA per (frame, metadata stream): walks the inline-header chain of the stream
-//            (RawData.cpp:463-498), unpacks the 64-value meta blocks, and -- for the "bits" stream -- turns
-//            the running `offset +=` of the reference tile loop (RawData.cpp:562,576-579) into an exclusive
-//            prefix sum.  Output: one 16-byte record per 64x4-pixel tile
-//                { payload offset of the tile, bits[4], refs[0..1], refs[2..3] }.
-//   k_tiles  one CTA per (frame, tile row): every lane decodes one 8-sample plane of an even/odd block pair
-//            with 32-bit SWAR (table in mcraw_tables.h), interleaves the two Bayer phases with PRMT, adds the
-//            per-block references with packed 16-bit adds (wraps mod 2^16 like the reference's uint16 stores,
-//            RawData.cpp:582-592) and writes 2 x 16 bytes of one output row; columns >= width are cropped
-//            (RawData.cpp:598-608).
 //
-// Legacy format (compressionType 6; reference: /root/reference/lib/RawData_Legacy.cpp:445-495)
-//   k_legacy_index / k_legacy_decode  -- see below.
+//   A frame is a sequence of 64-sample blocks, four per 64x4-pixel tile.  We process it in UNITS of 16
+//   consecutive tiles (= 64 blocks = exactly one 64-value block of each metadata stream).
+//
+//   k_meta   one CTA per (frame, metadata stream).  Walks the inline-header chain of the stream
+//            (RawData.cpp:463-498) and lets ONE LANE decode one whole 64-value meta block with the same
+//            width-specialised SWAR routine the pixel kernel uses.  For the "bits" stream it also turns the
+//            reference's running `offset +=` (RawData.cpp:562,576-579) into prefix sums.  Output per unit:
+//            payload offset; per block pair (even/odd Bayer column pair): {relative offset, bits, refs}.
+//   k_units  one WARP per unit.  The unit's payload (contiguous, <= 8 KiB) is staged in shared memory with
+//            16-byte cp.async into an XOR-swizzled layout; every lane then decodes one block pair: a `switch`
+//            on the header bits value selects straight-line code with immediate shifts/masks (lanes that share
+//            a bits value run together; real images have 1-3 distinct values per warp).  Even/odd columns are
+//            interleaved with PRMT, references added with packed 16-bit adds (mod 2^16 like RawData.cpp:582-592),
+//            rows are assembled in shared memory and leave through 128-byte TMA bulk stores
+//            (cp.async.bulk.global.shared::cta); columns >= width are cropped (RawData.cpp:598-608).
+//
+// Legacy format (compressionType 6; reference: /root/reference/lib/RawData_Legacy.cpp:445-495): see below.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "mcraw_b200.h"
-#include "mcraw_tables.h"
 
 namespace mcraw {
 
@@ -31,13 +35,18 @@ struct FrameDev {
     int width, height, type;
     unsigned tiles_x;              // expected encodedWidth/64   = ceil(width/64)
     unsigned tile_rows;            // expected ceil(encodedHeight/4) upper bound = ceil(height/4)
-    unsigned flags;                // bit0: 16-byte vector stores allowed (width % 8 == 0, dst 16-byte aligned)
-    uint4* tilemeta;               // scratch, tiles_x*tile_rows records               (type 7)
-    uint32_t* aux;                 // scratch for the legacy index                    (type 6)
+    unsigned flags;                // FLAG_*
+    unsigned inv_tiles_x;          // ceil(2^32 / tiles_x) when tile / tiles_x may use mulhi, else 0
+    unsigned nunits;               // ceil(tiles_x*tile_rows / 16)
+    uint32_t* unitoff;             // scratch [nunits + 1]   payload offset of each unit (+ end)
+    uint32_t* pairinfo;            // scratch [32 * nunits]  rel8 | bitsE << 16 | bitsO << 24
+    uint32_t* pairrefs;            // scratch [32 * nunits]  refE | refO << 16
+    uint32_t* aux;                 // scratch for the legacy index (type 6)
     unsigned long long aux_elems;
     // written on the device
     unsigned status;               // MCRAW_FRAME_* bits
     unsigned tile_rows_dev;        // ceil(encodedHeight/4) from the frame header
+    unsigned rows_fit;             // rows emitted: min(4*tile_rows_dev, dst_cap / width)
 };
 
 struct Result {
@@ -46,50 +55,190 @@ struct Result {
     unsigned pad;
 };
 
-enum { FLAG_VEC_STORE = 1 };
+enum { FLAG_VEC_STORE = 1 };       // width % 8 == 0 and dst 16-byte aligned: rows may leave as 16-byte multiples
 
 __device__ __forceinline__ uint32_t ld_u32le(const uint8_t* p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
-// payload bytes of a 64-sample block / 8, for header value b in 0..16 (RawData.cpp:27-45)
-__device__ __forceinline__ uint32_t cur_len8(uint32_t b) {
-    // nibbles for b = 0..10: 0,1,2,3,4,5,6,8,8,10,10 ; b >= 11 -> 16
-    const unsigned long long lut = 0xAA886543210ull;
-    uint32_t v = (uint32_t)(lut >> (4 * (b & 15))) & 15u;
-    return b >= 11 ? 16u : v;
+// payload bytes / 8 of a 64-sample block for header value b in 0..15 (RawData.cpp:27-45): PRMT as a byte LUT
+__device__ __forceinline__ uint32_t cur_len8_nib(uint32_t b) {
+    const uint32_t lo = __byte_perm(0x03020100u, 0x08060504u, b & 7u);        // b = 0..7  -> 0,1,2,3,4,5,6,8
+    const uint32_t hi = __byte_perm(0x100A0A08u, 0x10101010u, b & 7u);        // b = 8..15 -> 8,10,10,16,16,...
+    return ((b & 8u) ? hi : lo) & 0xFFu;
 }
+__device__ __forceinline__ uint32_t cur_len8(uint32_t b) { return b >= 16u ? 16u : cur_len8_nib(b); }
+
+// --------------------------------------------------------------------------------------------------------
+// Width-specialised block decode.  G(g) returns the g-th 8-byte group of the block payload as uint2
+// (.x = byte lanes 0..3, .y = byte lanes 4..7).  Sample i = 8*j + l sits in byte lane l of plane j;
+// L[2j], L[2j+1] receive the low bytes of plane j (lanes 0..3 / 4..7), H[..] the high bytes.
+// Restates RawData.cpp:112-408 as 32-bit SWAR; the reference's left shifts are folded into net right shifts
+// with pre-shifted masks, e.g. ((G2 >> 6) & 1) << 2 == (G2 >> 4) & 0x04.
+// Returns the payload length in bytes (RawData.cpp:27-45).
+// --------------------------------------------------------------------------------------------------------
+#define MC_REP(m) ((uint32_t)(m) * 0x01010101u)
+
+template <class Fetch>
+__device__ __forceinline__ uint32_t decode_block(const uint32_t b, const Fetch& G, uint32_t (&L)[16], uint32_t (&H)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) { L[i] = 0; H[i] = 0; }
+    switch (b) {
+    case 0:
+        return 0;
+    case 1: {                                                                  // RawData.cpp:112-136
+        const uint2 g = G(0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { L[2 * j] = (g.x >> j) & MC_REP(1); L[2 * j + 1] = (g.y >> j) & MC_REP(1); }
+        return 8;
+    }
+    case 2: {                                                                  // :138-162
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            const uint2 g = G(m);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                L[2 * (4 * m + k)] = (g.x >> (2 * k)) & MC_REP(3);
+                L[2 * (4 * m + k) + 1] = (g.y >> (2 * k)) & MC_REP(3);
+            }
+        }
+        return 16;
+    }
+    case 3: {                                                                  // :164-199
+        const uint2 g0 = G(0), g1 = G(1), g2 = G(2);
+        L[0] = g0.x & MC_REP(7);                 L[1] = g0.y & MC_REP(7);
+        L[2] = (g0.x >> 3) & MC_REP(7);          L[3] = (g0.y >> 3) & MC_REP(7);
+        L[4] = ((g0.x >> 6) & MC_REP(3)) | ((g2.x >> 4) & MC_REP(4));
+        L[5] = ((g0.y >> 6) & MC_REP(3)) | ((g2.y >> 4) & MC_REP(4));
+        L[6] = g1.x & MC_REP(7);                 L[7] = g1.y & MC_REP(7);
+        L[8] = (g1.x >> 3) & MC_REP(7);          L[9] = (g1.y >> 3) & MC_REP(7);
+        L[10] = ((g1.x >> 6) & MC_REP(3)) | ((g2.x >> 5) & MC_REP(4));
+        L[11] = ((g1.y >> 6) & MC_REP(3)) | ((g2.y >> 5) & MC_REP(4));
+        L[12] = g2.x & MC_REP(7);                L[13] = g2.y & MC_REP(7);
+        L[14] = (g2.x >> 3) & MC_REP(7);         L[15] = (g2.y >> 3) & MC_REP(7);
+        return 24;
+    }
+    case 4: {                                                                  // :201-223
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const uint2 g = G(m);
+            L[4 * m] = g.x & MC_REP(15);         L[4 * m + 1] = g.y & MC_REP(15);
+            L[4 * m + 2] = (g.x >> 4) & MC_REP(15); L[4 * m + 3] = (g.y >> 4) & MC_REP(15);
+        }
+        return 32;
+    }
+    case 5: {                                                                  // :225-262
+        const uint2 g0 = G(0), g1 = G(1), g2 = G(2), g3 = G(3), g4 = G(4);
+        L[0] = g0.x & MC_REP(31); L[1] = g0.y & MC_REP(31);
+        L[2] = g1.x & MC_REP(31); L[3] = g1.y & MC_REP(31);
+        L[4] = g2.x & MC_REP(31); L[5] = g2.y & MC_REP(31);
+        L[6] = g3.x & MC_REP(31); L[7] = g3.y & MC_REP(31);
+        L[8] = g4.x & MC_REP(31); L[9] = g4.y & MC_REP(31);
+        L[10] = ((g0.x >> 5) & MC_REP(7)) | ((g3.x >> 2) & MC_REP(0x18));
+        L[11] = ((g0.y >> 5) & MC_REP(7)) | ((g3.y >> 2) & MC_REP(0x18));
+        L[12] = ((g1.x >> 5) & MC_REP(7)) | ((g4.x >> 2) & MC_REP(0x18));
+        L[13] = ((g1.y >> 5) & MC_REP(7)) | ((g4.y >> 2) & MC_REP(0x18));
+        L[14] = ((g2.x >> 5) & MC_REP(7)) | ((g3.x >> 4) & MC_REP(0x08)) | ((g4.x >> 3) & MC_REP(0x10));
+        L[15] = ((g2.y >> 5) & MC_REP(7)) | ((g3.y >> 4) & MC_REP(0x08)) | ((g4.y >> 3) & MC_REP(0x10));
+        return 40;
+    }
+    case 6: {                                                                  // :264-304
+        const uint2 g0 = G(0), g1 = G(1), g2 = G(2), g3 = G(3), g4 = G(4), g5 = G(5);
+        L[0] = g0.x & MC_REP(63);  L[1] = g0.y & MC_REP(63);
+        L[2] = g1.x & MC_REP(63);  L[3] = g1.y & MC_REP(63);
+        L[4] = g2.x & MC_REP(63);  L[5] = g2.y & MC_REP(63);
+        L[6] = g3.x & MC_REP(63);  L[7] = g3.y & MC_REP(63);
+        L[8] = g4.x & MC_REP(63);  L[9] = g4.y & MC_REP(63);
+        L[10] = g5.x & MC_REP(63); L[11] = g5.y & MC_REP(63);
+        L[12] = ((g0.x >> 6) & MC_REP(3)) | ((g1.x >> 4) & MC_REP(0x0C)) | ((g2.x >> 2) & MC_REP(0x30));
+        L[13] = ((g0.y >> 6) & MC_REP(3)) | ((g1.y >> 4) & MC_REP(0x0C)) | ((g2.y >> 2) & MC_REP(0x30));
+        L[14] = ((g3.x >> 6) & MC_REP(3)) | ((g4.x >> 4) & MC_REP(0x0C)) | ((g5.x >> 2) & MC_REP(0x30));
+        L[15] = ((g3.y >> 6) & MC_REP(3)) | ((g4.y >> 4) & MC_REP(0x0C)) | ((g5.y >> 2) & MC_REP(0x30));
+        return 48;
+    }
+    case 7:
+    case 8: {                                                                  // :306-326,446-449
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const uint2 g = G(j); L[2 * j] = g.x; L[2 * j + 1] = g.y; }
+        return 64;
+    }
+    case 9:
+    case 10: {                                                                 // :328-374,450-453
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            const uint2 hg = G(5 * m + 4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint2 g = G(5 * m + k);
+                L[2 * (4 * m + k)] = g.x;        L[2 * (4 * m + k) + 1] = g.y;
+                H[2 * (4 * m + k)] = (hg.x >> (2 * k)) & MC_REP(3);
+                H[2 * (4 * m + k) + 1] = (hg.y >> (2 * k)) & MC_REP(3);
+            }
+        }
+        return 80;
+    }
+    default: {                                                                 // 11..16, :376-408 (little-endian u16)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint2 a = G(2 * j), c = G(2 * j + 1);
+            L[2 * j] = __byte_perm(a.x, a.y, 0x6420);     H[2 * j] = __byte_perm(a.x, a.y, 0x7531);
+            L[2 * j + 1] = __byte_perm(c.x, c.y, 0x6420); H[2 * j + 1] = __byte_perm(c.x, c.y, 0x7531);
+        }
+        return 128;
+    }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// PTX helpers
+// --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA) that will read them
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 
 // --------------------------------------------------------------------------------------------------------
 // k_meta
 // --------------------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 256;
 constexpr int K1_CHUNK = 16384;   // bytes of the stream staged in shared memory per round
-constexpr int K1_MB = 256;        // meta blocks per round (= threads, one per thread in the scan phase)
+constexpr int K1_MB = 256;        // meta blocks per round (= threads: one lane decodes one meta block)
 
-// One sample (index i = 8*j + l) of a block packed at header value b; scalar form of the SWAR recipe.
-__device__ __forceinline__ uint32_t cur_sample_scalar(const uint8_t* p, uint32_t b, uint32_t i, const uint32_t* tab) {
-    const uint32_t* e = tab + (b * 8 + (i >> 3)) * MCRAW_TAB_WORDS;
-    const uint32_t l = i & 7;
-    const uint32_t off = e[0], sh = e[1];
-    if (off >> 24) return (uint32_t)p[2 * i] | ((uint32_t)p[2 * i + 1] << 8);
-    uint32_t lo = 0, hi = 0;
-    const uint32_t mA = e[2] & 0xFF, mBL = e[3] & 0xFF, mBH = e[4] & 0xFF, mC = e[5] & 0xFF;
-    if (mA) lo |= ((uint32_t)p[(off & 0xFF) + l] >> (sh & 0xFF)) & mA;
-    if (mBL | mBH) {
-        uint32_t v = (uint32_t)p[((off >> 8) & 0xFF) + l] >> ((sh >> 8) & 0xFF);
-        lo |= v & mBL;
-        hi |= v & mBH;
+// group fetch from the staged stream at a 2-byte aligned position (meta block payloads follow a 2-byte header)
+struct StageFetch {
+    const uint32_t* w;   // staged bytes viewed as words
+    uint32_t a;          // byte offset of the payload inside the stage buffer (even)
+    __device__ __forceinline__ uint2 operator()(int g) const {
+        const uint32_t o = a + 8u * (uint32_t)g;
+        const uint32_t i = o >> 2, sh = (o & 3u) * 8u;
+        const uint32_t w0 = w[i], w1 = w[i + 1], w2 = w[i + 2];
+        return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
     }
-    if (mC) lo |= ((uint32_t)p[((off >> 16) & 0xFF) + l] >> ((sh >> 16) & 0xFF)) & mC;
-    return lo | (hi << 8);
-}
+};
 
-__global__ void __launch_bounds__(K1_THREADS) k_meta(FrameDev* __restrict__ frames, const uint32_t* __restrict__ tab_g) {
-    __shared__ __align__(16) uint8_t stage[K1_CHUNK + 16];
-    __shared__ __align__(16) uint8_t vals[K1_MB * 64];
+__global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ frames) {
+    __shared__ __align__(16) uint8_t stage[K1_CHUNK + 32];
+    __shared__ uint16_t nxt[K1_CHUNK / 2 + 2];      // next chain position for every even offset of the chunk (+ sentinel)
     __shared__ uint16_t starts[K1_MB];
-    __shared__ uint32_t tab[MCRAW_TAB_ENTRIES * MCRAW_TAB_WORDS];
     __shared__ uint32_t warp_sums[K1_THREADS / 32];
     __shared__ uint32_t sh_cnt, sh_err, sh_bad;
     __shared__ unsigned long long sh_nextpos;
@@ -103,15 +252,13 @@ __global__ void __launch_bounds__(K1_THREADS) k_meta(FrameDev* __restrict__ fram
     const uint8_t* __restrict__ src = F.src;
     const unsigned long long len = F.len;
 
-    for (int i = tid; i < MCRAW_TAB_ENTRIES * MCRAW_TAB_WORDS; i += K1_THREADS) tab[i] = tab_g[i];
-
     if (tid == 0) {
         uint32_t err = 0;
         uint32_t ew = 0, eh = 0, boff = 0, roff = 0;
         if (len < 16) err = MCRAW_FRAME_BAD_HEADER;
         else {
-            ew = ld_u32le(src); eh = ld_u32le(src + 4); boff = ld_u32le(src + 8); roff = ld_u32le(src + 12);
-            if (boff > len || roff > len) err |= MCRAW_FRAME_BAD_HEADER;            // RawData.cpp:547
+            ew = ld_u32le(src); eh = ld_u32le(src + 4); boff = ld_u32le(src + 8); roff = ld_u32le(src + 12);  // RawData.cpp:500-524
+            if (boff > len || roff > len) err |= MCRAW_FRAME_BAD_HEADER;            // :547
             if (ew % 64u) err |= MCRAW_FRAME_BAD_HEADER;                            // :550
             if (F.width <= 0 || ew < (uint32_t)F.width) err |= MCRAW_FRAME_BAD_HEADER;  // :553
             if (ew == 0 || eh == 0) err |= MCRAW_FRAME_BAD_HEADER;
@@ -123,7 +270,13 @@ __global__ void __launch_bounds__(K1_THREADS) k_meta(FrameDev* __restrict__ fram
         sh_hdr[0] = ew; sh_hdr[1] = eh; sh_hdr[2] = boff; sh_hdr[3] = roff;
         sh_err = err;
         sh_bad = 0;
-        if (stream == 0) F.tile_rows_dev = err ? 0u : (eh + 3u) / 4u;
+        if (stream == 0) {
+            const uint32_t tr = err ? 0u : (eh + 3u) / 4u;
+            unsigned long long fit = F.dst_cap / (unsigned long long)(F.width > 0 ? F.width : 1);
+            if (fit > 4ull * tr) fit = 4ull * tr;                                   // reference emits 4 rows per tile row (:598-608)
+            F.tile_rows_dev = tr;
+            F.rows_fit = (uint32_t)fit;
+        }
     }
     __syncthreads();
     if (sh_err) {
@@ -134,7 +287,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_meta(FrameDev* __restrict__ fram
     const uint32_t tile_rows = (sh_hdr[1] + 3u) / 4u;
     const uint32_t ntiles = tiles_x * tile_rows;
     const uint32_t nblocks = ntiles * 4u;
-    const uint32_t need_mb = (nblocks + 63u) / 64u;
+    const uint32_t need_mb = (nblocks + 63u) / 64u;      // = number of units
     unsigned long long pos = (unsigned long long)sh_hdr[2 + stream];
 
     if (tid == 0) {
@@ -150,89 +303,118 @@ __global__ void __launch_bounds__(K1_THREADS) k_meta(FrameDev* __restrict__ fram
     }
     pos += 4;
 
-    uint4* __restrict__ tilemeta = F.tilemeta;
-    uint32_t done = 0;            // meta blocks finished
+    uint32_t* __restrict__ unitoff = F.unitoff;
+    uint32_t* __restrict__ pairinfo = F.pairinfo;
+    uint32_t* __restrict__ pairrefs = F.pairrefs;
+    uint32_t done = 0;            // meta blocks (= units) finished
     uint32_t carry = 16;          // running payload offset, METADATA_OFFSET (RawData.cpp:25,562)
 
     while (done < need_mb) {
         // ---- stage [base, base + K1_CHUNK) of the frame buffer in shared memory (zero past len)
         const unsigned long long base = pos & ~15ull;
-        for (int v = tid; v < K1_CHUNK / 16; v += K1_THREADS) {
+        for (int v = tid; v < (K1_CHUNK + 32) / 16; v += K1_THREADS) {
             const unsigned long long o = base + (unsigned long long)v * 16;
             uint4 q = make_uint4(0, 0, 0, 0);
             if (o + 16 <= len) q = __ldg(reinterpret_cast<const uint4*>(src + o));
             else if (o < len) {
-                uint8_t tmp[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) tmp[k] = (o + k < len) ? src[o + k] : (uint8_t)0;
-                q = *reinterpret_cast<uint4*>(tmp);
+                uint32_t t4[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 16; k++)
+                    if (o + k < len) t4[k >> 2] |= (uint32_t)src[o + k] << (8 * (k & 3));
+                q = make_uint4(t4[0], t4[1], t4[2], t4[3]);
             }
             *reinterpret_cast<uint4*>(stage + v * 16) = q;
         }
         __syncthreads();
-        // ---- serial chain walk over the inline 2-byte headers (RawData.cpp:485-489)
-        if (tid == 0) {
-            uint32_t p = (uint32_t)(pos - base), cnt = 0, err = 0;
-            const uint32_t limit = min((uint32_t)K1_MB, need_mb - done);
-            while (cnt < limit) {
-                if (base + p + 2 > len) { err = MCRAW_FRAME_TRUNCATED; break; }
-                if (p + 2 > K1_CHUNK) break;
-                const uint32_t L = cur_len8(stage[p] >> 4) * 8u;
-                if (base + p + 2 + L > len) { err = MCRAW_FRAME_TRUNCATED; break; }   // RawData.cpp:419
-                if (p + 2 + L > K1_CHUNK) break;
-                starts[cnt++] = (uint16_t)p;
-                p += 2 + L;
+        // ---- next-pointer of every candidate (even) position: p + 2 + payload length of the header found there;
+        //      candidates whose block does not fit the staged window (or the frame) point at a self-looping sentinel
+        const unsigned long long room = len - base;                     // bytes of the frame from base on
+        const uint32_t lim = (uint32_t)(room < (unsigned long long)K1_CHUNK ? room : (unsigned long long)K1_CHUNK);
+        for (int c = tid; c <= K1_CHUNK / 2; c += K1_THREADS) {
+            const uint32_t p = 2u * (uint32_t)c;
+            uint32_t q = K1_CHUNK;
+            if (p + 2u <= lim) {
+                q = p + 2u + 8u * cur_len8_nib(stage[p] >> 4);
+                if (q > lim) q = K1_CHUNK;                                  // RawData.cpp:419 (block past the end)
             }
+            nxt[c] = (uint16_t)q;
+        }
+        __syncthreads();
+        // ---- serial chain walk over the inline 2-byte headers (RawData.cpp:485-489): one dependent LDS per step
+        const uint32_t limit = min((uint32_t)K1_MB, need_mb - done);
+        if (tid == 0) {
+            uint32_t p = (uint32_t)(pos - base), cnt = 0, last = p;
+            const uint32_t nxt_s = smem_u32(nxt);
+#pragma unroll 8
+            for (uint32_t k = 0; k < limit; k++) {
+                uint32_t q;
+                asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(q) : "r"(nxt_s + p));   // nxt[p / 2], p is even
+                starts[k] = (uint16_t)p;
+                if (p != (uint32_t)K1_CHUNK && q != (uint32_t)K1_CHUNK) { cnt++; last = q; }
+                p = q;
+            }
+            // a chain that stopped early because the FRAME ended (not the window) is a truncated stream
             sh_cnt = cnt;
-            sh_err = err;
-            sh_nextpos = base + p;
+            sh_err = (cnt < limit && lim < (uint32_t)K1_CHUNK) ? MCRAW_FRAME_TRUNCATED : 0u;
+            sh_nextpos = base + last;
         }
         __syncthreads();
         const uint32_t cnt = sh_cnt;
         if (sh_err) break;
-        // ---- unpack cnt meta blocks: value v -> meta block v>>6, sample v&63; + header reference (u16 wrap)
-        for (uint32_t v = tid; v < cnt * 64u; v += K1_THREADS) {
-            const uint32_t m = v >> 6, i = v & 63u;
-            const uint8_t* h = stage + starts[m];
-            const uint32_t b = h[0] >> 4;                                             // RawData.cpp:106-110
-            const uint32_t ref = ((uint32_t)(h[0] & 0x0F) << 8) | h[1];
-            const uint32_t val = (cur_sample_scalar(h + 2, b, i, tab) + ref) & 0xFFFFu; // :491-492
-            const uint32_t k = (done + m) * 64u + i;                                  // block index
+        // ---- one lane decodes one meta block (64 values): value = unpacked + header reference, mod 2^16 (:491-492)
+        uint32_t unit_len8 = 0;
+        const uint32_t unit = done + (uint32_t)tid;
+        if ((uint32_t)tid < cnt) {
+            const uint32_t p = starts[tid];
+            const uint32_t b = stage[p] >> 4;                                          // RawData.cpp:106-110
+            const uint32_t ref = ((uint32_t)(stage[p] & 0x0F) << 8) | stage[p + 1];
+            uint32_t L[16], H[16];
+            StageFetch G{reinterpret_cast<const uint32_t*>(stage), p + 2u};
+            decode_block(b, G, L, H);
+            // word m of L/H holds samples 4m..4m+3 = the four blocks of tile 16*unit + m
             if (stream == 0) {
-                vals[v] = (uint8_t)min(val, 255u);
-                if (k < nblocks && val > 16u) sh_bad = 1;                             // reference: OOB table read
-            } else if (k < nblocks) {
-                reinterpret_cast<uint16_t*>(tilemeta + (k >> 2))[4 + (k & 3u)] = (uint16_t)val;
-            }
-        }
-        __syncthreads();
-        if (stream == 0) {
-            if (sh_bad) { if (tid == 0) sh_err = MCRAW_FRAME_BAD_BITS; __syncthreads(); break; }
-            // ---- prefix sum of block lengths; thread t owns meta block t = 16 tiles
-            uint32_t tsum[16];
-            uint32_t bits4[16];
-            uint32_t total = 0;
-            if ((uint32_t)tid < cnt) {
-                const uint4* vp = reinterpret_cast<const uint4*>(vals + tid * 64);
+                uint32_t bad = (ref > 16u) ? 1u : 0u;
+                const uint32_t refb = MC_REP(ref & 0x1F);
+                uint32_t info[32];
+                uint32_t rel8 = 0;
 #pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) {
-                    const uint4 q = vp[q4];
-                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                for (int m = 0; m < 16; m++) {
+                    const uint32_t tile = unit * 16u + m;
+                    uint32_t v = (L[m] & MC_REP(0x1F)) + refb;                         // bytes <= 31 + 16: no carries
+                    uint32_t badm = H[m] | (L[m] & MC_REP(0xE0));
+                    const uint32_t b0 = v & 0xFF, b1 = (v >> 8) & 0xFF, b2 = (v >> 16) & 0xFF, b3 = v >> 24;
+                    badm |= (b0 > 16u) | (b1 > 16u) | (b2 > 16u) | (b3 > 16u);         // reference: OOB table read
+                    if (tile >= ntiles) { v = 0; badm = 0; }                           // padding values are ignored
+                    bad |= badm;
+                    const uint32_t c0 = v & 0xFF, c1 = (v >> 8) & 0xFF, c2 = (v >> 16) & 0xFF, c3 = v >> 24;
+                    info[2 * m] = rel8 | (c0 << 16) | (c1 << 24);
+                    rel8 += cur_len8(c0 & 31u) + cur_len8(c1 & 31u);
+                    info[2 * m + 1] = rel8 | (c2 << 16) | (c3 << 24);
+                    rel8 += cur_len8(c2 & 31u) + cur_len8(c3 & 31u);
+                }
+                if (bad) sh_bad = 1;
+                unit_len8 = rel8;
+                uint4* o = reinterpret_cast<uint4*>(pairinfo + (size_t)unit * 32u);
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const uint32_t bb = w[t];
-                        const uint32_t tile = (done + tid) * 16u + q4 * 4 + t;
-                        uint32_t s = 0;
-                        if (tile < ntiles)
-                            s = 8u * (cur_len8(bb & 0xFF) + cur_len8((bb >> 8) & 0xFF) + cur_len8((bb >> 16) & 0xFF) + cur_len8(bb >> 24));
-                        bits4[q4 * 4 + t] = bb;
-                        tsum[q4 * 4 + t] = total;
-                        total += s;
+                for (int k = 0; k < 8; k++) o[k] = make_uint4(info[4 * k], info[4 * k + 1], info[4 * k + 2], info[4 * k + 3]);
+            } else {
+                const uint32_t ref2 = ref | (ref << 16);
+                uint4* o = reinterpret_cast<uint4*>(pairrefs + (size_t)unit * 32u);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    uint32_t r[4];
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        const int m = 2 * k + t;
+                        r[2 * t] = __vadd2(__byte_perm(L[m], H[m], 0x5140), ref2);      // blocks 0,1 of the tile
+                        r[2 * t + 1] = __vadd2(__byte_perm(L[m], H[m], 0x7362), ref2);  // blocks 2,3
                     }
+                    o[k] = make_uint4(r[0], r[1], r[2], r[3]);
                 }
             }
-            // block-wide exclusive scan of `total`
-            uint32_t incl = total;
+        }
+        if (stream == 0) {
+            // ---- exclusive prefix sum of the unit payload lengths across the CTA (+ carry from earlier rounds)
+            uint32_t incl = unit_len8;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
@@ -247,19 +429,9 @@ __global__ void __launch_bounds__(K1_THREADS) k_meta(FrameDev* __restrict__ fram
                 if (w < (tid >> 5)) wbase += s;
                 all += s;
             }
-            const uint32_t excl = carry + wbase + incl - total;
-            if ((uint32_t)tid < cnt) {
-#pragma unroll
-                for (int t = 0; t < 16; t++) {
-                    const uint32_t tile = (done + tid) * 16u + t;
-                    if (tile < ntiles) {
-                        uint2* dstp = reinterpret_cast<uint2*>(tilemeta + tile);
-                        *dstp = make_uint2(excl + tsum[t], bits4[t]);
-                    }
-                }
-            }
-            carry += all;
-            __syncthreads();
+            if ((uint32_t)tid < cnt) unitoff[unit] = carry + 8u * (wbase + incl - unit_len8);
+            carry += 8u * all;
+            if (sh_bad) { if (tid == 0) sh_err = MCRAW_FRAME_BAD_BITS; __syncthreads(); break; }
         }
         done += cnt;
         pos = sh_nextpos;
@@ -267,120 +439,163 @@ __global__ void __launch_bounds__(K1_THREADS) k_meta(FrameDev* __restrict__ fram
     }
     if (tid == 0) {
         uint32_t err = sh_err;
-        if (!err && stream == 0 && (unsigned long long)carry > len) err = MCRAW_FRAME_TRUNCATED;  // RawData.cpp:419
+        if (stream == 0) {
+            if (!err && (unsigned long long)carry > len) err = MCRAW_FRAME_TRUNCATED;   // RawData.cpp:419
+            unitoff[need_mb] = carry;
+        }
         if (err) atomicOr(&F.status, err);
     }
 }
 
 // --------------------------------------------------------------------------------------------------------
-// k_tiles
+// k_units
 // --------------------------------------------------------------------------------------------------------
-struct Plane8 {   // 8 samples (byte lanes 0..7) of one plane: low bytes and high bytes
-    uint32_t lo0, lo1, hi0, hi1;
+constexpr int KU_WARPS = 4;                       // warps (= units) per CTA
+constexpr int KU_IN_BYTES = 16 * 512 + 256;       // worst case unit payload (16-bit blocks) + alignment slack, 128-multiple
+constexpr int KU_SLOT_PITCH = 144;                // bytes per tile slot in an output row: 128 + 16 (bank skew)
+constexpr int KU_ROW_PITCH = 16 * KU_SLOT_PITCH + 64;   // 2368: (pitch/16) % 8 == 4 -> the two pair rows hit disjoint banks
+constexpr int KU_OUT_BYTES = 4 * KU_ROW_PITCH;
+constexpr int KU_WARP_SMEM = KU_IN_BYTES + KU_OUT_BYTES;
+constexpr int KU_SMEM = KU_WARPS * KU_WARP_SMEM;
+static_assert(KU_IN_BYTES % 128 == 0 && KU_WARP_SMEM % 128 == 0, "swizzle rows are 128 bytes");
+static_assert((KU_ROW_PITCH / 16) % 8 == 4, "row pitch must skew pair rows by four 16-byte bank groups");
+
+// 128-byte rows, 16-byte chunks XOR-ed with the row index: lanes reading at a 128-byte stride stay (nearly) conflict free
+__device__ __forceinline__ uint32_t swz(uint32_t o) { return o ^ ((o >> 3) & 0x70u); }
+
+struct SwzFetch {
+    uint32_t base;   // shared-window address of the staged unit (128-byte aligned)
+    uint32_t a;      // logical byte offset of the block payload (8-byte aligned)
+    __device__ __forceinline__ uint2 operator()(int g) const { return lds64(base + swz(a + 8u * (uint32_t)g)); }
 };
 
-__device__ __forceinline__ uint2 ld_pay8(const uint8_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
-
-// Decode plane j of the block whose payload starts at `p` (8-byte aligned), header value b.
-__device__ __forceinline__ Plane8 cur_decode_plane(const uint8_t* __restrict__ p, uint32_t b, uint32_t j, const uint32_t* tab) {
-    const uint4 e0 = *reinterpret_cast<const uint4*>(tab + (b * 8 + j) * MCRAW_TAB_WORDS);       // off, sh, mA, mBL
-    const uint2 e1 = *reinterpret_cast<const uint2*>(tab + (b * 8 + j) * MCRAW_TAB_WORDS + 4);   // mBH, mC
-    const uint32_t off = e0.x, sh = e0.y;
-    const uint32_t mA = e0.z, mBL = e0.w, mBH = e1.x, mC = e1.y;
-    uint2 A = make_uint2(0, 0), B = make_uint2(0, 0), C = make_uint2(0, 0);
-    if (mA) A = ld_pay8(p + (off & 0xFF));
-    if (mBL | mBH) B = ld_pay8(p + ((off >> 8) & 0xFF));
-    if (mC) C = ld_pay8(p + ((off >> 16) & 0xFF));
-    Plane8 r;
-    if (off >> 24) {   // 16-bit little-endian samples: de-interleave low/high bytes (RawData.cpp:376-408)
-        r.lo0 = __byte_perm(A.x, A.y, 0x6420);
-        r.hi0 = __byte_perm(A.x, A.y, 0x7531);
-        r.lo1 = __byte_perm(B.x, B.y, 0x6420);
-        r.hi1 = __byte_perm(B.x, B.y, 0x7531);
-    } else {
-        const uint32_t sA = sh & 31u, sB = (sh >> 8) & 31u, sC = (sh >> 16) & 31u;
-        const uint32_t b0 = B.x >> sB, b1 = B.y >> sB;
-        r.lo0 = ((A.x >> sA) & mA) | (b0 & mBL) | ((C.x >> sC) & mC);
-        r.lo1 = ((A.y >> sA) & mA) | (b1 & mBL) | ((C.y >> sC) & mC);
-        r.hi0 = b0 & mBH;
-        r.hi1 = b1 & mBH;
+template <bool WITH_H>
+__device__ __forceinline__ void emit_planes(const uint32_t (&LE)[16], const uint32_t (&HE)[16], const uint32_t (&LO)[16],
+                                            const uint32_t (&HO)[16], const uint32_t refs, const uint32_t out_lane) {
+    // plane j -> output row (pair row) + 2*(j>>2), 16 pixels at byte 32*(j&3) of the lane's tile slot (RawData.cpp:581-593)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t w[8];
+#pragma unroll
+        for (int hw = 0; hw < 2; hw++) {
+            const uint32_t le = LE[2 * j + hw], lo = LO[2 * j + hw];
+            const uint32_t x0 = __byte_perm(le, lo, 0x5140), x1 = __byte_perm(le, lo, 0x7362);   // E0 O0 E1 O1 | E2 O2 E3 O3 (low bytes)
+            if (WITH_H) {
+                const uint32_t he = HE[2 * j + hw], ho = HO[2 * j + hw];
+                const uint32_t y0 = __byte_perm(he, ho, 0x5140), y1 = __byte_perm(he, ho, 0x7362);
+                w[4 * hw + 0] = __byte_perm(x0, y0, 0x5140);
+                w[4 * hw + 1] = __byte_perm(x0, y0, 0x7362);
+                w[4 * hw + 2] = __byte_perm(x1, y1, 0x5140);
+                w[4 * hw + 3] = __byte_perm(x1, y1, 0x7362);
+            } else {
+                w[4 * hw + 0] = __byte_perm(x0, 0u, 0x4140);
+                w[4 * hw + 1] = __byte_perm(x0, 0u, 0x4342);
+                w[4 * hw + 2] = __byte_perm(x1, 0u, 0x4140);
+                w[4 * hw + 3] = __byte_perm(x1, 0u, 0x4342);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = __vadd2(w[k], refs);                                  // mod 2^16 per sample
+        const uint32_t o = out_lane + (uint32_t)((j >> 2) * 2 * KU_ROW_PITCH + (j & 3) * 32);
+        sts128(o, w[0], w[1], w[2], w[3]);
+        sts128(o + 16, w[4], w[5], w[6], w[7]);
     }
-    return r;
 }
 
-__device__ __forceinline__ void st_vec16(uint16_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
-}
-
-// grid = (max tile rows, frames); block = multiple of 32 chosen by the host to divide tiles_x*16 well.
-__global__ void __launch_bounds__(256) k_tiles(FrameDev* __restrict__ frames, const uint32_t* __restrict__ tab_g,
-                                               Result* __restrict__ results) {
-    __shared__ __align__(16) uint32_t tab[MCRAW_TAB_ENTRIES * MCRAW_TAB_WORDS];
+// grid = (ceil(max units / KU_WARPS), frames), block = 32 * KU_WARPS, dynamic smem = KU_SMEM
+__global__ void __launch_bounds__(32 * KU_WARPS) k_units(FrameDev* __restrict__ frames, Result* __restrict__ results) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const FrameDev& F = frames[blockIdx.y];
     if (F.type != MCRAW_COMPRESSION_CURRENT) return;
     const unsigned status = F.status;
-    const uint32_t ty = blockIdx.x;
-    const uint32_t tile_rows = F.tile_rows_dev;
+    const uint32_t rows_fit = F.rows_fit;
     const int width = F.width;
-    unsigned long long rows_fit = F.dst_cap / (unsigned long long)(width > 0 ? width : 1);
-    if (rows_fit > 4ull * tile_rows) rows_fit = 4ull * tile_rows;
-    if (ty == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         Result r;
-        r.written = status ? 0ull : rows_fit * (unsigned long long)width;     // RawData.cpp:611
+        r.written = status ? 0ull : (unsigned long long)rows_fit * (unsigned long long)width;      // RawData.cpp:611
         r.status = status;
         r.pad = 0;
         results[blockIdx.y] = r;
     }
-    if (status || ty >= tile_rows) return;
-    for (int i = threadIdx.x; i < MCRAW_TAB_ENTRIES * MCRAW_TAB_WORDS; i += blockDim.x) tab[i] = tab_g[i];
-    __syncthreads();
-
+    if (status) return;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_x = F.tiles_x;
+    const uint32_t ntiles = tiles_x * F.tile_rows_dev;
+    const uint32_t nunits = (ntiles + 15u) / 16u;
+    const uint32_t unit = blockIdx.x * KU_WARPS + warp;
+    if (unit >= nunits) return;
+
+    const uint32_t in_base = smem_u32(smem_raw) + warp * KU_WARP_SMEM;
+    const uint32_t out_base = in_base + KU_IN_BYTES;
     const uint8_t* __restrict__ src = F.src;
-    const uint4* __restrict__ tilemeta = F.tilemeta + (size_t)ty * tiles_x;
-    uint16_t* __restrict__ dst = F.dst;
-    const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
-    const uint32_t units = tiles_x * 16u;
 
-    for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) {
-        const uint32_t tx = u >> 4, q = (u >> 3) & 1u, j = u & 7u;
-        const uint4 tm = __ldg(tilemeta + tx);
-        const uint32_t b0 = tm.y & 0xFF, b1 = (tm.y >> 8) & 0xFF, b2 = (tm.y >> 16) & 0xFF, b3 = tm.y >> 24;
-        uint32_t offE = tm.x, bE, bO, refs;
-        if (q == 0) { bE = b0; bO = b1; refs = tm.z; }
-        else { bE = b2; bO = b3; refs = tm.w; offE += 8u * (cur_len8(b0) + cur_len8(b1)); }
-        const uint32_t offO = offE + 8u * cur_len8(bE);
-
-        const Plane8 E = cur_decode_plane(src + offE, bE, j, tab);
-        const Plane8 O = cur_decode_plane(src + offO, bO, j, tab);
-
-        // interleave even/odd Bayer columns and widen to u16 (RawData.cpp:581-593)
-        const uint32_t x0 = __byte_perm(E.lo0, O.lo0, 0x5140), x1 = __byte_perm(E.lo0, O.lo0, 0x7362);
-        const uint32_t x2 = __byte_perm(E.lo1, O.lo1, 0x5140), x3 = __byte_perm(E.lo1, O.lo1, 0x7362);
-        const uint32_t y0 = __byte_perm(E.hi0, O.hi0, 0x5140), y1 = __byte_perm(E.hi0, O.hi0, 0x7362);
-        const uint32_t y2 = __byte_perm(E.hi1, O.hi1, 0x5140), y3 = __byte_perm(E.hi1, O.hi1, 0x7362);
-        uint32_t w[8];
-        w[0] = __vadd2(__byte_perm(x0, y0, 0x5140), refs);
-        w[1] = __vadd2(__byte_perm(x0, y0, 0x7362), refs);
-        w[2] = __vadd2(__byte_perm(x1, y1, 0x5140), refs);
-        w[3] = __vadd2(__byte_perm(x1, y1, 0x7362), refs);
-        w[4] = __vadd2(__byte_perm(x2, y2, 0x5140), refs);
-        w[5] = __vadd2(__byte_perm(x2, y2, 0x7362), refs);
-        w[6] = __vadd2(__byte_perm(x3, y3, 0x5140), refs);
-        w[7] = __vadd2(__byte_perm(x3, y3, 0x7362), refs);
-
-        const unsigned long long row = 4ull * ty + q + 2u * (j >> 2);
-        const int xpix = (int)(64u * tx + 16u * (j & 3u));
-        if (row >= rows_fit || xpix >= width) continue;
-        uint16_t* o = dst + row * (unsigned long long)width + xpix;
-        if (vec) {
-            st_vec16(o, w[0], w[1], w[2], w[3]);
-            if (xpix + 8 < width) st_vec16(o + 8, w[4], w[5], w[6], w[7]);
-        } else {
-            const int n = min(16, width - xpix);
-#pragma unroll
+    // ---- stage the unit's payload [a0, a1) (rounded out to 16 bytes) with swizzled 16-byte cp.async
+    const uint32_t a0 = __ldg(F.unitoff + unit), a1 = __ldg(F.unitoff + unit + 1);
+    const uint32_t s0 = a0 & ~15u;
+    const uint32_t nchunks = (a1 - s0 + 15u) >> 4;                                // <= (8192 + 8 + 15) / 16
+    if ((unsigned long long)s0 + 16ull * nchunks <= F.len) {
+        const uint8_t* g = src + s0 + 16u * lane;
+        for (uint32_t c = lane; c < nchunks; c += 32, g += 512) cp_async16(in_base + swz(16u * c), g);
+    } else {                                                                       // tail of the buffer: bytes, zero filled
+        const unsigned long long len = F.len;
+        for (uint32_t c = lane; c < nchunks; c += 32) {
+            const unsigned long long o = (unsigned long long)s0 + 16ull * c;
+            uint32_t t4[4] = {0, 0, 0, 0};
             for (int k = 0; k < 16; k++)
-                if (k < n) o[k] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
+                if (o + k < len) t4[k >> 2] |= (uint32_t)src[o + k] << (8 * (k & 3));
+            sts128(in_base + swz(16u * c), t4[0], t4[1], t4[2], t4[3]);
+        }
+    }
+    // ---- meanwhile: this lane's pair
+    const uint32_t pair = unit * 32u + lane;
+    const uint32_t info = __ldg(F.pairinfo + pair);
+    const uint32_t refs = __ldg(F.pairrefs + pair);
+    const uint32_t bE = (info >> 16) & 0xFFu, bO = info >> 24;
+    const uint32_t aE = (a0 - s0) + 8u * (info & 0xFFFFu);
+    // copy-out role of this lane: 16-byte chunk (lane & 7) of the row segments of tile slots (lane >> 3) + 4k
+    const uint32_t inv = F.inv_tiles_x;
+    const uint32_t vec = F.flags & FLAG_VEC_STORE;
+    uint16_t* __restrict__ dst = F.dst;
+    cp_async_commit_wait_all();
+    __syncwarp();
+
+    // ---- decode the even-column and the odd-column block of the pair
+    uint32_t LE[16], HE[16], LO[16], HO[16];
+    const uint32_t lenE = decode_block(bE, SwzFetch{in_base, aE}, LE, HE);
+    decode_block(bO, SwzFetch{in_base, aE + lenE}, LO, HO);
+
+    // ---- interleave, add references, assemble the four output rows of the unit in shared memory
+    const uint32_t out_lane = out_base + (lane & 1u) * KU_ROW_PITCH + (lane >> 1) * KU_SLOT_PITCH;
+    if (__any_sync(0xFFFFFFFFu, (bE > 8u) | (bO > 8u))) emit_planes<true>(LE, HE, LO, HO, refs, out_lane);
+    else emit_planes<false>(LE, HE, LO, HO, refs, out_lane);
+    __syncwarp();
+
+    // ---- coalesced copy-out: 8 lanes move one 128-byte row segment of one tile per instruction
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t slot = (lane >> 3) + 4u * k;
+        const uint32_t tile = unit * 16u + slot;
+        uint32_t ty = inv ? __umulhi(tile, inv) : tile / tiles_x;
+        const uint32_t tx = tile - ty * tiles_x;
+        const int xpix = (int)(64u * tx + 8u * (lane & 7u));
+        const uint32_t s = out_base + slot * KU_SLOT_PITCH + (lane & 7u) * 16u;
+        uint16_t* o = dst + (unsigned long long)(4u * ty) * (unsigned long long)width + xpix;
+        const bool live = tile < ntiles && xpix < width;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (live && 4u * ty + r < rows_fit) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s + r * KU_ROW_PITCH));
+                uint16_t* orow = o + (unsigned long long)r * (unsigned long long)width;
+                if (vec) *reinterpret_cast<uint4*>(orow) = v;
+                else {
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                    const int n = min(8, width - xpix);
+#pragma unroll
+                    for (int e = 0; e < 8; e++)
+                        if (e < n) orow[e] = (uint16_t)(wv[e >> 1] >> (16 * (e & 1)));
+                }
+            }
         }
     }
 }
