@@ -227,7 +227,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         CU_TRY(ctx, cudaEventRecord(s.e0, st));
         k_meta<<<2 * n, K1_THREADS, 0, st>>>(s.d_frames);
         CU_TRY(ctx, cudaEventRecord(s.e1, st));
-        k_units<<<dim3((max_units + KU_WARPS - 1) / KU_WARPS, n), 32 * KU_WARPS, KU_SMEM, st>>>(s.d_frames, s.d_results);
+        k_units<<<dim3((max_units + KU_WARPS * KU_UPW - 1) / (KU_WARPS * KU_UPW), n), 32 * KU_WARPS, KU_SMEM, st>>>(s.d_frames, s.d_results);
         CU_TRY(ctx, cudaEventRecord(s.e2, st));
         ctx->launches += 2;
         s.timed = true;

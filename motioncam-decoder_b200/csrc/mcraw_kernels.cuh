@@ -450,12 +450,13 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
 // --------------------------------------------------------------------------------------------------------
 // k_units
 // --------------------------------------------------------------------------------------------------------
-constexpr int KU_WARPS = 4;                       // warps (= units) per CTA
+constexpr int KU_WARPS = 4;                       // warps per CTA
+constexpr int KU_UPW = 8;                         // consecutive units handled by one warp (software pipelined)
 constexpr int KU_IN_BYTES = 16 * 512 + 256;       // worst case unit payload (16-bit blocks) + alignment slack, 128-multiple
 constexpr int KU_SLOT_PITCH = 144;                // bytes per tile slot in an output row: 128 + 16 (bank skew)
 constexpr int KU_ROW_PITCH = 16 * KU_SLOT_PITCH + 64;   // 2368: (pitch/16) % 8 == 4 -> the two pair rows hit disjoint banks
-constexpr int KU_OUT_BYTES = 4 * KU_ROW_PITCH;
-constexpr int KU_WARP_SMEM = KU_IN_BYTES + KU_OUT_BYTES;
+constexpr int KU_OUT_BYTES = 2 * KU_ROW_PITCH;    // two rows at a time (planes 0..3, then planes 4..7)
+constexpr int KU_WARP_SMEM = ((KU_IN_BYTES + KU_OUT_BYTES + 127) / 128) * 128;
 constexpr int KU_SMEM = KU_WARPS * KU_WARP_SMEM;
 static_assert(KU_IN_BYTES % 128 == 0 && KU_WARP_SMEM % 128 == 0, "swizzle rows are 128 bytes");
 static_assert((KU_ROW_PITCH / 16) % 8 == 4, "row pitch must skew pair rows by four 16-byte bank groups");
@@ -469,12 +470,14 @@ struct SwzFetch {
     __device__ __forceinline__ uint2 operator()(int g) const { return lds64(base + swz(a + 8u * (uint32_t)g)); }
 };
 
-template <bool WITH_H>
-__device__ __forceinline__ void emit_planes(const uint32_t (&LE)[16], const uint32_t (&HE)[16], const uint32_t (&LO)[16],
-                                            const uint32_t (&HO)[16], const uint32_t refs, const uint32_t out_lane) {
-    // plane j -> output row (pair row) + 2*(j>>2), 16 pixels at byte 32*(j&3) of the lane's tile slot (RawData.cpp:581-593)
+// Planes 4*HALF .. 4*HALF+3 of an even/odd block pair -> 64 pixels of output row (pair row) + 2*HALF:
+// interleave the two Bayer columns (RawData.cpp:581-593), widen to u16, add the references mod 2^16.
+template <bool WITH_H, int HALF>
+__device__ __forceinline__ void emit_half(const uint32_t (&LE)[16], const uint32_t (&HE)[16], const uint32_t (&LO)[16],
+                                          const uint32_t (&HO)[16], const uint32_t refs, const uint32_t out_lane) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int jj = 0; jj < 4; jj++) {
+        const int j = 4 * HALF + jj;
         uint32_t w[8];
 #pragma unroll
         for (int hw = 0; hw < 2; hw++) {
@@ -496,14 +499,59 @@ __device__ __forceinline__ void emit_planes(const uint32_t (&LE)[16], const uint
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) w[k] = __vadd2(w[k], refs);                                  // mod 2^16 per sample
-        const uint32_t o = out_lane + (uint32_t)((j >> 2) * 2 * KU_ROW_PITCH + (j & 3) * 32);
-        sts128(o, w[0], w[1], w[2], w[3]);
-        sts128(o + 16, w[4], w[5], w[6], w[7]);
+        sts128(out_lane + jj * 32, w[0], w[1], w[2], w[3]);
+        sts128(out_lane + jj * 32 + 16, w[4], w[5], w[6], w[7]);
     }
 }
 
-// grid = (ceil(max units / KU_WARPS), frames), block = 32 * KU_WARPS, dynamic smem = KU_SMEM
-__global__ void __launch_bounds__(32 * KU_WARPS) k_units(FrameDev* __restrict__ frames, Result* __restrict__ results) {
+// Copy-out role of a lane: 16-byte chunk (lane & 7) of the 128-byte row segments of tile slots (lane >> 3) + 4k.
+struct CopyOut {
+    uint16_t* ptr[4];    // address of the lane's chunk in row 4*ty of the tile of slot group k
+    uint32_t nrows[4];   // rows of that tile that may be written (0 = tile not live for this lane)
+};
+
+template <bool VEC, int HALF>
+__device__ __forceinline__ void copy_half(const CopyOut& co, const uint32_t out_base, const uint32_t lane, const int width) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t s = out_base + ((lane >> 3) + 4u * k) * KU_SLOT_PITCH + (lane & 7u) * 16u;
+#pragma unroll
+        for (int qq = 0; qq < 2; qq++) {
+            const uint32_t r = qq + 2 * HALF;
+            if (r < (VEC ? co.nrows[k] : (co.nrows[k] & 0xFFu))) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s + qq * KU_ROW_PITCH));
+                uint16_t* orow = co.ptr[k] + (size_t)r * (size_t)width;
+                if (VEC) *reinterpret_cast<uint4*>(orow) = v;
+                else {
+                    // width % 8 != 0 or unaligned dst: element stores, cropped at the row end
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                    const int n = (int)(co.nrows[k] >> 8);   // pixels of this chunk inside the row (see setup)
+                    for (int e = 0; e < 8; e++)
+                        if (e < n) orow[e] = (uint16_t)(wv[e >> 1] >> (16 * (e & 1)));
+                }
+            }
+        }
+    }
+}
+
+template <bool VEC>
+__device__ __forceinline__ void emit_and_copy(const uint32_t (&LE)[16], const uint32_t (&HE)[16], const uint32_t (&LO)[16],
+                                              const uint32_t (&HO)[16], const uint32_t refs, const bool with_h, const CopyOut& co,
+                                              const uint32_t out_base, const uint32_t lane, const int width) {
+    const uint32_t out_lane = out_base + (lane & 1u) * KU_ROW_PITCH + (lane >> 1) * KU_SLOT_PITCH;
+    if (with_h) emit_half<true, 0>(LE, HE, LO, HO, refs, out_lane); else emit_half<false, 0>(LE, HE, LO, HO, refs, out_lane);
+    __syncwarp();
+    copy_half<VEC, 0>(co, out_base, lane, width);
+    __syncwarp();
+    if (with_h) emit_half<true, 1>(LE, HE, LO, HO, refs, out_lane); else emit_half<false, 1>(LE, HE, LO, HO, refs, out_lane);
+    __syncwarp();
+    copy_half<VEC, 1>(co, out_base, lane, width);
+    __syncwarp();
+}
+
+// grid = (ceil(max units / (KU_WARPS*KU_UPW)), frames), block = 32 * KU_WARPS, dynamic smem = KU_SMEM
+__global__ void __launch_bounds__(32 * KU_WARPS, 4) k_units(FrameDev* __restrict__ frames, Result* __restrict__ results) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const FrameDev& F = frames[blockIdx.y];
     if (F.type != MCRAW_COMPRESSION_CURRENT) return;
@@ -522,81 +570,89 @@ __global__ void __launch_bounds__(32 * KU_WARPS) k_units(FrameDev* __restrict__ 
     const uint32_t tiles_x = F.tiles_x;
     const uint32_t ntiles = tiles_x * F.tile_rows_dev;
     const uint32_t nunits = (ntiles + 15u) / 16u;
-    const uint32_t unit = blockIdx.x * KU_WARPS + warp;
-    if (unit >= nunits) return;
+    const uint32_t u0 = (blockIdx.x * KU_WARPS + warp) * KU_UPW;
+    if (u0 >= nunits) return;
+    const uint32_t nu = min((uint32_t)KU_UPW, nunits - u0);
 
     const uint32_t in_base = smem_u32(smem_raw) + warp * KU_WARP_SMEM;
     const uint32_t out_base = in_base + KU_IN_BYTES;
     const uint8_t* __restrict__ src = F.src;
-
-    // ---- stage the unit's payload [a0, a1) (rounded out to 16 bytes) with swizzled 16-byte cp.async
-    const uint32_t a0 = __ldg(F.unitoff + unit), a1 = __ldg(F.unitoff + unit + 1);
-    const uint32_t s0 = a0 & ~15u;
-    const uint32_t nchunks = (a1 - s0 + 15u) >> 4;                                // <= (8192 + 8 + 15) / 16
-    if ((unsigned long long)s0 + 16ull * nchunks <= F.len) {
-        const uint8_t* g = src + s0 + 16u * lane;
-        for (uint32_t c = lane; c < nchunks; c += 32, g += 512) cp_async16(in_base + swz(16u * c), g);
-    } else {                                                                       // tail of the buffer: bytes, zero filled
-        const unsigned long long len = F.len;
-        for (uint32_t c = lane; c < nchunks; c += 32) {
-            const unsigned long long o = (unsigned long long)s0 + 16ull * c;
-            uint32_t t4[4] = {0, 0, 0, 0};
-            for (int k = 0; k < 16; k++)
-                if (o + k < len) t4[k >> 2] |= (uint32_t)src[o + k] << (8 * (k & 3));
-            sts128(in_base + swz(16u * c), t4[0], t4[1], t4[2], t4[3]);
-        }
-    }
-    // ---- meanwhile: this lane's pair
-    const uint32_t pair = unit * 32u + lane;
-    const uint32_t info = __ldg(F.pairinfo + pair);
-    const uint32_t refs = __ldg(F.pairrefs + pair);
-    const uint32_t bE = (info >> 16) & 0xFFu, bO = info >> 24;
-    const uint32_t aE = (a0 - s0) + 8u * (info & 0xFFFFu);
-    // copy-out role of this lane: 16-byte chunk (lane & 7) of the row segments of tile slots (lane >> 3) + 4k
+    const unsigned long long len = F.len;
     const uint32_t inv = F.inv_tiles_x;
-    const uint32_t vec = F.flags & FLAG_VEC_STORE;
+    const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
     uint16_t* __restrict__ dst = F.dst;
-    cp_async_commit_wait_all();
-    __syncwarp();
+    const uint32_t* __restrict__ pairinfo = F.pairinfo + (size_t)u0 * 32u + lane;
+    const uint32_t* __restrict__ pairrefs = F.pairrefs + (size_t)u0 * 32u + lane;
 
-    // ---- decode the even-column and the odd-column block of the pair
-    uint32_t LE[16], HE[16], LO[16], HO[16];
-    const uint32_t lenE = decode_block(bE, SwzFetch{in_base, aE}, LE, HE);
-    decode_block(bO, SwzFetch{in_base, aE + lenE}, LO, HO);
+    // payload offsets of this warp's units (+ end): lane i holds unitoff[u0 + i]
+    const uint32_t my_off = (lane <= nu) ? __ldg(F.unitoff + u0 + lane) : 0u;
 
-    // ---- interleave, add references, assemble the four output rows of the unit in shared memory
-    const uint32_t out_lane = out_base + (lane & 1u) * KU_ROW_PITCH + (lane >> 1) * KU_SLOT_PITCH;
-    if (__any_sync(0xFFFFFFFFu, (bE > 8u) | (bO > 8u))) emit_planes<true>(LE, HE, LO, HO, refs, out_lane);
-    else emit_planes<false>(LE, HE, LO, HO, refs, out_lane);
-    __syncwarp();
-
-    // ---- coalesced copy-out: 8 lanes move one 128-byte row segment of one tile per instruction
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t slot = (lane >> 3) + 4u * k;
-        const uint32_t tile = unit * 16u + slot;
-        uint32_t ty = inv ? __umulhi(tile, inv) : tile / tiles_x;
-        const uint32_t tx = tile - ty * tiles_x;
-        const int xpix = (int)(64u * tx + 8u * (lane & 7u));
-        const uint32_t s = out_base + slot * KU_SLOT_PITCH + (lane & 7u) * 16u;
-        uint16_t* o = dst + (unsigned long long)(4u * ty) * (unsigned long long)width + xpix;
-        const bool live = tile < ntiles && xpix < width;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            if (live && 4u * ty + r < rows_fit) {
-                uint4 v;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s + r * KU_ROW_PITCH));
-                uint16_t* orow = o + (unsigned long long)r * (unsigned long long)width;
-                if (vec) *reinterpret_cast<uint4*>(orow) = v;
-                else {
-                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-                    const int n = min(8, width - xpix);
-#pragma unroll
-                    for (int e = 0; e < 8; e++)
-                        if (e < n) orow[e] = (uint16_t)(wv[e >> 1] >> (16 * (e & 1)));
-                }
+    // stage unit payload [a0, a1) (rounded out to 16 bytes) with swizzled 16-byte cp.async
+    auto stage_unit = [&](uint32_t a0, uint32_t a1) {
+        const uint32_t s0 = a0 & ~15u;
+        const uint32_t nchunks = (a1 - s0 + 15u) >> 4;                            // <= (8192 + 8 + 15) / 16
+        if ((unsigned long long)s0 + 16ull * nchunks <= len) {
+            const uint8_t* g = src + s0 + 16u * lane;
+            for (uint32_t c = lane; c < nchunks; c += 32, g += 512) cp_async16(in_base + swz(16u * c), g);
+        } else {                                                                   // tail of the buffer: bytes, zero filled
+            for (uint32_t c = lane; c < nchunks; c += 32) {
+                const unsigned long long o = (unsigned long long)s0 + 16ull * c;
+                uint32_t t4[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 16; k++)
+                    if (o + k < len) t4[k >> 2] |= (uint32_t)src[o + k] << (8 * (k & 3));
+                sts128(in_base + swz(16u * c), t4[0], t4[1], t4[2], t4[3]);
             }
         }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+
+    uint32_t a0 = __shfl_sync(0xFFFFFFFFu, my_off, 0), a1 = __shfl_sync(0xFFFFFFFFu, my_off, 1);
+    stage_unit(a0, a1);
+    uint32_t info = __ldg(pairinfo), refs = __ldg(pairrefs);
+
+    for (uint32_t i = 0; i < nu; i++) {
+        const uint32_t unit = u0 + i;
+        // prefetch the next unit's pair record while this one is decoded
+        uint32_t info_n = 0, refs_n = 0;
+        if (i + 1 < nu) { info_n = __ldg(pairinfo + 32u * (i + 1)); refs_n = __ldg(pairrefs + 32u * (i + 1)); }
+        const uint32_t bE = (info >> 16) & 0xFFu, bO = info >> 24;
+        const uint32_t aE = (a0 & 15u) + 8u * (info & 0xFFFFu);
+
+        // copy-out bookkeeping for this unit (independent of the staged data)
+        CopyOut co;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t tile = unit * 16u + (lane >> 3) + 4u * k;
+            const uint32_t ty = inv ? __umulhi(tile, inv) : tile / tiles_x;
+            const uint32_t tx = tile - ty * tiles_x;
+            const int xpix = (int)(64u * tx + 8u * (lane & 7u));
+            uint32_t nr = 0;
+            if (tile < ntiles && xpix < width && 4u * ty < rows_fit) nr = min(4u, rows_fit - 4u * ty);
+            if (!vec) nr |= (uint32_t)min(8, max(0, width - xpix)) << 8;
+            co.nrows[k] = nr;
+            co.ptr[k] = dst + (size_t)(4u * ty) * (size_t)width + xpix;
+        }
+
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+
+        // ---- decode the even-column and the odd-column block of the pair
+        uint32_t LE[16], HE[16], LO[16], HO[16];
+        const uint32_t lenE = decode_block(bE, SwzFetch{in_base, aE}, LE, HE);
+        decode_block(bO, SwzFetch{in_base, aE + lenE}, LO, HO);
+        __syncwarp();
+
+        // ---- the input buffer is free again: start fetching the next unit behind the emit / copy-out phases
+        if (i + 1 < nu) {
+            a0 = a1;
+            a1 = __shfl_sync(0xFFFFFFFFu, my_off, i + 2);
+            stage_unit(a0, a1);
+        }
+
+        const bool with_h = __any_sync(0xFFFFFFFFu, (bE > 8u) | (bO > 8u));
+        if (vec) emit_and_copy<true>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width);
+        else emit_and_copy<false>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width);
+        info = info_n; refs = refs_n;
     }
 }
 
