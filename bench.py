@@ -304,10 +304,10 @@ def main():
 
     # ---- roofline of the dominant kernel from the events recorded around it inside the timed region
     peak, peak_src = measured_peak()
-    chunks = max(1, c1 - c0)
-    main_ms = (k1 - k0) / chunks
+    chunks = max(1, c1 - c0)                      # launches of the dominant kernel inside the timed region
+    main_ms = (k1 - k0) / chunks                  # mean duration of one launch (CUDA events around the kernel)
     meta_ms = (m1 - m0) / chunks
-    alg_main = pay_bytes + out_bytes
+    alg_main = (pay_bytes + out_bytes) * args.steps / chunks   # algorithmic bytes one launch is responsible for
     achieved = alg_main / (main_ms * 1e-3) / 1e9 if main_ms > 0 else 0.0
     traffic = None
     try:
@@ -374,6 +374,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_tiles" if ct == 7 else "k_legacy_decode",
                          "algorithmic_bytes_per_launch": alg_main, "kernel_ms_per_launch": main_ms,
+                         "launches_per_step": chunks / args.steps,
                          "meta_kernel_ms_per_launch": meta_ms, "peak_source": peak_src,
                          "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,
                                         "bytes_per_step": comp_bytes + out_bytes, "frac_of_8000": step_gbs / 8000.0}},

@@ -10,6 +10,7 @@
 
 #include "mcraw_b200.h"
 #include "mcraw_kernels.cuh"
+#include "mcraw_legacy.cuh"
 
 using namespace mcraw;
 
@@ -144,9 +145,9 @@ int harvest(mcraw_ctx* ctx, Slot& s) {
 
 // Validate descriptors and build the device-side frame records; tilemeta holds an OFFSET until rebased.
 int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t first_index, std::vector<FrameDev>& out,
-            size_t& scratch, uint32_t& max_tile_rows, uint32_t& max_units, bool& any7, bool& any6) {
+            size_t& scratch, uint32_t& max_tile_rows, uint32_t& max_units, uint32_t& max_ltiles, bool& any7, bool& any6) {
     out.resize(n);
-    scratch = 0; max_tile_rows = 0; max_units = 0; any7 = any6 = false;
+    scratch = 0; max_tile_rows = 0; max_units = 0; max_ltiles = 0; any7 = any6 = false;
     for (uint32_t i = 0; i < n; i++) {
         const mcraw_frame_desc& d = descs[i];
         const std::string who = "frame " + std::to_string(first_index + i);
@@ -179,6 +180,18 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
             max_units = std::max(max_units, f.nunits);
         } else if (d.compression_type == MCRAW_COMPRESSION_LEGACY) {
             any6 = true;
+            if (d.len >= ((uint64_t)1 << 40)) return fail_arg(ctx, who + ": legacy frame buffer too large");
+            const uint64_t nseg = (d.len + LG_SEG - 1) / LG_SEG;
+            const uint64_t ntile = std::max<uint64_t>(1, (nseg + LG_TILE_SEGS - 1) / LG_TILE_SEGS);
+            if (ntile > 0x7FFFFFFFull) return fail_arg(ctx, who + ": legacy frame buffer too large");
+            // scratch layout (offsets for now): segment maps | tile maps | tile states
+            f.lg_segmap = reinterpret_cast<uint16_t*>(scratch);
+            scratch += ((size_t)ntile * LG_TILE_SEGS * LG_STATES * 2 + 15) & ~(size_t)15;
+            f.lg_tilemap = reinterpret_cast<uint32_t*>(scratch);
+            scratch += ((size_t)ntile * LG_STATES * 4 + 15) & ~(size_t)15;
+            f.lg_tilestate = reinterpret_cast<uint32_t*>(scratch);
+            scratch += ((size_t)ntile * 2 * 4 + 15) & ~(size_t)15;
+            max_ltiles = std::max<uint32_t>(max_ltiles, (uint32_t)ntile);
         } else {
             f.status = MCRAW_FRAME_BAD_TYPE;
         }
@@ -207,8 +220,8 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (rc) return rc;
 
     std::vector<FrameDev> frames;
-    size_t scratch; uint32_t max_tile_rows, max_units; bool any7, any6;
-    rc = prepare(ctx, descs, n, result_offset, frames, scratch, max_tile_rows, max_units, any7, any6);
+    size_t scratch; uint32_t max_tile_rows, max_units, max_ltiles; bool any7, any6;
+    rc = prepare(ctx, descs, n, result_offset, frames, scratch, max_tile_rows, max_units, max_ltiles, any7, any6);
     if (rc) return rc;
     rc = slot_reserve(ctx, s, n, scratch);
     if (rc) return rc;
@@ -217,21 +230,32 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
             frames[i].unitoff = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].unitoff));
             frames[i].pairinfo = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].pairinfo));
             frames[i].pairrefs = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].pairrefs));
+        } else if (frames[i].type == MCRAW_COMPRESSION_LEGACY) {
+            frames[i].lg_segmap = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].lg_segmap));
+            frames[i].lg_tilemap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].lg_tilemap));
+            frames[i].lg_tilestate = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].lg_tilestate));
         }
         s.h_frames[i] = frames[i];
     }
     s.n = n; s.result_offset = result_offset; s.batch_id = ctx->batch_id; s.timed = false;
     CU_TRY(ctx, cudaMemcpyAsync(s.d_frames, s.h_frames, sizeof(FrameDev) * n, cudaMemcpyHostToDevice, st));
     CU_TRY(ctx, cudaMemsetAsync(s.d_results, 0, sizeof(Result) * n, st));
-    if (any7) {
-        CU_TRY(ctx, cudaEventRecord(s.e0, st));
-        k_meta<<<2 * n, K1_THREADS, 0, st>>>(s.d_frames);
-        CU_TRY(ctx, cudaEventRecord(s.e1, st));
-        k_units<<<dim3((max_units + KU_WARPS * KU_UPW - 1) / (KU_WARPS * KU_UPW), n), 32 * KU_WARPS, KU_SMEM, st>>>(s.d_frames, s.d_results);
-        CU_TRY(ctx, cudaEventRecord(s.e2, st));
+    // index kernels between e0 and e1, pixel kernels between e1 and e2
+    CU_TRY(ctx, cudaEventRecord(s.e0, st));
+    if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, st>>>(s.d_frames); ctx->launches += 1; }
+    if (any6) {
+        k_legacy_maps<<<dim3(max_ltiles, n), LG_THREADS, LG_MAPS_SMEM, st>>>(s.d_frames);
+        k_legacy_scan<<<n, LG_THREADS, 0, st>>>(s.d_frames, s.d_results);
         ctx->launches += 2;
-        s.timed = true;
     }
+    CU_TRY(ctx, cudaEventRecord(s.e1, st));
+    if (any7) {
+        k_units<<<dim3((max_units + KU_WARPS * KU_UPW - 1) / (KU_WARPS * KU_UPW), n), 32 * KU_WARPS, KU_SMEM, st>>>(s.d_frames, s.d_results);
+        ctx->launches += 1;
+    }
+    if (any6) { k_legacy_decode<<<dim3(max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(s.d_frames); ctx->launches += 1; }
+    CU_TRY(ctx, cudaEventRecord(s.e2, st));
+    s.timed = any7 || any6;
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaMemcpyAsync(s.h_results, s.d_results, sizeof(Result) * n, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaEventRecord(s.done, st));
@@ -293,8 +317,9 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
     for (auto& cs : ctx->copy_streams)
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
-    if (cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess) {
-        ctx->err = "cudaFuncSetAttribute(k_units, smem) failed"; return bail(MCRAW_ERR_CUDA);
+    if (cudaFuncSetAttribute(k_meta, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess) {
+        ctx->err = "cudaFuncSetAttribute(smem) failed"; return bail(MCRAW_ERR_CUDA);
     }
     for (auto& s : ctx->slots) {
         if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&s.e0) != cudaSuccess ||

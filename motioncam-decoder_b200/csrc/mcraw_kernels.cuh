@@ -18,7 +18,7 @@
 //            rows are assembled in shared memory and leave through 128-byte TMA bulk stores
 //            (cp.async.bulk.global.shared::cta); columns >= width are cropped (RawData.cpp:598-608).
 //
-// Legacy format (compressionType 6; reference: /root/reference/lib/RawData_Legacy.cpp:445-495): see below.
+// Legacy format (compressionType 6; reference: /root/reference/lib/RawData_Legacy.cpp:445-495): mcraw_legacy.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -41,8 +41,9 @@ struct FrameDev {
     uint32_t* unitoff;             // scratch [nunits + 1]   payload offset of each unit (+ end)
     uint32_t* pairinfo;            // scratch [32 * nunits]  rel8 | bitsE << 16 | bitsO << 24
     uint32_t* pairrefs;            // scratch [32 * nunits]  refE | refO << 16
-    uint32_t* aux;                 // scratch for the legacy index (type 6)
-    unsigned long long aux_elems;
+    uint16_t* lg_segmap;           // legacy scratch [32 * tiles][17]  transfer map of every 1 KiB segment
+    uint32_t* lg_tilemap;          // legacy scratch [tiles][17]       transfer map of every 32 KiB tile
+    uint32_t* lg_tilestate;        // legacy scratch [tiles][2]        entry offset / first block ordinal of every tile
     // written on the device
     unsigned status;               // MCRAW_FRAME_* bits
     unsigned tile_rows_dev;        // ceil(encodedHeight/4) from the frame header
@@ -235,13 +236,31 @@ struct StageFetch {
     }
 };
 
+constexpr int K1_NXT_BYTES = K1_CHUNK + 16;                       // u16 per even offset, byte offset == stream offset
+constexpr int K1_SMEM = (K1_CHUNK + 32) + 2 * K1_NXT_BYTES + 2 * (K1_MB + 8) + 2 * (K1_MB / 4 + 8);   // stage, nxt1, nxt4, ends, anchors
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// grid = 2 * frames, block = K1_THREADS, dynamic smem = K1_SMEM
 __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ frames) {
-    __shared__ __align__(16) uint8_t stage[K1_CHUNK + 32];
-    __shared__ uint16_t nxt[K1_CHUNK / 2 + 2];      // next chain position for every even offset of the chunk (+ sentinel)
-    __shared__ uint16_t starts[K1_MB];
+    extern __shared__ __align__(16) uint8_t k1_smem[];
+    uint8_t* stage = k1_smem;                                                        // K1_CHUNK + 32 bytes of the stream
+    const uint32_t stage_s = smem_u32(stage);
+    const uint32_t nxt1_s = stage_s + K1_CHUNK + 32;                                 // next position after 1 block
+    const uint32_t nxt4_s = nxt1_s + K1_NXT_BYTES;                                   // ... after 4 blocks
+    uint16_t* ends = reinterpret_cast<uint16_t*>(k1_smem + (K1_CHUNK + 32) + 2 * K1_NXT_BYTES);     // [K1_MB] position after block t
+    uint16_t* anchors = ends + (K1_MB + 8);                                        // [K1_MB / 4 + 1]
     __shared__ uint32_t warp_sums[K1_THREADS / 32];
-    __shared__ uint32_t sh_cnt, sh_err, sh_bad;
-    __shared__ unsigned long long sh_nextpos;
+    __shared__ uint32_t sh_err, sh_bad;
     __shared__ uint32_t sh_hdr[4];
 
     const int f = blockIdx.x >> 1;
@@ -257,7 +276,8 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
         uint32_t ew = 0, eh = 0, boff = 0, roff = 0;
         if (len < 16) err = MCRAW_FRAME_BAD_HEADER;
         else {
-            ew = ld_u32le(src); eh = ld_u32le(src + 4); boff = ld_u32le(src + 8); roff = ld_u32le(src + 12);  // RawData.cpp:500-524
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));                // RawData.cpp:500-524 (little-endian u32 x 4)
+            ew = h.x; eh = h.y; boff = h.z; roff = h.w;
             if (boff > len || roff > len) err |= MCRAW_FRAME_BAD_HEADER;            // :547
             if (ew % 64u) err |= MCRAW_FRAME_BAD_HEADER;                            // :550
             if (F.width <= 0 || ew < (uint32_t)F.width) err |= MCRAW_FRAME_BAD_HEADER;  // :553
@@ -267,11 +287,17 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
                 if ((eh + 3u) / 4u > F.tile_rows) err |= MCRAW_FRAME_GEOMETRY;
             }
         }
+        const uint32_t tr = err ? 0u : (eh + 3u) / 4u;
+        unsigned long long pos0 = stream ? roff : boff;
+        if (!err) {
+            const uint32_t nb = (ew / 64u) * tr * 4u;
+            if (pos0 + 4 > len) err = MCRAW_FRAME_TRUNCATED;
+            else if (ld_u32le(src + pos0) < nb) err = MCRAW_FRAME_BAD_META_COUNT;   // RawData.cpp:470-476
+        }
         sh_hdr[0] = ew; sh_hdr[1] = eh; sh_hdr[2] = boff; sh_hdr[3] = roff;
         sh_err = err;
         sh_bad = 0;
         if (stream == 0) {
-            const uint32_t tr = err ? 0u : (eh + 3u) / 4u;
             unsigned long long fit = F.dst_cap / (unsigned long long)(F.width > 0 ? F.width : 1);
             if (fit > 4ull * tr) fit = 4ull * tr;                                   // reference emits 4 rows per tile row (:598-608)
             F.tile_rows_dev = tr;
@@ -286,22 +312,8 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
     const uint32_t tiles_x = sh_hdr[0] / 64u;
     const uint32_t tile_rows = (sh_hdr[1] + 3u) / 4u;
     const uint32_t ntiles = tiles_x * tile_rows;
-    const uint32_t nblocks = ntiles * 4u;
-    const uint32_t need_mb = (nblocks + 63u) / 64u;      // = number of units
-    unsigned long long pos = (unsigned long long)sh_hdr[2 + stream];
-
-    if (tid == 0) {
-        uint32_t err = 0;
-        if (pos + 4 > len) err = MCRAW_FRAME_TRUNCATED;
-        else if (ld_u32le(src + pos) < nblocks) err = MCRAW_FRAME_BAD_META_COUNT;  // RawData.cpp:470-476
-        sh_err = err;
-    }
-    __syncthreads();
-    if (sh_err) {
-        if (tid == 0) atomicOr(&F.status, sh_err);
-        return;
-    }
-    pos += 4;
+    const uint32_t need_mb = (ntiles * 4u + 63u) / 64u;  // = number of units
+    unsigned long long pos = (unsigned long long)sh_hdr[2 + stream] + 4;
 
     uint32_t* __restrict__ unitoff = F.unitoff;
     uint32_t* __restrict__ pairinfo = F.pairinfo;
@@ -310,61 +322,123 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
     uint32_t carry = 16;          // running payload offset, METADATA_OFFSET (RawData.cpp:25,562)
 
     while (done < need_mb) {
-        // ---- stage [base, base + K1_CHUNK) of the frame buffer in shared memory (zero past len)
+        // ---- stage [base, base + K1_CHUNK + 32) of the frame buffer in shared memory (zero past len)
         const unsigned long long base = pos & ~15ull;
-        for (int v = tid; v < (K1_CHUNK + 32) / 16; v += K1_THREADS) {
-            const unsigned long long o = base + (unsigned long long)v * 16;
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (o + 16 <= len) q = __ldg(reinterpret_cast<const uint4*>(src + o));
-            else if (o < len) {
-                uint32_t t4[4] = {0, 0, 0, 0};
-                for (int k = 0; k < 16; k++)
-                    if (o + k < len) t4[k >> 2] |= (uint32_t)src[o + k] << (8 * (k & 3));
-                q = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+        {
+            uint4 q[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int v = tid + k * K1_THREADS;
+                const unsigned long long o = base + (unsigned long long)v * 16;
+                q[k] = make_uint4(0, 0, 0, 0);
+                if (v < (K1_CHUNK + 32) / 16) {
+                    if (o + 16 <= len) q[k] = __ldg(reinterpret_cast<const uint4*>(src + o));
+                    else if (o < len) {
+                        uint32_t t4[4] = {0, 0, 0, 0};
+                        for (int e = 0; e < 16; e++)
+                            if (o + e < len) t4[e >> 2] |= (uint32_t)src[o + e] << (8 * (e & 3));
+                        q[k] = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+                    }
+                }
             }
-            *reinterpret_cast<uint4*>(stage + v * 16) = q;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int v = tid + k * K1_THREADS;
+                if (v < (K1_CHUNK + 32) / 16) *reinterpret_cast<uint4*>(stage + v * 16) = q[k];
+            }
         }
         __syncthreads();
-        // ---- next-pointer of every candidate (even) position: p + 2 + payload length of the header found there;
-        //      candidates whose block does not fit the staged window (or the frame) point at a self-looping sentinel
-        const unsigned long long room = len - base;                     // bytes of the frame from base on
+        // ---- nxt1[p] = p + 2 + payload length of the header at p for every even p whose block fits the window and
+        //      the frame (RawData.cpp:419), else a self-looping sentinel.  16 stream bytes = 8 candidates per step.
+        const unsigned long long room = len - base;
         const uint32_t lim = (uint32_t)(room < (unsigned long long)K1_CHUNK ? room : (unsigned long long)K1_CHUNK);
-        for (int c = tid; c <= K1_CHUNK / 2; c += K1_THREADS) {
-            const uint32_t p = 2u * (uint32_t)c;
-            uint32_t q = K1_CHUNK;
-            if (p + 2u <= lim) {
-                q = p + 2u + 8u * cur_len8_nib(stage[p] >> 4);
-                if (q > lim) q = K1_CHUNK;                                  // RawData.cpp:419 (block past the end)
+        constexpr uint32_t SENT = K1_CHUNK;
+#pragma unroll
+        for (int k = 0; k < K1_CHUNK / 16 / K1_THREADS; k++) {
+            const uint32_t v = tid + k * K1_THREADS;
+            const uint4 d = lds128(stage_s + 16u * v);
+            const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t pr[2];
+#pragma unroll
+                for (int hlf = 0; hlf < 2; hlf++) {
+                    const uint32_t p = 16u * v + 4u * i + 2u * hlf;
+                    const uint32_t hb = (w[i] >> (16 * hlf + 4)) & 15u;
+                    uint32_t q = p + 2u + 8u * cur_len8_nib(hb);
+                    if (q > lim) q = SENT;
+                    pr[hlf] = q;
+                }
+                o[i] = pr[0] | (pr[1] << 16);
             }
-            nxt[c] = (uint16_t)q;
+            sts128(nxt1_s + 16u * v, o[0], o[1], o[2], o[3]);
+        }
+        if (tid == 0) { sts128(nxt1_s + SENT, SENT * 0x10001u, SENT * 0x10001u, SENT * 0x10001u, SENT * 0x10001u);
+                        sts128(nxt4_s + SENT, SENT * 0x10001u, SENT * 0x10001u, SENT * 0x10001u, SENT * 0x10001u); }
+        __syncthreads();
+        // ---- pointer doubling: nxt2 = nxt1 o nxt1 (kept in the nxt4 array), then nxt4 = nxt2 o nxt2 in place
+#pragma unroll
+        for (int k = 0; k < K1_CHUNK / 16 / K1_THREADS; k++) {
+            const uint32_t v = tid + k * K1_THREADS;
+            const uint4 d = lds128(nxt1_s + 16u * v);
+            const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) o[i] = lds_u16(nxt1_s + (w[i] & 0xFFFFu)) | (lds_u16(nxt1_s + (w[i] >> 16)) << 16);
+            sts128(nxt4_s + 16u * v, o[0], o[1], o[2], o[3]);
         }
         __syncthreads();
-        // ---- serial chain walk over the inline 2-byte headers (RawData.cpp:485-489): one dependent LDS per step
+        {
+            uint32_t o[K1_CHUNK / 16 / K1_THREADS][4];
+#pragma unroll
+            for (int k = 0; k < K1_CHUNK / 16 / K1_THREADS; k++) {
+                const uint32_t v = tid + k * K1_THREADS;
+                const uint4 d = lds128(nxt4_s + 16u * v);
+                const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) o[k][i] = lds_u16(nxt4_s + (w[i] & 0xFFFFu)) | (lds_u16(nxt4_s + (w[i] >> 16)) << 16);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < K1_CHUNK / 16 / K1_THREADS; k++) sts128(nxt4_s + 16u * (tid + k * K1_THREADS), o[k][0], o[k][1], o[k][2], o[k][3]);
+        }
+        __syncthreads();
+        // ---- serial part of the chain walk (RawData.cpp:485-489), 4 blocks per dependent shared-memory load
         const uint32_t limit = min((uint32_t)K1_MB, need_mb - done);
         if (tid == 0) {
-            uint32_t p = (uint32_t)(pos - base), cnt = 0, last = p;
-            const uint32_t nxt_s = smem_u32(nxt);
-#pragma unroll 8
-            for (uint32_t k = 0; k < limit; k++) {
-                uint32_t q;
-                asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(q) : "r"(nxt_s + p));   // nxt[p / 2], p is even
-                starts[k] = (uint16_t)p;
-                if (p != (uint32_t)K1_CHUNK && q != (uint32_t)K1_CHUNK) { cnt++; last = q; }
-                p = q;
+            uint32_t p = (uint32_t)(pos - base);
+            const uint32_t hops = (limit >> 2) + 1u;
+#pragma unroll 4
+            for (uint32_t k = 0; k < hops; k++) {
+                anchors[k] = (uint16_t)p;
+                p = lds_u16(nxt4_s + p);
             }
-            // a chain that stopped early because the FRAME ended (not the window) is a truncated stream
-            sh_cnt = cnt;
-            sh_err = (cnt < limit && lim < (uint32_t)K1_CHUNK) ? MCRAW_FRAME_TRUNCATED : 0u;
-            sh_nextpos = base + last;
         }
         __syncthreads();
-        const uint32_t cnt = sh_cnt;
-        if (sh_err) break;
+        // ---- every thread finishes its own position: t blocks from the start = anchor[t / 4] + (t % 4) single steps
+        uint32_t my_start = SENT;
+        bool valid = false;
+        if ((uint32_t)tid < limit) {
+            uint32_t p = anchors[tid >> 2];
+            for (int r = 0; r < (tid & 3); r++) p = lds_u16(nxt1_s + p);
+            my_start = p;
+            const uint32_t e = lds_u16(nxt1_s + p);                       // SENT when the block does not fit
+            ends[tid] = (uint16_t)e;
+            valid = p != SENT && e != SENT;
+        }
+        const uint32_t cnt = (uint32_t)__syncthreads_count(valid);     // validity is monotone along the chain
+        if (cnt < limit && lim < (uint32_t)K1_CHUNK) {                  // the chain ran into the end of the FRAME
+            if (tid == 0) sh_err = MCRAW_FRAME_TRUNCATED;
+            __syncthreads();
+            break;
+        }
+        const unsigned long long nextpos = cnt ? base + ends[cnt - 1] : pos;
         // ---- one lane decodes one meta block (64 values): value = unpacked + header reference, mod 2^16 (:491-492)
         uint32_t unit_len8 = 0;
         const uint32_t unit = done + (uint32_t)tid;
         if ((uint32_t)tid < cnt) {
-            const uint32_t p = starts[tid];
+            const uint32_t p = my_start;
             const uint32_t b = stage[p] >> 4;                                          // RawData.cpp:106-110
             const uint32_t ref = ((uint32_t)(stage[p] & 0x0F) << 8) | stage[p + 1];
             uint32_t L[16], H[16];
@@ -434,7 +508,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
             if (sh_bad) { if (tid == 0) sh_err = MCRAW_FRAME_BAD_BITS; __syncthreads(); break; }
         }
         done += cnt;
-        pos = sh_nextpos;
+        pos = nextpos;
         __syncthreads();
     }
     if (tid == 0) {
