@@ -1,0 +1,78 @@
+"""GPU parity: the CUDA path (through the C-ABI, ctypes) against the oracle on the shared seeded vectors,
+legacy frame format (compressionType 6, RawData_Legacy.cpp:445-495).  Bit-exact or fail."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import vectors
+from test_gpu_current import _check_batch, ctx  # noqa: F401  (shared fixture / helper)
+
+pytestmark = pytest.mark.gpu
+
+
+def test_legacy_vectors_batched(ctx):
+    from motioncam_decoder_b200 import capi
+    _check_batch(ctx, vectors.legacy_vectors(small=True), capi.COMPRESSION_LEGACY, ol.oracle_decode_legacy)
+
+
+def test_legacy_vectors_one_by_one_host_call(ctx):
+    from motioncam_decoder_b200 import capi
+    for name, s, w, h, img in vectors.legacy_vectors(small=True):
+        n, got = ctx.decode_host(s, w, h, capi.COMPRESSION_LEGACY)
+        n_or, want = ol.oracle_decode_legacy(s, w, h)
+        assert n == n_or == w * h, name
+        assert np.array_equal(got, want), name
+
+
+def test_legacy_full_size(ctx):
+    """C4 geometry: 4000x3000, 750 000 chained blocks, ~9 MB -> 282 tiles of 32 KiB."""
+    from motioncam_decoder_b200 import capi
+    vecs = [v for v in vectors.legacy_vectors(small=False) if v[0] == "legacy_c4"]
+    _check_batch(ctx, vecs, capi.COMPRESSION_LEGACY, ol.oracle_decode_legacy)
+
+
+def test_legacy_constant_width_regions(ctx):
+    """Chains that never merge: every block the same width (uniform noise), so each of the 17 candidate entry
+    offsets of a segment leads to a different exit -- the full transfer map is needed, not a guess."""
+    from motioncam_decoder_b200 import capi, testvec as tv
+    vecs = []
+    for k, hb in enumerate([1, 3, 7, 10, 15]):
+        img = tv.gen_uniform(2048, 24, 0, (1 << min(hb, 12)) - 1, seed=300 + k)
+        vecs.append((f"const_nib{hb}", tv.encode_legacy(img, policy=tv.POLICY_FORCE, policy_arg=hb, seed=k), 2048, 24, img))
+    _check_batch(ctx, vecs, capi.COMPRESSION_LEGACY, ol.oracle_decode_legacy)
+
+
+def test_mixed_batch_both_formats(ctx):
+    """One batch may mix compression types and sizes (mcraw_frame_desc.compression_type per frame)."""
+    from motioncam_decoder_b200 import capi
+    cur = vectors.current_vectors(small=True)[:6]
+    leg = vectors.legacy_vectors(small=True)[:6]
+    frames, want = [], []
+    for (a, b) in zip(cur, leg):
+        frames.append((a[1], a[2], a[3], capi.COMPRESSION_CURRENT)); want.append(ol.oracle_decode(a[1], a[2], a[3]))
+        frames.append((b[1], b[2], b[3], capi.COMPRESSION_LEGACY)); want.append(ol.oracle_decode_legacy(b[1], b[2], b[3]))
+    batch = capi.DeviceBatch(ctx, frames)
+    batch.fill_outputs(0xA5A5)
+    written, status = batch.decode()
+    for i, (n, img) in enumerate(want):
+        assert status[i] == 0 and written[i] == n
+        assert np.array_equal(batch.fetch(i), img)
+    batch.free()
+
+
+def test_legacy_rejects_truncated(ctx):
+    """The reference leaves stale samples when the chain runs into the end of the buffer
+    (RawData_Legacy.cpp:387,398); here the frame fails with 0, like the oracle."""
+    from motioncam_decoder_b200 import capi, testvec as tv
+    img = tv.gen_photon(640, 16, 1023, seed=5)
+    good = tv.encode_legacy(img)
+    cases = [good[: len(good) // 2].copy(), good[: len(good) - 1].copy(), good[:1].copy()]
+    frames = [(s, 640, 16, capi.COMPRESSION_LEGACY) for s in cases] + [(good, 640, 16, capi.COMPRESSION_LEGACY)]
+    batch = capi.DeviceBatch(ctx, frames)
+    written, status = batch.decode()
+    for i, s in enumerate(cases):
+        assert written[i] == 0 and status[i] & capi.FRAME_TRUNCATED, (i, written[i], status[i])
+        assert ol.oracle_decode_legacy(s, 640, 16)[0] == 0
+    assert written[-1] == 640 * 16 and status[-1] == 0
+    assert np.array_equal(batch.fetch(len(cases)), img)
+    batch.free()
