@@ -1,0 +1,80 @@
+// motioncam/Decoder.hpp -- .mcraw container reader with the public surface of the reference's
+// lib/include/motioncam/Decoder.hpp:28-73 (same names, argument meaning, exception types and messages), decoding
+// frames on the B200 instead of the host.
+//
+// Differences that a caller can observe:
+//   * the file is read with positional reads (pread), so the FILE* position is never moved; like the reference,
+//     one Decoder instance is meant for one thread;
+//   * frames with equal timestamps keep their index order (the reference's std::sort leaves it unspecified);
+//   * loadFrames() / loadFramesDevice() are additions: many frames per call, one batched device decode.
+#pragma once
+#include <motioncam/Container.hpp>
+#include <nlohmann/json.hpp>
+
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace motioncam {
+
+typedef int64_t Timestamp;
+typedef std::pair<Timestamp, std::vector<int16_t>> AudioChunk;   // (timestampNs or -1, interleaved int16 PCM)
+
+class MotionCamException : public std::runtime_error {
+public:
+    MotionCamException(const std::string& error) : runtime_error(error) {}
+};
+
+class IOException : public MotionCamException {
+public:
+    IOException(const std::string& error) : MotionCamException(error) {}
+};
+
+class AudioChunkLoader {
+public:
+    virtual bool next(AudioChunk& output) = 0;
+    virtual ~AudioChunkLoader() = default;
+};
+
+// Where one frame lives in the file (what the batched feeders need to read it without the JSON round trip).
+struct FrameLocation {
+    Timestamp timestamp;
+    int64_t payloadOffset;     // file offset of the compressed frame bytes (after the BUFFER Item header)
+    uint32_t payloadSize;      // Item::size of the BUFFER record
+};
+
+class Decoder {
+public:
+    Decoder(const std::string& path);
+    Decoder(FILE* file);       // takes ownership: the handle is closed by the destructor
+    ~Decoder();
+    Decoder(const Decoder&) = delete;
+    Decoder& operator=(const Decoder&) = delete;
+
+    const nlohmann::json& getContainerMetadata() const;
+    const std::vector<Timestamp>& getFrames() const;                // sorted by timestamp
+    void loadFrame(const Timestamp timestamp, std::vector<uint8_t>& outData, nlohmann::json& outMetadata);
+    int audioSampleRateHz() const;
+    int numAudioChannels() const;
+    void loadAudio(std::vector<AudioChunk>& outAudioChunks);        // appends every chunk of the audio index
+    AudioChunkLoader& loadAudio() const;                            // one chunk per next(); position persists
+
+    // ---- additions (batched, B200) -------------------------------------------------------------------
+    // Locate a frame's compressed bytes; throws IOException like loadFrame for unknown timestamps.
+    FrameLocation locateFrame(const Timestamp timestamp) const;
+    // Read the frame's compressed bytes into dst (payloadSize bytes, e.g. pinned memory) and parse its JSON.
+    void readFrame(const FrameLocation& where, uint8_t* dst, nlohmann::json& outMetadata) const;
+    // loadFrame for many timestamps: one overlapped H2D + batched decode + D2H.  outData[i] / outMetadata[i]
+    // are what loadFrame(timestamps[i], ...) would have produced; the same exceptions are thrown.
+    void loadFrames(const std::vector<Timestamp>& timestamps, std::vector<std::vector<uint8_t>>& outData,
+                    std::vector<nlohmann::json>& outMetadata);
+
+private:
+    struct Impl;
+    std::unique_ptr<Impl> m;
+};
+
+}  // namespace motioncam

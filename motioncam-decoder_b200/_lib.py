@@ -16,4 +16,4 @@ def load(path):
         raise ImportError(
             f"{os.path.basename(path)} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
             f"or `make -C {CSRC}` first (there is no CPU fallback for the decode path)")
-    return ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+    return ctypes.CDLL(path)   # RTLD_LOCAL: the reference checker exports the same C++ symbols

@@ -1,0 +1,350 @@
+// Decoder.cpp -- .mcraw container reader (host side of the decode path) behind the reference's public API.
+//
+// Mirrors the observable behaviour of /root/reference/lib/Decoder.cpp (open/index :116-151,237-315; loadFrame
+// :184-235; audio :42-93,169-182) -- same exception types and messages, same ordering rules -- but is organised
+// for the B200 path: the file is indexed once into FrameLocation records and read with pread (no shared file
+// position), frames are decoded on the device through motioncam::raw::Decode* (one frame) or through
+// mcraw_decode_batch_host (loadFrames: pinned staging, overlapped H2D, one batched decode).
+#include <motioncam/Decoder.hpp>
+#include <motioncam/RawData.hpp>
+
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+#include "dropin_ctx.hpp"
+
+namespace motioncam {
+
+namespace {
+
+constexpr int kCompressionLegacy = MCRAW_COMPRESSION_LEGACY;    // Decoder.cpp:20
+constexpr int kCompressionCurrent = MCRAW_COMPRESSION_CURRENT;  // Decoder.cpp:21
+
+// Positional file access.  A short read is the reference's "Failed to read data" (Decoder.cpp:36-40).
+class FileView {
+public:
+    explicit FileView(FILE* f) : mFile(f), mFd(fileno(f)) {
+        struct stat st;
+        mSize = (mFd >= 0 && fstat(mFd, &st) == 0) ? static_cast<int64_t>(st.st_size) : -1;
+    }
+    ~FileView() {
+        if (mFile) std::fclose(mFile);
+    }
+    int64_t size() const { return mSize; }
+    bool tryRead(int64_t offset, void* dst, size_t bytes) const {
+        uint8_t* p = static_cast<uint8_t*>(dst);
+        while (bytes) {
+            const ssize_t n = ::pread(mFd, p, bytes, static_cast<off_t>(offset));
+            if (n <= 0) return false;
+            p += n; offset += n; bytes -= static_cast<size_t>(n);
+        }
+        return true;
+    }
+    void read(int64_t offset, void* dst, size_t bytes) const {
+        if (!tryRead(offset, dst, bytes)) throw IOException("Failed to read data");
+    }
+
+private:
+    FILE* mFile;
+    int mFd;
+    int64_t mSize;
+};
+
+// One audio chunk (Decoder.cpp:42-75).  false = unreachable offset (the reference's failed seek).
+bool readAudioChunk(const FileView& file, const BufferOffset& where, AudioChunk& out) {
+    if (where.offset < 0) return false;
+    int64_t pos = where.offset;
+    Item item{};
+    file.read(pos, &item, sizeof item);
+    pos += sizeof item;
+    if (item.type != Type::AUDIO_DATA) throw IOException("Invalid audio data");
+    std::vector<int16_t> samples((static_cast<size_t>(item.size) + 1) / 2);
+    file.read(pos, samples.data(), item.size);
+    pos += item.size;
+    // newer files append the chunk's timestamp; the reference reads the next record header unconditionally
+    Item next{};
+    file.read(pos, &next, sizeof next);
+    pos += sizeof next;
+    Timestamp ts = -1;
+    if (next.type == Type::AUDIO_DATA_METADATA) {
+        AudioMetadata md{};
+        file.read(pos, &md, sizeof md);
+        ts = md.timestampNs;
+    }
+    out = std::make_pair(ts, std::move(samples));
+    return true;
+}
+
+class SequentialAudioLoader : public AudioChunkLoader {
+public:
+    SequentialAudioLoader(const FileView& file, const std::vector<BufferOffset>& offsets) : mFile(file), mOffsets(offsets) {}
+    bool next(AudioChunk& output) override {
+        if (mNext >= mOffsets.size()) return false;
+        if (!readAudioChunk(mFile, mOffsets[mNext], output)) return false;
+        ++mNext;
+        return true;
+    }
+
+private:
+    const FileView& mFile;
+    const std::vector<BufferOffset>& mOffsets;
+    size_t mNext = 0;
+};
+
+struct FrameGeometry { int width, height, compressionType; };
+
+FrameGeometry geometryOf(const nlohmann::json& meta) {
+    FrameGeometry g;
+    g.width = meta["width"];                       // Decoder.cpp:216-218 (json type errors propagate)
+    g.height = meta["height"];
+    g.compressionType = meta["compressionType"];
+    return g;
+}
+
+}  // namespace
+
+struct Decoder::Impl {
+    explicit Impl(FILE* f) : file(f) {}
+
+    FileView file;
+    nlohmann::json containerMetadata;
+    std::vector<BufferOffset> frameIndex;               // sorted by timestamp
+    std::vector<Timestamp> frameList;
+    std::map<Timestamp, BufferOffset> frameByTimestamp; // first record wins for equal timestamps
+    std::vector<BufferOffset> audioIndex;
+    std::unique_ptr<AudioChunkLoader> audioLoader;
+    std::vector<uint8_t> scratch;                       // compressed bytes of the frame being loaded
+
+    void open();
+    void readFrameIndex();
+    void findAudioIndex();
+};
+
+void Decoder::Impl::open() {
+    // Decoder.cpp:116-151
+    Header header{};
+    file.read(0, &header, sizeof header);
+    if (header.version != CONTAINER_VERSION) throw IOException("Invalid container version");
+    if (std::memcmp(header.ident, CONTAINER_ID, sizeof CONTAINER_ID) != 0) throw IOException("Invalid header id");
+    Item item{};
+    file.read(sizeof header, &item, sizeof item);
+    if (item.type != Type::METADATA) throw IOException("Invalid camera metadata");
+    std::string text(item.size, '\0');
+    file.read(sizeof header + sizeof item, &text[0], item.size);
+    containerMetadata = nlohmann::json::parse(text);
+
+    readFrameIndex();
+    findAudioIndex();
+    audioLoader.reset(new SequentialAudioLoader(file, audioIndex));
+}
+
+void Decoder::Impl::readFrameIndex() {
+    // the trailer is the last Item + BufferIndex of the file (Decoder.cpp:237-264)
+    const int64_t trailer = static_cast<int64_t>(sizeof(Item) + sizeof(BufferIndex));
+    if (file.size() < trailer) throw IOException("Failed to get end chunk");
+    Item item{};
+    file.read(file.size() - trailer, &item, sizeof item);
+    if (item.type != Type::BUFFER_INDEX) throw IOException("Invalid file");
+    BufferIndex index{};
+    file.read(file.size() - static_cast<int64_t>(sizeof(BufferIndex)), &index, sizeof index);
+    if (static_cast<uint32_t>(index.magicNumber) != INDEX_MAGIC_NUMBER) throw IOException("Corrupted file");
+    if (index.numOffsets < 0 || index.indexDataOffset < 0) throw IOException("Invalid index");
+    frameIndex.resize(static_cast<size_t>(index.numOffsets));
+    file.read(index.indexDataOffset, frameIndex.data(), sizeof(BufferOffset) * frameIndex.size());
+
+    // timestamp order; equal timestamps keep index order and the first one is the one loadFrame finds (:266-279)
+    std::stable_sort(frameIndex.begin(), frameIndex.end(),
+                     [](const BufferOffset& a, const BufferOffset& b) { return a.timestamp < b.timestamp; });
+    frameList.reserve(frameIndex.size());
+    for (const BufferOffset& o : frameIndex) {
+        frameList.push_back(o.timestamp);
+        frameByTimestamp.insert({o.timestamp, o});
+    }
+}
+
+void Decoder::Impl::findAudioIndex() {
+    // The audio index is found by walking records forward from the frame with the largest timestamp
+    // (Decoder.cpp:281-315); anything unexpected simply ends the walk.
+    if (frameIndex.empty()) return;
+    int64_t pos = frameIndex.back().offset;
+    if (pos < 0) return;
+    for (;;) {
+        Item item{};
+        if (!file.tryRead(pos, &item, sizeof item)) break;
+        pos += sizeof item;
+        if (item.type == Type::BUFFER || item.type == Type::METADATA || item.type == Type::AUDIO_DATA ||
+            item.type == Type::AUDIO_DATA_METADATA) {
+            pos += item.size;
+        } else if (item.type == Type::AUDIO_INDEX) {
+            AudioIndex index{};
+            file.read(pos, &index, sizeof index);
+            pos += sizeof index;
+            if (index.numOffsets < 0) throw IOException("Failed to read data");
+            audioIndex.resize(static_cast<size_t>(index.numOffsets));
+            file.read(pos, audioIndex.data(), sizeof(BufferOffset) * audioIndex.size());
+            pos += static_cast<int64_t>(sizeof(BufferOffset) * audioIndex.size());
+        } else {
+            break;
+        }
+    }
+}
+
+Decoder::Decoder(FILE* file) {
+    if (!file) throw IOException("Invalid file");
+    m.reset(new Impl(file));
+    m->open();
+}
+
+Decoder::Decoder(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw IOException("Failed to open " + path);
+    m.reset(new Impl(f));
+    m->open();
+}
+
+Decoder::~Decoder() = default;
+
+const std::vector<Timestamp>& Decoder::getFrames() const { return m->frameList; }
+const nlohmann::json& Decoder::getContainerMetadata() const { return m->containerMetadata; }
+int Decoder::audioSampleRateHz() const { return m->containerMetadata["extraData"]["audioSampleRate"]; }   // :161-163
+int Decoder::numAudioChannels() const { return m->containerMetadata["extraData"]["audioChannels"]; }      // :165-167
+
+void Decoder::loadAudio(std::vector<AudioChunk>& outAudioChunks) {
+    for (const BufferOffset& o : m->audioIndex) {
+        AudioChunk chunk;
+        if (!readAudioChunk(m->file, o, chunk)) continue;
+        outAudioChunks.emplace_back(std::move(chunk));
+    }
+}
+
+AudioChunkLoader& Decoder::loadAudio() const { return *m->audioLoader; }
+
+FrameLocation Decoder::locateFrame(const Timestamp timestamp) const {
+    const auto it = m->frameByTimestamp.find(timestamp);
+    if (it == m->frameByTimestamp.end())
+        throw IOException("Frame not found (timestamp: " + std::to_string(timestamp) + ")");
+    if (it->second.offset < 0) throw IOException("Invalid offset");
+    Item item{};
+    m->file.read(it->second.offset, &item, sizeof item);
+    if (item.type != Type::BUFFER) throw IOException("Invalid buffer type");
+    FrameLocation where;
+    where.timestamp = timestamp;
+    where.payloadOffset = it->second.offset + static_cast<int64_t>(sizeof item);
+    where.payloadSize = item.size;
+    return where;
+}
+
+void Decoder::readFrame(const FrameLocation& where, uint8_t* dst, nlohmann::json& outMetadata) const {
+    m->file.read(where.payloadOffset, dst, where.payloadSize);
+    int64_t pos = where.payloadOffset + where.payloadSize;
+    Item item{};
+    m->file.read(pos, &item, sizeof item);
+    pos += sizeof item;
+    if (item.type != Type::METADATA) throw IOException("Invalid metadata");
+    std::string text(item.size, '\0');
+    m->file.read(pos, &text[0], item.size);
+    outMetadata = nlohmann::json::parse(text);
+}
+
+void Decoder::loadFrame(const Timestamp timestamp, std::vector<uint8_t>& outData, nlohmann::json& outMetadata) {
+    const FrameLocation where = locateFrame(timestamp);
+    m->scratch.resize(where.payloadSize);
+    readFrame(where, m->scratch.data(), outMetadata);
+    const FrameGeometry g = geometryOf(outMetadata);
+    outData.resize(sizeof(uint16_t) * static_cast<size_t>(g.width) * static_cast<size_t>(g.height));   // :221-222
+    uint16_t* pixels = reinterpret_cast<uint16_t*>(outData.data());
+    if (g.compressionType == kCompressionCurrent) {
+        if (raw::Decode(pixels, g.width, g.height, m->scratch.data(), m->scratch.size()) == 0)
+            throw IOException("Failed to uncompress frame");
+    } else if (g.compressionType == kCompressionLegacy) {
+        if (raw::DecodeLegacy(pixels, g.width, g.height, m->scratch.data(), m->scratch.size()) == 0)
+            throw IOException("Failed to uncompress legacy frame");
+    } else {
+        throw IOException("Invalid compression type");
+    }
+}
+
+void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<std::vector<uint8_t>>& outData,
+                         std::vector<nlohmann::json>& outMetadata) {
+    const size_t n = timestamps.size();
+    outData.resize(n);
+    outMetadata.assign(n, nlohmann::json());
+    if (n == 0) return;
+    mcraw_ctx* ctx = detail::threadContext();
+    if (!ctx) throw IOException("Failed to uncompress frame");
+
+    struct Cleanup {
+        mcraw_ctx* ctx;
+        void* pinnedIn = nullptr;
+        void* pinnedOut = nullptr;
+        void* devOut = nullptr;
+        ~Cleanup() {
+            if (pinnedIn) mcraw_host_free_pinned(ctx, pinnedIn);
+            if (pinnedOut) mcraw_host_free_pinned(ctx, pinnedOut);
+            if (devOut) mcraw_device_free(ctx, devOut);
+        }
+    } mem{ctx};
+
+    // ---- locate, size and read every frame straight into one pinned buffer (256-byte aligned slots)
+    std::vector<FrameLocation> where(n);
+    std::vector<size_t> inOff(n), outOff(n);
+    size_t inBytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        where[i] = locateFrame(timestamps[i]);
+        inOff[i] = inBytes;
+        inBytes += (static_cast<size_t>(where[i].payloadSize) + 255) & ~static_cast<size_t>(255);
+    }
+    if (mcraw_host_alloc_pinned(ctx, inBytes + 256, &mem.pinnedIn) != MCRAW_OK) throw IOException(mcraw_last_error(ctx));
+    uint8_t* in = static_cast<uint8_t*>(mem.pinnedIn);
+    std::vector<FrameGeometry> geo(n);
+    size_t outBytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        readFrame(where[i], in + inOff[i], outMetadata[i]);
+        geo[i] = geometryOf(outMetadata[i]);
+        if (geo[i].compressionType != kCompressionCurrent && geo[i].compressionType != kCompressionLegacy)
+            throw IOException("Invalid compression type");
+        outOff[i] = outBytes;
+        const size_t bytes = sizeof(uint16_t) * static_cast<size_t>(geo[i].width) * static_cast<size_t>(geo[i].height);
+        outBytes += (bytes + 255) & ~static_cast<size_t>(255);
+    }
+    if (mcraw_device_alloc(ctx, outBytes + 256, &mem.devOut) != MCRAW_OK ||
+        mcraw_host_alloc_pinned(ctx, outBytes + 256, &mem.pinnedOut) != MCRAW_OK)
+        throw IOException(mcraw_last_error(ctx));
+
+    // ---- one batched decode: H2D on the context's side streams overlaps the kernels
+    std::vector<mcraw_frame_desc> descs(n);
+    for (size_t i = 0; i < n; i++) {
+        mcraw_frame_desc& d = descs[i];
+        std::memset(&d, 0, sizeof d);
+        d.src = in + inOff[i];
+        d.len = where[i].payloadSize;
+        d.width = geo[i].width;
+        d.height = geo[i].height;
+        d.compression_type = geo[i].compressionType;
+        d.dst = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(mem.devOut) + outOff[i]);
+        d.dst_capacity_elems = static_cast<uint64_t>(geo[i].width) * static_cast<uint64_t>(geo[i].height);
+    }
+    std::vector<uint64_t> written(n);
+    if (mcraw_decode_batch_host(ctx, descs.data(), static_cast<uint32_t>(n), nullptr) != MCRAW_OK ||
+        mcraw_batch_wait(ctx, written.data(), nullptr, static_cast<uint32_t>(n)) != MCRAW_OK)
+        throw IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(ctx));
+    for (size_t i = 0; i < n; i++) {
+        if (written[i] == 0)
+            throw IOException(geo[i].compressionType == kCompressionCurrent ? "Failed to uncompress frame"
+                                                                             : "Failed to uncompress legacy frame");
+    }
+    if (mcraw_memcpy_d2h(ctx, mem.pinnedOut, mem.devOut, outBytes, nullptr) != MCRAW_OK ||
+        mcraw_stream_sync(ctx, nullptr) != MCRAW_OK)
+        throw IOException(mcraw_last_error(ctx));
+    for (size_t i = 0; i < n; i++) {
+        const size_t bytes = sizeof(uint16_t) * static_cast<size_t>(geo[i].width) * static_cast<size_t>(geo[i].height);
+        outData[i].resize(bytes);
+        std::memcpy(outData[i].data(), static_cast<uint8_t*>(mem.pinnedOut) + outOff[i], bytes);
+    }
+}
+
+}  // namespace motioncam

@@ -1,0 +1,29 @@
+// cwrap.cpp -- flat C view (prefix mcb200_) of this repo's drop-in motioncam::Decoder / motioncam::raw, so the
+// Python tests drive it and the compiled reference (prefix mcref_, oracle/ref_shim.cpp) through identical code.
+#define MC_PREFIX mcb200_
+#include "decoder_cwrap.inc"
+
+extern "C" {
+
+// Decoder::loadFrames (batched addition): loads every listed timestamp, keeps the frames in the handle.
+// Returns the number of frames, or -1 with decoder_last_error() set.
+
+int64_t mcb200_decoder_load_frames(void* hv, const int64_t* timestamps, int64_t n, uint8_t** out_ptrs, int64_t* out_sizes) {
+    HandleT* h = static_cast<HandleT*>(hv);
+    try {
+        std::vector<motioncam::Timestamp> ts(timestamps, timestamps + n);
+        static thread_local std::vector<std::vector<uint8_t>> data;
+        std::vector<nlohmann::json> meta;
+        h->dec->loadFrames(ts, data, meta);
+        for (int64_t i = 0; i < n; i++) {
+            out_ptrs[i] = data[i].data();
+            out_sizes[i] = static_cast<int64_t>(data[i].size());
+        }
+        return n;
+    } catch (const std::exception& e) {
+        h->error = e.what();
+        return -1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+"""Python view of the drop-in C++ API (motioncam::Decoder, motioncam::raw::Decode*) through the flat C wrappers
+of csrc/decoder_cwrap.inc.  The same class drives this repo's library (prefix ``mcb200_``) and -- in tests only --
+the compiled reference (prefix ``mcref_``, oracle/_ref/libmcraw_ref.so), so both are exercised by identical code.
+"""
+import ctypes
+import json
+
+import numpy as np
+
+from . import _lib
+
+
+class DecoderError(RuntimeError):
+    """An exception thrown by the C++ Decoder (message = e.what())."""
+
+
+def _bind(c, prefix):
+    vp, i64, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
+    f = lambda name: getattr(c, prefix + name)  # noqa: E731
+    for name in ("decode", "decode_legacy"):
+        f(name).argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, sz]
+        f(name).restype = sz
+    f("decoder_open").argtypes = [ctypes.c_char_p, ctypes.c_char_p, sz]
+    f("decoder_open").restype = vp
+    f("decoder_close").argtypes = [vp]
+    f("decoder_close").restype = None
+    f("decoder_last_error").argtypes = [vp]
+    f("decoder_last_error").restype = ctypes.c_char_p
+    f("decoder_num_frames").argtypes = [vp]
+    f("decoder_num_frames").restype = i64
+    f("decoder_frames").argtypes = [vp, ctypes.POINTER(i64)]
+    f("decoder_frames").restype = None
+    for name in ("decoder_container_metadata", "decoder_frame_metadata"):
+        f(name).argtypes = [vp, ctypes.c_char_p, sz]
+        f(name).restype = sz
+    f("decoder_load_frame").argtypes = [vp, i64]
+    f("decoder_load_frame").restype = i64
+    f("decoder_frame_data").argtypes = [vp]
+    f("decoder_frame_data").restype = vp
+    f("decoder_audio_sample_rate").argtypes = [vp]
+    f("decoder_audio_channels").argtypes = [vp]
+    f("decoder_load_audio").argtypes = [vp, ctypes.c_int]
+    f("decoder_load_audio").restype = i64
+    for name in ("decoder_audio_chunk_timestamp", "decoder_audio_chunk_samples"):
+        f(name).argtypes = [vp, i64]
+        f(name).restype = i64
+    f("decoder_audio_chunk_data").argtypes = [vp, i64]
+    f("decoder_audio_chunk_data").restype = vp
+    if prefix == "mcb200_":
+        c.mcb200_decoder_load_frames.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+        c.mcb200_decoder_load_frames.restype = i64
+    return c
+
+
+_libs = {}
+
+
+def library(path=None, prefix="mcb200_"):
+    key = (path, prefix)
+    if key not in _libs:
+        c = _lib.load(_lib.LIB_DROPIN) if path is None else ctypes.CDLL(path)
+        _libs[key] = _bind(c, prefix)
+    return _libs[key]
+
+
+def raw_decode(stream, width, height, legacy=False, lib=None, prefix="mcb200_", fill=0xA5A5):
+    """motioncam::raw::Decode / DecodeLegacy: host bytes in, (elements written, host uint16 image) out."""
+    c = lib or library()
+    src = np.ascontiguousarray(stream, dtype=np.uint8)
+    out = np.full(width * height + 64, fill, dtype=np.uint16)
+    fn = getattr(c, prefix + ("decode_legacy" if legacy else "decode"))
+    n = fn(out.ctypes.data, width, height, src.ctypes.data, src.size)
+    assert np.all(out[width * height:] == fill), "decoder wrote past width*height"
+    return int(n), out[:width * height].reshape(height, width)
+
+
+class Decoder:
+    """motioncam::Decoder (Decoder.hpp:47-73)."""
+
+    def __init__(self, path, lib=None, prefix="mcb200_"):
+        self._c = lib or library()
+        self._p = prefix
+        err = ctypes.create_string_buffer(1024)
+        self._h = self._f("decoder_open")(str(path).encode(), err, len(err))
+        if not self._h:
+            raise DecoderError(err.value.decode())
+
+    def _f(self, name):
+        return getattr(self._c, self._p + name)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._f("decoder_close")(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _text(self, name):
+        n = self._f(name)(self._h, None, 0)
+        buf = ctypes.create_string_buffer(n + 1)
+        self._f(name)(self._h, buf, n + 1)
+        return buf.value.decode()
+
+    def _raise(self):
+        raise DecoderError(self._f("decoder_last_error")(self._h).decode())
+
+    def get_container_metadata(self):
+        return json.loads(self._text("decoder_container_metadata"))
+
+    def get_frames(self):
+        n = self._f("decoder_num_frames")(self._h)
+        arr = (ctypes.c_int64 * max(1, n))()
+        self._f("decoder_frames")(self._h, arr)
+        return list(arr[:n])
+
+    def load_frame(self, timestamp):
+        """-> (bytes-sized np.uint8 array of 2*width*height, frame metadata dict)."""
+        n = self._f("decoder_load_frame")(self._h, int(timestamp))
+        if n < 0:
+            self._raise()
+        ptr = self._f("decoder_frame_data")(self._h)
+        data = np.frombuffer((ctypes.c_uint8 * n).from_address(ptr), dtype=np.uint8).copy() if n else np.empty(0, np.uint8)
+        return data, json.loads(self._text("decoder_frame_metadata"))
+
+    def load_frames(self, timestamps):
+        """Batched addition (this repo's library only): -> list of np.uint8 arrays."""
+        n = len(timestamps)
+        ts = (ctypes.c_int64 * max(1, n))(*timestamps)
+        ptrs = (ctypes.c_void_p * max(1, n))()
+        sizes = (ctypes.c_int64 * max(1, n))()
+        r = self._c.mcb200_decoder_load_frames(self._h, ts, n, ptrs, sizes)
+        if r < 0:
+            self._raise()
+        return [np.frombuffer((ctypes.c_uint8 * sizes[i]).from_address(ptrs[i]), dtype=np.uint8).copy() for i in range(n)]
+
+    def audio_sample_rate_hz(self):
+        v = self._f("decoder_audio_sample_rate")(self._h)
+        if v < 0:
+            self._raise()
+        return v
+
+    def num_audio_channels(self):
+        v = self._f("decoder_audio_channels")(self._h)
+        if v < 0:
+            self._raise()
+        return v
+
+    def load_audio(self, use_loader=False):
+        """-> list of (timestamp_ns or -1, np.int16 array).  use_loader: the AudioChunkLoader::next loop."""
+        n = self._f("decoder_load_audio")(self._h, int(use_loader))
+        if n < 0:
+            self._raise()
+        out = []
+        for i in range(n):
+            ns = self._f("decoder_audio_chunk_samples")(self._h, i)
+            ptr = self._f("decoder_audio_chunk_data")(self._h, i)
+            data = np.frombuffer((ctypes.c_int16 * ns).from_address(ptr), dtype=np.int16).copy() if ns else np.empty(0, np.int16)
+            out.append((self._f("decoder_audio_chunk_timestamp")(self._h, i), data))
+        return out

@@ -1,0 +1,131 @@
+"""CPU: the host side of the path -- .mcraw container open / index / audio pass-through of this repo's drop-in
+motioncam::Decoder against the compiled reference Decoder (oracle/_ref) on synthetic files written by
+testvec.write_mcraw.  No frame is decoded here (that needs the GPU: tests/test_gpu_dropin.py)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from motioncam_decoder_b200 import _lib, hostapi, testvec as tv
+
+needs_dropin = pytest.mark.skipif(not os.path.exists(_lib.LIB_DROPIN), reason="drop-in library not built (needs nvcc)")
+pytestmark = needs_dropin
+
+
+def _ref_lib():
+    return hostapi.library(ol.REF_SO, "mcref_")
+
+
+def _clip(tmp_path, name="clip.mcraw", order=(2, 0, 1, 3), with_audio=True):
+    """Four tiny frames (both formats) written out of timestamp order + audio chunks with and without metadata."""
+    frames = []
+    for i, k in enumerate(order):
+        w, h = 64 + 32 * k, 8
+        img = tv.gen_photon(w, h, 1023, seed=10 + k)
+        legacy = bool(k & 1)
+        frames.append({"timestamp": 1000 + 10 * k, "data": tv.encode_legacy(img) if legacy else tv.encode_current(img),
+                       "width": w, "height": h, "compressionType": 6 if legacy else 7})
+    audio = []
+    if with_audio:
+        rng = np.random.default_rng(5)
+        audio = [(123456789, rng.integers(-32768, 32767, 960, dtype=np.int16)),
+                 (None, rng.integers(-32768, 32767, 481, dtype=np.int16)),      # odd sample count, no metadata item
+                 (223456789, rng.integers(-32768, 32767, 2, dtype=np.int16))]
+    path = str(tmp_path / name)
+    tv.write_mcraw(path, frames, audio)
+    return path, frames, audio
+
+
+def _open_both(path):
+    ours = hostapi.Decoder(path)
+    ref = hostapi.Decoder(path, lib=_ref_lib(), prefix="mcref_") if ol.have_ref() else None
+    return ours, ref
+
+
+def test_open_index_metadata(tmp_path):
+    path, frames, _ = _clip(tmp_path)
+    ours, ref = _open_both(path)
+    assert ours.get_frames() == sorted(f["timestamp"] for f in frames)      # Decoder.cpp:266-279
+    assert ours.get_container_metadata() == tv.DEFAULT_CONTAINER_METADATA
+    assert ours.audio_sample_rate_hz() == 48000 and ours.num_audio_channels() == 2
+    if ref:
+        assert ours.get_frames() == ref.get_frames()
+        assert ours.get_container_metadata() == ref.get_container_metadata()
+        assert (ours.audio_sample_rate_hz(), ours.num_audio_channels()) == (ref.audio_sample_rate_hz(), ref.num_audio_channels())
+
+
+@pytest.mark.parametrize("use_loader", [False, True])
+def test_audio_pass_through(tmp_path, use_loader):
+    path, _, audio = _clip(tmp_path)
+    ours, ref = _open_both(path)
+    got = ours.load_audio(use_loader)
+    assert len(got) == len(audio)
+    for (ts, data), (want_ts, want) in zip(got, audio):
+        assert ts == (-1 if want_ts is None else want_ts)                   # Decoder.cpp:58-70
+        assert data.size == (want.nbytes + 1) // 2 and np.array_equal(data[:want.size], want)
+    if ref:
+        want = ref.load_audio(use_loader)
+        assert [(t, d.tobytes()) for t, d in got] == [(t, d.tobytes()) for t, d in want]
+    if use_loader:
+        assert ours.load_audio(True) == []      # the loader's position persists (Decoder.cpp:83-93)
+        if ref:
+            assert ref.load_audio(True) == []
+
+
+def test_no_audio_and_empty_index(tmp_path):
+    path, _, _ = _clip(tmp_path, with_audio=False)
+    ours, ref = _open_both(path)
+    assert ours.load_audio() == [] and (ref is None or ref.load_audio() == [])
+    p2 = str(tmp_path / "empty.mcraw")
+    tv.write_mcraw(p2, [], [])
+    ours, ref = _open_both(p2)
+    assert ours.get_frames() == [] and (ref is None or ref.get_frames() == [])
+
+
+def _expect_error(fn, ref_fn, text=None):
+    with pytest.raises(hostapi.DecoderError) as e:
+        fn()
+    if text is not None:
+        assert str(e.value) == text
+    if ref_fn is not None:
+        with pytest.raises(hostapi.DecoderError) as r:
+            ref_fn()
+        assert str(e.value) == str(r.value), "error text differs from the reference"
+
+
+def test_error_messages_match_reference(tmp_path):
+    path, frames, _ = _clip(tmp_path)
+    raw = open(path, "rb").read()
+    have_ref = ol.have_ref()
+
+    def opener(p, ref):
+        return (lambda: hostapi.Decoder(p, lib=_ref_lib(), prefix="mcref_")) if ref else (lambda: hostapi.Decoder(p))
+
+    def case(name, data, text):
+        p = str(tmp_path / name)
+        with open(p, "wb") as f:
+            f.write(data)
+        _expect_error(opener(p, False), opener(p, True) if have_ref else None, text)
+
+    case("badver.mcraw", raw[:7] + b"\x02" + raw[8:], "Invalid container version")          # Decoder.cpp:123-124
+    case("badid.mcraw", b"NOTION " + raw[7:], "Invalid header id")                            # :126-127
+    case("badmeta.mcraw", raw[:8] + struct.pack("<I", 2) + raw[12:], "Invalid camera metadata")   # :133-134
+    case("short.mcraw", raw[:20], None)                                                       # reads fail
+    case("badtrailer.mcraw", raw[:-24] + struct.pack("<I", 3) + raw[-20:], "Invalid file")    # :245-246
+    case("badmagic.mcraw", raw[:-16] + struct.pack("<i", 0x1234) + raw[-12:], "Corrupted file")   # :252-253
+    missing = str(tmp_path / "does_not_exist.mcraw")
+    _expect_error(opener(missing, False), opener(missing, True) if have_ref else None, "Failed to open " + missing)
+
+    ours, ref = _open_both(path)
+    _expect_error(lambda: ours.load_frame(42), (lambda: ref.load_frame(42)) if ref else None,
+                  "Frame not found (timestamp: 42)")                                          # :185-186
+
+
+def test_exports_reference_symbols():
+    """The drop-in library exports the reference's mangled codec symbols (RawData.hpp:25-37)."""
+    import ctypes
+    c = ctypes.CDLL(_lib.LIB_DROPIN)
+    for sym in ("_ZN9motioncam3raw6DecodeEPtiiPKhm", "_ZN9motioncam3raw12DecodeLegacyEPtiiPKhm"):
+        assert hasattr(c, sym), sym

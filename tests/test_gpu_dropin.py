@@ -1,0 +1,104 @@
+"""GPU: the drop-in C++ API (motioncam::Decoder::loadFrame / loadFrames, motioncam::raw::Decode*) of this repo
+against the compiled reference and the oracle, on synthetic .mcraw files."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import vectors
+from motioncam_decoder_b200 import hostapi, testvec as tv
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_lib():
+    return hostapi.library(ol.REF_SO, "mcref_")
+
+
+def _clip(tmp_path, n=10):
+    frames, images = [], {}
+    sizes = [(1928, 16), (640, 12), (4080, 8), (100, 4), (64, 4), (2048, 24)]
+    for k in range(n):
+        w, h = sizes[k % len(sizes)]
+        legacy = k % 3 == 1
+        if legacy and h % 4:
+            h += 4 - h % 4
+        img = tv.gen_photon(w, h, 4095 if k % 2 else 1023, seed=40 + k)
+        ts = 5_000_000 + 33_333 * ((k * 7) % n)          # written out of order
+        frames.append({"timestamp": ts, "data": tv.encode_legacy(img) if legacy else tv.encode_current(img, policy=tv.POLICY_ALIASES, seed=k),
+                       "width": w, "height": h, "compressionType": 6 if legacy else 7, "iso": 100 + k})
+        images[ts] = img
+    rng = np.random.default_rng(1)
+    audio = [(1000 * i, rng.integers(-3000, 3000, 1920, dtype=np.int16)) for i in range(4)]
+    path = str(tmp_path / "clip.mcraw")
+    tv.write_mcraw(path, frames, audio)
+    return path, frames, images, audio
+
+
+def test_load_frame_matches_reference(tmp_path):
+    path, frames, images, audio = _clip(tmp_path)
+    ours = hostapi.Decoder(path)
+    ref = hostapi.Decoder(path, lib=_ref_lib(), prefix="mcref_") if ol.have_ref() else None
+    stamps = ours.get_frames()
+    assert stamps == sorted(images)
+    for ts in stamps:
+        data, meta = ours.load_frame(ts)
+        img = images[ts]
+        assert data.size == img.size * 2
+        assert np.array_equal(data.view(np.uint16).reshape(img.shape), img), ts
+        assert meta["width"] == img.shape[1] and meta["height"] == img.shape[0]
+        if ref:
+            rdata, rmeta = ref.load_frame(ts)
+            assert np.array_equal(data, rdata) and meta == rmeta
+    got = ours.load_audio()
+    assert [(t, d.tobytes()) for t, d in got] == [(t, np.asarray(d).tobytes()) for t, d in audio]
+
+
+def test_load_frames_batched(tmp_path):
+    path, frames, images, _ = _clip(tmp_path, n=12)
+    ours = hostapi.Decoder(path)
+    stamps = ours.get_frames()
+    order = stamps[::-1] + stamps[:3]                      # any order, repeats allowed
+    out = ours.load_frames(order)
+    for ts, data in zip(order, out):
+        img = images[ts]
+        assert np.array_equal(data.view(np.uint16).reshape(img.shape), img), ts
+    assert ours.load_frames([]) == []
+    with pytest.raises(hostapi.DecoderError, match="Frame not found"):
+        ours.load_frames([stamps[0], 1])
+
+
+def test_raw_decode_symbols():
+    """motioncam::raw::Decode / DecodeLegacy (host in, host out) == oracle on the shared vectors."""
+    for name, s, w, h, img in vectors.current_vectors(small=True)[::3]:
+        n, got = hostapi.raw_decode(s, w, h)
+        n_or, want = ol.oracle_decode(s, w, h)
+        assert n == n_or and np.array_equal(got, want), name
+    for name, s, w, h, img in vectors.legacy_vectors(small=True)[::3]:
+        n, got = hostapi.raw_decode(s, w, h, legacy=True)
+        n_or, want = ol.oracle_decode_legacy(s, w, h)
+        assert n == n_or and np.array_equal(got, want), name
+
+
+def test_decode_failures_raise_like_reference(tmp_path):
+    img = tv.gen_photon(128, 8, 1023, seed=3)
+    bad = tv.encode_current(img)
+    bad[0:4] = np.frombuffer(np.uint32(96).tobytes(), dtype=np.uint8)       # encodedWidth % 64 != 0 -> Decode returns 0
+    frames = [
+        {"timestamp": 1, "data": bad, "width": 128, "height": 8, "compressionType": 7},
+        {"timestamp": 2, "data": tv.encode_current(img), "width": 128, "height": 8, "compressionType": 5},
+        {"timestamp": 3, "data": tv.encode_current(img), "width": 128, "height": 8, "compressionType": 7},
+    ]
+    path = str(tmp_path / "bad.mcraw")
+    tv.write_mcraw(path, frames, [])
+    ours = hostapi.Decoder(path)
+    ref = hostapi.Decoder(path, lib=_ref_lib(), prefix="mcref_") if ol.have_ref() else None
+    for ts, text in [(1, "Failed to uncompress frame"), (2, "Invalid compression type")]:
+        with pytest.raises(hostapi.DecoderError) as e:
+            ours.load_frame(ts)
+        assert str(e.value) == text                                          # Decoder.cpp:225-233
+        if ref:
+            with pytest.raises(hostapi.DecoderError) as r:
+                ref.load_frame(ts)
+            assert str(r.value) == text
+    data, _ = ours.load_frame(3)
+    assert np.array_equal(data.view(np.uint16).reshape(8, 128), img)
