@@ -9,7 +9,7 @@ One step = one pass of the hot path over one batch (the whole workload clip) of 
             C-ABI (mcraw_decode_batch), timed with CUDA events on the launching stream, max over ranks.
   e2e       the same batch through mcraw_decode_batch_host: compressed frames in PINNED HOST memory, H2D on
             side streams overlapped with decode, per-frame results read back to the host every step.
-  roofline  dominant kernel (k_tiles / k_legacy_decode): algorithmic bytes per launch / mean launch duration
+  roofline  dominant kernel (k_units / k_legacy_decode): algorithmic bytes per launch / mean launch duration
             from CUDA events recorded around that kernel inside the timed region.
   cpu_baseline  the unmodified reference (oracle/_ref) on all host cores over a bounded sample (rank 0, N=1).
 Multi-GPU: one process per GPU (torchrun), frames are independent -> every rank decodes its own clip, no
@@ -73,9 +73,10 @@ def measured_peak():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the benchmark runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, interval=0.02):
         super().__init__(daemon=True)
         self.index = index
+        self.interval = interval   # NVML queries are not free for the GPU: a 4 ms poll cost ~10 % of a 0.33 ms step
         self.samples = []   # (t, sm_mhz, reasons_mask)
         self.stop_flag = False
         self.max_mhz = None
@@ -104,7 +105,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.perf_counter(), mhz, reasons))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(self.interval)
 
     def summary(self, windows):
         if not self.ok or not self.samples:
@@ -372,10 +373,10 @@ def main():
                              f"(> 126 MB L2), no flush needed",
                        "parallelism": f"frame-parallel, {world} rank(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_tiles" if ct == 7 else "k_legacy_decode",
+                         "traffic": traffic, "kernel": "k_units" if ct == 7 else "k_legacy_decode",
                          "algorithmic_bytes_per_launch": alg_main, "kernel_ms_per_launch": main_ms,
                          "launches_per_step": chunks / args.steps,
-                         "meta_kernel_ms_per_launch": meta_ms, "peak_source": peak_src,
+                         "index_kernels_ms_per_launch": meta_ms, "peak_source": peak_src,
                          "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,
                                         "bytes_per_step": comp_bytes + out_bytes, "frac_of_8000": step_gbs / 8000.0}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": comp_bytes, "d2h_bytes_per_step": 16 * frames,

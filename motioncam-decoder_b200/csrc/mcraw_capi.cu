@@ -18,17 +18,20 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSlots = 6;              // chunks (sub-batches) that may be in flight per context
+constexpr int kSlots = 16;             // chunks (sub-batches) that may be in flight per context
 constexpr uint32_t kMaxGridY = 32768;  // frames per launch
 constexpr int kStage = 3;              // device staging buffers of the host-input pipeline
 constexpr size_t kStageBytes = 48u << 20;
 constexpr int kCopyStreams = 2;
 
 struct Slot {
-    FrameDev* h_frames = nullptr;   // pinned
-    FrameDev* d_frames = nullptr;
+    // one pinned / device buffer pair per chunk: [FrameDev x n | WorkItem x items]
+    uint8_t* h_up = nullptr;        // pinned
+    uint8_t* d_up = nullptr;
+    size_t up_bytes = 0;
+    // device-written words: [queue counter (16 B) | FrameState x n | Result x n]; nothing here needs zeroing by the host
+    uint8_t* d_dyn = nullptr;
     Result* h_results = nullptr;    // pinned
-    Result* d_results = nullptr;
     uint32_t cap_frames = 0;
     uint8_t* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -38,6 +41,11 @@ struct Slot {
     uint32_t n = 0;
     uint32_t result_offset = 0;     // index of this chunk's first frame inside the logical batch
     uint64_t batch_id = 0;
+    // the plan this slot's device tables were built for (see enqueue_chunk)
+    std::vector<mcraw_frame_desc> plan_descs;
+    bool plan_valid = false, any7 = false, any6 = false;
+    uint32_t max_ltiles = 0, nitems = 0;
+    size_t items_off = 0, plan_bytes = 0;
 };
 
 struct Stage {
@@ -58,6 +66,9 @@ struct mcraw_ctx {
     Stage stages[kStage];
     int stage_cur = 0;
     uint64_t launches = 0;
+    std::vector<FrameDev> tmp_frames;
+    std::vector<WorkItem> tmp_items;
+    uint32_t resident_ctas = 0;     // CTAs of k_units the device holds at once
     uint64_t batch_id = 0;
     uint32_t batch_n = 0;
     std::vector<uint64_t> res_written;
@@ -95,19 +106,24 @@ int bind(mcraw_ctx* ctx) {
     return MCRAW_OK;
 }
 
-int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t scratch) {
+int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t up_bytes, size_t scratch) {
     if (n > s.cap_frames) {
         uint32_t cap = std::max<uint32_t>(n, s.cap_frames * 2 + 64);
-        if (s.h_frames) cudaFreeHost(s.h_frames);
         if (s.h_results) cudaFreeHost(s.h_results);
-        if (s.d_frames) cudaFree(s.d_frames);
-        if (s.d_results) cudaFree(s.d_results);
-        s.h_frames = nullptr; s.h_results = nullptr; s.d_frames = nullptr; s.d_results = nullptr; s.cap_frames = 0;
-        CU_TRY(ctx, cudaMallocHost(&s.h_frames, sizeof(FrameDev) * cap));
+        if (s.d_dyn) cudaFree(s.d_dyn);
+        s.h_results = nullptr; s.d_dyn = nullptr; s.cap_frames = 0;
         CU_TRY(ctx, cudaMallocHost(&s.h_results, sizeof(Result) * cap));
-        CU_TRY(ctx, cudaMalloc(&s.d_frames, sizeof(FrameDev) * cap));
-        CU_TRY(ctx, cudaMalloc(&s.d_results, sizeof(Result) * cap));
+        CU_TRY(ctx, cudaMalloc(&s.d_dyn, 16 + (sizeof(FrameState) + sizeof(Result)) * cap));
         s.cap_frames = cap;
+    }
+    if (up_bytes > s.up_bytes) {
+        size_t cap = std::max(up_bytes, s.up_bytes + s.up_bytes / 2);
+        if (s.h_up) cudaFreeHost(s.h_up);
+        if (s.d_up) cudaFree(s.d_up);
+        s.h_up = nullptr; s.d_up = nullptr; s.up_bytes = 0;
+        CU_TRY(ctx, cudaMallocHost(&s.h_up, cap));
+        CU_TRY(ctx, cudaMalloc(&s.d_up, cap));
+        s.up_bytes = cap;
     }
     if (scratch > s.scratch_bytes) {
         size_t cap = std::max(scratch, s.scratch_bytes + s.scratch_bytes / 2);
@@ -150,14 +166,14 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
     scratch = 0; max_tile_rows = 0; max_units = 0; max_ltiles = 0; any7 = any6 = false;
     for (uint32_t i = 0; i < n; i++) {
         const mcraw_frame_desc& d = descs[i];
-        const std::string who = "frame " + std::to_string(first_index + i);
+        auto who = [&] { return "frame " + std::to_string(first_index + i); };   // only built on the error paths
         FrameDev f;
         std::memset(&f, 0, sizeof f);
-        if (!d.src || !d.dst) return fail_arg(ctx, who + ": null src/dst");
+        if (!d.src || !d.dst) return fail_arg(ctx, who() + ": null src/dst");
         if (d.width <= 0 || d.height <= 0 || d.width > 65536 || d.height > 65536)
-            return fail_arg(ctx, who + ": unsupported width/height");
+            return fail_arg(ctx, who() + ": unsupported width/height");
         if (((uintptr_t)d.src & 15) || ((uintptr_t)d.dst & 1))
-            return fail_arg(ctx, who + ": src must be 16-byte aligned, dst 2-byte aligned");
+            return fail_arg(ctx, who() + ": src must be 16-byte aligned, dst 2-byte aligned");
         f.src = d.src; f.len = d.len; f.dst = d.dst; f.dst_cap = d.dst_capacity_elems;
         f.width = d.width; f.height = d.height; f.type = d.compression_type;
         f.tiles_x = (uint32_t)(d.width + 63) / 64;
@@ -170,8 +186,9 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
             f.inv_tiles_x = (ntiles * f.tiles_x < (1ull << 32)) ? (uint32_t)(((1ull << 32) + f.tiles_x - 1) / f.tiles_x) : 0u;
             if (f.tiles_x == 1) f.inv_tiles_x = 0;   // 2^32 does not fit; plain division
             // scratch layout (offsets for now, rebased on the slot's buffer): unitoff | pairinfo | pairrefs
+            // (128-byte aligned: a frame's scratch never shares a cache line with another frame's)
             f.unitoff = reinterpret_cast<uint32_t*>(scratch);
-            scratch += (((size_t)f.nunits + 1) * 4 + 15) & ~(size_t)15;
+            scratch += (((size_t)f.nunits + 1) * 4 + 127) & ~(size_t)127;
             f.pairinfo = reinterpret_cast<uint32_t*>(scratch);
             scratch += (size_t)f.nunits * 32 * 4;
             f.pairrefs = reinterpret_cast<uint32_t*>(scratch);
@@ -180,10 +197,10 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
             max_units = std::max(max_units, f.nunits);
         } else if (d.compression_type == MCRAW_COMPRESSION_LEGACY) {
             any6 = true;
-            if (d.len >= ((uint64_t)1 << 40)) return fail_arg(ctx, who + ": legacy frame buffer too large");
+            if (d.len >= ((uint64_t)1 << 40)) return fail_arg(ctx, who() + ": legacy frame buffer too large");
             const uint64_t nseg = (d.len + LG_SEG - 1) / LG_SEG;
             const uint64_t ntile = std::max<uint64_t>(1, (nseg + LG_TILE_SEGS - 1) / LG_TILE_SEGS);
-            if (ntile > 0x7FFFFFFFull) return fail_arg(ctx, who + ": legacy frame buffer too large");
+            if (ntile > 0x7FFFFFFFull) return fail_arg(ctx, who() + ": legacy frame buffer too large");
             // scratch layout (offsets for now): segment maps | tile maps | tile states
             f.lg_segmap = reinterpret_cast<uint16_t*>(scratch);
             scratch += ((size_t)ntile * LG_TILE_SEGS * LG_STATES * 2 + 15) & ~(size_t)15;
@@ -191,10 +208,9 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
             scratch += ((size_t)ntile * LG_STATES * 4 + 15) & ~(size_t)15;
             f.lg_tilestate = reinterpret_cast<uint32_t*>(scratch);
             scratch += ((size_t)ntile * 2 * 4 + 15) & ~(size_t)15;
+            scratch = (scratch + 127) & ~(size_t)127;
             max_ltiles = std::max<uint32_t>(max_ltiles, (uint32_t)ntile);
-        } else {
-            f.status = MCRAW_FRAME_BAD_TYPE;
-        }
+        }   // any other type: no work is queued, mcraw_batch_wait reports MCRAW_FRAME_BAD_TYPE
         out[i] = f;
     }
     return MCRAW_OK;
@@ -211,7 +227,30 @@ int begin_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n) {
     return MCRAW_OK;
 }
 
-// Enqueue one chunk (device-resident sources) of the current logical batch on `st`.
+// Pixel work list of the current-format frames of a chunk (see k_units), in frame order.  Items shrink towards the end
+// of the list so that the persistent warps finish together (guided self-scheduling).
+void build_items(const std::vector<FrameDev>& frames, uint32_t resident_ctas, std::vector<WorkItem>& items) {
+    items.clear();
+    uint64_t remaining = 0;
+    for (const FrameDev& f : frames)
+        if (f.type == MCRAW_COMPRESSION_CURRENT) remaining += f.nunits;
+    const uint64_t warps = (uint64_t)std::max<uint32_t>(resident_ctas, 1) * KU_WARPS;
+    for (uint32_t i = 0; i < frames.size(); i++) {
+        if (frames[i].type != MCRAW_COMPRESSION_CURRENT) continue;
+        const uint32_t nunits = frames[i].nunits;
+        for (uint32_t u = 0; u < nunits;) {
+            // an item never holds more than about half of an even share of what is left
+            const uint32_t take = std::min<uint32_t>(nunits - u, (uint32_t)std::min<uint64_t>(KU_UPW, std::max<uint64_t>(1, remaining / (2 * warps))));
+            items.push_back(WorkItem{i, u | ((take - 1) << 27)});
+            u += take;
+            remaining -= take;
+        }
+    }
+}
+
+// Enqueue one chunk (device-resident sources) of the current logical batch on `st`.  Everything stays on that one
+// stream: on this platform a cross-stream event dependency costs tens of microseconds, more than the index kernels it
+// could hide (measured: profiles/README.md).
 int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st) {
     if (n == 0) return MCRAW_OK;
     ctx->cur = (ctx->cur + 1) % kSlots;
@@ -219,45 +258,73 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     int rc = harvest(ctx, s);
     if (rc) return rc;
 
-    std::vector<FrameDev> frames;
-    size_t scratch; uint32_t max_tile_rows, max_units, max_ltiles; bool any7, any6;
-    rc = prepare(ctx, descs, n, result_offset, frames, scratch, max_tile_rows, max_units, max_ltiles, any7, any6);
-    if (rc) return rc;
-    rc = slot_reserve(ctx, s, n, scratch);
-    if (rc) return rc;
-    for (uint32_t i = 0; i < n; i++) {
-        if (frames[i].type == MCRAW_COMPRESSION_CURRENT) {
-            frames[i].unitoff = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].unitoff));
-            frames[i].pairinfo = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].pairinfo));
-            frames[i].pairrefs = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].pairrefs));
-        } else if (frames[i].type == MCRAW_COMPRESSION_LEGACY) {
-            frames[i].lg_segmap = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].lg_segmap));
-            frames[i].lg_tilemap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].lg_tilemap));
-            frames[i].lg_tilestate = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(frames[i].lg_tilestate));
+    // A slot remembers the descriptors it was last built for: a caller that decodes into a ring of buffers presents the
+    // same descriptors again and again, and then the device-side tables of the slot are still valid -- nothing to
+    // validate, build or upload.
+    const bool hit = s.plan_valid && s.plan_descs.size() == n && std::memcmp(s.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
+    if (!hit) {
+        s.plan_valid = false;
+        std::vector<FrameDev>& frames = ctx->tmp_frames;     // reused across calls: no allocation in steady state
+        std::vector<WorkItem>& items = ctx->tmp_items;
+        size_t scratch; uint32_t max_tile_rows, max_units;
+        rc = prepare(ctx, descs, n, result_offset, frames, scratch, max_tile_rows, max_units, s.max_ltiles, s.any7, s.any6);
+        if (rc) return rc;
+        items.clear();
+        if (s.any7) build_items(frames, ctx->resident_ctas, items);
+        s.items_off = (sizeof(FrameDev) * n + 15) & ~(size_t)15;
+        s.nitems = (uint32_t)items.size();
+        s.plan_bytes = (s.items_off + sizeof(WorkItem) * items.size() + 15) & ~(size_t)15;
+        rc = slot_reserve(ctx, s, n, s.plan_bytes, scratch);
+        if (rc) return rc;
+        FrameDev* h_frames = reinterpret_cast<FrameDev*>(s.h_up);
+        for (uint32_t i = 0; i < n; i++) {
+            FrameDev& f = frames[i];
+            if (f.type == MCRAW_COMPRESSION_CURRENT) {
+                f.unitoff = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.unitoff));
+                f.pairinfo = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.pairinfo));
+                f.pairrefs = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.pairrefs));
+            } else if (f.type == MCRAW_COMPRESSION_LEGACY) {
+                f.lg_segmap = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_segmap));
+                f.lg_tilemap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilemap));
+                f.lg_tilestate = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilestate));
+            }
+            h_frames[i] = f;
         }
-        s.h_frames[i] = frames[i];
+        if (!items.empty()) std::memcpy(s.h_up + s.items_off, items.data(), sizeof(WorkItem) * items.size());
+        s.plan_descs.assign(descs, descs + n);
     }
-    s.n = n; s.result_offset = result_offset; s.batch_id = ctx->batch_id; s.timed = false;
-    CU_TRY(ctx, cudaMemcpyAsync(s.d_frames, s.h_frames, sizeof(FrameDev) * n, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemsetAsync(s.d_results, 0, sizeof(Result) * n, st));
-    // index kernels between e0 and e1, pixel kernels between e1 and e2
+    uint32_t* d_counter = reinterpret_cast<uint32_t*>(s.d_dyn);
+    FrameState* d_states = reinterpret_cast<FrameState*>(s.d_dyn + 16);
+    Result* d_results = reinterpret_cast<Result*>(s.d_dyn + 16 + sizeof(FrameState) * n);
+    const FrameDev* d_frames = reinterpret_cast<const FrameDev*>(s.d_up);
+    const WorkItem* d_items = reinterpret_cast<const WorkItem*>(s.d_up + s.items_off);
+    const bool any7 = s.any7, any6 = s.any6;
+    s.n = n; s.result_offset = result_offset; s.batch_id = ctx->batch_id;
+
+    // descriptor + work list upload and the index kernels between e0 and e1, the pixel kernels between e1 and e2
     CU_TRY(ctx, cudaEventRecord(s.e0, st));
-    if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, st>>>(s.d_frames); ctx->launches += 1; }
+    if (!hit) {
+        CU_TRY(ctx, cudaMemcpyAsync(s.d_up, s.h_up, s.plan_bytes, cudaMemcpyHostToDevice, st));
+        s.plan_valid = true;
+    }
+    if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, st>>>(d_frames, d_states, d_counter); ctx->launches += 1; }
     if (any6) {
-        k_legacy_maps<<<dim3(max_ltiles, n), LG_THREADS, LG_MAPS_SMEM, st>>>(s.d_frames);
-        k_legacy_scan<<<n, LG_THREADS, 0, st>>>(s.d_frames, s.d_results);
+        k_legacy_maps<<<dim3(s.max_ltiles, n), LG_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
+        k_legacy_scan<<<n, LG_THREADS, 0, st>>>(d_frames, d_states, d_results);
         ctx->launches += 2;
     }
     CU_TRY(ctx, cudaEventRecord(s.e1, st));
     if (any7) {
-        k_units<<<dim3((max_units + KU_WARPS * KU_UPW - 1) / (KU_WARPS * KU_UPW), n), 32 * KU_WARPS, KU_SMEM, st>>>(s.d_frames, s.d_results);
+        const uint32_t want = (s.nitems + KU_WARPS - 1) / KU_WARPS;
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(ctx->resident_ctas, 1), want));
+        k_units<<<grid, KD_THREADS, KU_SMEM, st>>>(d_frames, d_states, d_results, d_items, s.nitems, d_counter);
         ctx->launches += 1;
     }
-    if (any6) { k_legacy_decode<<<dim3(max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(s.d_frames); ctx->launches += 1; }
+    if (any6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
     CU_TRY(ctx, cudaEventRecord(s.e2, st));
     s.timed = any7 || any6;
     CU_TRY(ctx, cudaGetLastError());
-    CU_TRY(ctx, cudaMemcpyAsync(s.h_results, s.d_results, sizeof(Result) * n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(s.h_results, d_results, sizeof(Result) * n, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaEventRecord(s.done, st));
     s.in_flight = true;
     return MCRAW_OK;
@@ -321,6 +388,14 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess) {
         ctx->err = "cudaFuncSetAttribute(smem) failed"; return bail(MCRAW_ERR_CUDA);
     }
+    {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_units, KD_THREADS, KU_SMEM) != cudaSuccess || per_sm < 1) {
+            ctx->err = "k_units does not fit on this device"; return bail(MCRAW_ERR_CUDA);
+        }
+        if (const char* e = getenv("MCRAW_UNITS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
+    }
     for (auto& s : ctx->slots) {
         if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&s.e0) != cudaSuccess ||
             cudaEventCreate(&s.e1) != cudaSuccess || cudaEventCreate(&s.e2) != cudaSuccess) {
@@ -342,10 +417,10 @@ void mcraw_ctx_destroy(mcraw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& s : ctx->slots) {
-        if (s.h_frames) cudaFreeHost(s.h_frames);
+        if (s.h_up) cudaFreeHost(s.h_up);
+        if (s.d_up) cudaFree(s.d_up);
         if (s.h_results) cudaFreeHost(s.h_results);
-        if (s.d_frames) cudaFree(s.d_frames);
-        if (s.d_results) cudaFree(s.d_results);
+        if (s.d_dyn) cudaFree(s.d_dyn);
         if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.done) cudaEventDestroy(s.done);
         if (s.e0) cudaEventDestroy(s.e0);

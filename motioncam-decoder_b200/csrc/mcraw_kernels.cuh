@@ -5,18 +5,20 @@
 //   A frame is a sequence of 64-sample blocks, four per 64x4-pixel tile.  We process it in UNITS of 16
 //   consecutive tiles (= 64 blocks = exactly one 64-value block of each metadata stream).
 //
-//   k_meta   one CTA per (frame, metadata stream).  Walks the inline-header chain of the stream
-//            (RawData.cpp:463-498) and lets ONE LANE decode one whole 64-value meta block with the same
-//            width-specialised SWAR routine the pixel kernel uses.  For the "bits" stream it also turns the
-//            reference's running `offset +=` (RawData.cpp:562,576-579) into prefix sums.  Output per unit:
-//            payload offset; per block pair (even/odd Bayer column pair): {relative offset, bits, refs}.
-//   k_units  one WARP per unit.  The unit's payload (contiguous, <= 8 KiB) is staged in shared memory with
+//   k_meta   one CTA per (frame, metadata stream).  Resolves the inline-header chain of the stream
+//            (RawData.cpp:463-498) by pointer doubling over every candidate position of a staged window, then lets
+//            ONE LANE decode one whole 64-value meta block with the same width-specialised SWAR routine the pixel
+//            kernel uses.  For the "bits" stream it also turns the reference's running `offset +=`
+//            (RawData.cpp:562,576-579) into prefix sums.  Output per unit: payload offset; per block pair
+//            (even/odd Bayer column pair): {relative offset, bits, refs}.
+//   k_units  persistent; every WARP takes items (a few consecutive units of one frame) from a queue and decodes one
+//            unit at a time.  The unit's payload (contiguous, <= 8 KiB) is staged in shared memory with
 //            16-byte cp.async into an XOR-swizzled layout; every lane then decodes one block pair: a `switch`
 //            on the header bits value selects straight-line code with immediate shifts/masks (lanes that share
 //            a bits value run together; real images have 1-3 distinct values per warp).  Even/odd columns are
 //            interleaved with PRMT, references added with packed 16-bit adds (mod 2^16 like RawData.cpp:582-592),
-//            rows are assembled in shared memory and leave through 128-byte TMA bulk stores
-//            (cp.async.bulk.global.shared::cta); columns >= width are cropped (RawData.cpp:598-608).
+//            rows are assembled in shared memory and leave as coalesced 16-byte stores; columns >= width are
+//            cropped (RawData.cpp:598-608).
 //
 // Legacy format (compressionType 6; reference: /root/reference/lib/RawData_Legacy.cpp:445-495): mcraw_legacy.cuh.
 #pragma once
@@ -44,8 +46,12 @@ struct FrameDev {
     uint16_t* lg_segmap;           // legacy scratch [32 * tiles][17]  transfer map of every 1 KiB segment
     uint32_t* lg_tilemap;          // legacy scratch [tiles][17]       transfer map of every 32 KiB tile
     uint32_t* lg_tilestate;        // legacy scratch [tiles][2]        entry offset / first block ordinal of every tile
-    // written on the device
-    unsigned status;               // MCRAW_FRAME_* bits
+};
+
+// Per-frame words written by the index kernels and read by the pixel kernels.  Every word is written on every path
+// (no host-side zeroing): status[s] by the CTA of metadata stream s (legacy: [0] by k_legacy_scan, [1] = 0).
+struct FrameState {
+    unsigned status[2];            // MCRAW_FRAME_* bits
     unsigned tile_rows_dev;        // ceil(encodedHeight/4) from the frame header
     unsigned rows_fit;             // rows emitted: min(4*tile_rows_dev, dst_cap / width)
 };
@@ -251,7 +257,8 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // grid = 2 * frames, block = K1_THREADS, dynamic smem = K1_SMEM
-__global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ frames) {
+__global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restrict__ frames, FrameState* __restrict__ states,
+                                                        uint32_t* __restrict__ queue_counter) {
     extern __shared__ __align__(16) uint8_t k1_smem[];
     uint8_t* stage = k1_smem;                                                        // K1_CHUNK + 32 bytes of the stream
     const uint32_t stage_s = smem_u32(stage);
@@ -263,9 +270,11 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
     __shared__ uint32_t sh_err, sh_bad;
     __shared__ uint32_t sh_hdr[4];
 
+    if (blockIdx.x == 0 && threadIdx.x == 0) *queue_counter = 0;      // k_units' item queue (it runs after this kernel)
     const int f = blockIdx.x >> 1;
     const int stream = blockIdx.x & 1;   // 0 = bits, 1 = refs
-    FrameDev& F = frames[f];
+    const FrameDev& F = frames[f];
+    FrameState& S = states[f];
     if (F.type != MCRAW_COMPRESSION_CURRENT) return;
     const int tid = threadIdx.x;
     const uint8_t* __restrict__ src = F.src;
@@ -300,13 +309,13 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
         if (stream == 0) {
             unsigned long long fit = F.dst_cap / (unsigned long long)(F.width > 0 ? F.width : 1);
             if (fit > 4ull * tr) fit = 4ull * tr;                                   // reference emits 4 rows per tile row (:598-608)
-            F.tile_rows_dev = tr;
-            F.rows_fit = (uint32_t)fit;
+            S.tile_rows_dev = tr;
+            S.rows_fit = (uint32_t)fit;
         }
     }
     __syncthreads();
     if (sh_err) {
-        if (tid == 0) atomicOr(&F.status, sh_err);
+        if (tid == 0) S.status[stream] = sh_err;
         return;
     }
     const uint32_t tiles_x = sh_hdr[0] / 64u;
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(FrameDev* __restrict__ f
             if (!err && (unsigned long long)carry > len) err = MCRAW_FRAME_TRUNCATED;   // RawData.cpp:419
             unitoff[need_mb] = carry;
         }
-        if (err) atomicOr(&F.status, err);
+        S.status[stream] = err;
     }
 }
 
@@ -624,42 +633,41 @@ __device__ __forceinline__ void emit_and_copy(const uint32_t (&LE)[16], const ui
     __syncwarp();
 }
 
-// grid = (ceil(max units / (KU_WARPS*KU_UPW)), frames), block = 32 * KU_WARPS, dynamic smem = KU_SMEM
-__global__ void __launch_bounds__(32 * KU_WARPS, 4) k_units(FrameDev* __restrict__ frames, Result* __restrict__ results) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const FrameDev& F = frames[blockIdx.y];
-    if (F.type != MCRAW_COMPRESSION_CURRENT) return;
-    const unsigned status = F.status;
-    const uint32_t rows_fit = F.rows_fit;
+// The pixel work of one item: the calling WARP decodes units [u0, u0 + upw) of the frame.
+// The per-unit records written by k_meta are single-use: they are read with ld.global.cg (L2 only).
+// smem_warp: the warp's KU_WARP_SMEM bytes.
+__device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& S, Result* __restrict__ result,
+                                           const uint32_t u0, const uint32_t upw, uint8_t* smem_warp) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned status = __ldcg(&S.status[0]) | __ldcg(&S.status[1]);
+    const uint32_t rows_fit = __ldcg(&S.rows_fit);
     const int width = F.width;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (u0 == 0 && lane == 0) {
         Result r;
         r.written = status ? 0ull : (unsigned long long)rows_fit * (unsigned long long)width;      // RawData.cpp:611
         r.status = status;
         r.pad = 0;
-        results[blockIdx.y] = r;
+        *result = r;
     }
     if (status) return;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_x = F.tiles_x;
-    const uint32_t ntiles = tiles_x * F.tile_rows_dev;
+    const uint32_t ntiles = tiles_x * __ldcg(&S.tile_rows_dev);
     const uint32_t nunits = (ntiles + 15u) / 16u;
-    const uint32_t u0 = (blockIdx.x * KU_WARPS + warp) * KU_UPW;
     if (u0 >= nunits) return;
-    const uint32_t nu = min((uint32_t)KU_UPW, nunits - u0);
+    const uint32_t nu = min(upw, nunits - u0);
 
-    const uint32_t in_base = smem_u32(smem_raw) + warp * KU_WARP_SMEM;
+    const uint32_t in_base = smem_u32(smem_warp);
     const uint32_t out_base = in_base + KU_IN_BYTES;
     const uint8_t* __restrict__ src = F.src;
     const unsigned long long len = F.len;
     const uint32_t inv = F.inv_tiles_x;
     const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
     uint16_t* __restrict__ dst = F.dst;
-    const uint32_t* __restrict__ pairinfo = F.pairinfo + (size_t)u0 * 32u + lane;
-    const uint32_t* __restrict__ pairrefs = F.pairrefs + (size_t)u0 * 32u + lane;
+    const uint32_t* pairinfo = F.pairinfo + (size_t)u0 * 32u + lane;
+    const uint32_t* pairrefs = F.pairrefs + (size_t)u0 * 32u + lane;
 
     // payload offsets of this warp's units (+ end): lane i holds unitoff[u0 + i]
-    const uint32_t my_off = (lane <= nu) ? __ldg(F.unitoff + u0 + lane) : 0u;
+    const uint32_t my_off = (lane <= nu) ? __ldcg(F.unitoff + u0 + lane) : 0u;
 
     // stage unit payload [a0, a1) (rounded out to 16 bytes) with swizzled 16-byte cp.async
     auto stage_unit = [&](uint32_t a0, uint32_t a1) {
@@ -682,13 +690,13 @@ __global__ void __launch_bounds__(32 * KU_WARPS, 4) k_units(FrameDev* __restrict
 
     uint32_t a0 = __shfl_sync(0xFFFFFFFFu, my_off, 0), a1 = __shfl_sync(0xFFFFFFFFu, my_off, 1);
     stage_unit(a0, a1);
-    uint32_t info = __ldg(pairinfo), refs = __ldg(pairrefs);
+    uint32_t info = __ldcg(pairinfo), refs = __ldcg(pairrefs);
 
     for (uint32_t i = 0; i < nu; i++) {
         const uint32_t unit = u0 + i;
         // prefetch the next unit's pair record while this one is decoded
         uint32_t info_n = 0, refs_n = 0;
-        if (i + 1 < nu) { info_n = __ldg(pairinfo + 32u * (i + 1)); refs_n = __ldg(pairrefs + 32u * (i + 1)); }
+        if (i + 1 < nu) { info_n = __ldcg(pairinfo + 32u * (i + 1)); refs_n = __ldcg(pairrefs + 32u * (i + 1)); }
         const uint32_t bE = (info >> 16) & 0xFFu, bO = info >> 24;
         const uint32_t aE = (a0 & 15u) + 8u * (info & 0xFFFFu);
 
@@ -727,6 +735,38 @@ __global__ void __launch_bounds__(32 * KU_WARPS, 4) k_units(FrameDev* __restrict
         if (vec) emit_and_copy<true>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width);
         else emit_and_copy<false>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width);
         info = info_n; refs = refs_n;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// k_units: the pixel work of the whole batch in one persistent launch (grid = resident CTAs, or fewer for small
+// batches).  Every WARP takes items (frame, first unit, units) from a queue in global memory, so there is no wave
+// quantisation: the host ends the item list with progressively smaller items (build_items()) and warps never wait for
+// each other.  Runs after k_meta on the same stream.
+// block = KD_THREADS, dynamic smem = KU_SMEM
+// --------------------------------------------------------------------------------------------------------
+struct WorkItem {
+    uint32_t frame;
+    uint32_t what;     // bits 0..26 = first unit, bits 27..30 = units - 1
+};
+constexpr int KD_THREADS = 32 * KU_WARPS;
+
+__global__ void __launch_bounds__(KD_THREADS, 4)
+k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states, Result* __restrict__ results,
+        const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counter) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint8_t* smem_warp = smem_raw + (threadIdx.x >> 5) * KU_WARP_SMEM;
+    uint32_t it = 0;
+    if (lane == 0) it = atomicAdd(counter, 1u);
+    it = __shfl_sync(0xFFFFFFFFu, it, 0);
+    while (it < nitems) {
+        const WorkItem w = items[it];
+        uint32_t nxt = 0;
+        if (lane == 0) nxt = atomicAdd(counter, 1u);       // take the next item early
+        units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 15u) + 1u, smem_warp);
+        __syncwarp();
+        it = __shfl_sync(0xFFFFFFFFu, nxt, 0);
     }
 }
 

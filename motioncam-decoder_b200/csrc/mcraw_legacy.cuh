@@ -60,10 +60,10 @@ __device__ __forceinline__ void lg_stage(uint8_t* sm, const uint8_t* __restrict_
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LG_MAPS_SMEM = LG_TILE + LG_TILE_SEGS * 18 * 2;
 
-__global__ void __launch_bounds__(LG_THREADS) k_legacy_maps(FrameDev* __restrict__ frames) {
+__global__ void __launch_bounds__(LG_THREADS) k_legacy_maps(const FrameDev* __restrict__ frames) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     const FrameDev& F = frames[blockIdx.y];
-    if (F.type != MCRAW_COMPRESSION_LEGACY || F.status) return;
+    if (F.type != MCRAW_COMPRESSION_LEGACY) return;
     const unsigned long long len = F.len;
     const uint32_t nseg = (uint32_t)((len + LG_SEG - 1) / LG_SEG);
     const uint32_t tile = blockIdx.x;
@@ -114,10 +114,11 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_maps(FrameDev* __restrict
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LG_SCAN_TILES = 512;    // tile maps staged per round
 
-__global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(FrameDev* __restrict__ frames, Result* __restrict__ results) {
+__global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(const FrameDev* __restrict__ frames, FrameState* __restrict__ states,
+                                                            Result* __restrict__ results) {
     __shared__ uint32_t tm[LG_SCAN_TILES * LG_STATES];
     __shared__ uint32_t sh_state, sh_base;
-    FrameDev& F = frames[blockIdx.x];
+    const FrameDev& F = frames[blockIdx.x];
     if (F.type != MCRAW_COMPRESSION_LEGACY) return;
     const int tid = threadIdx.x;
     const unsigned long long len = F.len;
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(FrameDev* __restrict
     const uint32_t ntile = (nseg + LG_TILE_SEGS - 1) / LG_TILE_SEGS;
     const unsigned long long ppr = ((unsigned long long)F.width + 31ull) / 32ull;          // RawData_Legacy.cpp:34-36,449
     const unsigned long long need = 2ull * ppr * (unsigned long long)F.height;              // :478-482
-    unsigned status = F.status;
-    if (!status && len == 0) status = MCRAW_FRAME_TRUNCATED;
+    unsigned status = 0;
+    if (len == 0) status = MCRAW_FRAME_TRUNCATED;
     if (!status && F.dst_cap < (unsigned long long)F.width * (unsigned long long)F.height) status = MCRAW_FRAME_GEOMETRY;
     if (tid == 0) { sh_state = 0; sh_base = 0; }
     __syncthreads();
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(FrameDev* __restrict
         if ((unsigned long long)sh_base < need) status = MCRAW_FRAME_TRUNCATED;   // reference: stale samples (:387,398)
     }
     if (tid == 0) {
-        F.status = status;
+        states[blockIdx.x].status[0] = status;
+        states[blockIdx.x].status[1] = 0;
         Result r;
         r.written = status ? 0ull : (unsigned long long)F.width * (unsigned long long)F.height;   // :494
         r.status = status;
@@ -232,10 +234,10 @@ constexpr int LG_DEC_DATA = LG_TILE + LG_OVERRUN;
 constexpr int LG_DEC_SMEM = LG_DEC_DATA + LG_TILE_SEGS * 18 * 2 /*maps*/ + LG_TILE_SEGS * (LG_SLOTS / 8) /*bitmaps*/ +
                             (LG_THREADS / 32) * LG_SLOTS * 2 /*lists*/ + LG_TILE_SEGS * 8 /*entry, base*/;
 
-__global__ void __launch_bounds__(LG_THREADS) k_legacy_decode(FrameDev* __restrict__ frames) {
+__global__ void __launch_bounds__(LG_THREADS) k_legacy_decode(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     const FrameDev& F = frames[blockIdx.y];
-    if (F.type != MCRAW_COMPRESSION_LEGACY || F.status) return;
+    if (F.type != MCRAW_COMPRESSION_LEGACY || states[blockIdx.y].status[0]) return;
     const unsigned long long len = F.len;
     const uint32_t nseg = (uint32_t)((len + LG_SEG - 1) / LG_SEG);
     const uint32_t tile = blockIdx.x;
