@@ -208,6 +208,10 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
             scratch += ((size_t)ntile * LG_STATES * 4 + 15) & ~(size_t)15;
             f.lg_tilestate = reinterpret_cast<uint32_t*>(scratch);
             scratch += ((size_t)ntile * 2 * 4 + 15) & ~(size_t)15;
+            f.lg_bitmap = reinterpret_cast<uint32_t*>(scratch);
+            scratch += (size_t)ntile * LG_TILE_SEGS * LG_BM_WORDS * 4;
+            f.lg_segx = reinterpret_cast<uint16_t*>(scratch);
+            scratch += ((size_t)ntile * LG_TILE_SEGS * 2 + 15) & ~(size_t)15;
             scratch = (scratch + 127) & ~(size_t)127;
             max_ltiles = std::max<uint32_t>(max_ltiles, (uint32_t)ntile);
         }   // any other type: no work is queued, mcraw_batch_wait reports MCRAW_FRAME_BAD_TYPE
@@ -287,6 +291,8 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
                 f.lg_segmap = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_segmap));
                 f.lg_tilemap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilemap));
                 f.lg_tilestate = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilestate));
+                f.lg_bitmap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_bitmap));
+                f.lg_segx = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_segx));
             }
             h_frames[i] = f;
         }
@@ -385,7 +391,9 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     for (auto& cs : ctx->copy_streams)
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
     if (cudaFuncSetAttribute(k_meta, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess) {
+        cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_legacy_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_MAPS_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_legacy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_DEC_SMEM) != cudaSuccess) {
         ctx->err = "cudaFuncSetAttribute(smem) failed"; return bail(MCRAW_ERR_CUDA);
     }
     {

@@ -46,6 +46,8 @@ struct FrameDev {
     uint16_t* lg_segmap;           // legacy scratch [32 * tiles][17]  transfer map of every 1 KiB segment
     uint32_t* lg_tilemap;          // legacy scratch [tiles][17]       transfer map of every 32 KiB tile
     uint32_t* lg_tilestate;        // legacy scratch [tiles][2]        entry offset / first block ordinal of every tile
+    uint32_t* lg_bitmap;           // legacy scratch [32 * tiles][16]  block starts past the merge point of every segment
+    uint16_t* lg_segx;             // legacy scratch [32 * tiles]      merge point of every segment (0xFFFF: none)
 };
 
 // Per-frame words written by the index kernels and read by the pixel kernels.  Every word is written on every path

@@ -41,6 +41,13 @@ __device__ __forceinline__ uint32_t leg_len(uint32_t b) { return b <= 10u ? 2u *
 // stage [tile_off, tile_off + nbytes) of the frame into shared memory, zero past len (16-byte granules)
 __device__ __forceinline__ void lg_stage(uint8_t* sm, const uint8_t* __restrict__ src, unsigned long long len,
                                          unsigned long long tile_off, int nbytes, int tid) {
+    if (tile_off + (unsigned long long)nbytes <= len) {                       // the common case: wholly inside the buffer
+        const uint4* g = reinterpret_cast<const uint4*>(src + tile_off);
+        uint4* d = reinterpret_cast<uint4*>(sm);
+#pragma unroll 4
+        for (int v = tid; v < nbytes / 16; v += LG_THREADS) d[v] = __ldg(g + v);
+        return;
+    }
     for (int v = tid; v < nbytes / 16; v += LG_THREADS) {
         const unsigned long long o = tile_off + 16ull * (unsigned)v;
         uint4 q = make_uint4(0, 0, 0, 0);
@@ -55,10 +62,35 @@ __device__ __forceinline__ void lg_stage(uint8_t* sm, const uint8_t* __restrict_
     }
 }
 
+// Walk a chain from p to its first block start at or beyond `stop`.  CHECK: the segment lies near the end of the buffer,
+// so a block may fail the reference's bound (RawData_Legacy.cpp:387,398: decoded only if offset + 2 + payload < len).
+template <bool CHECK>
+__device__ __forceinline__ void lg_walk(const uint8_t* seg, uint32_t& p, uint32_t& cnt, bool& dead, const uint32_t stop,
+                                        const uint32_t rel_len) {
+    while (p < stop) {
+        const uint32_t b = (uint32_t)seg[p] >> 4;
+        const uint32_t q = p + 2u + (b > 10u ? 32u : 2u * b);
+        if (CHECK && q >= rel_len) { dead = true; break; }
+        p = q;
+        cnt++;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// k_legacy_maps: grid = (max tiles, frames), block = LG_THREADS, dynamic smem = LG_TILE + 2 * 32 * 18
+// k_legacy_maps: grid = (max tiles, frames), block = LG_THREADS, dynamic smem = LG_MAPS_SMEM
+//
+// Phase 1 (a warp per segment, 17 lanes): the 17 candidate chains are walked only until they have MERGED -- chains
+//   that meet at one block start are the same chain from there on, and with blocks of varying length that happens
+//   within a few blocks.  Merging is tested at barrier lines 64, 128, 256, 512 bytes into the segment: every lane
+//   walks to its first block start at or beyond the line; if all 17 agree on it (X), the segment's map is
+//   "entry e -> pre[e] blocks, then the common chain from X".  Chains that have not merged by 512 (constant-width
+//   regions) are simply walked to the end of the segment: the full map, no shortcut.
+// Phase 2 (one lane per segment): the common chain from X to the end of the segment, marking every block start in a
+//   bitmap that k_legacy_decode reuses, so nothing past X is ever walked twice or 17-fold.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LG_MAPS_SMEM = LG_TILE + LG_TILE_SEGS * 18 * 2;
+constexpr int LG_BM_WORDS = LG_SLOTS / 32;                  // bitmap words per segment
+constexpr uint32_t LG_NO_X = 0xFFFFu;                       // segment has no merge point (full map, no bitmap)
+constexpr int LG_MAPS_SMEM = LG_TILE + LG_TILE_SEGS * 18 * 2 + LG_TILE_SEGS * LG_BM_WORDS * 4 + LG_TILE_SEGS * 2;
 
 __global__ void __launch_bounds__(LG_THREADS) k_legacy_maps(const FrameDev* __restrict__ frames) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
@@ -70,31 +102,78 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_maps(const FrameDev* __re
     if ((unsigned long long)tile * LG_TILE_SEGS >= nseg) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* data = lg_smem;
-    uint16_t* maps = reinterpret_cast<uint16_t*>(lg_smem + LG_TILE);          // [32][18]
+    uint16_t* maps = reinterpret_cast<uint16_t*>(lg_smem + LG_TILE);                                  // [32][18]
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_TILE + LG_TILE_SEGS * 36);            // [32][16]
+    uint16_t* segx = reinterpret_cast<uint16_t*>(lg_smem + LG_TILE + LG_TILE_SEGS * 36 + LG_TILE_SEGS * LG_BM_WORDS * 4);
     const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
     lg_stage(data, F.src, len, tile_off, LG_TILE, tid);
+    for (int i = tid; i < LG_TILE_SEGS * LG_BM_WORDS; i += LG_THREADS) bitmap[i] = 0;
     __syncthreads();
 
     const uint32_t segs_here = min((uint32_t)LG_TILE_SEGS, nseg - tile * LG_TILE_SEGS);
+    // ---- phase 1
     for (uint32_t s = warp; s < segs_here; s += LG_THREADS / 32) {
-        if (lane < LG_STATES) {
-            const unsigned long long seg_abs = tile_off + (unsigned long long)s * LG_SEG;
-            const uint8_t* seg = data + s * LG_SEG;
-            uint32_t p = 2u * lane, cnt = 0;
-            bool dead = false;
-            while (p < (uint32_t)LG_SEG) {
-                // RawData_Legacy.cpp:387,398: a block is decoded only if offset + 2 + payload < len
-                const uint32_t L = leg_len(seg[p] >> 4);
-                if (seg_abs + p + 2u + L >= len) { dead = true; break; }
-                p += 2u + L;
-                cnt++;
-            }
-            const uint32_t m = (dead ? LG_DEAD : (p - LG_SEG) >> 1) | (cnt << 5);
-            maps[s * 18 + lane] = (uint16_t)m;
-            F.lg_segmap[((size_t)tile * LG_TILE_SEGS + s) * LG_STATES + lane] = (uint16_t)m;
+        const unsigned long long seg_abs = tile_off + (unsigned long long)s * LG_SEG;
+        // RawData_Legacy.cpp:387,398: a block is decoded only if offset + 2 + payload < len; as a segment-relative bound
+        const uint32_t rel_len = (uint32_t)min(len - seg_abs, (unsigned long long)(1u << 30));
+        const uint8_t* seg = data + s * LG_SEG;
+        const bool active = lane < LG_STATES;
+        const bool check = rel_len < (uint32_t)(LG_SEG + 40);                     // warp-uniform: only the last segments of a frame
+        uint32_t p = active ? 2u * lane : 0xFFFF0000u, cnt = 0;                   // idle lanes never enter the walk
+        bool dead = false;
+        uint32_t x = LG_NO_X;
+        // merge test at 64, 96, ..., 256, 320, ..., 512 bytes; chains still apart at 512 are walked to the end
+        for (uint32_t line = 64;; line += (line < 256u ? 32u : 64u)) {
+            const uint32_t stop = line > 512u ? (uint32_t)LG_SEG : line;
+            if (check) { if (!dead) lg_walk<true>(seg, p, cnt, dead, stop, rel_len); }
+            else lg_walk<false>(seg, p, cnt, dead, stop, rel_len);
+            if (stop == (uint32_t)LG_SEG) break;                                  // walked to the end: full map
+            const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, p, 0);
+            const bool agree = __all_sync(0xFFFFFFFFu, !active || (!dead && p == p0));
+            if (agree && p0 < (uint32_t)LG_SEG) { x = p0; break; }
         }
+        if (active) {
+            if (x == LG_NO_X) maps[s * 18 + lane] = (uint16_t)((dead ? LG_DEAD : (p - LG_SEG) >> 1) | (cnt << 5));
+            else maps[s * 18 + lane] = (uint16_t)cnt;                             // pre[e]; completed in phase 2
+        }
+        if (lane == 0) segx[s] = (uint16_t)x;
     }
     __syncthreads();
+    // ---- phase 2
+    if (warp == 0 && (uint32_t)lane < segs_here && segx[lane] != LG_NO_X) {
+        const uint32_t s = lane;
+        const unsigned long long seg_abs = tile_off + (unsigned long long)s * LG_SEG;
+        const uint32_t rel_len = (uint32_t)min(len - seg_abs, (unsigned long long)(1u << 30));
+        const uint8_t* seg = data + s * LG_SEG;
+        uint32_t* bm = bitmap + s * LG_BM_WORDS;
+        uint32_t p = segx[s], cnt = 0;
+        bool dead = false;
+        // one bitmap word covers 64 bytes of the segment: walk word by word, collecting the starts in a register
+        for (uint32_t wd = p >> 6; wd < (uint32_t)LG_BM_WORDS && !dead; wd++) {
+            uint32_t acc = 0;
+            const uint32_t stop = 64u * (wd + 1u);
+            while (p < stop) {
+                const uint32_t b = (uint32_t)seg[p] >> 4;
+                const uint32_t q = p + 2u + (b > 10u ? 32u : 2u * b);
+                if (q >= rel_len) { dead = true; break; }
+                acc |= 1u << ((p >> 1) & 31u);
+                p = q;
+                cnt++;
+            }
+            bm[wd] = acc;
+        }
+        const uint32_t ex = dead ? LG_DEAD : (p - LG_SEG) >> 1;
+        for (int e = 0; e < LG_STATES; e++) maps[s * 18 + e] = (uint16_t)(ex | (((uint32_t)maps[s * 18 + e] + cnt) << 5));
+    }
+    __syncthreads();
+    // ---- results of the tile: segment maps, merge points and bitmaps for k_legacy_decode; the composed tile map
+    const size_t seg0 = (size_t)tile * LG_TILE_SEGS;
+    for (uint32_t i = tid; i < segs_here * LG_STATES; i += LG_THREADS) {
+        const uint32_t s = i / LG_STATES, e = i - s * LG_STATES;
+        F.lg_segmap[seg0 * LG_STATES + i] = maps[s * 18 + e];
+    }
+    for (uint32_t i = tid; i < segs_here * LG_BM_WORDS; i += LG_THREADS) F.lg_bitmap[seg0 * LG_BM_WORDS + i] = bitmap[i];
+    if ((uint32_t)tid < segs_here) F.lg_segx[seg0 + tid] = segx[tid];
     if (warp == 0 && lane < LG_STATES) {
         uint32_t state = lane, total = 0;
         for (uint32_t s = 0; s < segs_here; s++) {
@@ -167,9 +246,20 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(const FrameDev* __re
 // ---------------------------------------------------------------------------------------------------------
 // k_legacy_decode
 // ---------------------------------------------------------------------------------------------------------
-// 16 samples of W bits each, MSB-first contiguous (RawData_Legacy.cpp:38-358), from big-endian words be[].
+// 16 samples of W bits each, MSB-first contiguous (RawData_Legacy.cpp:38-358).  w: the staged tile as words, pi / psh:
+// word index and bit shift of the first payload byte (the payload starts 2-byte aligned).
 template <int W>
-__device__ __forceinline__ void leg_unpack(const uint32_t (&be)[9], uint32_t (&v)[16]) {
+__device__ __forceinline__ void leg_unpack(const uint32_t* w, const uint32_t pi, const uint32_t psh, uint32_t (&v)[16]) {
+    constexpr int NW = (W + 1) / 2;                   // payload words: 2 * W bytes
+    uint32_t be[NW + 1];
+    uint32_t lo = w[pi];
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t hi = w[pi + k + 1];
+        be[k] = __byte_perm(__funnelshift_r(lo, hi, psh), 0u, 0x0123);            // big-endian view of payload bytes 4k .. 4k+3
+        lo = hi;
+    }
+    be[NW] = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int bit = k * W, i = bit >> 5, sh = bit & 31;
@@ -184,57 +274,35 @@ __device__ __forceinline__ void leg_unpack(const uint32_t (&be)[9], uint32_t (&v
 __device__ __forceinline__ uint32_t leg_block(const uint8_t* data, uint32_t o, uint32_t (&v)[16], uint32_t& ref) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(data);
     const uint32_t i0 = o >> 2, sh = (o & 2u) * 8u;
-    // bytes o .. o+35 as little-endian words aligned to the block start
-    uint32_t a = w[i0], b = w[i0 + 1];
-    const uint32_t h = __funnelshift_r(a, b, sh);
+    const uint32_t h = __funnelshift_r(w[i0], w[i0 + 1], sh);                    // bytes o .. o+3
     const uint32_t bits = (h >> 4) & 15u;                                        // RawData_Legacy.cpp:372-375
     ref = ((h & 15u) << 8) | ((h >> 8) & 0xFFu);
-    const uint32_t L = leg_len(bits);
-    // payload words (big-endian view) starting at byte o + 2
-    uint32_t be[9];
     const uint32_t pi = (o + 2u) >> 2, psh = ((o + 2u) & 2u) * 8u;
-    const int nw = (int)((L + 3u) >> 2);
-#pragma unroll
-    for (int k = 0; k < 9; k++) be[k] = 0;
-    {
-        uint32_t lo = w[pi];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (k < nw) {
-                const uint32_t hi = w[pi + k + 1];
-                be[k] = __byte_perm(__funnelshift_r(lo, hi, psh), 0u, 0x0123);
-                lo = hi;
-            }
-        }
-    }
     switch (bits) {
     case 0:
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = 0;                                   // :402-404
-        break;
-    case 1: leg_unpack<1>(be, v); break;
-    case 2: leg_unpack<2>(be, v); break;
-    case 3: leg_unpack<3>(be, v); break;
-    case 4: leg_unpack<4>(be, v); break;
-    case 5: leg_unpack<5>(be, v); break;
-    case 6: leg_unpack<6>(be, v); break;
-    case 7: leg_unpack<7>(be, v); break;
-    case 8: leg_unpack<8>(be, v); break;
-    case 9: leg_unpack<9>(be, v); break;
-    case 10: leg_unpack<10>(be, v); break;
-    default:                                                                     // 11..15 -> 16-bit big-endian (:360-370,395)
-#pragma unroll
-        for (int k = 0; k < 8; k++) { v[2 * k] = be[k] >> 16; v[2 * k + 1] = be[k] & 0xFFFFu; }
-        break;
+        return 2u;
+    case 1: leg_unpack<1>(w, pi, psh, v); return 4u;
+    case 2: leg_unpack<2>(w, pi, psh, v); return 6u;
+    case 3: leg_unpack<3>(w, pi, psh, v); return 8u;
+    case 4: leg_unpack<4>(w, pi, psh, v); return 10u;
+    case 5: leg_unpack<5>(w, pi, psh, v); return 12u;
+    case 6: leg_unpack<6>(w, pi, psh, v); return 14u;
+    case 7: leg_unpack<7>(w, pi, psh, v); return 16u;
+    case 8: leg_unpack<8>(w, pi, psh, v); return 18u;
+    case 9: leg_unpack<9>(w, pi, psh, v); return 20u;
+    case 10: leg_unpack<10>(w, pi, psh, v); return 22u;
+    default: leg_unpack<16>(w, pi, psh, v); return 34u;                          // 11..15 -> 16-bit big-endian (:360-370,395)
     }
-    return 2u + L;
 }
 
 constexpr int LG_DEC_DATA = LG_TILE + LG_OVERRUN;
-constexpr int LG_DEC_SMEM = LG_DEC_DATA + LG_TILE_SEGS * 18 * 2 /*maps*/ + LG_TILE_SEGS * (LG_SLOTS / 8) /*bitmaps*/ +
-                            (LG_THREADS / 32) * LG_SLOTS * 2 /*lists*/ + LG_TILE_SEGS * 8 /*entry, base*/;
+constexpr int LG_MAX_PAIRS = LG_TILE / 4;             // a pair is at least two 2-byte blocks
+constexpr int LG_DEC_SMEM = LG_DEC_DATA + LG_TILE_SEGS * 18 * 2 /*maps*/ + LG_TILE_SEGS * LG_BM_WORDS * 4 /*bitmaps*/ +
+                            LG_MAX_PAIRS * 2 /*pair list*/ + (LG_TILE_SEGS + 1) * 8 /*entry, base*/ + LG_TILE_SEGS * 2 /*merge points*/;
 
-__global__ void __launch_bounds__(LG_THREADS) k_legacy_decode(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
+__global__ void __launch_bounds__(LG_THREADS, 4) k_legacy_decode(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     const FrameDev& F = frames[blockIdx.y];
     if (F.type != MCRAW_COMPRESSION_LEGACY || states[blockIdx.y].status[0]) return;
@@ -244,17 +312,18 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_decode(const FrameDev* __
     if ((unsigned long long)tile * LG_TILE_SEGS >= nseg) return;
     const uint32_t tile_entry = F.lg_tilestate[2 * (size_t)tile];
     const uint32_t tile_base = F.lg_tilestate[2 * (size_t)tile + 1];
-    const uint32_t ppr = ((uint32_t)F.width + 31u) / 32u;
-    const unsigned long long need = 2ull * ppr * (unsigned long long)F.height;
+    const uint32_t ppr = ((uint32_t)F.width + 31u) / 32u;                            // pairs per row (RawData_Legacy.cpp:34-36)
+    const unsigned long long need = 2ull * ppr * (unsigned long long)F.height;       // blocks of the image (:478-482), < 2^33
     if (tile_entry == LG_DEAD || (unsigned long long)tile_base >= need) return;      // nothing of the image starts here
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* data = lg_smem;
     uint16_t* maps = reinterpret_cast<uint16_t*>(lg_smem + LG_DEC_DATA);                          // [32][18]
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_DEC_DATA + LG_TILE_SEGS * 36);    // [32][16]
-    uint16_t* lists = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(bitmap) + LG_TILE_SEGS * (LG_SLOTS / 8));
-    uint32_t* seg_entry = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(lists) + (LG_THREADS / 32) * LG_SLOTS * 2);
-    uint32_t* seg_base = seg_entry + LG_TILE_SEGS;
+    uint16_t* plist = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(bitmap) + LG_TILE_SEGS * LG_BM_WORDS * 4);
+    uint32_t* seg_entry = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(plist) + LG_MAX_PAIRS * 2);   // [33]
+    uint32_t* seg_base = seg_entry + LG_TILE_SEGS + 1;                                            // [33]: [32] = end of the tile
+    uint16_t* segx = reinterpret_cast<uint16_t*>(seg_base + LG_TILE_SEGS + 1);
 
     const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
     const uint32_t segs_here = min((uint32_t)LG_TILE_SEGS, nseg - tile * LG_TILE_SEGS);
@@ -263,7 +332,10 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_decode(const FrameDev* __
         const uint32_t s = i / LG_STATES, e = i - s * LG_STATES;
         maps[s * 18 + e] = F.lg_segmap[((size_t)tile * LG_TILE_SEGS + s) * LG_STATES + e];
     }
-    for (uint32_t i = tid; i < LG_TILE_SEGS * (LG_SLOTS / 32); i += LG_THREADS) bitmap[i] = 0;
+    // block starts past each segment's merge point come from k_legacy_maps
+    for (uint32_t i = tid; i < LG_TILE_SEGS * LG_BM_WORDS; i += LG_THREADS)
+        bitmap[i] = i < segs_here * LG_BM_WORDS ? F.lg_bitmap[(size_t)tile * LG_TILE_SEGS * LG_BM_WORDS + i] : 0u;
+    if ((uint32_t)tid < LG_TILE_SEGS) segx[tid] = (uint32_t)tid < segs_here ? F.lg_segx[(size_t)tile * LG_TILE_SEGS + tid] : (uint16_t)LG_NO_X;
     __syncthreads();
     // ---- entry offset and first block ordinal of every segment of the tile
     if (tid == 0) {
@@ -277,84 +349,86 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_decode(const FrameDev* __
                 state = m & 31u;
             }
         }
+        seg_base[LG_TILE_SEGS] = base;
     }
     __syncthreads();
-    // ---- one lane per segment: walk the (now known) chain and mark the block starts
+    // ---- one lane per segment: walk the (now known) chain from its entry to the merge point -- a few blocks; the whole
+    //      segment only where the candidate chains never merged -- and add those block starts to the bitmap
     if (warp == 0) {
         const uint32_t s = lane;
         const uint32_t e = seg_entry[s];
         if (e != LG_DEAD) {
             const unsigned long long seg_abs = tile_off + (unsigned long long)s * LG_SEG;
+            const uint32_t rel_len = (uint32_t)min(len - seg_abs, (unsigned long long)(1u << 30));
             const uint8_t* seg = data + s * LG_SEG;
-            uint32_t* bm = bitmap + s * (LG_SLOTS / 32);
+            uint32_t* bm = bitmap + s * LG_BM_WORDS;
+            const uint32_t stop = segx[s] == LG_NO_X ? (uint32_t)LG_SEG : (uint32_t)segx[s];
             uint32_t p = 2u * e;
-            uint32_t cur_word = p >> 6, acc = 0;
-            while (p < (uint32_t)LG_SEG) {
-                const uint32_t L = leg_len(seg[p] >> 4);
-                if (seg_abs + p + 2u + L >= len) break;
-                const uint32_t slot = p >> 1, wd = slot >> 5;
-                if (wd != cur_word) { bm[cur_word] = acc; acc = 0; cur_word = wd; }
-                acc |= 1u << (slot & 31u);
-                p += 2u + L;
+            while (p < stop) {
+                const uint32_t q = p + 2u + leg_len(seg[p] >> 4);
+                if (q >= rel_len) break;
+                bm[p >> 6] |= 1u << ((p >> 1) & 31u);
+                p = q;
             }
-            if (cur_word < (uint32_t)(LG_SLOTS / 32)) bm[cur_word] = acc;
         }
     }
     __syncthreads();
-    // ---- decode: every warp takes segments warp, warp + 8, ...; a lane decodes one block pair at a time
-    const int width = F.width;
-    uint16_t* __restrict__ dst = F.dst;
-    const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
-    uint16_t* list = lists + warp * LG_SLOTS;
+    // ---- pair list of the tile: every block with an even ordinal leads a pair (even-column block, then odd-column block,
+    //      RawData_Legacy.cpp:480-481); plist[q] = (tile-relative offset of the leader) / 2 for pair ordinal p_first + q
+    const uint32_t p_first = (tile_base + 1u) >> 1;
+    uint32_t npairs = ((seg_base[LG_TILE_SEGS] + 1u) >> 1) - p_first;
+    npairs = (uint32_t)min((unsigned long long)npairs, (need >> 1) - (unsigned long long)p_first);
     for (uint32_t s = warp; s < segs_here; s += LG_THREADS / 32) {
         if (seg_entry[s] == LG_DEAD) break;
-        const uint32_t wordv = lane < (uint32_t)(LG_SLOTS / 32) ? bitmap[s * (LG_SLOTS / 32) + lane] : 0u;
+        const uint32_t wordv = lane < (uint32_t)LG_BM_WORDS ? bitmap[s * LG_BM_WORDS + lane] : 0u;
         const uint32_t c = __popc(wordv);
         uint32_t incl = c;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        for (int d = 1; d < LG_BM_WORDS; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= (uint32_t)d) incl += o;
         }
-        const uint32_t nblk = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        {
-            uint32_t wv = wordv, k = incl - c;
-            while (wv) {
-                const uint32_t b = __ffs(wv) - 1;
-                wv &= wv - 1;
-                list[k++] = (uint16_t)(32u * lane + b);
+        uint32_t ord = seg_base[s] + incl - c;               // ordinal of the first block start in this lane's word
+        uint32_t wv = wordv;
+        while (wv) {
+            const uint32_t b = __ffs(wv) - 1;
+            wv &= wv - 1;
+            const uint32_t q = (ord >> 1) - p_first;
+            if (!(ord & 1u) && q < npairs) plist[q] = (uint16_t)(s * (LG_SEG / 2) + 32u * lane + b);
+            ord++;
+        }
+    }
+    __syncthreads();
+    // ---- decode: a lane takes one block pair at a time -> 32 consecutive pixels
+    const int width = F.width;
+    uint16_t* __restrict__ dst = F.dst;
+    const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
+    uint32_t P = p_first + (uint32_t)tid;
+    uint32_t y = P / ppr, xq = P - y * ppr;
+    for (uint32_t q = tid; q < npairs; q += LG_THREADS) {
+        const uint32_t o = 2u * (uint32_t)plist[q];
+        uint32_t vE[16], vO[16], refE, refO;
+        const uint32_t lenE = leg_block(data, o, vE, refE);
+        leg_block(data, o + lenE, vO, refO);
+        const uint32_t refs = refE | (refO << 16);
+        const int x = (int)(32u * xq);
+        uint32_t px[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = __vadd2(vE[k] | (vO[k] << 16), refs);    // :483-486, + reference mod 2^16
+        uint16_t* orow = dst + (size_t)y * (size_t)width + x;
+        if (vec && x + 32 <= width) {
+            uint4* o4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+            for (int k = 0; k < 4; k++) o4[k] = make_uint4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {                                            // crop at width (:490)
+                if (x + 2 * k < width) orow[2 * k] = (uint16_t)px[k];
+                if (x + 2 * k + 1 < width) orow[2 * k + 1] = (uint16_t)(px[k] >> 16);
             }
         }
-        __syncwarp();
-        const uint32_t base = seg_base[s];
-        const uint32_t j0 = base & 1u;                       // an odd first block belongs to the pair led from the previous segment
-        for (uint32_t j = j0 + 2u * lane; j < nblk; j += 64u) {
-            const unsigned long long P = ((unsigned long long)base + j) >> 1;      // pair ordinal in the frame
-            if (2ull * P >= need) break;
-            const uint32_t o = s * LG_SEG + 2u * (uint32_t)list[j];
-            uint32_t vE[16], vO[16], refE, refO;
-            const uint32_t lenE = leg_block(data, o, vE, refE);
-            leg_block(data, o + lenE, vO, refO);
-            const uint32_t y = (uint32_t)(P / ppr), xq = (uint32_t)(P - (unsigned long long)y * ppr);
-            const int x = (int)(32u * xq);
-            uint32_t px[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++)                                            // :483-486, u16 wrap
-                px[k] = ((vE[k] + refE) & 0xFFFFu) | ((vO[k] + refO) << 16);
-            uint16_t* orow = dst + (size_t)y * (size_t)width + x;
-            if (vec && x + 32 <= width) {
-                uint4* o4 = reinterpret_cast<uint4*>(orow);
-#pragma unroll
-                for (int k = 0; k < 4; k++) o4[k] = make_uint4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 16; k++) {                                      // crop at width (:490)
-                    if (x + 2 * k < width) orow[2 * k] = (uint16_t)px[k];
-                    if (x + 2 * k + 1 < width) orow[2 * k + 1] = (uint16_t)(px[k] >> 16);
-                }
-            }
-        }
-        __syncwarp();
+        xq += LG_THREADS;                                                             // the pair LG_THREADS further on
+        while (xq >= ppr) { xq -= ppr; y++; }
     }
 }
 
