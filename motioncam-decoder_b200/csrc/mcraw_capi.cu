@@ -198,20 +198,17 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
         } else if (d.compression_type == MCRAW_COMPRESSION_LEGACY) {
             any6 = true;
             if (d.len >= ((uint64_t)1 << 40)) return fail_arg(ctx, who() + ": legacy frame buffer too large");
-            const uint64_t nseg = (d.len + LG_SEG - 1) / LG_SEG;
-            const uint64_t ntile = std::max<uint64_t>(1, (nseg + LG_TILE_SEGS - 1) / LG_TILE_SEGS);
+            const uint64_t ntile = std::max<uint64_t>(1, (d.len + LG_TILE - 1) / LG_TILE);
             if (ntile > 0x7FFFFFFFull) return fail_arg(ctx, who() + ": legacy frame buffer too large");
-            // scratch layout (offsets for now): segment maps | tile maps | tile states
-            f.lg_segmap = reinterpret_cast<uint16_t*>(scratch);
-            scratch += ((size_t)ntile * LG_TILE_SEGS * LG_STATES * 2 + 15) & ~(size_t)15;
+            // scratch layout (offsets for now): tile maps | tile states | bitmaps | merge points
             f.lg_tilemap = reinterpret_cast<uint32_t*>(scratch);
             scratch += ((size_t)ntile * LG_STATES * 4 + 15) & ~(size_t)15;
             f.lg_tilestate = reinterpret_cast<uint32_t*>(scratch);
             scratch += ((size_t)ntile * 2 * 4 + 15) & ~(size_t)15;
             f.lg_bitmap = reinterpret_cast<uint32_t*>(scratch);
-            scratch += (size_t)ntile * LG_TILE_SEGS * LG_BM_WORDS * 4;
-            f.lg_segx = reinterpret_cast<uint16_t*>(scratch);
-            scratch += ((size_t)ntile * LG_TILE_SEGS * 2 + 15) & ~(size_t)15;
+            scratch += (size_t)ntile * LG_TILE_WORDS * 4;
+            f.lg_merge = reinterpret_cast<uint16_t*>(scratch);
+            scratch += ((size_t)ntile * LG_STATES * 2 + 15) & ~(size_t)15;
             scratch = (scratch + 127) & ~(size_t)127;
             max_ltiles = std::max<uint32_t>(max_ltiles, (uint32_t)ntile);
         }   // any other type: no work is queued, mcraw_batch_wait reports MCRAW_FRAME_BAD_TYPE
@@ -288,11 +285,10 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
                 f.pairinfo = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.pairinfo));
                 f.pairrefs = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.pairrefs));
             } else if (f.type == MCRAW_COMPRESSION_LEGACY) {
-                f.lg_segmap = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_segmap));
                 f.lg_tilemap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilemap));
                 f.lg_tilestate = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilestate));
                 f.lg_bitmap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_bitmap));
-                f.lg_segx = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_segx));
+                f.lg_merge = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_merge));
             }
             h_frames[i] = f;
         }
@@ -315,7 +311,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     }
     if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, st>>>(d_frames, d_states, d_counter); ctx->launches += 1; }
     if (any6) {
-        k_legacy_maps<<<dim3(s.max_ltiles, n), LG_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
+        k_legacy_maps<<<dim3(s.max_ltiles, n), LG_MAPS_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
         k_legacy_scan<<<n, LG_THREADS, 0, st>>>(d_frames, d_states, d_results);
         ctx->launches += 2;
     }

@@ -43,11 +43,10 @@ struct FrameDev {
     uint32_t* unitoff;             // scratch [nunits + 1]   payload offset of each unit (+ end)
     uint32_t* pairinfo;            // scratch [32 * nunits]  rel8 | bitsE << 16 | bitsO << 24
     uint32_t* pairrefs;            // scratch [32 * nunits]  refE | refO << 16
-    uint16_t* lg_segmap;           // legacy scratch [32 * tiles][17]  transfer map of every 1 KiB segment
-    uint32_t* lg_tilemap;          // legacy scratch [tiles][17]       transfer map of every 32 KiB tile
-    uint32_t* lg_tilestate;        // legacy scratch [tiles][2]        entry offset / first block ordinal of every tile
-    uint32_t* lg_bitmap;           // legacy scratch [32 * tiles][16]  block starts past the merge point of every segment
-    uint16_t* lg_segx;             // legacy scratch [32 * tiles]      merge point of every segment (0xFFFF: none)
+    uint32_t* lg_tilemap;          // legacy scratch [tiles][17]   transfer map of every 32 KiB tile: exit | blocks << 5
+    uint32_t* lg_tilestate;        // legacy scratch [tiles][2]    entry offset (| LG_SLOW) / first block ordinal of every tile
+    uint32_t* lg_bitmap;           // legacy scratch [tiles][512]  block starts of every tile (one bit per 2 bytes)
+    uint16_t* lg_merge;            // legacy scratch [tiles][17]   where the chain of entry e meets the chain of entry 0
 };
 
 // Per-frame words written by the index kernels and read by the pixel kernels.  Every word is written on every path

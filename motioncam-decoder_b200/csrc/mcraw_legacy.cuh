@@ -5,33 +5,42 @@
 // (bits nibble, 12-bit reference) followed by 2*bits payload bytes (32 for nibbles 11..15): block k+1 starts
 // where block k ends, so the reference finds the blocks with 750 000 dependent steps per 4000x3000 frame.
 //
-// Here the chain is resolved in parallel.  All block lengths are even and <= 34 bytes, so the true chain enters
-// any fixed byte SEGMENT at one of 17 even offsets (0, 2, ..., 32):
+// Here the chain is resolved in parallel.  Two facts carry it:
+//   (1) all block lengths are even and <= 34 bytes, so the chain enters any fixed byte range at one of 17 even offsets;
+//   (2) two chains that ever share a block start are identical from there on, and with blocks of varying length chains
+//       started anywhere MERGE within a few blocks.  Nothing relies on (2) for correctness -- only for speed.
 //
-//   k_legacy_maps    one CTA per TILE of 32 segments of 1 KiB.  The tile is staged in shared memory; for every
-//                    segment, 17 lanes walk the 17 candidate chains and record the TRANSFER MAP
-//                    entry offset -> (exit offset into the next segment, blocks started, chain died).
-//                    The CTA then composes its 32 segment maps into one tile map.
+//   k_legacy_maps    one CTA per TILE of 32 KiB, staged in shared memory.  One lane per 1 KiB segment walks a GUESSED
+//                    chain (from the start of its segment) and marks its block starts in a bitmap; then every lane
+//                    re-walks from where its left neighbour's chain actually ends, only until it meets its own marks
+//                    (self-synchronisation), repeated until no entry changes.  The result is the exact chain C0 of the
+//                    tile for tile entry offset 0.  For the other 16 possible entry offsets, 16 lanes walk until they
+//                    meet C0: entry e -> (merge point, blocks before it).  Output: the tile's transfer map
+//                    entry -> (exit offset, block count), C0's bitmap, the merge points.
 //   k_legacy_scan    one CTA per frame: composes the tile maps front to back from entry offset 0 (serial, but only
 //                    len / 32 KiB steps in shared memory) -> entry offset and first block ordinal of every tile;
 //                    checks that the chain holds the 2 * (paddedWidth / 32) * height blocks the frame needs
-//                    (RawData_Legacy.cpp:478-482) and writes the per-frame result.
-//   k_legacy_decode  one CTA per tile: re-stages the tile, resolves the entry of each of its segments from the
-//                    segment maps, marks the block starts of every segment in a shared-memory bitmap (one lane per
-//                    segment), then every lane decodes block PAIRS (even-column block + odd-column block,
-//                    :480-481): MSB-first bit extraction with funnel shifts (:38-370), + reference mod 2^16,
+//                    (RawData_Legacy.cpp:478-482), writes the per-frame result, and (one thread per tile) patches
+//                    each tile's bitmap for its true entry: the few blocks before the merge point.
+//   k_legacy_decode  one CTA per tile: stages the tile and its bitmap, turns the bitmap into the list of block PAIRS
+//                    (even-column block + odd-column block, :480-481) with prefix popcounts, then every lane decodes one
+//                    pair at a time: MSB-first bit extraction with funnel shifts (:38-370), + reference mod 2^16,
 //                    column interleave (:483-486) in registers, 16-byte stores, crop at width (:490).
 #pragma once
 #include "mcraw_kernels.cuh"
 
 namespace mcraw {
 
-constexpr int LG_SEG = 1024;                 // bytes per segment
-constexpr int LG_SLOTS = LG_SEG / 2;         // candidate (even) block starts per segment
+constexpr int LG_SEG = 1024;                 // bytes per segment (one lane of the index warp)
 constexpr int LG_TILE_SEGS = 32;             // segments per tile
 constexpr int LG_TILE = LG_SEG * LG_TILE_SEGS;
+constexpr int LG_TILE_SLOTS = LG_TILE / 2;   // candidate (even) block starts per tile
+constexpr int LG_TILE_WORDS = LG_TILE_SLOTS / 32;   // bitmap words per tile
+constexpr int LG_SEG_WORDS = LG_SEG / 64;    // bitmap words per segment
 constexpr int LG_STATES = 17;                // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;             // exit code of a chain that ran into the end of the buffer
+constexpr uint32_t LG_NO_MERGE = 0xFFFFu;    // merge point of an entry whose chain never meets C0 inside the tile
+constexpr uint32_t LG_SLOW = 0x100u;         // tile state flag: k_legacy_decode has to walk the tile itself
 constexpr int LG_THREADS = 256;
 constexpr int LG_OVERRUN = 80;               // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it
 
@@ -39,16 +48,24 @@ constexpr int LG_OVERRUN = 80;               // a pair led inside the tile ends 
 __device__ __forceinline__ uint32_t leg_len(uint32_t b) { return b <= 10u ? 2u * b : 32u; }
 
 // stage [tile_off, tile_off + nbytes) of the frame into shared memory, zero past len (16-byte granules)
+template <int NT>
 __device__ __forceinline__ void lg_stage(uint8_t* sm, const uint8_t* __restrict__ src, unsigned long long len,
                                          unsigned long long tile_off, int nbytes, int tid) {
     if (tile_off + (unsigned long long)nbytes <= len) {                       // the common case: wholly inside the buffer
         const uint4* g = reinterpret_cast<const uint4*>(src + tile_off);
         uint4* d = reinterpret_cast<uint4*>(sm);
-#pragma unroll 4
-        for (int v = tid; v < nbytes / 16; v += LG_THREADS) d[v] = __ldg(g + v);
+        int v = tid;
+        for (; v + 7 * NT < nbytes / 16; v += 8 * NT) {                        // eight loads in flight per thread
+            uint4 q[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = __ldg(g + v + k * NT);
+#pragma unroll
+            for (int k = 0; k < 8; k++) d[v + k * NT] = q[k];
+        }
+        for (; v < nbytes / 16; v += NT) d[v] = __ldg(g + v);
         return;
     }
-    for (int v = tid; v < nbytes / 16; v += LG_THREADS) {
+    for (int v = tid; v < nbytes / 16; v += NT) {
         const unsigned long long o = tile_off + 16ull * (unsigned)v;
         uint4 q = make_uint4(0, 0, 0, 0);
         if (o + 16 <= len) q = __ldg(reinterpret_cast<const uint4*>(src + o));
@@ -62,130 +79,138 @@ __device__ __forceinline__ void lg_stage(uint8_t* sm, const uint8_t* __restrict_
     }
 }
 
-// Walk a chain from p to its first block start at or beyond `stop`.  CHECK: the segment lies near the end of the buffer,
-// so a block may fail the reference's bound (RawData_Legacy.cpp:387,398: decoded only if offset + 2 + payload < len).
-template <bool CHECK>
-__device__ __forceinline__ void lg_walk(const uint8_t* seg, uint32_t& p, uint32_t& cnt, bool& dead, const uint32_t stop,
-                                        const uint32_t rel_len) {
-    while (p < stop) {
-        const uint32_t b = (uint32_t)seg[p] >> 4;
-        const uint32_t q = p + 2u + (b > 10u ? 32u : 2u * b);
-        if (CHECK && q >= rel_len) { dead = true; break; }
-        p = q;
-        cnt++;
-    }
+// total length of the block whose header byte is hb (RawData_Legacy.cpp:13-32,395)
+__device__ __forceinline__ uint32_t leg_step(uint32_t hb) {
+    const uint32_t b = hb >> 4;
+    return 2u + (b > 10u ? 32u : 2u * b);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_legacy_maps: grid = (max tiles, frames), block = LG_THREADS, dynamic smem = LG_MAPS_SMEM
-//
-// Phase 1 (a warp per segment, 17 lanes): the 17 candidate chains are walked only until they have MERGED -- chains
-//   that meet at one block start are the same chain from there on, and with blocks of varying length that happens
-//   within a few blocks.  Merging is tested at barrier lines 64, 128, 256, 512 bytes into the segment: every lane
-//   walks to its first block start at or beyond the line; if all 17 agree on it (X), the segment's map is
-//   "entry e -> pre[e] blocks, then the common chain from X".  Chains that have not merged by 512 (constant-width
-//   regions) are simply walked to the end of the segment: the full map, no shortcut.
-// Phase 2 (one lane per segment): the common chain from X to the end of the segment, marking every block start in a
-//   bitmap that k_legacy_decode reuses, so nothing past X is ever walked twice or 17-fold.
+// k_legacy_maps: grid = (max tiles, frames), block = LG_MAPS_THREADS, dynamic smem = LG_MAPS_SMEM
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LG_BM_WORDS = LG_SLOTS / 32;                  // bitmap words per segment
-constexpr uint32_t LG_NO_X = 0xFFFFu;                       // segment has no merge point (full map, no bitmap)
-constexpr int LG_MAPS_SMEM = LG_TILE + LG_TILE_SEGS * 18 * 2 + LG_TILE_SEGS * LG_BM_WORDS * 4 + LG_TILE_SEGS * 2;
+constexpr int LG_MAPS_THREADS = 128;
+constexpr int LG_MAPS_SMEM = LG_TILE + LG_TILE_WORDS * 4;
 
-__global__ void __launch_bounds__(LG_THREADS) k_legacy_maps(const FrameDev* __restrict__ frames) {
+// One lane, one segment: walk from byte offset p (segment-relative) to the end of the segment.  Block starts go into
+// bm[] (one word per 64 bytes).  With MERGE, the walk stops at the first position that is already marked in bm[] --
+// from there on the old marks are this chain's own -- and the old marks before that position are dropped.
+// rel: bytes from the segment start to the end of the buffer (RawData_Legacy.cpp:387,398: a block is decoded only if
+// offset + 2 + payload < len).  Returns true if the chain ended at an undecodable block.
+template <bool MERGE>
+__device__ __forceinline__ bool lg_walk_segment(const uint8_t* seg, uint32_t& p, uint32_t (&bm)[LG_SEG_WORDS], const uint32_t rel) {
+    bool merged = false, dead = false;
+#pragma unroll
+    for (int wd = 0; wd < LG_SEG_WORDS; wd++) {
+        if (merged) continue;                                  // the old marks from the merge point on are this chain's
+        const uint32_t stop = 64u * (wd + 1);
+        if (dead || p >= stop) { bm[wd] = 0; continue; }       // before the entry, or after the chain ended: no block starts
+        const uint32_t old = bm[wd];
+        uint32_t acc = 0;
+        while (p < stop) {
+            const uint32_t bit = 1u << ((p >> 1) & 31u);
+            if (MERGE && (old & bit)) { merged = true; acc |= old & ~(bit - 1u); break; }
+            const uint32_t q = p + leg_step(seg[p]);
+            if (q >= rel) { dead = true; break; }
+            acc |= bit;
+            p = q;
+        }
+        bm[wd] = acc;
+    }
+    return dead;
+}
+
+__global__ void __launch_bounds__(LG_MAPS_THREADS) k_legacy_maps(const FrameDev* __restrict__ frames) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     const FrameDev& F = frames[blockIdx.y];
     if (F.type != MCRAW_COMPRESSION_LEGACY) return;
     const unsigned long long len = F.len;
-    const uint32_t nseg = (uint32_t)((len + LG_SEG - 1) / LG_SEG);
+    const uint32_t ntile = (uint32_t)((len + LG_TILE - 1) / LG_TILE);
     const uint32_t tile = blockIdx.x;
-    if ((unsigned long long)tile * LG_TILE_SEGS >= nseg) return;
+    if (tile >= ntile) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* data = lg_smem;
-    uint16_t* maps = reinterpret_cast<uint16_t*>(lg_smem + LG_TILE);                                  // [32][18]
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_TILE + LG_TILE_SEGS * 36);            // [32][16]
-    uint16_t* segx = reinterpret_cast<uint16_t*>(lg_smem + LG_TILE + LG_TILE_SEGS * 36 + LG_TILE_SEGS * LG_BM_WORDS * 4);
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_TILE);                                // [LG_TILE_WORDS]
     const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
-    lg_stage(data, F.src, len, tile_off, LG_TILE, tid);
-    for (int i = tid; i < LG_TILE_SEGS * LG_BM_WORDS; i += LG_THREADS) bitmap[i] = 0;
+    const uint32_t tile_rel = (uint32_t)min(len - tile_off, (unsigned long long)(1u << 30));        // bytes to the end of the buffer
+    lg_stage<LG_MAPS_THREADS>(data, F.src, len, tile_off, LG_TILE, tid);
     __syncthreads();
+    if (warp != 0) return;
 
-    const uint32_t segs_here = min((uint32_t)LG_TILE_SEGS, nseg - tile * LG_TILE_SEGS);
-    // ---- phase 1
-    for (uint32_t s = warp; s < segs_here; s += LG_THREADS / 32) {
-        const unsigned long long seg_abs = tile_off + (unsigned long long)s * LG_SEG;
-        // RawData_Legacy.cpp:387,398: a block is decoded only if offset + 2 + payload < len; as a segment-relative bound
-        const uint32_t rel_len = (uint32_t)min(len - seg_abs, (unsigned long long)(1u << 30));
-        const uint8_t* seg = data + s * LG_SEG;
-        const bool active = lane < LG_STATES;
-        const bool check = rel_len < (uint32_t)(LG_SEG + 40);                     // warp-uniform: only the last segments of a frame
-        uint32_t p = active ? 2u * lane : 0xFFFF0000u, cnt = 0;                   // idle lanes never enter the walk
-        bool dead = false;
-        uint32_t x = LG_NO_X;
-        // merge test at 64, 96, ..., 256, 320, ..., 512 bytes; chains still apart at 512 are walked to the end
-        for (uint32_t line = 64;; line += (line < 256u ? 32u : 64u)) {
-            const uint32_t stop = line > 512u ? (uint32_t)LG_SEG : line;
-            if (check) { if (!dead) lg_walk<true>(seg, p, cnt, dead, stop, rel_len); }
-            else lg_walk<false>(seg, p, cnt, dead, stop, rel_len);
-            if (stop == (uint32_t)LG_SEG) break;                                  // walked to the end: full map
-            const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, p, 0);
-            const bool agree = __all_sync(0xFFFFFFFFu, !active || (!dead && p == p0));
-            if (agree && p0 < (uint32_t)LG_SEG) { x = p0; break; }
-        }
-        if (active) {
-            if (x == LG_NO_X) maps[s * 18 + lane] = (uint16_t)((dead ? LG_DEAD : (p - LG_SEG) >> 1) | (cnt << 5));
-            else maps[s * 18 + lane] = (uint16_t)cnt;                             // pre[e]; completed in phase 2
-        }
-        if (lane == 0) segx[s] = (uint16_t)x;
-    }
-    __syncthreads();
-    // ---- phase 2
-    if (warp == 0 && (uint32_t)lane < segs_here && segx[lane] != LG_NO_X) {
-        const uint32_t s = lane;
-        const unsigned long long seg_abs = tile_off + (unsigned long long)s * LG_SEG;
-        const uint32_t rel_len = (uint32_t)min(len - seg_abs, (unsigned long long)(1u << 30));
-        const uint8_t* seg = data + s * LG_SEG;
-        uint32_t* bm = bitmap + s * LG_BM_WORDS;
-        uint32_t p = segx[s], cnt = 0;
-        bool dead = false;
-        // one bitmap word covers 64 bytes of the segment: walk word by word, collecting the starts in a register
-        for (uint32_t wd = p >> 6; wd < (uint32_t)LG_BM_WORDS && !dead; wd++) {
-            uint32_t acc = 0;
-            const uint32_t stop = 64u * (wd + 1u);
-            while (p < stop) {
-                const uint32_t b = (uint32_t)seg[p] >> 4;
-                const uint32_t q = p + 2u + (b > 10u ? 32u : 2u * b);
-                if (q >= rel_len) { dead = true; break; }
-                acc |= 1u << ((p >> 1) & 31u);
-                p = q;
-                cnt++;
+    // ---- chain C0 (tile entry offset 0): lane s owns segment s
+    const uint32_t seg_rel = tile_rel > (uint32_t)lane * LG_SEG ? tile_rel - (uint32_t)lane * LG_SEG : 0u;
+    const uint8_t* seg = data + lane * LG_SEG;
+    uint32_t bm[LG_SEG_WORDS];
+#pragma unroll
+    for (int wd = 0; wd < LG_SEG_WORDS; wd++) bm[wd] = 0;
+    constexpr uint32_t NONE = 0xFFu;               // "no chain arrives here" (a predecessor's chain is dead)
+    uint32_t entry = 0, p = 0;
+    bool dead = lg_walk_segment<false>(seg, p, bm, seg_rel);
+    uint32_t exitv = dead ? NONE : p - LG_SEG;     // byte offset into the next segment
+    for (;;) {
+        uint32_t e = __shfl_up_sync(0xFFFFFFFFu, exitv, 1);
+        if (lane == 0) e = 0;
+        const bool upd = e != entry;
+        if (upd) {
+            entry = e;
+            if (e == NONE) {
+#pragma unroll
+                for (int wd = 0; wd < LG_SEG_WORDS; wd++) bm[wd] = 0;
+                exitv = NONE;
+            } else {
+                p = e;
+                // drop the old marks before the entry, then walk until the old chain is met
+                dead = lg_walk_segment<true>(seg, p, bm, seg_rel);
+                if (dead) exitv = NONE;
+                else if (p >= (uint32_t)LG_SEG) exitv = p - LG_SEG;      // walked to the end without meeting the old chain
+                // else: merged -> the old exit stands
             }
-            bm[wd] = acc;
         }
-        const uint32_t ex = dead ? LG_DEAD : (p - LG_SEG) >> 1;
-        for (int e = 0; e < LG_STATES; e++) maps[s * 18 + e] = (uint16_t)(ex | (((uint32_t)maps[s * 18 + e] + cnt) << 5));
+        if (!__any_sync(0xFFFFFFFFu, upd)) break;
     }
-    __syncthreads();
-    // ---- results of the tile: segment maps, merge points and bitmaps for k_legacy_decode; the composed tile map
-    const size_t seg0 = (size_t)tile * LG_TILE_SEGS;
-    for (uint32_t i = tid; i < segs_here * LG_STATES; i += LG_THREADS) {
-        const uint32_t s = i / LG_STATES, e = i - s * LG_STATES;
-        F.lg_segmap[seg0 * LG_STATES + i] = maps[s * 18 + e];
-    }
-    for (uint32_t i = tid; i < segs_here * LG_BM_WORDS; i += LG_THREADS) F.lg_bitmap[seg0 * LG_BM_WORDS + i] = bitmap[i];
-    if ((uint32_t)tid < segs_here) F.lg_segx[seg0 + tid] = segx[tid];
-    if (warp == 0 && lane < LG_STATES) {
-        uint32_t state = lane, total = 0;
-        for (uint32_t s = 0; s < segs_here; s++) {
-            const uint32_t m = maps[s * 18 + state];
-            total += m >> 5;
-            state = m & 31u;
-            if (state == LG_DEAD) break;
+#pragma unroll
+    for (int wd = 0; wd < LG_SEG_WORDS; wd++) bitmap[lane * LG_SEG_WORDS + wd] = bm[wd];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int wd = 0; wd < LG_SEG_WORDS; wd++) cnt += __popc(bm[wd]);
+    uint32_t total0 = cnt;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) total0 += __shfl_xor_sync(0xFFFFFFFFu, total0, d);
+    // exit of C0 from the tile: the last segment's; a dead chain anywhere, or the end of the buffer, ends it
+    uint32_t exit0 = __shfl_sync(0xFFFFFFFFu, exitv, 31);
+    const bool last_tile = tile + 1 == ntile;
+    exit0 = (exit0 == NONE || last_tile) ? LG_DEAD : exit0 >> 1;
+    __syncwarp();
+
+    // ---- the other entry offsets: walk until C0 is met
+    uint32_t* const bmw = bitmap;
+    if (lane < LG_STATES) {
+        uint32_t q = 2u * lane, pre = 0, m = LG_NO_MERGE, ex = exit0, count;
+        bool d2 = false;
+        if (lane == 0) { m = 0; count = total0; }
+        else {
+            for (;;) {
+                if (q >= (uint32_t)LG_TILE) { ex = (q - LG_TILE) >> 1; break; }                       // never met C0 in this tile
+                if ((bmw[q >> 6] >> ((q >> 1) & 31u)) & 1u) { m = q >> 1; break; }
+                const uint32_t nq = q + leg_step(data[q]);
+                if (nq >= tile_rel) { d2 = true; break; }
+                q = nq;
+                pre++;
+            }
+            if (m != LG_NO_MERGE) {
+                // blocks of C0 from the merge point on = total0 - (marks before it)
+                uint32_t before = 0;
+                for (uint32_t w = 0; w < (m >> 5); w++) before += __popc(bmw[w]);
+                before += __popc(bmw[m >> 5] & ((1u << (m & 31u)) - 1u));
+                count = pre + total0 - before;
+            } else {
+                count = pre;
+                if (d2 || last_tile) ex = LG_DEAD;
+            }
         }
-        // running off the end of the buffer without meeting an undecodable block also ends the chain
-        if (state != LG_DEAD && tile * LG_TILE_SEGS + segs_here == nseg) state = LG_DEAD;
-        F.lg_tilemap[(size_t)tile * LG_STATES + lane] = state | (total << 5);
+        F.lg_tilemap[(size_t)tile * LG_STATES + lane] = ex | (count << 5);
+        F.lg_merge[(size_t)tile * LG_STATES + lane] = (uint16_t)m;
     }
+    for (int i = lane; i < LG_TILE_WORDS; i += 32) F.lg_bitmap[(size_t)tile * LG_TILE_WORDS + i] = bitmap[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -201,8 +226,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(const FrameDev* __re
     if (F.type != MCRAW_COMPRESSION_LEGACY) return;
     const int tid = threadIdx.x;
     const unsigned long long len = F.len;
-    const uint32_t nseg = (uint32_t)((len + LG_SEG - 1) / LG_SEG);
-    const uint32_t ntile = (nseg + LG_TILE_SEGS - 1) / LG_TILE_SEGS;
+    const uint32_t ntile = (uint32_t)((len + LG_TILE - 1) / LG_TILE);
     const unsigned long long ppr = ((unsigned long long)F.width + 31ull) / 32ull;          // RawData_Legacy.cpp:34-36,449
     const unsigned long long need = 2ull * ppr * (unsigned long long)F.height;              // :478-482
     unsigned status = 0;
@@ -240,6 +264,28 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(const FrameDev* __re
         r.status = status;
         r.pad = 0;
         results[blockIdx.x] = r;
+    }
+    if (status) return;
+    // ---- one thread per tile: the bitmap holds chain C0; for a tile entered at offset e != 0 the blocks before the merge
+    //      point of e are different -- walk those few blocks and patch the words in front of the merge point
+    for (uint32_t t = tid; t < ntile; t += LG_THREADS) {
+        const uint32_t e = F.lg_tilestate[2 * (size_t)t];
+        if (e == 0 || e == LG_DEAD) continue;
+        const uint32_t m = F.lg_merge[(size_t)t * LG_STATES + e];
+        if (m == LG_NO_MERGE) { F.lg_tilestate[2 * (size_t)t] = e | LG_SLOW; continue; }
+        const uint8_t* __restrict__ tsrc = F.src + (unsigned long long)t * LG_TILE;
+        uint32_t* bmw = F.lg_bitmap + (size_t)t * LG_TILE_WORDS;
+        uint32_t p = 2u * e;                                    // byte offset inside the tile; the merge point is at byte 2 * m
+        for (uint32_t w = 0; w <= (m >> 5); w++) {
+            uint32_t acc = 0;
+            const uint32_t stop = min(64u * (w + 1u), 2u * m);
+            while (p < stop) {
+                acc |= 1u << ((p >> 1) & 31u);
+                p += leg_step(__ldg(tsrc + p));
+            }
+            if (w == (m >> 5)) acc |= bmw[w] & ~((1u << (m & 31u)) - 1u);          // C0's marks from the merge point on stay
+            bmw[w] = acc;
+        }
     }
 }
 
@@ -299,103 +345,84 @@ __device__ __forceinline__ uint32_t leg_block(const uint8_t* data, uint32_t o, u
 
 constexpr int LG_DEC_DATA = LG_TILE + LG_OVERRUN;
 constexpr int LG_MAX_PAIRS = LG_TILE / 4;             // a pair is at least two 2-byte blocks
-constexpr int LG_DEC_SMEM = LG_DEC_DATA + LG_TILE_SEGS * 18 * 2 /*maps*/ + LG_TILE_SEGS * LG_BM_WORDS * 4 /*bitmaps*/ +
-                            LG_MAX_PAIRS * 2 /*pair list*/ + (LG_TILE_SEGS + 1) * 8 /*entry, base*/ + LG_TILE_SEGS * 2 /*merge points*/;
+constexpr int LG_DEC_SMEM = LG_DEC_DATA + LG_TILE_WORDS * 4 /*bitmap*/ + LG_MAX_PAIRS * 2 /*pair list*/ + 64 /*warp sums*/;
+static_assert(LG_TILE_WORDS == 2 * LG_THREADS, "k_legacy_decode gives every thread two bitmap words");
 
 __global__ void __launch_bounds__(LG_THREADS, 4) k_legacy_decode(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     const FrameDev& F = frames[blockIdx.y];
     if (F.type != MCRAW_COMPRESSION_LEGACY || states[blockIdx.y].status[0]) return;
     const unsigned long long len = F.len;
-    const uint32_t nseg = (uint32_t)((len + LG_SEG - 1) / LG_SEG);
+    const uint32_t ntile = (uint32_t)((len + LG_TILE - 1) / LG_TILE);
     const uint32_t tile = blockIdx.x;
-    if ((unsigned long long)tile * LG_TILE_SEGS >= nseg) return;
-    const uint32_t tile_entry = F.lg_tilestate[2 * (size_t)tile];
+    if (tile >= ntile) return;
+    const uint32_t tile_state = F.lg_tilestate[2 * (size_t)tile];
     const uint32_t tile_base = F.lg_tilestate[2 * (size_t)tile + 1];
     const uint32_t ppr = ((uint32_t)F.width + 31u) / 32u;                            // pairs per row (RawData_Legacy.cpp:34-36)
     const unsigned long long need = 2ull * ppr * (unsigned long long)F.height;       // blocks of the image (:478-482), < 2^33
-    if (tile_entry == LG_DEAD || (unsigned long long)tile_base >= need) return;      // nothing of the image starts here
+    if ((tile_state & 31u) == LG_DEAD || (unsigned long long)tile_base >= need) return;      // nothing of the image starts here
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* data = lg_smem;
-    uint16_t* maps = reinterpret_cast<uint16_t*>(lg_smem + LG_DEC_DATA);                          // [32][18]
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_DEC_DATA + LG_TILE_SEGS * 36);    // [32][16]
-    uint16_t* plist = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(bitmap) + LG_TILE_SEGS * LG_BM_WORDS * 4);
-    uint32_t* seg_entry = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(plist) + LG_MAX_PAIRS * 2);   // [33]
-    uint32_t* seg_base = seg_entry + LG_TILE_SEGS + 1;                                            // [33]: [32] = end of the tile
-    uint16_t* segx = reinterpret_cast<uint16_t*>(seg_base + LG_TILE_SEGS + 1);
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_DEC_DATA);                        // [LG_TILE_WORDS]
+    uint16_t* plist = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(bitmap) + LG_TILE_WORDS * 4);
+    uint32_t* warp_sums = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(plist) + LG_MAX_PAIRS * 2);
 
     const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
-    const uint32_t segs_here = min((uint32_t)LG_TILE_SEGS, nseg - tile * LG_TILE_SEGS);
-    lg_stage(data, F.src, len, tile_off, LG_DEC_DATA, tid);
-    for (uint32_t i = tid; i < segs_here * LG_STATES; i += LG_THREADS) {
-        const uint32_t s = i / LG_STATES, e = i - s * LG_STATES;
-        maps[s * 18 + e] = F.lg_segmap[((size_t)tile * LG_TILE_SEGS + s) * LG_STATES + e];
-    }
-    // block starts past each segment's merge point come from k_legacy_maps
-    for (uint32_t i = tid; i < LG_TILE_SEGS * LG_BM_WORDS; i += LG_THREADS)
-        bitmap[i] = i < segs_here * LG_BM_WORDS ? F.lg_bitmap[(size_t)tile * LG_TILE_SEGS * LG_BM_WORDS + i] : 0u;
-    if ((uint32_t)tid < LG_TILE_SEGS) segx[tid] = (uint32_t)tid < segs_here ? F.lg_segx[(size_t)tile * LG_TILE_SEGS + tid] : (uint16_t)LG_NO_X;
-    __syncthreads();
-    // ---- entry offset and first block ordinal of every segment of the tile
-    if (tid == 0) {
-        uint32_t state = tile_entry, base = tile_base;
-        for (uint32_t s = 0; s < LG_TILE_SEGS; s++) {
-            seg_entry[s] = s < segs_here ? state : LG_DEAD;
-            seg_base[s] = base;
-            if (s < segs_here && state != LG_DEAD) {
-                const uint32_t m = maps[s * 18 + state];
-                base += m >> 5;
-                state = m & 31u;
-            }
-        }
-        seg_base[LG_TILE_SEGS] = base;
-    }
-    __syncthreads();
-    // ---- one lane per segment: walk the (now known) chain from its entry to the merge point -- a few blocks; the whole
-    //      segment only where the candidate chains never merged -- and add those block starts to the bitmap
-    if (warp == 0) {
-        const uint32_t s = lane;
-        const uint32_t e = seg_entry[s];
-        if (e != LG_DEAD) {
-            const unsigned long long seg_abs = tile_off + (unsigned long long)s * LG_SEG;
-            const uint32_t rel_len = (uint32_t)min(len - seg_abs, (unsigned long long)(1u << 30));
-            const uint8_t* seg = data + s * LG_SEG;
-            uint32_t* bm = bitmap + s * LG_BM_WORDS;
-            const uint32_t stop = segx[s] == LG_NO_X ? (uint32_t)LG_SEG : (uint32_t)segx[s];
-            uint32_t p = 2u * e;
-            while (p < stop) {
-                const uint32_t q = p + 2u + leg_len(seg[p] >> 4);
-                if (q >= rel_len) break;
-                bm[p >> 6] |= 1u << ((p >> 1) & 31u);
+    lg_stage<LG_THREADS>(data, F.src, len, tile_off, LG_DEC_DATA, tid);
+    if (tile_state & LG_SLOW) {
+        // the chain entering this tile never meets C0 inside it (blocks of one constant width): walk it here
+        for (int i = tid; i < LG_TILE_WORDS; i += LG_THREADS) bitmap[i] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t tile_rel = (uint32_t)min(len - tile_off, (unsigned long long)(1u << 30));
+            uint32_t p = 2u * (tile_state & 31u);
+            while (p < (uint32_t)LG_TILE) {
+                const uint32_t q = p + leg_step(data[p]);
+                if (q >= tile_rel) break;
+                bitmap[p >> 6] |= 1u << ((p >> 1) & 31u);
                 p = q;
             }
         }
+    } else {
+        for (int i = tid; i < LG_TILE_WORDS; i += LG_THREADS) bitmap[i] = F.lg_bitmap[(size_t)tile * LG_TILE_WORDS + i];
     }
     __syncthreads();
     // ---- pair list of the tile: every block with an even ordinal leads a pair (even-column block, then odd-column block,
-    //      RawData_Legacy.cpp:480-481); plist[q] = (tile-relative offset of the leader) / 2 for pair ordinal p_first + q
-    const uint32_t p_first = (tile_base + 1u) >> 1;
-    uint32_t npairs = ((seg_base[LG_TILE_SEGS] + 1u) >> 1) - p_first;
-    npairs = (uint32_t)min((unsigned long long)npairs, (need >> 1) - (unsigned long long)p_first);
-    for (uint32_t s = warp; s < segs_here; s += LG_THREADS / 32) {
-        if (seg_entry[s] == LG_DEAD) break;
-        const uint32_t wordv = lane < (uint32_t)LG_BM_WORDS ? bitmap[s * LG_BM_WORDS + lane] : 0u;
-        const uint32_t c = __popc(wordv);
-        uint32_t incl = c;
+    //      RawData_Legacy.cpp:480-481); plist[q] = (tile-relative offset of the leader) / 2 for pair ordinal p_first + q.
+    //      Ordinals come from prefix popcounts of the bitmap: thread t owns words 2t and 2t+1.
+    const uint32_t w0 = bitmap[2 * tid], w1 = bitmap[2 * tid + 1];
+    const uint32_t c = __popc(w0) + __popc(w1);
+    uint32_t incl = c;
 #pragma unroll
-        for (int d = 1; d < LG_BM_WORDS; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (uint32_t)d) incl += o;
-        }
-        uint32_t ord = seg_base[s] + incl - c;               // ordinal of the first block start in this lane's word
-        uint32_t wv = wordv;
-        while (wv) {
-            const uint32_t b = __ffs(wv) - 1;
-            wv &= wv - 1;
-            const uint32_t q = (ord >> 1) - p_first;
-            if (!(ord & 1u) && q < npairs) plist[q] = (uint16_t)(s * (LG_SEG / 2) + 32u * lane + b);
-            ord++;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < LG_THREADS / 32; w++) {
+        const uint32_t v = warp_sums[w];
+        if (w < warp) before += v;
+        total += v;
+    }
+    const uint32_t p_first = (tile_base + 1u) >> 1;
+    uint32_t npairs = ((tile_base + total + 1u) >> 1) - p_first;
+    npairs = (uint32_t)min((unsigned long long)npairs, (need >> 1) - (unsigned long long)p_first);
+    {
+        uint32_t ord = tile_base + before + incl - c;        // ordinal of the first block start in this thread's words
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t wv = h ? w1 : w0;
+            while (wv) {
+                const uint32_t b = __ffs(wv) - 1;
+                wv &= wv - 1;
+                const uint32_t q = (ord >> 1) - p_first;
+                if (!(ord & 1u) && q < npairs) plist[q] = (uint16_t)(32u * (2u * tid + h) + b);
+                ord++;
+            }
         }
     }
     __syncthreads();
