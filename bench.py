@@ -229,9 +229,15 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # Libraries (NCCL prints its version) write to the C-level stdout; the driver wants exactly ONE JSON line there.
+    # Everything else goes to stderr: fd 1 is pointed at fd 2 and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
-    from motioncam_decoder_b200 import capi
+    from motioncam_decoder_b200 import capi, numa
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -239,6 +245,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the decode path is CUDA only (no CPU fallback)")
     torch.cuda.set_device(local)
+    props = torch.cuda.get_device_properties(local)
+    try:
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        placement = numa.bind_to_gpu_node(bdf)
+    except AttributeError:
+        placement = "numa: torch does not expose the PCI address, not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -319,14 +331,18 @@ def main():
     step_gbs = (comp_bytes + out_bytes) * args.steps / (ms * 1e-3) / 1e9
 
     # ---- end to end: pinned host inputs -> H2D on side streams -> decode -> results to host, every step
-    pinned = []
+    # one pinned ring holding the clip back to back (256-byte aligned frames), as a container reader would fill it
+    offs, total = [], 0
+    for i in range(frames):
+        offs.append(total)
+        total += (len(streams[i % len(streams)]) + 255) & ~255
+    ring_ptr, ring = ctx.pinned_array(total + 256)
+    pinned = [ring_ptr]
     hitems = []
     for i in range(frames):
         s = streams[i % len(streams)]
-        ptr, arr = ctx.pinned_array(len(s) + 16)
-        arr[:len(s)] = s
-        pinned.append(ptr)
-        hitems.append((ptr, len(s), w, h, ct, dst_ptrs[i], w * h))
+        ring[offs[i]:offs[i] + len(s)] = s
+        hitems.append((ring_ptr + offs[i], len(s), w, h, ct, dst_ptrs[i], w * h))
     hdescs, hn = capi.Context.make_descs(hitems)
     ctx.decode_batch_host(hdescs, hn, sh)
     written, status = ctx.batch_wait(hn)
@@ -382,14 +398,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": comp_bytes, "d2h_bytes_per_step": 16 * frames,
                     "steps": e2e_steps, "ms_per_step": float(ems.item()) / e2e_steps,
                     "h2d_gbs": comp_bytes * e2e_steps / (float(ems.item()) * 1e-3) / 1e9,
-                    "path": "mcraw_decode_batch_host: pinned host -> staged H2D on side streams -> decode -> device u16, "
-                            "per-frame results D2H"},
+                    "path": "mcraw_decode_batch_host: pinned host ring -> staged H2D on side streams -> decode -> device u16, "
+                            "per-frame results D2H", "placement": placement},
             "gpu_launches": launches,
             "clocks": clocks,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     for p in src_ptrs + dst_ptrs:
         ctx.device_free(p)
