@@ -105,8 +105,11 @@ int mcraw_stream_sync(mcraw_ctx* ctx, void* stream);
 uint64_t mcraw_kernel_launches(const mcraw_ctx* ctx);
 /* CUDA-event time of the decode kernels of the last waited batch, in milliseconds (0 if unavailable). */
 float mcraw_last_batch_kernel_ms(const mcraw_ctx* ctx);
-/* Sum of CUDA-event times (ms) of the metadata kernels and of the main decode kernels over every chunk this
- * context has completed, and the number of chunks.  Waits for in-flight work.  bench.py reads deltas. */
+/* Kernel timing is off by default (the event records cost ~8 us per batch on the stream).  every_n_chunks = n > 0 brackets
+ * the index kernels and the pixel kernels of every n-th chunk with CUDA events; 0 switches it off again. */
+int mcraw_set_kernel_timing(mcraw_ctx* ctx, uint32_t every_n_chunks);
+/* Sum of CUDA-event times (ms) of the index kernels and of the pixel kernels over the TIMED chunks this context has
+ * completed, and their number.  Waits for in-flight work.  bench.py reads deltas. */
 int mcraw_kernel_time_totals(mcraw_ctx* ctx, double* meta_ms, double* main_ms, uint64_t* chunks);
 const char* mcraw_version(void);
 

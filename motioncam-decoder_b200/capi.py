@@ -39,7 +39,7 @@ EXPORTED = [
     "mcraw_decode_batch", "mcraw_decode_batch_host", "mcraw_batch_wait", "mcraw_decode_host",
     "mcraw_device_alloc", "mcraw_device_free", "mcraw_host_alloc_pinned", "mcraw_host_free_pinned",
     "mcraw_memcpy_h2d", "mcraw_memcpy_d2h", "mcraw_stream_sync", "mcraw_kernel_launches",
-    "mcraw_last_batch_kernel_ms", "mcraw_kernel_time_totals",
+    "mcraw_last_batch_kernel_ms", "mcraw_kernel_time_totals", "mcraw_set_kernel_timing",
 ]
 
 _c = None
@@ -75,6 +75,7 @@ def lib():
         c.mcraw_last_batch_kernel_ms.restype = ctypes.c_float
         c.mcraw_kernel_time_totals.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(u64)]
+        c.mcraw_set_kernel_timing.argtypes = [vp, u32]
         _c = c
     return _c
 
@@ -191,6 +192,10 @@ class Context:
         self._check(self._c.mcraw_kernel_time_totals(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)),
                     "mcraw_kernel_time_totals")
         return a.value, b.value, n.value
+
+    def set_kernel_timing(self, every_n_chunks):
+        """Bracket the kernels of every n-th chunk with CUDA events (0 = off, the default)."""
+        self._check(self._c.mcraw_set_kernel_timing(self._h, every_n_chunks), "mcraw_set_kernel_timing")
 
     @property
     def last_batch_kernel_ms(self):

@@ -29,9 +29,9 @@ struct Slot {
     uint8_t* h_up = nullptr;        // pinned
     uint8_t* d_up = nullptr;
     size_t up_bytes = 0;
-    // device-written words: [queue counter (16 B) | FrameState x n | Result x n]; nothing here needs zeroing by the host
+    // device-written words: [queue counter (16 B) | FrameState x n]; nothing here needs zeroing by the host
     uint8_t* d_dyn = nullptr;
-    Result* h_results = nullptr;    // pinned
+    Result* h_results = nullptr;    // pinned; written by the kernels directly (zero-copy), read by harvest()
     uint32_t cap_frames = 0;
     uint8_t* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -68,6 +68,8 @@ struct mcraw_ctx {
     uint64_t launches = 0;
     std::vector<FrameDev> tmp_frames;
     std::vector<WorkItem> tmp_items;
+    uint32_t timing_every = 0;      // record kernel-timing events on every n-th chunk (0 = never)
+    uint64_t chunk_seq = 0;
     uint32_t resident_ctas = 0;     // CTAs of k_units the device holds at once
     uint64_t batch_id = 0;
     uint32_t batch_n = 0;
@@ -113,7 +115,7 @@ int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t up_bytes, size_t sc
         if (s.d_dyn) cudaFree(s.d_dyn);
         s.h_results = nullptr; s.d_dyn = nullptr; s.cap_frames = 0;
         CU_TRY(ctx, cudaMallocHost(&s.h_results, sizeof(Result) * cap));
-        CU_TRY(ctx, cudaMalloc(&s.d_dyn, 16 + (sizeof(FrameState) + sizeof(Result)) * cap));
+        CU_TRY(ctx, cudaMalloc(&s.d_dyn, 16 + sizeof(FrameState) * cap));
         s.cap_frames = cap;
     }
     if (up_bytes > s.up_bytes) {
@@ -297,14 +299,15 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     }
     uint32_t* d_counter = reinterpret_cast<uint32_t*>(s.d_dyn);
     FrameState* d_states = reinterpret_cast<FrameState*>(s.d_dyn + 16);
-    Result* d_results = reinterpret_cast<Result*>(s.d_dyn + 16 + sizeof(FrameState) * n);
+    Result* d_results = s.h_results;   // pinned host memory: the kernels write the 16-byte per-frame results straight to the host
     const FrameDev* d_frames = reinterpret_cast<const FrameDev*>(s.d_up);
     const WorkItem* d_items = reinterpret_cast<const WorkItem*>(s.d_up + s.items_off);
     const bool any7 = s.any7, any6 = s.any6;
     s.n = n; s.result_offset = result_offset; s.batch_id = ctx->batch_id;
 
     // descriptor + work list upload and the index kernels between e0 and e1, the pixel kernels between e1 and e2
-    CU_TRY(ctx, cudaEventRecord(s.e0, st));
+    const bool timed = ctx->timing_every && (ctx->chunk_seq++ % ctx->timing_every) == 0;
+    if (timed) CU_TRY(ctx, cudaEventRecord(s.e0, st));
     if (!hit) {
         CU_TRY(ctx, cudaMemcpyAsync(s.d_up, s.h_up, s.plan_bytes, cudaMemcpyHostToDevice, st));
         s.plan_valid = true;
@@ -315,7 +318,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         k_legacy_scan<<<n, LG_THREADS, 0, st>>>(d_frames, d_states, d_results);
         ctx->launches += 2;
     }
-    CU_TRY(ctx, cudaEventRecord(s.e1, st));
+    if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
     if (any7) {
         const uint32_t want = (s.nitems + KU_WARPS - 1) / KU_WARPS;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(ctx->resident_ctas, 1), want));
@@ -323,10 +326,9 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         ctx->launches += 1;
     }
     if (any6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
-    CU_TRY(ctx, cudaEventRecord(s.e2, st));
-    s.timed = any7 || any6;
+    if (timed) CU_TRY(ctx, cudaEventRecord(s.e2, st));
+    s.timed = timed && (any7 || any6);
     CU_TRY(ctx, cudaGetLastError());
-    CU_TRY(ctx, cudaMemcpyAsync(s.h_results, d_results, sizeof(Result) * n, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaEventRecord(s.done, st));
     s.in_flight = true;
     return MCRAW_OK;
@@ -449,6 +451,12 @@ const char* mcraw_last_error(const mcraw_ctx* ctx) { return ctx ? ctx->err.c_str
 int mcraw_ctx_device(const mcraw_ctx* ctx) { return ctx ? ctx->device : -1; }
 uint64_t mcraw_kernel_launches(const mcraw_ctx* ctx) { return ctx ? ctx->launches : 0; }
 float mcraw_last_batch_kernel_ms(const mcraw_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
+
+int mcraw_set_kernel_timing(mcraw_ctx* ctx, uint32_t every_n_chunks) {
+    if (!ctx) return MCRAW_ERR_ARG;
+    ctx->timing_every = every_n_chunks;
+    return MCRAW_OK;
+}
 
 int mcraw_kernel_time_totals(mcraw_ctx* ctx, double* meta_ms, double* main_ms, uint64_t* chunks) {
     if (!ctx) return MCRAW_ERR_ARG;
