@@ -316,7 +316,8 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (any6) {
         k_legacy_maps<<<dim3(s.max_ltiles, n), LG_MAPS_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
         k_legacy_scan<<<n, LG_THREADS, 0, st>>>(d_frames, d_states, d_results);
-        ctx->launches += 2;
+        k_legacy_fix<<<dim3((s.max_ltiles + LG_THREADS - 1) / LG_THREADS, n), LG_THREADS, 0, st>>>(d_frames, d_states);
+        ctx->launches += 3;
     }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
     if (any7) {

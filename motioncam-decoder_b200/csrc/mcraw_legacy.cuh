@@ -31,7 +31,7 @@
 
 namespace mcraw {
 
-constexpr int LG_SEG = 1024;                 // bytes per segment (one lane of the index warp)
+constexpr int LG_SEG = 512;                  // bytes per segment (one lane of the index warp)
 constexpr int LG_TILE_SEGS = 32;             // segments per tile
 constexpr int LG_TILE = LG_SEG * LG_TILE_SEGS;
 constexpr int LG_TILE_SLOTS = LG_TILE / 2;   // candidate (even) block starts per tile
@@ -41,7 +41,7 @@ constexpr int LG_STATES = 17;                // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;             // exit code of a chain that ran into the end of the buffer
 constexpr uint32_t LG_NO_MERGE = 0xFFFFu;    // merge point of an entry whose chain never meets C0 inside the tile
 constexpr uint32_t LG_SLOW = 0x100u;         // tile state flag: k_legacy_decode has to walk the tile itself
-constexpr int LG_THREADS = 256;
+constexpr int LG_THREADS = 128;
 constexpr int LG_OVERRUN = 80;               // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it
 
 // payload bytes of a 16-sample block for header nibble b (RawData_Legacy.cpp:13-32, min(16, bits) at :395)
@@ -89,7 +89,10 @@ __device__ __forceinline__ uint32_t leg_step(uint32_t hb) {
 // k_legacy_maps: grid = (max tiles, frames), block = LG_MAPS_THREADS, dynamic smem = LG_MAPS_SMEM
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LG_MAPS_THREADS = 128;
-constexpr int LG_MAPS_SMEM = LG_TILE + LG_TILE_WORDS * 4;
+constexpr int LG_SEG_PITCH = LG_SEG + 16;      // segments are 16 bytes apart in shared memory: lane s walks segment s, and at a
+                                               // pitch of LG_SEG all 32 lanes would hit the same bank on every hop
+constexpr int LG_MAPS_DATA = LG_TILE_SEGS * LG_SEG_PITCH;
+constexpr int LG_MAPS_SMEM = LG_MAPS_DATA + LG_TILE_WORDS * 4;
 
 // One lane, one segment: walk from byte offset p (segment-relative) to the end of the segment.  Block starts go into
 // bm[] (one word per 64 bytes).  With MERGE, the walk stops at the first position that is already marked in bm[] --
@@ -129,16 +132,36 @@ __global__ void __launch_bounds__(LG_MAPS_THREADS) k_legacy_maps(const FrameDev*
     if (tile >= ntile) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* data = lg_smem;
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_TILE);                                // [LG_TILE_WORDS]
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_MAPS_DATA);                           // [LG_TILE_WORDS]
     const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
     const uint32_t tile_rel = (uint32_t)min(len - tile_off, (unsigned long long)(1u << 30));        // bytes to the end of the buffer
-    lg_stage<LG_MAPS_THREADS>(data, F.src, len, tile_off, LG_TILE, tid);
+    // stage the tile, segment s at s * LG_SEG_PITCH (zero past the end of the buffer)
+    if (tile_off + LG_TILE <= len) {
+        const uint4* g = reinterpret_cast<const uint4*>(F.src + tile_off);
+        constexpr int PER = LG_TILE / 16 / LG_MAPS_THREADS;
+        uint4 q[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) q[k] = __ldg(g + tid + k * LG_MAPS_THREADS);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int v = tid + k * LG_MAPS_THREADS;
+            *reinterpret_cast<uint4*>(data + 16 * v + 16 * (v / (LG_SEG / 16))) = q[k];
+        }
+    } else {
+        for (int v = tid; v < LG_TILE / 16; v += LG_MAPS_THREADS) {
+            const unsigned long long o = tile_off + 16ull * (unsigned)v;
+            uint32_t t4[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 16; k++)
+                if (o + k < len) t4[k >> 2] |= (uint32_t)F.src[o + k] << (8 * (k & 3));
+            *reinterpret_cast<uint4*>(data + 16 * v + 16 * (v / (LG_SEG / 16))) = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+        }
+    }
     __syncthreads();
     if (warp != 0) return;
 
     // ---- chain C0 (tile entry offset 0): lane s owns segment s
     const uint32_t seg_rel = tile_rel > (uint32_t)lane * LG_SEG ? tile_rel - (uint32_t)lane * LG_SEG : 0u;
-    const uint8_t* seg = data + lane * LG_SEG;
+    const uint8_t* seg = data + lane * LG_SEG_PITCH;
     uint32_t bm[LG_SEG_WORDS];
 #pragma unroll
     for (int wd = 0; wd < LG_SEG_WORDS; wd++) bm[wd] = 0;
@@ -191,7 +214,7 @@ __global__ void __launch_bounds__(LG_MAPS_THREADS) k_legacy_maps(const FrameDev*
             for (;;) {
                 if (q >= (uint32_t)LG_TILE) { ex = (q - LG_TILE) >> 1; break; }                       // never met C0 in this tile
                 if ((bmw[q >> 6] >> ((q >> 1) & 31u)) & 1u) { m = q >> 1; break; }
-                const uint32_t nq = q + leg_step(data[q]);
+                const uint32_t nq = q + leg_step(data[q + 16u * (q / (uint32_t)LG_SEG)]);
                 if (nq >= tile_rel) { d2 = true; break; }
                 q = nq;
                 pre++;
@@ -242,16 +265,16 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(const FrameDev* __re
             if (tid == 0) {
                 uint32_t state = sh_state, base = sh_base;
                 for (uint32_t t = 0; t < nt; t++) {
-                    F.lg_tilestate[2 * (size_t)(t0 + t)] = state;
-                    F.lg_tilestate[2 * (size_t)(t0 + t) + 1] = base;
-                    if (state != LG_DEAD) {
-                        const uint32_t m = tm[t * LG_STATES + state];
-                        base += m >> 5;
-                        state = m & 31u;
-                    }
+                    uint32_t m = 0;
+                    if (state != LG_DEAD) m = tm[t * LG_STATES + state];
+                    tm[t * LG_STATES] = state;               // entries of this tile are no longer needed: reuse two of them
+                    tm[t * LG_STATES + 1] = base;
+                    if (state != LG_DEAD) { base += m >> 5; state = m & 31u; }
                 }
                 sh_state = state; sh_base = base;
             }
+            __syncthreads();
+            for (uint32_t i = tid; i < 2 * nt; i += LG_THREADS) F.lg_tilestate[2 * (size_t)t0 + i] = tm[(i >> 1) * LG_STATES + (i & 1u)];
             __syncthreads();
         }
         if ((unsigned long long)sh_base < need) status = MCRAW_FRAME_TRUNCATED;   // reference: stale samples (:387,398)
@@ -265,27 +288,35 @@ __global__ void __launch_bounds__(LG_THREADS) k_legacy_scan(const FrameDev* __re
         r.pad = 0;
         results[blockIdx.x] = r;
     }
-    if (status) return;
-    // ---- one thread per tile: the bitmap holds chain C0; for a tile entered at offset e != 0 the blocks before the merge
-    //      point of e are different -- walk those few blocks and patch the words in front of the merge point
-    for (uint32_t t = tid; t < ntile; t += LG_THREADS) {
-        const uint32_t e = F.lg_tilestate[2 * (size_t)t];
-        if (e == 0 || e == LG_DEAD) continue;
-        const uint32_t m = F.lg_merge[(size_t)t * LG_STATES + e];
-        if (m == LG_NO_MERGE) { F.lg_tilestate[2 * (size_t)t] = e | LG_SLOW; continue; }
-        const uint8_t* __restrict__ tsrc = F.src + (unsigned long long)t * LG_TILE;
-        uint32_t* bmw = F.lg_bitmap + (size_t)t * LG_TILE_WORDS;
-        uint32_t p = 2u * e;                                    // byte offset inside the tile; the merge point is at byte 2 * m
-        for (uint32_t w = 0; w <= (m >> 5); w++) {
-            uint32_t acc = 0;
-            const uint32_t stop = min(64u * (w + 1u), 2u * m);
-            while (p < stop) {
-                acc |= 1u << ((p >> 1) & 31u);
-                p += leg_step(__ldg(tsrc + p));
-            }
-            if (w == (m >> 5)) acc |= bmw[w] & ~((1u << (m & 31u)) - 1u);          // C0's marks from the merge point on stay
-            bmw[w] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_legacy_fix: grid = (ceil(max tiles / LG_THREADS), frames), one THREAD per tile.  The bitmap holds chain C0; for a tile
+// entered at offset e != 0 the blocks before the merge point of e are different: walk those few blocks (headers straight
+// from global memory) and patch the words in front of the merge point.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LG_THREADS) k_legacy_fix(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
+    const FrameDev& F = frames[blockIdx.y];
+    if (F.type != MCRAW_COMPRESSION_LEGACY || states[blockIdx.y].status[0]) return;
+    const uint32_t ntile = (uint32_t)((F.len + LG_TILE - 1) / LG_TILE);
+    const uint32_t t = blockIdx.x * LG_THREADS + threadIdx.x;
+    if (t >= ntile) return;
+    const uint32_t e = F.lg_tilestate[2 * (size_t)t];
+    if (e == 0 || e == LG_DEAD) return;
+    const uint32_t m = F.lg_merge[(size_t)t * LG_STATES + e];
+    if (m == LG_NO_MERGE) { F.lg_tilestate[2 * (size_t)t] = e | LG_SLOW; return; }
+    const uint8_t* __restrict__ tsrc = F.src + (unsigned long long)t * LG_TILE;
+    uint32_t* bmw = F.lg_bitmap + (size_t)t * LG_TILE_WORDS;
+    uint32_t p = 2u * e;                                    // byte offset inside the tile; the merge point is at byte 2 * m
+    for (uint32_t w = 0; w <= (m >> 5); w++) {
+        uint32_t acc = 0;
+        const uint32_t stop = min(64u * (w + 1u), 2u * m);
+        while (p < stop) {
+            acc |= 1u << ((p >> 1) & 31u);
+            p += leg_step(__ldg(tsrc + p));
         }
+        if (w == (m >> 5)) acc |= bmw[w] & ~((1u << (m & 31u)) - 1u);          // C0's marks from the merge point on stay
+        bmw[w] = acc;
     }
 }
 
@@ -348,7 +379,7 @@ constexpr int LG_MAX_PAIRS = LG_TILE / 4;             // a pair is at least two 
 constexpr int LG_DEC_SMEM = LG_DEC_DATA + LG_TILE_WORDS * 4 /*bitmap*/ + LG_MAX_PAIRS * 2 /*pair list*/ + 64 /*warp sums*/;
 static_assert(LG_TILE_WORDS == 2 * LG_THREADS, "k_legacy_decode gives every thread two bitmap words");
 
-__global__ void __launch_bounds__(LG_THREADS, 4) k_legacy_decode(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
+__global__ void __launch_bounds__(LG_THREADS, 8) k_legacy_decode(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     const FrameDev& F = frames[blockIdx.y];
     if (F.type != MCRAW_COMPRESSION_LEGACY || states[blockIdx.y].status[0]) return;
