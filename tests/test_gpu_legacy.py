@@ -76,3 +76,34 @@ def test_legacy_rejects_truncated(ctx):
     assert written[-1] == 640 * 16 and status[-1] == 0
     assert np.array_equal(batch.fetch(len(cases)), img)
     batch.free()
+
+
+def test_legacy_full_size_properties(ctx):
+    """C4 geometry, flat+noise variant (2-byte blocks next to constant 22-byte blocks: chains that merge at once next
+    to chains that never do), several copies in one batch: every copy equals the source image."""
+    from motioncam_decoder_b200 import capi, testvec as tv
+    img = tv.gen_flatnoise(4000, 3000, 256, seed=9)
+    s = tv.encode_legacy(img)
+    frames = [(s, 4000, 3000, capi.COMPRESSION_LEGACY)] * 3
+    batch = capi.DeviceBatch(ctx, frames)
+    batch.fill_outputs(0x5A5A)
+    written, status = batch.decode()
+    assert not any(status) and all(w == 4000 * 3000 for w in written)
+    want = tv.fnv1a64(img)
+    assert [tv.fnv1a64(batch.fetch(i)) for i in range(3)] == [want] * 3
+    batch.free()
+
+
+def test_legacy_whole_frame_one_width(ctx):
+    """Worst case of the index: every block of the frame has the same non-zero width, so chains entered at different
+    offsets never meet (the tile maps fall back to walking, k_legacy_decode to its slow path)."""
+    from motioncam_decoder_b200 import capi, testvec as tv
+    for hb in (4, 10):
+        img = tv.gen_uniform(1024, 96, 0, (1 << hb) - 1, seed=77 + hb)
+        s = tv.encode_legacy(img, policy=tv.POLICY_FORCE, policy_arg=hb, seed=hb)
+        n_or, want = ol.oracle_decode_legacy(s, 1024, 96)
+        batch = capi.DeviceBatch(ctx, [(s, 1024, 96, capi.COMPRESSION_LEGACY)])
+        written, status = batch.decode()
+        assert status[0] == 0 and written[0] == n_or == 1024 * 96
+        assert np.array_equal(batch.fetch(0), want) and np.array_equal(want, img)
+        batch.free()
