@@ -89,18 +89,37 @@ __device__ __forceinline__ uint32_t leg_step(uint32_t hb) {
 // k_legacy_maps: grid = (max tiles, frames), block = LG_MAPS_THREADS, dynamic smem = LG_MAPS_SMEM
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LG_MAPS_THREADS = 128;
-constexpr int LG_SEG_PITCH = LG_SEG + 16;      // segments are 16 bytes apart in shared memory: lane s walks segment s, and at a
-                                               // pitch of LG_SEG all 32 lanes would hit the same bank on every hop
-constexpr int LG_MAPS_DATA = LG_TILE_SEGS * LG_SEG_PITCH;
+// The walks never look at payload bytes, only at "how far is the next block if a block started here": the tile is turned
+// into a table of half step lengths (1..17), one byte per even offset, while it passes through registers on its way in.
+constexpr int LG_NX_SEG = LG_SEG / 2;          // table bytes per segment
+constexpr int LG_NX_PITCH = LG_NX_SEG + 8;     // segments 8 bytes apart: lane s walks segment s, and at a pitch of LG_NX_SEG all
+                                               // 32 lanes would hit the same bank on every hop
+constexpr int LG_MAPS_DATA = LG_TILE_SEGS * LG_NX_PITCH;
 constexpr int LG_MAPS_SMEM = LG_MAPS_DATA + LG_TILE_WORDS * 4;
 
-// One lane, one segment: walk from byte offset p (segment-relative) to the end of the segment.  Block starts go into
+// half step lengths of the eight even offsets of 16 stream bytes (RawData_Legacy.cpp:13-32,395), packed low byte first
+__device__ __forceinline__ uint2 lg_half_steps(const uint4 q) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t nib = (w[i] >> (16 * h + 4)) & 15u;
+            const uint32_t half = 1u + (nib > 10u ? 16u : nib);
+            o[i >> 1] |= half << (8 * (2 * (i & 1) + h));
+        }
+    }
+    return make_uint2(o[0], o[1]);
+}
+
+// One lane, one segment (nx: its table of half step lengths): walk from byte offset p (segment-relative) to the end of the segment.  Block starts go into
 // bm[] (one word per 64 bytes).  With MERGE, the walk stops at the first position that is already marked in bm[] --
 // from there on the old marks are this chain's own -- and the old marks before that position are dropped.
 // rel: bytes from the segment start to the end of the buffer (RawData_Legacy.cpp:387,398: a block is decoded only if
 // offset + 2 + payload < len).  Returns true if the chain ended at an undecodable block.
 template <bool MERGE>
-__device__ __forceinline__ bool lg_walk_segment(const uint8_t* seg, uint32_t& p, uint32_t (&bm)[LG_SEG_WORDS], const uint32_t rel) {
+__device__ __forceinline__ bool lg_walk_segment(const uint8_t* nx, uint32_t& p, uint32_t (&bm)[LG_SEG_WORDS], const uint32_t rel) {
     bool merged = false, dead = false;
 #pragma unroll
     for (int wd = 0; wd < LG_SEG_WORDS; wd++) {
@@ -112,7 +131,7 @@ __device__ __forceinline__ bool lg_walk_segment(const uint8_t* seg, uint32_t& p,
         while (p < stop) {
             const uint32_t bit = 1u << ((p >> 1) & 31u);
             if (MERGE && (old & bit)) { merged = true; acc |= old & ~(bit - 1u); break; }
-            const uint32_t q = p + leg_step(seg[p]);
+            const uint32_t q = p + 2u * nx[p >> 1];
             if (q >= rel) { dead = true; break; }
             acc |= bit;
             p = q;
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(LG_MAPS_THREADS) k_legacy_maps(const FrameDev*
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_MAPS_DATA);                           // [LG_TILE_WORDS]
     const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
     const uint32_t tile_rel = (uint32_t)min(len - tile_off, (unsigned long long)(1u << 30));        // bytes to the end of the buffer
-    // stage the tile, segment s at s * LG_SEG_PITCH (zero past the end of the buffer)
+    // the tile passes through registers: only its step table lands in shared memory (segment s at s * LG_NX_PITCH)
     if (tile_off + LG_TILE <= len) {
         const uint4* g = reinterpret_cast<const uint4*>(F.src + tile_off);
         constexpr int PER = LG_TILE / 16 / LG_MAPS_THREADS;
@@ -145,7 +164,7 @@ __global__ void __launch_bounds__(LG_MAPS_THREADS) k_legacy_maps(const FrameDev*
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             const int v = tid + k * LG_MAPS_THREADS;
-            *reinterpret_cast<uint4*>(data + 16 * v + 16 * (v / (LG_SEG / 16))) = q[k];
+            *reinterpret_cast<uint2*>(data + 8 * v + 8 * (v / (LG_SEG / 16))) = lg_half_steps(q[k]);
         }
     } else {
         for (int v = tid; v < LG_TILE / 16; v += LG_MAPS_THREADS) {
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(LG_MAPS_THREADS) k_legacy_maps(const FrameDev*
             uint32_t t4[4] = {0, 0, 0, 0};
             for (int k = 0; k < 16; k++)
                 if (o + k < len) t4[k >> 2] |= (uint32_t)F.src[o + k] << (8 * (k & 3));
-            *reinterpret_cast<uint4*>(data + 16 * v + 16 * (v / (LG_SEG / 16))) = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+            *reinterpret_cast<uint2*>(data + 8 * v + 8 * (v / (LG_SEG / 16))) = lg_half_steps(make_uint4(t4[0], t4[1], t4[2], t4[3]));
         }
     }
     __syncthreads();
@@ -161,7 +180,7 @@ __global__ void __launch_bounds__(LG_MAPS_THREADS) k_legacy_maps(const FrameDev*
 
     // ---- chain C0 (tile entry offset 0): lane s owns segment s
     const uint32_t seg_rel = tile_rel > (uint32_t)lane * LG_SEG ? tile_rel - (uint32_t)lane * LG_SEG : 0u;
-    const uint8_t* seg = data + lane * LG_SEG_PITCH;
+    const uint8_t* seg = data + lane * LG_NX_PITCH;
     uint32_t bm[LG_SEG_WORDS];
 #pragma unroll
     for (int wd = 0; wd < LG_SEG_WORDS; wd++) bm[wd] = 0;
@@ -214,7 +233,7 @@ __global__ void __launch_bounds__(LG_MAPS_THREADS) k_legacy_maps(const FrameDev*
             for (;;) {
                 if (q >= (uint32_t)LG_TILE) { ex = (q - LG_TILE) >> 1; break; }                       // never met C0 in this tile
                 if ((bmw[q >> 6] >> ((q >> 1) & 31u)) & 1u) { m = q >> 1; break; }
-                const uint32_t nq = q + leg_step(data[q + 16u * (q / (uint32_t)LG_SEG)]);
+                const uint32_t nq = q + 2u * data[(q >> 1) + 8u * (q / (uint32_t)LG_SEG)];
                 if (nq >= tile_rel) { d2 = true; break; }
                 q = nq;
                 pre++;
