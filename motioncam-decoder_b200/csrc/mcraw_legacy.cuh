@@ -394,11 +394,12 @@ __device__ __forceinline__ uint32_t leg_block(const uint8_t* data, uint32_t o, u
 }
 
 constexpr int LG_DEC_DATA = LG_TILE + LG_OVERRUN;
-constexpr int LG_MAX_PAIRS = LG_TILE / 4;             // a pair is at least two 2-byte blocks
-constexpr int LG_DEC_SMEM = LG_DEC_DATA + LG_TILE_WORDS * 4 /*bitmap*/ + LG_MAX_PAIRS * 2 /*pair list*/ + 64 /*warp sums*/;
+constexpr int LG_PAIR_CHUNK = 1024;                   // pairs listed and decoded per pass (a tile holds ~700 for typical images,
+                                                      // up to LG_TILE / 4 when every block is 2 bytes: then several passes)
+constexpr int LG_DEC_SMEM = LG_DEC_DATA + LG_TILE_WORDS * 4 /*bitmap*/ + LG_PAIR_CHUNK * 2 /*pair list*/ + 64 /*warp sums*/;
 static_assert(LG_TILE_WORDS == 2 * LG_THREADS, "k_legacy_decode gives every thread two bitmap words");
 
-__global__ void __launch_bounds__(LG_THREADS, 8) k_legacy_decode(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
+__global__ void __launch_bounds__(LG_THREADS, 9) k_legacy_decode(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     const FrameDev& F = frames[blockIdx.y];
     if (F.type != MCRAW_COMPRESSION_LEGACY || states[blockIdx.y].status[0]) return;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(LG_THREADS, 8) k_legacy_decode(const FrameDev*
     uint8_t* data = lg_smem;
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LG_DEC_DATA);                        // [LG_TILE_WORDS]
     uint16_t* plist = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(bitmap) + LG_TILE_WORDS * 4);
-    uint32_t* warp_sums = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(plist) + LG_MAX_PAIRS * 2);
+    uint32_t* warp_sums = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(plist) + LG_PAIR_CHUNK * 2);
 
     const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
     lg_stage<LG_THREADS>(data, F.src, len, tile_off, LG_DEC_DATA, tid);
@@ -461,51 +462,56 @@ __global__ void __launch_bounds__(LG_THREADS, 8) k_legacy_decode(const FrameDev*
     const uint32_t p_first = (tile_base + 1u) >> 1;
     uint32_t npairs = ((tile_base + total + 1u) >> 1) - p_first;
     npairs = (uint32_t)min((unsigned long long)npairs, (need >> 1) - (unsigned long long)p_first);
-    {
-        uint32_t ord = tile_base + before + incl - c;        // ordinal of the first block start in this thread's words
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint32_t wv = h ? w1 : w0;
-            while (wv) {
-                const uint32_t b = __ffs(wv) - 1;
-                wv &= wv - 1;
-                const uint32_t q = (ord >> 1) - p_first;
-                if (!(ord & 1u) && q < npairs) plist[q] = (uint16_t)(32u * (2u * tid + h) + b);
-                ord++;
-            }
-        }
-    }
-    __syncthreads();
     // ---- decode: a lane takes one block pair at a time -> 32 consecutive pixels
     const int width = F.width;
     uint16_t* __restrict__ dst = F.dst;
     const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
-    uint32_t P = p_first + (uint32_t)tid;
-    uint32_t y = P / ppr, xq = P - y * ppr;
-    for (uint32_t q = tid; q < npairs; q += LG_THREADS) {
-        const uint32_t o = 2u * (uint32_t)plist[q];
-        uint32_t vE[16], vO[16], refE, refO;
-        const uint32_t lenE = leg_block(data, o, vE, refE);
-        leg_block(data, o + lenE, vO, refO);
-        const uint32_t refs = refE | (refO << 16);
-        const int x = (int)(32u * xq);
-        uint32_t px[16];
+    const uint32_t ord0 = tile_base + before + incl - c;     // ordinal of the first block start in this thread's words
+    for (uint32_t c0 = 0; c0 < npairs; c0 += LG_PAIR_CHUNK) {
+        const uint32_t cn = min((uint32_t)LG_PAIR_CHUNK, npairs - c0);
+        {
+            uint32_t ord = ord0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) px[k] = __vadd2(vE[k] | (vO[k] << 16), refs);    // :483-486, + reference mod 2^16
-        uint16_t* orow = dst + (size_t)y * (size_t)width + x;
-        if (vec && x + 32 <= width) {
-            uint4* o4 = reinterpret_cast<uint4*>(orow);
-#pragma unroll
-            for (int k = 0; k < 4; k++) o4[k] = make_uint4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 16; k++) {                                            // crop at width (:490)
-                if (x + 2 * k < width) orow[2 * k] = (uint16_t)px[k];
-                if (x + 2 * k + 1 < width) orow[2 * k + 1] = (uint16_t)(px[k] >> 16);
+            for (int h = 0; h < 2; h++) {
+                uint32_t wv = h ? w1 : w0;
+                while (wv) {
+                    const uint32_t b = __ffs(wv) - 1;
+                    wv &= wv - 1;
+                    const uint32_t q = (ord >> 1) - p_first - c0;       // wraps to a huge value for earlier passes' pairs
+                    if (!(ord & 1u) && q < cn) plist[q] = (uint16_t)(32u * (2u * tid + h) + b);
+                    ord++;
+                }
             }
         }
-        xq += LG_THREADS;                                                             // the pair LG_THREADS further on
-        while (xq >= ppr) { xq -= ppr; y++; }
+        __syncthreads();
+        uint32_t P = p_first + c0 + (uint32_t)tid;
+        uint32_t y = P / ppr, xq = P - y * ppr;
+        for (uint32_t q = tid; q < cn; q += LG_THREADS) {
+            const uint32_t o = 2u * (uint32_t)plist[q];
+            uint32_t vE[16], vO[16], refE, refO;
+            const uint32_t lenE = leg_block(data, o, vE, refE);
+            leg_block(data, o + lenE, vO, refO);
+            const uint32_t refs = refE | (refO << 16);
+            const int x = (int)(32u * xq);
+            uint32_t px[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) px[k] = __vadd2(vE[k] | (vO[k] << 16), refs);    // :483-486, + reference mod 2^16
+            uint16_t* orow = dst + (size_t)y * (size_t)width + x;
+            if (vec && x + 32 <= width) {
+                uint4* o4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+                for (int k = 0; k < 4; k++) o4[k] = make_uint4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {                                            // crop at width (:490)
+                    if (x + 2 * k < width) orow[2 * k] = (uint16_t)px[k];
+                    if (x + 2 * k + 1 < width) orow[2 * k + 1] = (uint16_t)(px[k] >> 16);
+                }
+            }
+            xq += LG_THREADS;                                                             // the pair LG_THREADS further on
+            while (xq >= ppr) { xq -= ppr; y++; }
+        }
+        __syncthreads();
     }
 }
 
