@@ -256,7 +256,7 @@ def main():
 
     desc, w, h, ct, frames, streams = make_streams(args.workload, args.frames)
     ctx = capi.Context(local)
-    ctx.set_kernel_timing(4)       # CUDA events around the kernels of every 4th batch inside the timed region
+    ctx.set_kernel_timing(8)       # CUDA events around the kernels of every 8th batch inside the timed region
     stream = torch.cuda.Stream()
     sh = stream.cuda_stream
 

@@ -46,6 +46,7 @@ struct Slot {
     bool plan_valid = false, any7 = false, any6 = false;
     uint32_t max_ltiles = 0, nitems = 0;
     size_t items_off = 0, plan_bytes = 0;
+    uint32_t flag_uses = 0;         // k_meta launches on this plan since its counters were zeroed
 };
 
 struct Stage {
@@ -68,6 +69,7 @@ struct mcraw_ctx {
     uint64_t launches = 0;
     std::vector<FrameDev> tmp_frames;
     std::vector<WorkItem> tmp_items;
+    bool overlap = getenv("MCRAW_NO_OVERLAP") == nullptr;   // k_units as a programmatic dependent of k_meta
     uint32_t timing_every = 0;      // record kernel-timing events on every n-th chunk (0 = never)
     uint64_t chunk_seq = 0;
     uint32_t resident_ctas = 0;     // CTAs of k_units the device holds at once
@@ -310,9 +312,12 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e0, st));
     if (!hit) {
         CU_TRY(ctx, cudaMemcpyAsync(s.d_up, s.h_up, s.plan_bytes, cudaMemcpyHostToDevice, st));
+        // the queue counters and the per-frame meta_done counters start from zero for a new plan
+        CU_TRY(ctx, cudaMemsetAsync(s.d_dyn, 0, 16 + sizeof(FrameState) * n, st));
+        s.flag_uses = 0;
         s.plan_valid = true;
     }
-    if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, st>>>(d_frames, d_states, d_counter); ctx->launches += 1; }
+    if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
     if (any6) {
         k_legacy_maps<<<dim3(s.max_ltiles, n), LG_MAPS_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
         k_legacy_scan<<<n, LG_THREADS, 0, st>>>(d_frames, d_states, d_results);
@@ -323,7 +328,20 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (any7) {
         const uint32_t want = (s.nitems + KU_WARPS - 1) / KU_WARPS;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(ctx->resident_ctas, 1), want));
-        k_units<<<grid, KD_THREADS, KU_SMEM, st>>>(d_frames, d_states, d_results, d_items, s.nitems, d_counter);
+        // Programmatic dependent launch: k_units becomes resident while k_meta's last wave is still running and synchronises
+        // per frame (see k_units).  Timed batches are launched the ordinary way, so that the events bracket one kernel each.
+        s.flag_uses += 1;
+        const bool pdl = ctx->overlap && !timed;
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(KD_THREADS); cfg.dynamicSmemBytes = KU_SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems, d_counter,
+                                       pdl ? 2u * s.flag_uses : 0u));
         ctx->launches += 1;
     }
     if (any6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }

@@ -55,6 +55,7 @@ struct FrameState {
     unsigned status[2];            // MCRAW_FRAME_* bits
     unsigned tile_rows_dev;        // ceil(encodedHeight/4) from the frame header
     unsigned rows_fit;             // rows emitted: min(4*tile_rows_dev, dst_cap / width)
+    unsigned meta_done;            // + 1 per metadata stream published by k_meta (k_units waits for 2 * uses of the slot's plan)
 };
 
 struct Result {
@@ -258,8 +259,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // grid = 2 * frames, block = K1_THREADS, dynamic smem = K1_SMEM
-__global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restrict__ frames, FrameState* __restrict__ states,
-                                                        uint32_t* __restrict__ queue_counter) {
+// Publish everything this CTA wrote for (frame, stream): every thread fences its own writes, then one thread bumps the
+// frame's counter.  k_units may be running already (programmatic dependent launch) and polls the counter.
+__device__ __forceinline__ void meta_publish(FrameState& S) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(&S.meta_done, 1u);
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restrict__ frames, FrameState* __restrict__ states) {
     extern __shared__ __align__(16) uint8_t k1_smem[];
     uint8_t* stage = k1_smem;                                                        // K1_CHUNK + 32 bytes of the stream
     const uint32_t stage_s = smem_u32(stage);
@@ -271,7 +279,8 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
     __shared__ uint32_t sh_err, sh_bad;
     __shared__ uint32_t sh_hdr[4];
 
-    if (blockIdx.x == 0 && threadIdx.x == 0) *queue_counter = 0;      // k_units' item queue (it runs after this kernel)
+    // k_units may be scheduled as soon as every CTA of this grid has got this far: it waits per frame, not per grid
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int f = blockIdx.x >> 1;
     const int stream = blockIdx.x & 1;   // 0 = bits, 1 = refs
     const FrameDev& F = frames[f];
@@ -317,6 +326,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
     __syncthreads();
     if (sh_err) {
         if (tid == 0) S.status[stream] = sh_err;
+        meta_publish(S);
         return;
     }
     const uint32_t tiles_x = sh_hdr[0] / 64u;
@@ -529,6 +539,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
         }
         S.status[stream] = err;
     }
+    meta_publish(S);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -752,23 +763,42 @@ struct WorkItem {
 };
 constexpr int KD_THREADS = 32 * KU_WARPS;
 
-__global__ void __launch_bounds__(KD_THREADS, 4)
+// counters[0]: next item; counters[1]: warps that have left the kernel (the last one resets both for the next launch).
+// flag_target != 0: launched as a programmatic dependent of k_meta, i.e. possibly while k_meta's last wave is still
+// running -- before touching a frame, lane 0 polls the frame's meta_done counter (relaxed loads served by L2).  The
+// loads that follow are issued only after the loop has seen the value (no speculation past the branch; the other lanes
+// wait at the warp barrier) and read L2 as well, so they see everything k_meta fenced before bumping the counter.
+// Three CTAs per SM (168 registers): the fourth buys 2 % of bandwidth and leaves no room for this logic without spills.
+__global__ void __launch_bounds__(KD_THREADS, 3)
 k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states, Result* __restrict__ results,
-        const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counter) {
+        const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     uint8_t* smem_warp = smem_raw + (threadIdx.x >> 5) * KU_WARP_SMEM;
     uint32_t it = 0;
-    if (lane == 0) it = atomicAdd(counter, 1u);
+    if (lane == 0) it = atomicAdd(&counters[0], 1u);
     it = __shfl_sync(0xFFFFFFFFu, it, 0);
     while (it < nitems) {
         const WorkItem w = items[it];
         uint32_t nxt = 0;
-        if (lane == 0) nxt = atomicAdd(counter, 1u);       // take the next item early
+        if (lane == 0) {
+            nxt = atomicAdd(&counters[0], 1u);             // take the next item early
+            if (flag_target) {
+                const unsigned* flag = &states[w.frame].meta_done;
+                unsigned v;
+                for (;;) {
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+                    if (v >= flag_target) break;
+                    __nanosleep(256);
+                }
+            }
+        }
+        __syncwarp();
         units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 15u) + 1u, smem_warp);
         __syncwarp();
         it = __shfl_sync(0xFFFFFFFFu, nxt, 0);
     }
+    if (lane == 0 && atomicAdd(&counters[1], 1u) == gridDim.x * KU_WARPS - 1u) { counters[0] = 0; counters[1] = 0; }
 }
 
 }  // namespace mcraw
