@@ -311,7 +311,11 @@ def main():
     m1, k1, c1 = ctx.kernel_time_totals()
     launches = ctx.kernel_launches - l0
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    per_rank_ms = [ms]
     if world > 1:
+        gathered = [torch.zeros_like(tms) for _ in range(world)]
+        dist.all_gather(gathered, tms)
+        per_rank_ms = [float(g.item()) for g in gathered]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
     value = world * pix * args.steps / (ms_max * 1e-3) / 1e6
@@ -381,7 +385,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "ms_per_step_by_rank": [round(v / args.steps, 5) for v in per_rank_ms],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16", "data": "synthetic",
             "config": {"workload": desc, "frames_per_gpu": frames, "distinct_frames": len(streams), "width": w, "height": h,
                        "compression_type": ct, "compressed_bytes_per_frame": comp_bytes / frames,
