@@ -366,30 +366,35 @@ __device__ __forceinline__ void leg_unpack(const uint32_t* w, const uint32_t pi,
     }
 }
 
-// Decode the block whose header sits at byte offset o (even) of the staged tile: returns its total length.
-__device__ __forceinline__ uint32_t leg_block(const uint8_t* data, uint32_t o, uint32_t (&v)[16], uint32_t& ref) {
+// The 2-byte header at byte offset o (even) of the staged tile, as the low 16 bits of the result (byte o first).
+__device__ __forceinline__ uint32_t leg_header(const uint8_t* data, uint32_t o) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(data);
-    const uint32_t i0 = o >> 2, sh = (o & 2u) * 8u;
-    const uint32_t h = __funnelshift_r(w[i0], w[i0 + 1], sh);                    // bytes o .. o+3
-    const uint32_t bits = (h >> 4) & 15u;                                        // RawData_Legacy.cpp:372-375
-    ref = ((h & 15u) << 8) | ((h >> 8) & 0xFFu);
+    const uint32_t i0 = o >> 2;
+    return (o & 2u) ? w[i0] >> 16 : w[i0];
+}
+__device__ __forceinline__ uint32_t leg_hdr_bits(uint32_t h) { return (h >> 4) & 15u; }                          // RawData_Legacy.cpp:372-375
+__device__ __forceinline__ uint32_t leg_hdr_ref(uint32_t h) { return ((h & 15u) << 8) | ((h >> 8) & 0xFFu); }
+
+// The 16 samples of the block at byte offset o whose header says `bits`.
+__device__ __forceinline__ void leg_payload(const uint8_t* data, uint32_t o, uint32_t bits, uint32_t (&v)[16]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(data);
     const uint32_t pi = (o + 2u) >> 2, psh = ((o + 2u) & 2u) * 8u;
     switch (bits) {
     case 0:
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = 0;                                   // :402-404
-        return 2u;
-    case 1: leg_unpack<1>(w, pi, psh, v); return 4u;
-    case 2: leg_unpack<2>(w, pi, psh, v); return 6u;
-    case 3: leg_unpack<3>(w, pi, psh, v); return 8u;
-    case 4: leg_unpack<4>(w, pi, psh, v); return 10u;
-    case 5: leg_unpack<5>(w, pi, psh, v); return 12u;
-    case 6: leg_unpack<6>(w, pi, psh, v); return 14u;
-    case 7: leg_unpack<7>(w, pi, psh, v); return 16u;
-    case 8: leg_unpack<8>(w, pi, psh, v); return 18u;
-    case 9: leg_unpack<9>(w, pi, psh, v); return 20u;
-    case 10: leg_unpack<10>(w, pi, psh, v); return 22u;
-    default: leg_unpack<16>(w, pi, psh, v); return 34u;                          // 11..15 -> 16-bit big-endian (:360-370,395)
+        break;
+    case 1: leg_unpack<1>(w, pi, psh, v); break;
+    case 2: leg_unpack<2>(w, pi, psh, v); break;
+    case 3: leg_unpack<3>(w, pi, psh, v); break;
+    case 4: leg_unpack<4>(w, pi, psh, v); break;
+    case 5: leg_unpack<5>(w, pi, psh, v); break;
+    case 6: leg_unpack<6>(w, pi, psh, v); break;
+    case 7: leg_unpack<7>(w, pi, psh, v); break;
+    case 8: leg_unpack<8>(w, pi, psh, v); break;
+    case 9: leg_unpack<9>(w, pi, psh, v); break;
+    case 10: leg_unpack<10>(w, pi, psh, v); break;
+    default: leg_unpack<16>(w, pi, psh, v); break;                               // 11..15 -> 16-bit big-endian (:360-370,395)
     }
 }
 
@@ -486,12 +491,18 @@ __global__ void __launch_bounds__(LG_THREADS, 9) k_legacy_decode(const FrameDev*
         __syncthreads();
         uint32_t P = p_first + c0 + (uint32_t)tid;
         uint32_t y = P / ppr, xq = P - y * ppr;
+        // the leader's offset and header are fetched one pair ahead; both headers of a pair before either payload
+        uint32_t o = 0, hE = 0;
+        if ((uint32_t)tid < cn) { o = 2u * (uint32_t)plist[tid]; hE = leg_header(data, o); }
         for (uint32_t q = tid; q < cn; q += LG_THREADS) {
-            const uint32_t o = 2u * (uint32_t)plist[q];
-            uint32_t vE[16], vO[16], refE, refO;
-            const uint32_t lenE = leg_block(data, o, vE, refE);
-            leg_block(data, o + lenE, vO, refO);
-            const uint32_t refs = refE | (refO << 16);
+            const uint32_t oE = o, bitsE = leg_hdr_bits(hE);
+            const uint32_t oO = oE + 2u + leg_len(bitsE);
+            const uint32_t hO = leg_header(data, oO);
+            const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
+            if (q + LG_THREADS < cn) { o = 2u * (uint32_t)plist[q + LG_THREADS]; hE = leg_header(data, o); }
+            uint32_t vE[16], vO[16];
+            leg_payload(data, oE, bitsE, vE);
+            leg_payload(data, oO, leg_hdr_bits(hO), vO);
             const int x = (int)(32u * xq);
             uint32_t px[16];
 #pragma unroll
