@@ -152,7 +152,7 @@ def test_host_batch_pipeline(ctx):
     from motioncam_decoder_b200 import capi, testvec as tv
     imgs = [tv.gen_photon(1920, 1080, 4095, seed=50 + k) for k in range(4)]
     streams = [tv.encode_current(im) for im in imgs]
-    n = 60                                   # > 48 MB of input: three staging chunks
+    n = 120                                  # > 192 MB of input: three staging chunks
     offs, total = [], 0
     for i in range(n):
         offs.append(total)
@@ -170,7 +170,7 @@ def test_host_batch_pipeline(ctx):
     written, status = ctx.batch_wait(m)
     assert not any(status) and all(w == 1920 * 1080 for w in written)
     out = np.empty((1080, 1920), dtype=np.uint16)
-    for i in (0, 1, 25, 26, 27, 51, 52, 59):   # around the chunk boundaries
+    for i in (0, 1, 51, 52, 53, 103, 104, 119):   # around the chunk boundaries
         ctx.d2h(out, dsts[i])
         assert np.array_equal(out, imgs[i % 4]), i
     for dp in dsts:
