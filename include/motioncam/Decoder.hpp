@@ -6,7 +6,7 @@
 //   * the file is read with positional reads (pread), so the FILE* position is never moved; like the reference,
 //     one Decoder instance is meant for one thread;
 //   * frames with equal timestamps keep their index order (the reference's std::sort leaves it unspecified);
-//   * loadFrames() / loadFramesDevice() are additions: many frames per call, one batched device decode.
+//   * loadFrames() / loadFramesToDevice() are additions: many frames per call, one batched device decode.
 #pragma once
 #include <motioncam/Container.hpp>
 #include <nlohmann/json.hpp>
@@ -71,6 +71,11 @@ public:
     // are what loadFrame(timestamps[i], ...) would have produced; the same exceptions are thrown.
     void loadFrames(const std::vector<Timestamp>& timestamps, std::vector<std::vector<uint8_t>>& outData,
                     std::vector<nlohmann::json>& outMetadata);
+    // The same, but the decoded frames stay on the GPU: dst[i] is a DEVICE pointer (16-byte aligned) with room for
+    // dstCapacityElems[i] uint16 (>= width*height of frame i).  Compressed frames go file -> pinned ring (kept by the
+    // Decoder and reused) -> staged H2D on side streams -> kernels; nothing is copied back.  Device: MCRAW_B200_DEVICE.
+    void loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint16_t* const* dst, const uint64_t* dstCapacityElems,
+                            std::vector<nlohmann::json>& outMetadata);
 
 private:
     struct Impl;

@@ -12,8 +12,13 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
+#include <mutex>
+#include <thread>
 
 #include "dropin_ctx.hpp"
 
@@ -118,6 +123,13 @@ struct Decoder::Impl {
     std::vector<BufferOffset> audioIndex;
     std::unique_ptr<AudioChunkLoader> audioLoader;
     std::vector<uint8_t> scratch;                       // compressed bytes of the frame being loaded
+    // pinned ring of loadFramesToDevice (allocated through the calling thread's device context, reused across calls)
+    void* ring = nullptr;
+    size_t ringBytes = 0;
+    mcraw_ctx* ringCtx = nullptr;
+    ~Impl() {
+        if (ring && ringCtx) mcraw_host_free_pinned(ringCtx, ring);
+    }
 
     void open();
     void readFrameIndex();
@@ -250,6 +262,42 @@ void Decoder::readFrame(const FrameLocation& where, uint8_t* dst, nlohmann::json
     outMetadata = nlohmann::json::parse(text);
 }
 
+namespace {
+
+// Read many frames (payload into base + off[i], JSON into meta[i]) with a few threads: one pread stream tops out at a few
+// GB/s of page-cache copy, far below what the H2D pipeline behind it can take.  positional reads: no shared state.
+void readFramesParallel(const Decoder& dec, const std::vector<FrameLocation>& where, uint8_t* base, const std::vector<size_t>& off,
+                        std::vector<nlohmann::json>& meta) {
+    const size_t n = where.size();
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    size_t cap = 8;
+    if (const char* e = std::getenv("MCRAW_READ_THREADS")) cap = std::max(1, std::atoi(e));
+    const size_t nthreads = std::min<size_t>({n, cap, hw});
+    if (nthreads <= 1) {
+        for (size_t i = 0; i < n; i++) dec.readFrame(where[i], base + off[i], meta[i]);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::exception_ptr failure;
+    std::mutex failureLock;
+    auto work = [&] {
+        try {
+            for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) dec.readFrame(where[i], base + off[i], meta[i]);
+        } catch (...) {
+            std::lock_guard<std::mutex> g(failureLock);
+            if (!failure) failure = std::current_exception();
+            next.store(n);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nthreads; t++) pool.emplace_back(work);
+    work();
+    for (std::thread& t : pool) t.join();
+    if (failure) std::rethrow_exception(failure);
+}
+
+}  // namespace
+
 void Decoder::loadFrame(const Timestamp timestamp, std::vector<uint8_t>& outData, nlohmann::json& outMetadata) {
     const FrameLocation where = locateFrame(timestamp);
     m->scratch.resize(where.payloadSize);
@@ -302,8 +350,8 @@ void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<s
     uint8_t* in = static_cast<uint8_t*>(mem.pinnedIn);
     std::vector<FrameGeometry> geo(n);
     size_t outBytes = 0;
+    readFramesParallel(*this, where, in, inOff, outMetadata);
     for (size_t i = 0; i < n; i++) {
-        readFrame(where[i], in + inOff[i], outMetadata[i]);
         geo[i] = geometryOf(outMetadata[i]);
         if (geo[i].compressionType != kCompressionCurrent && geo[i].compressionType != kCompressionLegacy)
             throw IOException("Invalid compression type");
@@ -345,6 +393,57 @@ void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<s
         outData[i].resize(bytes);
         std::memcpy(outData[i].data(), static_cast<uint8_t*>(mem.pinnedOut) + outOff[i], bytes);
     }
+}
+
+void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint16_t* const* dst, const uint64_t* dstCapacityElems,
+                                 std::vector<nlohmann::json>& outMetadata) {
+    const size_t n = timestamps.size();
+    outMetadata.assign(n, nlohmann::json());
+    if (n == 0) return;
+    mcraw_ctx* ctx = detail::threadContext();
+    if (!ctx) throw IOException("Failed to uncompress frame");
+
+    // ---- locate every frame and lay the ring out (256-byte aligned slots, back to back: one H2D copy per chunk)
+    std::vector<FrameLocation> where(n);
+    std::vector<size_t> off(n);
+    size_t bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        where[i] = locateFrame(timestamps[i]);
+        off[i] = bytes;
+        bytes += (static_cast<size_t>(where[i].payloadSize) + 255) & ~static_cast<size_t>(255);
+    }
+    if (bytes + 256 > m->ringBytes || m->ringCtx != ctx) {
+        if (m->ring && m->ringCtx) mcraw_host_free_pinned(m->ringCtx, m->ring);
+        m->ring = nullptr; m->ringBytes = 0; m->ringCtx = ctx;
+        const size_t want = bytes + bytes / 4 + 256;
+        if (mcraw_host_alloc_pinned(ctx, want, &m->ring) != MCRAW_OK) throw IOException(mcraw_last_error(ctx));
+        m->ringBytes = want;
+    }
+    uint8_t* ring = static_cast<uint8_t*>(m->ring);
+    std::vector<mcraw_frame_desc> descs(n);
+    readFramesParallel(*this, where, ring, off, outMetadata);
+    for (size_t i = 0; i < n; i++) {
+        const FrameGeometry g = geometryOf(outMetadata[i]);
+        if (g.compressionType != kCompressionCurrent && g.compressionType != kCompressionLegacy)
+            throw IOException("Invalid compression type");
+        mcraw_frame_desc& d = descs[i];
+        std::memset(&d, 0, sizeof d);
+        d.src = ring + off[i];
+        d.len = where[i].payloadSize;
+        d.width = g.width;
+        d.height = g.height;
+        d.compression_type = g.compressionType;
+        d.dst = dst[i];
+        d.dst_capacity_elems = dstCapacityElems[i];
+    }
+    std::vector<uint64_t> written(n);
+    if (mcraw_decode_batch_host(ctx, descs.data(), static_cast<uint32_t>(n), nullptr) != MCRAW_OK ||
+        mcraw_batch_wait(ctx, written.data(), nullptr, static_cast<uint32_t>(n)) != MCRAW_OK)
+        throw IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(ctx));
+    for (size_t i = 0; i < n; i++)
+        if (written[i] == 0)
+            throw IOException(descs[i].compression_type == kCompressionCurrent ? "Failed to uncompress frame"
+                                                                               : "Failed to uncompress legacy frame");
 }
 
 }  // namespace motioncam

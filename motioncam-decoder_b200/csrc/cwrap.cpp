@@ -26,4 +26,28 @@ int64_t mcb200_decoder_load_frames(void* hv, const int64_t* timestamps, int64_t 
     }
 }
 
+// Decoder::loadFramesToDevice: dst[i] are device pointers with room for cap[i] uint16.  Returns n, or -1 with
+// decoder_last_error() set.  The frame metadata of the last call stays readable through mcb200_decoder_frame_metadata_at.
+static thread_local std::vector<std::string> g_meta_text;
+
+int64_t mcb200_decoder_load_frames_to_device(void* hv, const int64_t* timestamps, int64_t n, uint16_t* const* dst, const uint64_t* cap) {
+    HandleT* h = static_cast<HandleT*>(hv);
+    try {
+        std::vector<motioncam::Timestamp> ts(timestamps, timestamps + n);
+        std::vector<nlohmann::json> meta;
+        h->dec->loadFramesToDevice(ts, dst, cap, meta);
+        g_meta_text.resize(meta.size());
+        for (size_t i = 0; i < meta.size(); i++) g_meta_text[i] = meta[i].dump();
+        return n;
+    } catch (const std::exception& e) {
+        h->error = e.what();
+        return -1;
+    }
+}
+
+size_t mcb200_decoder_frame_metadata_at(int64_t i, char* buf, size_t cap) {
+    if (i < 0 || static_cast<size_t>(i) >= g_meta_text.size()) return 0;
+    return copy_out(g_meta_text[static_cast<size_t>(i)], buf, cap);
+}
+
 }  // extern "C"

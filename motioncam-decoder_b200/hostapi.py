@@ -49,6 +49,10 @@ def _bind(c, prefix):
     if prefix == "mcb200_":
         c.mcb200_decoder_load_frames.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(vp), ctypes.POINTER(i64)]
         c.mcb200_decoder_load_frames.restype = i64
+        c.mcb200_decoder_load_frames_to_device.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64)]
+        c.mcb200_decoder_load_frames_to_device.restype = i64
+        c.mcb200_decoder_frame_metadata_at.argtypes = [i64, ctypes.c_char_p, sz]
+        c.mcb200_decoder_frame_metadata_at.restype = sz
     return c
 
 
@@ -142,6 +146,25 @@ class Decoder:
         if r < 0:
             self._raise()
         return [np.frombuffer((ctypes.c_uint8 * sizes[i]).from_address(ptrs[i]), dtype=np.uint8).copy() for i in range(n)]
+
+    def load_frames_to_device(self, timestamps, dst_ptrs, capacities, want_metadata=False):
+        """Batched addition: decode straight into device buffers (dst_ptrs[i]: device pointer, capacities[i]: uint16
+        elements).  Returns the list of frame metadata dicts when asked for it."""
+        n = len(timestamps)
+        ts = (ctypes.c_int64 * max(1, n))(*timestamps)
+        ptrs = (ctypes.c_void_p * max(1, n))(*dst_ptrs)
+        caps = (ctypes.c_uint64 * max(1, n))(*capacities)
+        if self._c.mcb200_decoder_load_frames_to_device(self._h, ts, n, ptrs, caps) < 0:
+            self._raise()
+        if not want_metadata:
+            return None
+        out = []
+        for i in range(n):
+            k = self._c.mcb200_decoder_frame_metadata_at(i, None, 0)
+            buf = ctypes.create_string_buffer(k + 1)
+            self._c.mcb200_decoder_frame_metadata_at(i, buf, k + 1)
+            out.append(json.loads(buf.value.decode()))
+        return out
 
     def audio_sample_rate_hz(self):
         v = self._f("decoder_audio_sample_rate")(self._h)

@@ -102,3 +102,30 @@ def test_decode_failures_raise_like_reference(tmp_path):
             assert str(r.value) == text
     data, _ = ours.load_frame(3)
     assert np.array_equal(data.view(np.uint16).reshape(8, 128), img)
+
+
+def test_load_frames_to_device(tmp_path):
+    """Decoder::loadFramesToDevice: file -> pinned ring -> staged H2D -> kernels, decoded frames stay on the GPU."""
+    from motioncam_decoder_b200 import capi
+    path, frames, images, _ = _clip(tmp_path, n=9)
+    ours = hostapi.Decoder(path)
+    stamps = ours.get_frames()
+    ctx = capi.Context(0)                      # only used here to allocate / read back device memory
+    ptrs, caps = [], []
+    for ts in stamps:
+        img = images[ts]
+        ptrs.append(ctx.device_alloc(img.size * 2))
+        caps.append(img.size)
+    for _ in range(2):                         # second call reuses the Decoder's pinned ring
+        metas = ours.load_frames_to_device(stamps, ptrs, caps, want_metadata=True)
+        for ts, p, meta in zip(stamps, ptrs, metas):
+            img = images[ts]
+            out = np.empty(img.shape, dtype=np.uint16)
+            ctx.d2h(out, p)
+            assert np.array_equal(out, img), ts
+            assert meta["width"] == img.shape[1] and meta["height"] == img.shape[0]
+    with pytest.raises(hostapi.DecoderError, match="Frame not found"):
+        ours.load_frames_to_device([12345], ptrs[:1], caps[:1])
+    for p in ptrs:
+        ctx.device_free(p)
+    ctx.close()
