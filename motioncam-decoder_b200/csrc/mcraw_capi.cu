@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -23,6 +25,7 @@ constexpr uint32_t kMaxGridY = 32768;  // frames per launch
 constexpr int kStage = 3;              // device staging buffers of the host-input pipeline
 constexpr size_t kStageBytes = 96u << 20;   // per-chunk overhead (cross-stream events) favours large chunks: 48 MB -> 51.6 GB/s, 96 MB -> 52.7 GB/s
 constexpr int kCopyStreams = 2;
+constexpr int kHostParts = 4;          // pieces (and threads) of the host-side copies of the single-frame call
 
 struct Slot {
     // one pinned / device buffer pair per chunk: [FrameDev x n | WorkItem x items]
@@ -87,6 +90,7 @@ struct mcraw_ctx {
     uint8_t* d_in = nullptr; size_t d_in_cap = 0;
     uint16_t* h_out = nullptr; size_t h_out_cap = 0;
     uint16_t* d_out = nullptr; size_t d_out_cap = 0;
+    cudaEvent_t part_done[kHostParts] = {};
 };
 
 namespace {
@@ -365,6 +369,15 @@ int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStrea
     return MCRAW_OK;
 }
 
+// Run fn(0) .. fn(parts - 1), one thread each (the caller takes part 0).
+template <typename Fn>
+void parallel_parts(int parts, Fn fn) {
+    std::vector<std::thread> pool;
+    for (int k = 1; k < parts; k++) pool.emplace_back(fn, k);
+    fn(0);
+    for (std::thread& t : pool) t.join();
+}
+
 template <typename T>
 int grow(mcraw_ctx* ctx, T*& p, size_t& cap, size_t need, bool pinned) {
     if (need <= cap) return MCRAW_OK;
@@ -457,6 +470,7 @@ void mcraw_ctx_destroy(mcraw_ctx* ctx) {
         if (g.copied) cudaEventDestroy(g.copied);
         if (g.freed) cudaEventDestroy(g.freed);
     }
+    for (auto& e : ctx->part_done) if (e) cudaEventDestroy(e);
     if (ctx->h_in) cudaFreeHost(ctx->h_in);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->d_in) cudaFree(ctx->d_in);
@@ -585,24 +599,47 @@ size_t mcraw_decode_host(mcraw_ctx* ctx, uint16_t* output, int width, int height
                          int compression_type) {
     if (!ctx || !output || !input || width <= 0 || height <= 0 || len == 0) return 0;
     if (bind(ctx)) return 0;
-    const size_t out_elems = (size_t)width * (size_t)height;
+    const size_t out_elems = (size_t)width * (size_t)height, out_bytes = out_elems * 2;
     if (grow(ctx, ctx->h_in, ctx->h_in_cap, len + 16, true) || grow(ctx, ctx->d_in, ctx->d_in_cap, len + 16, false) ||
-        grow(ctx, ctx->h_out, ctx->h_out_cap, out_elems * 2, true) || grow(ctx, ctx->d_out, ctx->d_out_cap, out_elems * 2, false))
+        grow(ctx, ctx->h_out, ctx->h_out_cap, out_bytes, true) || grow(ctx, ctx->d_out, ctx->d_out_cap, out_bytes, false))
         return 0;
-    std::memcpy(ctx->h_in, input, len);
+    for (auto& e : ctx->part_done)
+        if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return 0;
+    // The caller's buffers are pageable: the bytes go through pinned staging, and for a 25 MB frame the two host copies
+    // cost more than PCIe and the kernels together.  So large copies are cut into kHostParts pieces handled by as many
+    // threads, and on the way back every piece is copied out as soon as ITS device-to-host transfer has landed.
+    const int in_parts = len >= (2u << 20) ? kHostParts : 1, out_parts = out_bytes >= (2u << 20) ? kHostParts : 1;
+    parallel_parts(in_parts, [&](int k) {
+        const size_t a = len * k / in_parts, b = len * (k + 1) / in_parts;
+        std::memcpy(reinterpret_cast<uint8_t*>(ctx->h_in) + a, input + a, b - a);
+    });
     if (cudaMemcpyAsync(ctx->d_in, ctx->h_in, len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return 0;
     mcraw_frame_desc d;
     std::memset(&d, 0, sizeof d);
     d.src = ctx->d_in; d.len = len; d.width = width; d.height = height; d.compression_type = compression_type;
     d.dst = ctx->d_out; d.dst_capacity_elems = out_elems;
     if (enqueue(ctx, &d, 1, ctx->stream)) return 0;
+    // the transfers back are queued behind the kernels right away (16-byte aligned pieces)
+    auto part_begin = [&](int k) { return (out_bytes * k / out_parts) & ~(size_t)15; };
+    for (int k = 0; k < out_parts; k++) {
+        const size_t a = part_begin(k), b = k + 1 == out_parts ? out_bytes : part_begin(k + 1);
+        if (cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->h_out) + a, reinterpret_cast<uint8_t*>(ctx->d_out) + a, b - a,
+                            cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaEventRecord(ctx->part_done[k], ctx->stream) != cudaSuccess)
+            return 0;
+    }
     uint64_t written = 0;
-    if (mcraw_batch_wait(ctx, &written, nullptr, 1)) return 0;
-    if (written == 0 || written > out_elems) return 0;
-    if (cudaMemcpyAsync(ctx->h_out, ctx->d_out, written * 2, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
-    std::memcpy(output, ctx->h_out, written * 2);
-    return (size_t)written;
+    if (mcraw_batch_wait(ctx, &written, nullptr, 1)) return 0;          // kernels done; the copies back are still running
+    if (written == 0 || written > out_elems) { cudaStreamSynchronize(ctx->stream); return 0; }
+    const size_t valid = (size_t)written * 2;                            // the reference writes exactly this much (RawData.cpp:611)
+    const int device = ctx->device;
+    std::atomic<bool> ok{true};
+    parallel_parts(out_parts, [&](int k) {
+        const size_t a = part_begin(k), b = std::min(valid, k + 1 == out_parts ? out_bytes : part_begin(k + 1));
+        if (cudaSetDevice(device) != cudaSuccess || cudaEventSynchronize(ctx->part_done[k]) != cudaSuccess) { ok = false; return; }
+        if (b > a) std::memcpy(reinterpret_cast<uint8_t*>(output) + a, reinterpret_cast<uint8_t*>(ctx->h_out) + a, b - a);
+    });
+    return ok ? (size_t)written : 0;
 }
 
 int mcraw_device_alloc(mcraw_ctx* ctx, size_t bytes, void** out) {
