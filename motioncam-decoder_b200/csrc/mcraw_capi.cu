@@ -20,7 +20,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSlots = 16;             // chunks (sub-batches) that may be in flight per context
+constexpr int kSlots = 6;              // chunks (sub-batches) that may be in flight per context (each owns its scratch)
 constexpr uint32_t kMaxGridY = 32768;  // frames per launch
 constexpr int kStage = 3;              // device staging buffers of the host-input pipeline
 constexpr size_t kStageBytes = 96u << 20;   // per-chunk overhead (cross-stream events) favours large chunks: 48 MB -> 51.6 GB/s, 96 MB -> 52.7 GB/s
