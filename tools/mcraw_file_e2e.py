@@ -33,6 +33,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ["MCRAW_B200_DEVICE"] = str(local)       # device of the drop-in library's per-thread context
 
+    sys.stdout.flush()
+    json_fd = os.dup(1)            # libraries (NCCL) print to the C-level stdout: keep it for the one JSON line
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from motioncam_decoder_b200 import capi, hostapi, shard, testvec as tv
@@ -86,10 +89,10 @@ def main():
         audio_ok = [(t, d.tobytes()) for t, d in got] == [(-1 if t is None else t, np.asarray(d).tobytes()) for t, d in audio]
     if rank == 0:
         size = os.path.getsize(path)
-        print(json.dumps({"metric": "file_to_device_mpix_per_s", "value": args.frames * w * h * args.reps / dt / 1e6, "unit": "Mpix/s",
+        os.write(json_fd, (json.dumps({"metric": "file_to_device_mpix_per_s", "value": args.frames * w * h * args.reps / dt / 1e6, "unit": "Mpix/s",
                           "n_gpus": world, "frames": args.frames, "reps": args.reps, "workload": args.workload,
                           "file_bytes": size, "file_gb_per_s": size * args.reps / dt / 1e9, "frames_ok": ok, "audio_ok": audio_ok,
-                          "path": "file (page cache) -> pread into pinned ring -> staged H2D -> k_meta/k_units -> device u16"}))
+                          "path": "file (page cache) -> pread into pinned ring -> staged H2D -> k_meta/k_units -> device u16"}) + "\n").encode())
         try:
             os.remove(path)
         except OSError:
