@@ -431,7 +431,6 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_units, KD_THREADS, KU_SMEM) != cudaSuccess || per_sm < 1) {
             ctx->err = "k_units does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
-        if (const char* e = getenv("MCRAW_UNITS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
     }
     for (auto& s : ctx->slots) {
