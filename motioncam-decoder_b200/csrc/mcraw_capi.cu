@@ -193,14 +193,12 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
             f.nunits = (uint32_t)((ntiles + 15) / 16);
             f.inv_tiles_x = (ntiles * f.tiles_x < (1ull << 32)) ? (uint32_t)(((1ull << 32) + f.tiles_x - 1) / f.tiles_x) : 0u;
             if (f.tiles_x == 1) f.inv_tiles_x = 0;   // 2^32 does not fit; plain division
-            // scratch layout (offsets for now, rebased on the slot's buffer): unitoff | pairinfo | pairrefs
+            // scratch layout (offsets for now, rebased on the slot's buffer): unitoff | metarec
             // (128-byte aligned: a frame's scratch never shares a cache line with another frame's)
             f.unitoff = reinterpret_cast<uint32_t*>(scratch);
             scratch += (((size_t)f.nunits + 1) * 4 + 127) & ~(size_t)127;
-            f.pairinfo = reinterpret_cast<uint32_t*>(scratch);
-            scratch += (size_t)f.nunits * 32 * 4;
-            f.pairrefs = reinterpret_cast<uint32_t*>(scratch);
-            scratch += (size_t)f.nunits * 32 * 4;
+            f.metarec = reinterpret_cast<uint4*>(scratch);
+            scratch += ((size_t)f.nunits * 16 + 127) & ~(size_t)127;
             max_tile_rows = std::max(max_tile_rows, f.tile_rows);
             max_units = std::max(max_units, f.nunits);
         } else if (d.compression_type == MCRAW_COMPRESSION_LEGACY) {
@@ -290,8 +288,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
             FrameDev& f = frames[i];
             if (f.type == MCRAW_COMPRESSION_CURRENT) {
                 f.unitoff = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.unitoff));
-                f.pairinfo = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.pairinfo));
-                f.pairrefs = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.pairrefs));
+                f.metarec = reinterpret_cast<uint4*>(s.d_scratch + reinterpret_cast<size_t>(f.metarec));
             } else if (f.type == MCRAW_COMPRESSION_LEGACY) {
                 f.lg_tilemap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilemap));
                 f.lg_tilestate = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilestate));

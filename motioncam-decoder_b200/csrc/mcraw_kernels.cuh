@@ -6,14 +6,15 @@
 //   consecutive tiles (= 64 blocks = exactly one 64-value block of each metadata stream).
 //
 //   k_meta   one CTA per (frame, metadata stream).  Resolves the inline-header chain of the stream
-//            (RawData.cpp:463-498) by pointer doubling over every candidate position of a staged window, then lets
-//            ONE LANE decode one whole 64-value meta block with the same width-specialised SWAR routine the pixel
-//            kernel uses.  For the "bits" stream it also turns the reference's running `offset +=`
-//            (RawData.cpp:562,576-579) into prefix sums.  Output per unit: payload offset; per block pair
-//            (even/odd Bayer column pair): {relative offset, bits, refs}.
-//   k_units  persistent; every WARP takes items (a few consecutive units of one frame) from a queue and decodes one
-//            unit at a time.  The unit's payload (contiguous, <= 8 KiB) is staged in shared memory with
-//            16-byte cp.async into an XOR-swizzled layout; every lane then decodes one block pair: a `switch`
+//            (RawData.cpp:463-498) by pointer doubling over every candidate position of a staged window and records, per
+//            unit, where its metadata block is and what its header says.  For the "bits" stream ONE LANE also decodes one
+//            whole 64-value block (same width-specialised SWAR routine as the pixel kernel) to turn the reference's running
+//            `offset +=` (RawData.cpp:562,576-579) into prefix sums: the payload offset of every unit.
+//   k_units  persistent, launched as a programmatic dependent of k_meta; every WARP takes items (a few consecutive units of
+//            one frame) from a queue and decodes one unit at a time.  The unit's payload (contiguous, <= 8 KiB) and its two
+//            metadata blocks are staged in shared memory with 16-byte cp.async (payload XOR-swizzled); every lane pulls
+//            the two bits values and the two references of ITS block pair out of the metadata blocks (table-driven,
+//            mcraw_meta_table.h), a warp scan gives the pair's payload offset, and the lane decodes the pair: a `switch`
 //            on the header bits value selects straight-line code with immediate shifts/masks (lanes that share
 //            a bits value run together; real images have 1-3 distinct values per warp).  Even/odd columns are
 //            interleaved with PRMT, references added with packed 16-bit adds (mod 2^16 like RawData.cpp:582-592),
@@ -26,6 +27,7 @@
 #include <stdint.h>
 
 #include "mcraw_b200.h"
+#include "mcraw_meta_table.h"
 
 namespace mcraw {
 
@@ -41,8 +43,8 @@ struct FrameDev {
     unsigned inv_tiles_x;          // ceil(2^32 / tiles_x) when tile / tiles_x may use mulhi, else 0
     unsigned nunits;               // ceil(tiles_x*tile_rows / 16)
     uint32_t* unitoff;             // scratch [nunits + 1]   payload offset of each unit (+ end)
-    uint32_t* pairinfo;            // scratch [32 * nunits]  rel8 | bitsE << 16 | bitsO << 24
-    uint32_t* pairrefs;            // scratch [32 * nunits]  refE | refO << 16
+    uint4* metarec;                // scratch [nunits]  where the unit's two metadata blocks are: {offset of the bits block,
+                                   //                   offset of the refs block, header of the bits block, header of the refs block}
     uint32_t* lg_tilemap;          // legacy scratch [tiles][17]   transfer map of every 32 KiB tile: exit | blocks << 5
     uint32_t* lg_tilestate;        // legacy scratch [tiles][2]    entry offset (| LG_SLOW) / first block ordinal of every tile
     uint32_t* lg_bitmap;           // legacy scratch [tiles][512]  block starts of every tile (one bit per 2 bytes)
@@ -298,6 +300,8 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
             const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));                // RawData.cpp:500-524 (little-endian u32 x 4)
             ew = h.x; eh = h.y; boff = h.z; roff = h.w;
             if (boff > len || roff > len) err |= MCRAW_FRAME_BAD_HEADER;            // :547
+            if ((boff | roff) & 1u) err |= MCRAW_FRAME_BAD_HEADER;                  // every encoder output has even offsets (16 + 8k,
+                                                                                    // then blocks of 2 + 8m bytes); 16-bit loads rely on it
             if (ew % 64u) err |= MCRAW_FRAME_BAD_HEADER;                            // :550
             if (F.width <= 0 || ew < (uint32_t)F.width) err |= MCRAW_FRAME_BAD_HEADER;  // :553
             if (ew == 0 || eh == 0) err |= MCRAW_FRAME_BAD_HEADER;
@@ -336,8 +340,6 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
     unsigned long long pos = (unsigned long long)sh_hdr[2 + stream] + 4;
 
     uint32_t* __restrict__ unitoff = F.unitoff;
-    uint32_t* __restrict__ pairinfo = F.pairinfo;
-    uint32_t* __restrict__ pairrefs = F.pairrefs;
     uint32_t done = 0;            // meta blocks (= units) finished
     uint32_t carry = 16;          // running payload offset, METADATA_OFFSET (RawData.cpp:25,562)
 
@@ -454,56 +456,40 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
             break;
         }
         const unsigned long long nextpos = cnt ? base + ends[cnt - 1] : pos;
-        // ---- one lane decodes one meta block (64 values): value = unpacked + header reference, mod 2^16 (:491-492)
+        // ---- where the block is and what its header says go to the unit's record: k_units extracts the two values each
+        //      of its lanes needs straight from the block.  The bits stream is decoded here as well (one lane, one block of
+        //      64 values: value = unpacked + header reference, mod 2^16, :491-492) because the payload offset of a unit is
+        //      the sum of the lengths of all blocks before it.
         uint32_t unit_len8 = 0;
         const uint32_t unit = done + (uint32_t)tid;
         if ((uint32_t)tid < cnt) {
             const uint32_t p = my_start;
-            const uint32_t b = stage[p] >> 4;                                          // RawData.cpp:106-110
-            const uint32_t ref = ((uint32_t)(stage[p] & 0x0F) << 8) | stage[p + 1];
-            uint32_t L[16], H[16];
-            StageFetch G{reinterpret_cast<const uint32_t*>(stage), p + 2u};
-            decode_block(b, G, L, H);
-            // word m of L/H holds samples 4m..4m+3 = the four blocks of tile 16*unit + m
+            const uint32_t hdr = (uint32_t)stage[p] | ((uint32_t)stage[p + 1] << 8);
+            uint32_t* rec = reinterpret_cast<uint32_t*>(F.metarec + unit);
+            rec[stream] = (uint32_t)(base + p);
+            rec[2 + stream] = hdr;
             if (stream == 0) {
+                const uint32_t b = stage[p] >> 4;                                      // RawData.cpp:106-110
+                const uint32_t ref = ((uint32_t)(stage[p] & 0x0F) << 8) | stage[p + 1];
+                uint32_t L[16], H[16];
+                StageFetch G{reinterpret_cast<const uint32_t*>(stage), p + 2u};
+                decode_block(b, G, L, H);
+                // word m of L/H holds samples 4m..4m+3 = the four blocks of tile 16*unit + m
                 uint32_t bad = (ref > 16u) ? 1u : 0u;
                 const uint32_t refb = MC_REP(ref & 0x1F);
-                uint32_t info[32];
                 uint32_t rel8 = 0;
 #pragma unroll
                 for (int m = 0; m < 16; m++) {
                     const uint32_t tile = unit * 16u + m;
                     uint32_t v = (L[m] & MC_REP(0x1F)) + refb;                         // bytes <= 31 + 16: no carries
                     uint32_t badm = H[m] | (L[m] & MC_REP(0xE0));
-                    const uint32_t b0 = v & 0xFF, b1 = (v >> 8) & 0xFF, b2 = (v >> 16) & 0xFF, b3 = v >> 24;
-                    badm |= (b0 > 16u) | (b1 > 16u) | (b2 > 16u) | (b3 > 16u);         // reference: OOB table read
+                    badm |= (v + MC_REP(0x6F)) & MC_REP(0x80);                         // a byte > 16 (reference: OOB table read)
                     if (tile >= ntiles) { v = 0; badm = 0; }                           // padding values are ignored
                     bad |= badm;
-                    const uint32_t c0 = v & 0xFF, c1 = (v >> 8) & 0xFF, c2 = (v >> 16) & 0xFF, c3 = v >> 24;
-                    info[2 * m] = rel8 | (c0 << 16) | (c1 << 24);
-                    rel8 += cur_len8(c0 & 31u) + cur_len8(c1 & 31u);
-                    info[2 * m + 1] = rel8 | (c2 << 16) | (c3 << 24);
-                    rel8 += cur_len8(c2 & 31u) + cur_len8(c3 & 31u);
+                    rel8 += cur_len8(v & 31u) + cur_len8((v >> 8) & 31u) + cur_len8((v >> 16) & 31u) + cur_len8(v >> 24);
                 }
                 if (bad) sh_bad = 1;
                 unit_len8 = rel8;
-                uint4* o = reinterpret_cast<uint4*>(pairinfo + (size_t)unit * 32u);
-#pragma unroll
-                for (int k = 0; k < 8; k++) o[k] = make_uint4(info[4 * k], info[4 * k + 1], info[4 * k + 2], info[4 * k + 3]);
-            } else {
-                const uint32_t ref2 = ref | (ref << 16);
-                uint4* o = reinterpret_cast<uint4*>(pairrefs + (size_t)unit * 32u);
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    uint32_t r[4];
-#pragma unroll
-                    for (int t = 0; t < 2; t++) {
-                        const int m = 2 * k + t;
-                        r[2 * t] = __vadd2(__byte_perm(L[m], H[m], 0x5140), ref2);      // blocks 0,1 of the tile
-                        r[2 * t + 1] = __vadd2(__byte_perm(L[m], H[m], 0x7362), ref2);  // blocks 2,3
-                    }
-                    o[k] = make_uint4(r[0], r[1], r[2], r[3]);
-                }
             }
         }
         if (stream == 0) {
@@ -551,7 +537,9 @@ constexpr int KU_IN_BYTES = 16 * 512 + 256;       // worst case unit payload (16
 constexpr int KU_SLOT_PITCH = 144;                // bytes per tile slot in an output row: 128 + 16 (bank skew)
 constexpr int KU_ROW_PITCH = 16 * KU_SLOT_PITCH + 64;   // 2368: (pitch/16) % 8 == 4 -> the two pair rows hit disjoint banks
 constexpr int KU_OUT_BYTES = 2 * KU_ROW_PITCH;    // two rows at a time (planes 0..3, then planes 4..7)
-constexpr int KU_WARP_SMEM = ((KU_IN_BYTES + KU_OUT_BYTES + 127) / 128) * 128;
+constexpr int KU_META_BLOCK = 160;                // a staged metadata block: <= 15 bytes of alignment + 2 + 128, in 16-byte chunks
+constexpr int KU_META_BYTES = 2 * 2 * KU_META_BLOCK;   // (this unit, next unit) x (bits block, refs block)
+constexpr int KU_WARP_SMEM = ((KU_IN_BYTES + KU_OUT_BYTES + KU_META_BYTES + 127) / 128) * 128;
 constexpr int KU_SMEM = KU_WARPS * KU_WARP_SMEM;
 static_assert(KU_IN_BYTES % 128 == 0 && KU_WARP_SMEM % 128 == 0, "swizzle rows are 128 bytes");
 static_assert((KU_ROW_PITCH / 16) % 8 == 4, "row pitch must skew pair rows by four 16-byte bank groups");
@@ -648,8 +636,37 @@ __device__ __forceinline__ void emit_and_copy(const uint32_t (&LE)[16], const ui
 // The pixel work of one item: the calling WARP decodes units [u0, u0 + upw) of the frame.
 // The per-unit records written by k_meta are single-use: they are read with ld.global.cg (L2 only).
 // smem_warp: the warp's KU_WARP_SMEM bytes.
+// The two values a lane needs from a staged metadata block (samples 2*lane and 2*lane + 1: the lane's even- and
+// odd-column block): (unpacked + header reference) mod 2^16 (RawData.cpp:491-492); .x = even block, .y = odd block.
+// blk: shared-memory address of the staged block, whose header sits at byte (pos & 15).  For header values <= 10 up to
+// three byte PAIRS are picked by the table rows of the lane's plane; the 16-bit layout holds the samples themselves.
+__device__ __forceinline__ uint2 meta_values(const uint32_t blk, const uint32_t pos, const uint32_t hdr, const uint32_t* s_terms,
+                                             const uint32_t lane) {
+    const uint32_t hb = (hdr >> 4) & 15u;
+    const uint32_t ref = ((hdr & 15u) << 8) | ((hdr >> 8) & 0xFFu);                // RawData.cpp:106-110
+    const uint32_t pay = blk + (pos & 15u) + 2u;
+    uint32_t v0 = 0, v1 = 0;
+    if (hb > 10u) {                                                               // RawData.cpp:376-408
+        v0 = lds_u16(pay + 4u * lane);
+        v1 = lds_u16(pay + 4u * lane + 2u);
+    } else {
+        const uint32_t* row = s_terms + (hb * 8u + (lane >> 2)) * 3u;
+        const uint32_t b = 2u * (lane & 3u);
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const uint32_t term = row[t];
+            if (term >> 16) {
+                const uint32_t w = lds_u16(pay + 8u * mcraw_meta_term_group(term) + b);
+                v0 |= mcraw_meta_term(term, w & 0xFFu);
+                v1 |= mcraw_meta_term(term, w >> 8);
+            }
+        }
+    }
+    return make_uint2((v0 + ref) & 0xFFFFu, (v1 + ref) & 0xFFFFu);
+}
+
 __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& S, Result* __restrict__ result,
-                                           const uint32_t u0, const uint32_t upw, uint8_t* smem_warp) {
+                                           const uint32_t u0, const uint32_t upw, uint8_t* smem_warp, const uint32_t* s_terms) {
     const uint32_t lane = threadIdx.x & 31;
     const unsigned status = __ldcg(&S.status[0]) | __ldcg(&S.status[1]);
     const uint32_t rows_fit = __ldcg(&S.rows_fit);
@@ -675,11 +692,29 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
     const uint32_t inv = F.inv_tiles_x;
     const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
     uint16_t* __restrict__ dst = F.dst;
-    const uint32_t* pairinfo = F.pairinfo + (size_t)u0 * 32u + lane;
-    const uint32_t* pairrefs = F.pairrefs + (size_t)u0 * 32u + lane;
 
-    // payload offsets of this warp's units (+ end): lane i holds unitoff[u0 + i]
+    // payload offsets of this warp's units (+ end): lane i holds unitoff[u0 + i]; and their metadata records
     const uint32_t my_off = (lane <= nu) ? __ldcg(F.unitoff + u0 + lane) : 0u;
+    uint4 my_rec = make_uint4(0, 0, 0, 0);
+    if (lane < nu) my_rec = __ldcg(F.metarec + u0 + lane);
+    auto rec_of = [&](uint32_t i) {
+        return make_uint4(__shfl_sync(0xFFFFFFFFu, my_rec.x, i), __shfl_sync(0xFFFFFFFFu, my_rec.y, i),
+                          __shfl_sync(0xFFFFFFFFu, my_rec.z, i), __shfl_sync(0xFFFFFFFFu, my_rec.w, i));
+    };
+    // stage the two metadata blocks of a unit (16-byte chunks around them; nothing is read past the end of the buffer):
+    // lanes 0..9 the bits block, lanes 16..25 the refs block
+    const uint32_t meta_base = out_base + KU_OUT_BYTES;
+    auto stage_meta = [&](const uint4 r, uint32_t slot) {
+        const uint32_t k = lane & 15u;
+        if (k < (uint32_t)(KU_META_BLOCK / 16)) {
+            const uint32_t pos = lane < 16u ? r.x : r.y;
+            const unsigned long long a = (unsigned long long)(pos & ~15u) + 16ull * k;
+            const uint32_t n = a >= len ? 0u : (uint32_t)min(16ull, len - a);
+            const uint32_t d = meta_base + (slot * 2u + (lane >> 4)) * KU_META_BLOCK + 16u * k;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src + (n ? a : 0ull)), "r"(n) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
 
     // stage unit payload [a0, a1) (rounded out to 16 bytes) with swizzled 16-byte cp.async
     auto stage_unit = [&](uint32_t a0, uint32_t a1) {
@@ -701,16 +736,28 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
     };
 
     uint32_t a0 = __shfl_sync(0xFFFFFFFFu, my_off, 0), a1 = __shfl_sync(0xFFFFFFFFu, my_off, 1);
+    uint4 rec = rec_of(0);
+    stage_meta(rec, 0);           // committed BEFORE the payload: wait_group 1 then means "the metadata is in"
     stage_unit(a0, a1);
-    uint32_t info = __ldcg(pairinfo), refs = __ldcg(pairrefs);
 
     for (uint32_t i = 0; i < nu; i++) {
         const uint32_t unit = u0 + i;
-        // prefetch the next unit's pair record while this one is decoded
-        uint32_t info_n = 0, refs_n = 0;
-        if (i + 1 < nu) { info_n = __ldcg(pairinfo + 32u * (i + 1)); refs_n = __ldcg(pairrefs + 32u * (i + 1)); }
-        const uint32_t bE = (info >> 16) & 0xFFu, bO = info >> 24;
-        const uint32_t aE = (a0 & 15u) + 8u * (info & 0xFFFFu);
+        // ---- this lane's block pair: header bits values, references, payload offset inside the unit
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncwarp();
+        const uint32_t mb = meta_base + (i & 1u) * 2u * KU_META_BLOCK;
+        const uint2 vb = meta_values(mb, rec.x, rec.z, s_terms, lane), vr = meta_values(mb + KU_META_BLOCK, rec.y, rec.w, s_terms, lane);
+        const bool live = unit * 16u + (lane >> 1) < ntiles;                        // padding values of the last unit are ignored
+        const uint32_t bE = live ? vb.x & 0xFFu : 0u, bO = live ? vb.y & 0xFFu : 0u;    // k_meta has checked them: <= 16
+        const uint32_t refs = vr.x | (vr.y << 16);
+        const uint32_t len8 = cur_len8(bE) + cur_len8(bO);
+        uint32_t rel8 = len8;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, rel8, d);
+            if (lane >= (uint32_t)d) rel8 += o;
+        }
+        const uint32_t aE = (a0 & 15u) + 8u * (rel8 - len8);
 
         // copy-out bookkeeping for this unit (independent of the staged data)
         CopyOut co;
@@ -738,6 +785,8 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
 
         // ---- the input buffer is free again: start fetching the next unit behind the emit / copy-out phases
         if (i + 1 < nu) {
+            rec = rec_of(i + 1);
+            stage_meta(rec, (i + 1u) & 1u);
             a0 = a1;
             a1 = __shfl_sync(0xFFFFFFFFu, my_off, i + 2);
             stage_unit(a0, a1);
@@ -746,7 +795,6 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
         const bool with_h = __any_sync(0xFFFFFFFFu, (bE > 8u) | (bO > 8u));
         if (vec) emit_and_copy<true>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width);
         else emit_and_copy<false>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width);
-        info = info_n; refs = refs_n;
     }
 }
 
@@ -757,6 +805,8 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
 // each other.  Runs after k_meta on the same stream.
 // block = KD_THREADS, dynamic smem = KU_SMEM
 // --------------------------------------------------------------------------------------------------------
+__constant__ uint32_t c_meta_terms[MCRAW_META_ROWS][8][3] = MCRAW_META_TERMS_INIT;
+
 struct WorkItem {
     uint32_t frame;
     uint32_t what;     // bits 0..26 = first unit, bits 27..30 = units - 1
@@ -773,6 +823,9 @@ __global__ void __launch_bounds__(KD_THREADS, 3)
 k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states, Result* __restrict__ results,
         const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint32_t s_terms[MCRAW_META_ROWS * 8 * 3];
+    for (int i = threadIdx.x; i < MCRAW_META_ROWS * 8 * 3; i += KD_THREADS) s_terms[i] = (&c_meta_terms[0][0][0])[i];
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     uint8_t* smem_warp = smem_raw + (threadIdx.x >> 5) * KU_WARP_SMEM;
     uint32_t it = 0;
@@ -794,7 +847,7 @@ k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ stat
             }
         }
         __syncwarp();
-        units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 15u) + 1u, smem_warp);
+        units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 15u) + 1u, smem_warp, s_terms);
         __syncwarp();
         it = __shfl_sync(0xFFFFFFFFu, nxt, 0);
     }
