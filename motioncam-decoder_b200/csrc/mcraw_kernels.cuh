@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
                 // word m of L/H holds samples 4m..4m+3 = the four blocks of tile 16*unit + m
                 uint32_t bad = (ref > 16u) ? 1u : 0u;
                 const uint32_t refb = MC_REP(ref & 0x1F);
-                uint32_t rel8 = 0;
+                uint32_t acc[2] = {0, 0};                                              // byte-wise sums of 8 words each: <= 128 per byte
 #pragma unroll
                 for (int m = 0; m < 16; m++) {
                     const uint32_t tile = unit * 16u + m;
@@ -486,10 +486,12 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
                     badm |= (v + MC_REP(0x6F)) & MC_REP(0x80);                         // a byte > 16 (reference: OOB table read)
                     if (tile >= ntiles) { v = 0; badm = 0; }                           // padding values are ignored
                     bad |= badm;
-                    rel8 += cur_len8(v & 31u) + cur_len8((v >> 8) & 31u) + cur_len8((v >> 16) & 31u) + cur_len8(v >> 24);
+                    acc[m >> 3] += mcraw_len8x4(v & MC_REP(0x1F));                     // four block lengths at once
                 }
                 if (bad) sh_bad = 1;
-                unit_len8 = rel8;
+                const uint32_t s2 = (acc[0] & 0x00FF00FFu) + ((acc[0] >> 8) & 0x00FF00FFu) +
+                                    (acc[1] & 0x00FF00FFu) + ((acc[1] >> 8) & 0x00FF00FFu);
+                unit_len8 = (s2 & 0xFFFFu) + (s2 >> 16);
             }
         }
         if (stream == 0) {
@@ -637,32 +639,28 @@ __device__ __forceinline__ void emit_and_copy(const uint32_t (&LE)[16], const ui
 // The per-unit records written by k_meta are single-use: they are read with ld.global.cg (L2 only).
 // smem_warp: the warp's KU_WARP_SMEM bytes.
 // The two values a lane needs from a staged metadata block (samples 2*lane and 2*lane + 1: the lane's even- and
-// odd-column block): (unpacked + header reference) mod 2^16 (RawData.cpp:491-492); .x = even block, .y = odd block.
-// blk: shared-memory address of the staged block, whose header sits at byte (pos & 15).  For header values <= 10 up to
-// three byte PAIRS are picked by the table rows of the lane's plane; the 16-bit layout holds the samples themselves.
-__device__ __forceinline__ uint2 meta_values(const uint32_t blk, const uint32_t pos, const uint32_t hdr, const uint32_t* s_terms,
-                                             const uint32_t lane) {
+// odd-column block): (unpacked + header reference) mod 2^16 (RawData.cpp:491-492), as two 16-bit lanes of one word
+// (even block | odd block << 16).  blk: shared-memory address of the staged block, whose header sits at byte (pos & 15).
+// For header values <= 10 up to three byte PAIRS are picked by the table rows of the lane's plane; the 16-bit layout
+// holds the samples themselves.
+__device__ __forceinline__ uint32_t meta_values(const uint32_t blk, const uint32_t pos, const uint32_t hdr, const uint32_t* s_terms,
+                                                const uint32_t lane) {
     const uint32_t hb = (hdr >> 4) & 15u;
     const uint32_t ref = ((hdr & 15u) << 8) | ((hdr >> 8) & 0xFFu);                // RawData.cpp:106-110
     const uint32_t pay = blk + (pos & 15u) + 2u;
-    uint32_t v0 = 0, v1 = 0;
+    uint32_t v = 0;
     if (hb > 10u) {                                                               // RawData.cpp:376-408
-        v0 = lds_u16(pay + 4u * lane);
-        v1 = lds_u16(pay + 4u * lane + 2u);
+        v = lds_u16(pay + 4u * lane) | (lds_u16(pay + 4u * lane + 2u) << 16);
     } else {
         const uint32_t* row = s_terms + (hb * 8u + (lane >> 2)) * 3u;
         const uint32_t b = 2u * (lane & 3u);
 #pragma unroll
         for (int t = 0; t < 3; t++) {
             const uint32_t term = row[t];
-            if (term >> 16) {
-                const uint32_t w = lds_u16(pay + 8u * mcraw_meta_term_group(term) + b);
-                v0 |= mcraw_meta_term(term, w & 0xFFu);
-                v1 |= mcraw_meta_term(term, w >> 8);
-            }
+            if (term >> 16) v |= mcraw_meta_term_pair(term, lds_u16(pay + 8u * mcraw_meta_term_group(term) + b));
         }
     }
-    return make_uint2((v0 + ref) & 0xFFFFu, (v1 + ref) & 0xFFFFu);
+    return __vadd2(v, ref | (ref << 16));
 }
 
 __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& S, Result* __restrict__ result,
@@ -746,10 +744,10 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
         asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         __syncwarp();
         const uint32_t mb = meta_base + (i & 1u) * 2u * KU_META_BLOCK;
-        const uint2 vb = meta_values(mb, rec.x, rec.z, s_terms, lane), vr = meta_values(mb + KU_META_BLOCK, rec.y, rec.w, s_terms, lane);
+        const uint32_t vb = meta_values(mb, rec.x, rec.z, s_terms, lane);
+        const uint32_t refs = meta_values(mb + KU_META_BLOCK, rec.y, rec.w, s_terms, lane);
         const bool live = unit * 16u + (lane >> 1) < ntiles;                        // padding values of the last unit are ignored
-        const uint32_t bE = live ? vb.x & 0xFFu : 0u, bO = live ? vb.y & 0xFFu : 0u;    // k_meta has checked them: <= 16
-        const uint32_t refs = vr.x | (vr.y << 16);
+        const uint32_t bE = live ? vb & 0xFFu : 0u, bO = live ? (vb >> 16) & 0xFFu : 0u;   // k_meta has checked them: <= 16
         const uint32_t len8 = cur_len8(bE) + cur_len8(bO);
         uint32_t rel8 = len8;
 #pragma unroll

@@ -42,7 +42,36 @@
 static inline MC_HD uint32_t mcraw_meta_term(uint32_t term, uint32_t x) {
     return ((x >> ((term >> 4) & 7u)) & (term >> 16)) << ((term >> 8) & 15u);
 }
+/* The same term applied to TWO adjacent byte lanes at once: w = G_g[b] | G_g[b + 1] << 8.  Result: the two contributions in
+ * two 16-bit lanes (lane 0: byte lane b, lane 1: byte lane b + 1).  Every field of the table lies inside its byte
+ * (bit length of m <= 8 - s), so the bits that (w >> s) drags from the high byte into the low one are masked away. */
+static inline MC_HD uint32_t mcraw_meta_term_pair(uint32_t term, uint32_t w) {
+    const uint32_t pair = (w >> ((term >> 4) & 7u)) & ((term >> 16) * 0x0101u);
+    return ((pair & 0xFFu) | ((pair & 0xFF00u) << 8)) << ((term >> 8) & 15u);
+}
 /* Group index of a term (the byte to fetch is payload[8 * group + b]). */
 static inline MC_HD uint32_t mcraw_meta_term_group(uint32_t term) { return term & 15u; }
+
+/* Byte permute (PTX prmt, default mode): result byte i = byte (selector nibble i) of the 8 bytes {x, y}. */
+static inline MC_HD uint32_t mcraw_prmt(uint32_t x, uint32_t y, uint32_t s) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, y, s);
+#else
+    const uint64_t xy = (uint64_t)x | ((uint64_t)y << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((xy >> (8 * ((s >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+
+/* Payload bytes / 8 of four blocks at once: v holds four header bits values (0..16, RawData.cpp:27-45), one per byte. */
+static inline MC_HD uint32_t mcraw_len8x4(uint32_t v) {
+    const uint32_t n = v & 0x07070707u;
+    const uint32_t sel = mcraw_prmt(n | (n >> 4), 0u, 0x4420u);            /* nibble i = (value i) & 7 */
+    const uint32_t lo = mcraw_prmt(0x03020100u, 0x08060504u, sel);          /* values 0..7  -> 0,1,2,3,4,5,6,8 */
+    const uint32_t hi = mcraw_prmt(0x100A0A08u, 0x10101010u, sel);          /* values 8..15 -> 8,10,10,16,16,16,16,16 */
+    const uint32_t m8 = ((v >> 3) & 0x01010101u) * 0xFFu;                   /* bytes whose value is 8..15 */
+    return ((lo & ~m8) | (hi & m8)) + (v & 0x10101010u);                    /* value 16 -> 0 + 16 */
+}
 
 #endif /* MCRAW_META_TABLE_H */

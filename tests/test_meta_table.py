@@ -50,6 +50,10 @@ def lib(tmp_path_factory):
     c = ctypes.CDLL(so)
     c.meta_table_sample.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     c.meta_table_sample.restype = ctypes.c_uint
+    c.meta_table_pair.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    c.meta_table_pair.restype = ctypes.c_uint
+    c.meta_len8x4.argtypes = [ctypes.c_uint]
+    c.meta_len8x4.restype = ctypes.c_uint
     return c
 
 
@@ -60,6 +64,8 @@ def test_table_matches_layouts(lib):
             p = rng.integers(0, 256, 144, dtype=np.uint8)
             for i in range(64):
                 assert lib.meta_table_sample(p.ctypes.data, hb, i) == _sample(p, hb, i), (hb, i)
+            for i in range(0, 64, 2):           # the two-lane form k_units uses (a lane's even / odd block)
+                assert lib.meta_table_pair(p.ctypes.data, hb, i) == _sample(p, hb, i) | (_sample(p, hb, i + 1) << 16), (hb, i)
 
 
 def test_table_matches_the_oracle_decoder():
@@ -79,3 +85,14 @@ def test_table_matches_the_oracle_decoder():
             for i in rng.integers(0, 64, 16):
                 y, x = (c >> 1) + 2 * (int(i) >> 5), 2 * (int(i) & 31) + (c & 1)
                 assert img[y, x] == _sample(p, hb, int(i)), (hb, c, int(i))
+
+
+def test_len8x4(lib):
+    """Four block lengths per word (k_meta's payload prefix sums) against RawData.cpp:27-45."""
+    table = [0, 8, 16, 24, 32, 40, 48, 64, 64, 80, 80, 128, 128, 128, 128, 128, 128]
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        vals = [int(x) for x in rng.integers(0, 17, 4)]
+        v = vals[0] | (vals[1] << 8) | (vals[2] << 16) | (vals[3] << 24)
+        got = lib.meta_len8x4(v)
+        assert [(got >> (8 * i)) & 0xFF for i in range(4)] == [table[x] // 8 for x in vals], vals
