@@ -129,3 +129,17 @@ def test_exports_reference_symbols():
     c = ctypes.CDLL(_lib.LIB_DROPIN)
     for sym in ("_ZN9motioncam3raw6DecodeEPtiiPKhm", "_ZN9motioncam3raw12DecodeLegacyEPtiiPKhm"):
         assert hasattr(c, sym), sym
+
+
+def test_cli_synth_and_info(tmp_path):
+    """tools/mcraw_tool.py: write a synthetic clip, read its index back through the drop-in Decoder (CPU only)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = str(tmp_path / "cli.mcraw")
+    tool = os.path.join(root, "tools", "mcraw_tool.py")
+    subprocess.run([sys.executable, tool, "synth", path, "--frames", "3", "--width", "128", "--height", "8", "--legacy"], check=True)
+    out = subprocess.run([sys.executable, tool, "info", path], check=True, capture_output=True, text=True).stdout
+    info = json.loads(out)
+    assert info["frames"] == 3 and info["audio_chunks"] == 4 and info["audio_sample_rate_hz"] == 48000
