@@ -123,12 +123,61 @@ struct Decoder::Impl {
     std::vector<BufferOffset> audioIndex;
     std::unique_ptr<AudioChunkLoader> audioLoader;
     std::vector<uint8_t> scratch;                       // compressed bytes of the frame being loaded
-    // pinned ring of loadFramesToDevice (allocated through the calling thread's device context, reused across calls)
+    // The batched calls run on a device context of their own (created on first use, device $MCRAW_B200_DEVICE), so that
+    // the staging below lives and dies with the Decoder whatever thread destroys it.
+    mcraw_ctx* batchCtx = nullptr;
+    mcraw_ctx* batchContext() {
+        if (!batchCtx) {
+            int device = 0;
+            if (const char* e = std::getenv("MCRAW_B200_DEVICE")) device = std::atoi(e);
+            if (mcraw_ctx_create(device, &batchCtx) != MCRAW_OK) {
+                batchCtx = nullptr;
+                throw IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(nullptr));
+            }
+        }
+        return batchCtx;
+    }
+    // staging of the batched calls, grown on demand and reused:
+    // pinned ring for the compressed frames; for loadFrames also the decoded frames on the device and in pinned memory
     void* ring = nullptr;
     size_t ringBytes = 0;
+    void* devOut = nullptr;
+    size_t devOutBytes = 0;
+    void* pinnedOut = nullptr;
+    size_t pinnedOutBytes = 0;
     mcraw_ctx* ringCtx = nullptr;
+    void releaseStaging() {
+        if (ringCtx) {
+            if (ring) mcraw_host_free_pinned(ringCtx, ring);
+            if (pinnedOut) mcraw_host_free_pinned(ringCtx, pinnedOut);
+            if (devOut) mcraw_device_free(ringCtx, devOut);
+        }
+        ring = pinnedOut = devOut = nullptr;
+        ringBytes = pinnedOutBytes = devOutBytes = 0;
+    }
+    // make room for `in` bytes of compressed frames and (loadFrames only) `out` bytes of decoded frames
+    void reserveStaging(mcraw_ctx* ctx, size_t in, size_t out) {
+        if (ringCtx != ctx) { releaseStaging(); ringCtx = ctx; }
+        auto fail = [&] { throw IOException(mcraw_last_error(ctx)); };
+        if (in > ringBytes) {
+            if (ring) mcraw_host_free_pinned(ctx, ring);
+            ring = nullptr; ringBytes = 0;
+            if (mcraw_host_alloc_pinned(ctx, in + in / 4, &ring) != MCRAW_OK) fail();
+            ringBytes = in + in / 4;
+        }
+        if (out > devOutBytes) {
+            if (devOut) mcraw_device_free(ctx, devOut);
+            if (pinnedOut) mcraw_host_free_pinned(ctx, pinnedOut);
+            devOut = pinnedOut = nullptr; devOutBytes = pinnedOutBytes = 0;
+            if (mcraw_device_alloc(ctx, out + out / 4, &devOut) != MCRAW_OK) fail();
+            devOutBytes = out + out / 4;
+            if (mcraw_host_alloc_pinned(ctx, out + out / 4, &pinnedOut) != MCRAW_OK) fail();
+            pinnedOutBytes = out + out / 4;
+        }
+    }
     ~Impl() {
-        if (ring && ringCtx) mcraw_host_free_pinned(ringCtx, ring);
+        releaseStaging();
+        if (batchCtx) mcraw_ctx_destroy(batchCtx);
     }
 
     void open();
@@ -322,20 +371,7 @@ void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<s
     outData.resize(n);
     outMetadata.assign(n, nlohmann::json());
     if (n == 0) return;
-    mcraw_ctx* ctx = detail::threadContext();
-    if (!ctx) throw IOException("Failed to uncompress frame");
-
-    struct Cleanup {
-        mcraw_ctx* ctx;
-        void* pinnedIn = nullptr;
-        void* pinnedOut = nullptr;
-        void* devOut = nullptr;
-        ~Cleanup() {
-            if (pinnedIn) mcraw_host_free_pinned(ctx, pinnedIn);
-            if (pinnedOut) mcraw_host_free_pinned(ctx, pinnedOut);
-            if (devOut) mcraw_device_free(ctx, devOut);
-        }
-    } mem{ctx};
+    mcraw_ctx* ctx = m->batchContext();
 
     // ---- locate, size and read every frame straight into one pinned buffer (256-byte aligned slots)
     std::vector<FrameLocation> where(n);
@@ -346,8 +382,8 @@ void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<s
         inOff[i] = inBytes;
         inBytes += (static_cast<size_t>(where[i].payloadSize) + 255) & ~static_cast<size_t>(255);
     }
-    if (mcraw_host_alloc_pinned(ctx, inBytes + 256, &mem.pinnedIn) != MCRAW_OK) throw IOException(mcraw_last_error(ctx));
-    uint8_t* in = static_cast<uint8_t*>(mem.pinnedIn);
+    m->reserveStaging(ctx, inBytes + 256, 0);
+    uint8_t* in = static_cast<uint8_t*>(m->ring);
     std::vector<FrameGeometry> geo(n);
     size_t outBytes = 0;
     readFramesParallel(*this, where, in, inOff, outMetadata);
@@ -359,9 +395,7 @@ void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<s
         const size_t bytes = sizeof(uint16_t) * static_cast<size_t>(geo[i].width) * static_cast<size_t>(geo[i].height);
         outBytes += (bytes + 255) & ~static_cast<size_t>(255);
     }
-    if (mcraw_device_alloc(ctx, outBytes + 256, &mem.devOut) != MCRAW_OK ||
-        mcraw_host_alloc_pinned(ctx, outBytes + 256, &mem.pinnedOut) != MCRAW_OK)
-        throw IOException(mcraw_last_error(ctx));
+    m->reserveStaging(ctx, inBytes + 256, outBytes + 256);
 
     // ---- one batched decode: H2D on the context's side streams overlaps the kernels
     std::vector<mcraw_frame_desc> descs(n);
@@ -373,7 +407,7 @@ void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<s
         d.width = geo[i].width;
         d.height = geo[i].height;
         d.compression_type = geo[i].compressionType;
-        d.dst = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(mem.devOut) + outOff[i]);
+        d.dst = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(m->devOut) + outOff[i]);
         d.dst_capacity_elems = static_cast<uint64_t>(geo[i].width) * static_cast<uint64_t>(geo[i].height);
     }
     std::vector<uint64_t> written(n);
@@ -385,13 +419,13 @@ void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<s
             throw IOException(geo[i].compressionType == kCompressionCurrent ? "Failed to uncompress frame"
                                                                              : "Failed to uncompress legacy frame");
     }
-    if (mcraw_memcpy_d2h(ctx, mem.pinnedOut, mem.devOut, outBytes, nullptr) != MCRAW_OK ||
+    if (mcraw_memcpy_d2h(ctx, m->pinnedOut, m->devOut, outBytes, nullptr) != MCRAW_OK ||
         mcraw_stream_sync(ctx, nullptr) != MCRAW_OK)
         throw IOException(mcraw_last_error(ctx));
     for (size_t i = 0; i < n; i++) {
         const size_t bytes = sizeof(uint16_t) * static_cast<size_t>(geo[i].width) * static_cast<size_t>(geo[i].height);
         outData[i].resize(bytes);
-        std::memcpy(outData[i].data(), static_cast<uint8_t*>(mem.pinnedOut) + outOff[i], bytes);
+        std::memcpy(outData[i].data(), static_cast<uint8_t*>(m->pinnedOut) + outOff[i], bytes);
     }
 }
 
@@ -400,8 +434,7 @@ void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint1
     const size_t n = timestamps.size();
     outMetadata.assign(n, nlohmann::json());
     if (n == 0) return;
-    mcraw_ctx* ctx = detail::threadContext();
-    if (!ctx) throw IOException("Failed to uncompress frame");
+    mcraw_ctx* ctx = m->batchContext();
 
     // ---- locate every frame and lay the ring out (256-byte aligned slots, back to back: one H2D copy per chunk)
     std::vector<FrameLocation> where(n);
@@ -412,13 +445,7 @@ void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint1
         off[i] = bytes;
         bytes += (static_cast<size_t>(where[i].payloadSize) + 255) & ~static_cast<size_t>(255);
     }
-    if (bytes + 256 > m->ringBytes || m->ringCtx != ctx) {
-        if (m->ring && m->ringCtx) mcraw_host_free_pinned(m->ringCtx, m->ring);
-        m->ring = nullptr; m->ringBytes = 0; m->ringCtx = ctx;
-        const size_t want = bytes + bytes / 4 + 256;
-        if (mcraw_host_alloc_pinned(ctx, want, &m->ring) != MCRAW_OK) throw IOException(mcraw_last_error(ctx));
-        m->ringBytes = want;
-    }
+    m->reserveStaging(ctx, bytes + 256, 0);
     uint8_t* ring = static_cast<uint8_t*>(m->ring);
     std::vector<mcraw_frame_desc> descs(n);
     readFramesParallel(*this, where, ring, off, outMetadata);
