@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
 // k_units
 // --------------------------------------------------------------------------------------------------------
 constexpr int KU_WARPS = 4;                       // warps per CTA
-constexpr int KU_UPW = 8;                         // consecutive units handled by one warp (software pipelined)
+constexpr int KU_UPW = 24;                        // consecutive units handled by one warp (software pipelined)
 constexpr int KU_IN_BYTES = 16 * 512 + 256;       // worst case unit payload (16-bit blocks) + alignment slack, 128-multiple
 constexpr int KU_SLOT_PITCH = 144;                // bytes per tile slot in an output row: 128 + 16 (bank skew)
 constexpr int KU_ROW_PITCH = 16 * KU_SLOT_PITCH + 64;   // 2368: (pitch/16) % 8 == 4 -> the two pair rows hit disjoint banks
@@ -797,7 +797,7 @@ __constant__ uint32_t c_meta_terms[MCRAW_META_ROWS][8][3] = MCRAW_META_TERMS_INI
 
 struct WorkItem {
     uint32_t frame;
-    uint32_t what;     // bits 0..26 = first unit, bits 27..30 = units - 1
+    uint32_t what;     // bits 0..26 = first unit, bits 27..31 = units - 1 (<= 31: a warp keeps the unit offsets in its lanes)
 };
 constexpr int KD_THREADS = 32 * KU_WARPS;
 
@@ -835,7 +835,7 @@ k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ stat
             }
         }
         __syncwarp();
-        units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 15u) + 1u, smem_warp, s_terms);
+        units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 31u) + 1u, smem_warp, s_terms);
         __syncwarp();
         it = __shfl_sync(0xFFFFFFFFu, nxt, 0);
     }
