@@ -3,6 +3,8 @@
 #define MC_PREFIX mcb200_
 #include "decoder_cwrap.inc"
 
+#include <motioncam/Export.hpp>
+
 extern "C" {
 
 // Decoder::loadFrames (batched addition): loads every listed timestamp, keeps the frames in the handle.
@@ -48,6 +50,51 @@ int64_t mcb200_decoder_load_frames_to_device(void* hv, const int64_t* timestamps
 size_t mcb200_decoder_frame_metadata_at(int64_t i, char* buf, size_t cap) {
     if (i < 0 || static_cast<size_t>(i) >= g_meta_text.size()) return 0;
     return copy_out(g_meta_text[static_cast<size_t>(i)], buf, cap);
+}
+
+// ---- include/motioncam/Export.hpp ---------------------------------------------------------------------------------
+// 0 = written; 1 = an exception escaped (text in err).  Same shape as mcref_write_dng / mcref_write_audio in
+// oracle/ref_shim.cpp, which call the reference's example.cpp.
+int mcb200_write_dng(const char* path, const uint8_t* data, size_t bytes, const char* frame_json, const char* container_json,
+                     char* err, size_t errcap) {
+    try {
+        motioncam::DngWriter(nlohmann::json::parse(container_json)).write(path, data, bytes, nlohmann::json::parse(frame_json));
+        return 0;
+    } catch (const std::exception& e) {
+        copy_out(e.what(), err, errcap);
+        return 1;
+    }
+}
+
+int mcb200_write_audio(const char* path, int sample_rate_hz, int channels, const int16_t* samples, const int64_t* offsets,
+                       int64_t nchunks, char* err, size_t errcap) {
+    try {
+        std::vector<motioncam::AudioChunk> chunks;
+        for (int64_t i = 0; i < nchunks; i++)
+            chunks.emplace_back(-1, std::vector<int16_t>(samples + offsets[i], samples + offsets[i + 1]));
+        motioncam::writeAudio(path, sample_rate_hz, channels, chunks);
+        return 0;
+    } catch (const std::exception& e) {
+        copy_out(e.what(), err, errcap);
+        return 1;
+    }
+}
+
+// The example program's loop (audio.wav + frame_%06d.dng into out_dir) on the batched B200 decode.
+// Returns the number of frames written, or -1 (text in err).
+int64_t mcb200_export_clip(const char* input_path, const char* out_dir, int num_frames, int batch, int writer_threads,
+                           int write_audio, char* err, size_t errcap) {
+    try {
+        motioncam::ExportOptions opt;
+        opt.numFrames = num_frames;
+        if (batch > 0) opt.batch = batch;
+        if (writer_threads > 0) opt.writerThreads = writer_threads;
+        opt.writeAudio = write_audio != 0;
+        return static_cast<int64_t>(motioncam::exportClip(input_path, out_dir, opt, nullptr));
+    } catch (const std::exception& e) {
+        copy_out(e.what(), err, errcap);
+        return -1;
+    }
 }
 
 }  // extern "C"

@@ -46,7 +46,12 @@ def _bind(c, prefix):
         f(name).restype = i64
     f("decoder_audio_chunk_data").argtypes = [vp, i64]
     f("decoder_audio_chunk_data").restype = vp
+    f("write_dng").argtypes = [ctypes.c_char_p, vp, sz, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, sz]
+    f("write_audio").argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(i64), i64, ctypes.c_char_p, sz]
     if prefix == "mcb200_":
+        c.mcb200_export_clip.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_char_p, sz]
+        c.mcb200_export_clip.restype = i64
         c.mcb200_decoder_load_frames.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(vp), ctypes.POINTER(i64)]
         c.mcb200_decoder_load_frames.restype = i64
         c.mcb200_decoder_load_frames_to_device.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64)]
@@ -76,6 +81,44 @@ def raw_decode(stream, width, height, legacy=False, lib=None, prefix="mcb200_", 
     n = fn(out.ctypes.data, width, height, src.ctypes.data, src.size)
     assert np.all(out[width * height:] == fill), "decoder wrote past width*height"
     return int(n), out[:width * height].reshape(height, width)
+
+
+def write_dng(path, pixels, frame_metadata, container_metadata, lib=None, prefix="mcb200_"):
+    """motioncam::writeDng (include/motioncam/Export.hpp; the reference's example.cpp:55-139): one decoded frame
+    (uint16 array or its bytes) + its metadata -> an uncompressed CFA DNG at `path`."""
+    c = lib or library()
+    px = np.ascontiguousarray(pixels).view(np.uint8).reshape(-1)
+    err = ctypes.create_string_buffer(1024)
+    rc = getattr(c, prefix + "write_dng")(str(path).encode(), px.ctypes.data, px.size, json.dumps(frame_metadata).encode(),
+                                          json.dumps(container_metadata).encode(), err, len(err))
+    if rc != 0:
+        raise DecoderError(err.value.decode())
+
+
+def write_audio(path, sample_rate_hz, channels, chunks, lib=None, prefix="mcb200_"):
+    """motioncam::writeAudio (example.cpp:27-53): int16 chunks -> one 16-bit PCM WAV."""
+    c = lib or library()
+    chunks = [np.ascontiguousarray(x, dtype=np.int16).reshape(-1) for x in chunks]
+    flat = np.concatenate(chunks) if chunks else np.zeros(0, np.int16)
+    offs = np.zeros(len(chunks) + 1, dtype=np.int64)
+    if chunks:
+        offs[1:] = np.cumsum([x.size for x in chunks])
+    err = ctypes.create_string_buffer(1024)
+    rc = getattr(c, prefix + "write_audio")(str(path).encode(), int(sample_rate_hz), int(channels), flat.ctypes.data,
+                                            offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(chunks), err, len(err))
+    if rc != 0:
+        raise DecoderError(err.value.decode())
+
+
+def export_clip(path, out_dir, num_frames=-1, batch=16, writer_threads=4, audio=True):
+    """motioncam::exportClip: the reference's example program (audio.wav + frame_%06d.dng) on the batched B200 decode."""
+    c = library()
+    err = ctypes.create_string_buffer(1024)
+    n = c.mcb200_export_clip(str(path).encode(), str(out_dir).encode(), int(num_frames), int(batch), int(writer_threads),
+                             1 if audio else 0, err, len(err))
+    if n < 0:
+        raise DecoderError(err.value.decode())
+    return int(n)
 
 
 class Decoder:

@@ -1,7 +1,8 @@
 // ref_shim.cpp -- extern "C" access to the UNMODIFIED reference, for tests and the CPU baseline only.
 //
-// Compiled by oracle/Makefile together with /root/reference/lib/{RawData,RawData_Legacy,Decoder}.cpp
-// (sources read in place, never copied) into oracle/_ref/libmcraw_ref.so.  Nothing in the product links
+// Compiled by oracle/Makefile together with /root/reference/lib/{RawData,RawData_Legacy,Decoder}.cpp and
+// /root/reference/example.cpp (its main renamed on the command line; the DNG / WAV packaging it contains is the
+// checker for include/motioncam/Export.hpp) -- sources read in place, never copied -- into oracle/_ref/libmcraw_ref.so.  Nothing in the product links
 // or loads this library.
 #define MC_PREFIX mcref_
 #include "../motioncam-decoder_b200/csrc/decoder_cwrap.inc"
@@ -10,7 +11,39 @@
 #include <chrono>
 #include <thread>
 
+// Defined in the reference's example.cpp:27-53 and :55-139 (external linkage, global namespace).
+void writeAudio(const std::string& outputPath, const int sampleRateHz, const int numChannels, std::vector<motioncam::AudioChunk>& audioChunks);
+void writeDng(const std::string& outputPath, const std::vector<uint8_t>& data, const nlohmann::json& metadata, const nlohmann::json& containerMetadata);
+
 extern "C" {
+
+// 0 = written; 1 = an exception escaped (text in err).
+int mcref_write_dng(const char* path, const uint8_t* data, size_t bytes, const char* frame_json, const char* container_json,
+                    char* err, size_t errcap) {
+    try {
+        std::vector<uint8_t> v(data, data + bytes);
+        writeDng(path, v, nlohmann::json::parse(frame_json), nlohmann::json::parse(container_json));
+        return 0;
+    } catch (const std::exception& e) {
+        copy_out(e.what(), err, errcap);
+        return 1;
+    }
+}
+
+// chunk i = samples[offsets[i] .. offsets[i+1])
+int mcref_write_audio(const char* path, int sample_rate_hz, int channels, const int16_t* samples, const int64_t* offsets,
+                      int64_t nchunks, char* err, size_t errcap) {
+    try {
+        std::vector<motioncam::AudioChunk> chunks;
+        for (int64_t i = 0; i < nchunks; i++)
+            chunks.emplace_back(-1, std::vector<int16_t>(samples + offsets[i], samples + offsets[i + 1]));
+        writeAudio(path, sample_rate_hz, channels, chunks);
+        return 0;
+    } catch (const std::exception& e) {
+        copy_out(e.what(), err, errcap);
+        return 1;
+    }
+}
 
 // Frame-parallel timing of the reference codec on host cores:
 // `threads` threads each loop over their share of the frames (t, t+T, ...) `iters` times after `warmup`

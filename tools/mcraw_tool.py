@@ -5,9 +5,11 @@
     mcraw_tool.py synth  out.mcraw [--frames 8] [--width 1920] [--height 1080] [--legacy] [--audio-chunks 4]
     mcraw_tool.py info   clip.mcraw
     mcraw_tool.py decode clip.mcraw [-n N] [--out DIR] [--batch 32]     (needs a B200: there is no CPU decode path)
+    mcraw_tool.py export clip.mcraw [-n N] [--out DIR] [--batch 16] [--threads 4] [--no-audio]     (needs a B200)
 
-`decode` writes frame_%06d.u16 (little-endian 16-bit Bayer, width*height) + frame_%06d.json (the frame metadata) and
-audio.wav; DNG packaging (example.cpp:55-139) is outside the decode path and not reproduced.
+`decode` writes frame_%06d.u16 (little-endian 16-bit Bayer, width*height) + frame_000000.json (the frame metadata) and
+audio.wav.  `export` is the reference program itself: audio.wav + frame_%06d.dng, byte-identical to the files
+example.cpp writes (motioncam::exportClip, include/motioncam/Export.hpp; the compiled form is mcraw_export).
 """
 import argparse
 import json
@@ -77,6 +79,14 @@ def cmd_decode(a):
         print(f"decoded {done} frames and {len(chunks)} audio chunks into {a.out}")
 
 
+def cmd_export(a):
+    from motioncam_decoder_b200 import hostapi
+    os.makedirs(a.out, exist_ok=True)
+    n = hostapi.export_clip(a.file, a.out, num_frames=-1 if a.n is None else a.n, batch=a.batch, writer_threads=a.threads,
+                            audio=not a.no_audio)
+    print(f"exported {n} frames into {a.out}")
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -98,6 +108,14 @@ def main():
     s.add_argument("--out", default="mcraw_out")
     s.add_argument("--batch", type=int, default=32)
     s.set_defaults(fn=cmd_decode)
+    s = sub.add_parser("export")
+    s.add_argument("file")
+    s.add_argument("-n", type=int, default=None, help="number of frames (like the reference example's -n)")
+    s.add_argument("--out", default="mcraw_out")
+    s.add_argument("--batch", type=int, default=16)
+    s.add_argument("--threads", type=int, default=4)
+    s.add_argument("--no-audio", action="store_true")
+    s.set_defaults(fn=cmd_export)
     a = ap.parse_args()
     a.fn(a)
 
