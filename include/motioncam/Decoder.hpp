@@ -46,6 +46,12 @@ struct FrameLocation {
     uint32_t payloadSize;      // Item::size of the BUFFER record
 };
 
+// One decoded frame inside the Decoder's pinned result buffer (loadFramesPinned).
+struct FrameView {
+    const uint8_t* data;       // width*height little-endian uint16, row-major
+    size_t size;               // bytes
+};
+
 class Decoder {
 public:
     Decoder(const std::string& path);
@@ -71,6 +77,12 @@ public:
     // are what loadFrame(timestamps[i], ...) would have produced; the same exceptions are thrown.
     void loadFrames(const std::vector<Timestamp>& timestamps, std::vector<std::vector<uint8_t>>& outData,
                     std::vector<nlohmann::json>& outMetadata);
+    // loadFrames without the last host copy: outFrames[i] points into one of this Decoder's two pinned result buffers.
+    // The buffers alternate, so the views stay valid through the NEXT loadFrames/loadFramesPinned call and die with the
+    // one after it (or with the Decoder): a consumer that streams the pixels on -- file writers, sockets -- reads
+    // batch k where the D2H copy put it while batch k+1 is being decoded.
+    void loadFramesPinned(const std::vector<Timestamp>& timestamps, std::vector<FrameView>& outFrames,
+                          std::vector<nlohmann::json>& outMetadata);
     // The same, but the decoded frames stay on the GPU: dst[i] is a DEVICE pointer (16-byte aligned) with room for
     // dstCapacityElems[i] uint16 (>= width*height of frame i).  Compressed frames go file -> pinned ring (kept by the
     // Decoder and reused) -> staged H2D on side streams -> kernels; nothing is copied back.  Device: MCRAW_B200_DEVICE.

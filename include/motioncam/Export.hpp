@@ -59,7 +59,8 @@ std::vector<uint8_t> encodeAudio(int sampleRateHz, int numChannels, const std::v
 
 // The whole example program (example.cpp:141-203) on the batched path: audio.wav + frame_%06d.dng for the first
 // `numFrames` frames (negative = all) into `outputDir`; frames are decoded `batch` at a time on the GPU
-// (Decoder::loadFrames) and written by `writerThreads` threads while the next batch decodes.
+// (Decoder::loadFramesPinned) and written by `writerThreads` threads, straight from the pinned result buffer, while the
+// next batch decodes.
 // Returns the number of frames written.  `log` (may be null) receives the reference's progress lines.
 struct ExportOptions {
     int numFrames = -1;
@@ -67,6 +68,18 @@ struct ExportOptions {
     int writerThreads = 4;
     bool writeAudio = true;
 };
-size_t exportClip(const std::string& inputPath, const std::string& outputDir, const ExportOptions& options, std::FILE* log);
+// Where the time went (wall clock of the calling thread).
+struct ExportStats {
+    size_t frames = 0;
+    double totalSeconds = 0;
+    double openAndAudioSeconds = 0;    // container open + index, audio.wav
+    double decodeSeconds = 0;          // sum over batches of file read + H2D + kernels + D2H (Decoder::loadFramesPinned)
+    double firstBatchSeconds = 0;      // the part of decodeSeconds spent in the first batch: CUDA context, pinned allocations
+    double writerWaitSeconds = 0;      // main thread waiting for DNG writers
+    double steadySeconds = 0;          // from the end of the first batch's decode to the end: `frames` DNG writes and
+                                       // frames - batch decodes, overlapped
+};
+size_t exportClip(const std::string& inputPath, const std::string& outputDir, const ExportOptions& options, std::FILE* log,
+                  ExportStats* stats = nullptr);
 
 }  // namespace motioncam

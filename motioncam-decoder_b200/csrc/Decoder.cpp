@@ -138,22 +138,25 @@ struct Decoder::Impl {
         return batchCtx;
     }
     // staging of the batched calls, grown on demand and reused:
-    // pinned ring for the compressed frames; for loadFrames also the decoded frames on the device and in pinned memory
+    // pinned ring for the compressed frames; for loadFrames also the decoded frames on the device and in pinned memory.
+    // Two pinned result buffers alternate (outFlip), so the frames of one call can still be read while the next decodes.
     void* ring = nullptr;
     size_t ringBytes = 0;
     void* devOut = nullptr;
     size_t devOutBytes = 0;
-    void* pinnedOut = nullptr;
-    size_t pinnedOutBytes = 0;
+    void* pinnedOut[2] = {nullptr, nullptr};
+    size_t pinnedOutBytes[2] = {0, 0};
+    int outFlip = 0;
     mcraw_ctx* ringCtx = nullptr;
     void releaseStaging() {
         if (ringCtx) {
             if (ring) mcraw_host_free_pinned(ringCtx, ring);
-            if (pinnedOut) mcraw_host_free_pinned(ringCtx, pinnedOut);
+            for (void* p : pinnedOut)
+                if (p) mcraw_host_free_pinned(ringCtx, p);
             if (devOut) mcraw_device_free(ringCtx, devOut);
         }
-        ring = pinnedOut = devOut = nullptr;
-        ringBytes = pinnedOutBytes = devOutBytes = 0;
+        ring = devOut = pinnedOut[0] = pinnedOut[1] = nullptr;
+        ringBytes = devOutBytes = pinnedOutBytes[0] = pinnedOutBytes[1] = 0;
     }
     // make room for `in` bytes of compressed frames and (loadFrames only) `out` bytes of decoded frames
     void reserveStaging(mcraw_ctx* ctx, size_t in, size_t out) {
@@ -167,12 +170,16 @@ struct Decoder::Impl {
         }
         if (out > devOutBytes) {
             if (devOut) mcraw_device_free(ctx, devOut);
-            if (pinnedOut) mcraw_host_free_pinned(ctx, pinnedOut);
-            devOut = pinnedOut = nullptr; devOutBytes = pinnedOutBytes = 0;
+            devOut = nullptr; devOutBytes = 0;
             if (mcraw_device_alloc(ctx, out + out / 4, &devOut) != MCRAW_OK) fail();
             devOutBytes = out + out / 4;
-            if (mcraw_host_alloc_pinned(ctx, out + out / 4, &pinnedOut) != MCRAW_OK) fail();
-            pinnedOutBytes = out + out / 4;
+        }
+        if (out > pinnedOutBytes[outFlip]) {           // only the result buffer of the current call
+            void*& p = pinnedOut[outFlip];
+            if (p) mcraw_host_free_pinned(ctx, p);
+            p = nullptr; pinnedOutBytes[outFlip] = 0;
+            if (mcraw_host_alloc_pinned(ctx, out + out / 8, &p) != MCRAW_OK) fail();
+            pinnedOutBytes[outFlip] = out + out / 8;
         }
     }
     ~Impl() {
@@ -367,11 +374,23 @@ void Decoder::loadFrame(const Timestamp timestamp, std::vector<uint8_t>& outData
 
 void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<std::vector<uint8_t>>& outData,
                          std::vector<nlohmann::json>& outMetadata) {
+    std::vector<FrameView> views;
+    loadFramesPinned(timestamps, views, outMetadata);
+    outData.resize(views.size());
+    for (size_t i = 0; i < views.size(); i++) {
+        outData[i].resize(views[i].size);
+        std::memcpy(outData[i].data(), views[i].data, views[i].size);
+    }
+}
+
+void Decoder::loadFramesPinned(const std::vector<Timestamp>& timestamps, std::vector<FrameView>& outFrames,
+                               std::vector<nlohmann::json>& outMetadata) {
     const size_t n = timestamps.size();
-    outData.resize(n);
+    outFrames.assign(n, FrameView{nullptr, 0});
     outMetadata.assign(n, nlohmann::json());
     if (n == 0) return;
     mcraw_ctx* ctx = m->batchContext();
+    m->outFlip ^= 1;                                   // the previous call's frames stay where they are
 
     // ---- locate, size and read every frame straight into one pinned buffer (256-byte aligned slots)
     std::vector<FrameLocation> where(n);
@@ -419,13 +438,13 @@ void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<s
             throw IOException(geo[i].compressionType == kCompressionCurrent ? "Failed to uncompress frame"
                                                                              : "Failed to uncompress legacy frame");
     }
-    if (mcraw_memcpy_d2h(ctx, m->pinnedOut, m->devOut, outBytes, nullptr) != MCRAW_OK ||
+    uint8_t* const result = static_cast<uint8_t*>(m->pinnedOut[m->outFlip]);
+    if (mcraw_memcpy_d2h(ctx, result, m->devOut, outBytes, nullptr) != MCRAW_OK ||
         mcraw_stream_sync(ctx, nullptr) != MCRAW_OK)
         throw IOException(mcraw_last_error(ctx));
     for (size_t i = 0; i < n; i++) {
         const size_t bytes = sizeof(uint16_t) * static_cast<size_t>(geo[i].width) * static_cast<size_t>(geo[i].height);
-        outData[i].resize(bytes);
-        std::memcpy(outData[i].data(), static_cast<uint8_t*>(m->pinnedOut) + outOff[i], bytes);
+        outFrames[i] = FrameView{result + outOff[i], bytes};
     }
 }
 

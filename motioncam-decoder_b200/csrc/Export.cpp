@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -377,7 +378,13 @@ void writeAudio(const std::string& outputPath, int sampleRateHz, int numChannels
 // ---------------------------------------------------------------------------------------------------------------
 // The example program's loop on the batched decode
 // ---------------------------------------------------------------------------------------------------------------
-size_t exportClip(const std::string& inputPath, const std::string& outputDir, const ExportOptions& opt, std::FILE* log) {
+size_t exportClip(const std::string& inputPath, const std::string& outputDir, const ExportOptions& opt, std::FILE* log,
+                  ExportStats* stats) {
+    using Clock = std::chrono::steady_clock;
+    const auto seconds = [](Clock::time_point from, Clock::time_point to) { return std::chrono::duration<double>(to - from).count(); };
+    const Clock::time_point t0 = Clock::now();
+    if (stats) *stats = ExportStats();
+
     Decoder decoder(inputPath);
     const std::vector<Timestamp>& frames = decoder.getFrames();
     const nlohmann::json& containerMetadata = decoder.getContainerMetadata();
@@ -389,17 +396,24 @@ size_t exportClip(const std::string& inputPath, const std::string& outputDir, co
         decoder.loadAudio(chunks);
         writeAudio(dir + "audio.wav", decoder.audioSampleRateHz(), decoder.numAudioChannels(), chunks);
     }
+    const Clock::time_point tAudio = Clock::now();
+    if (stats) stats->openAndAudioSeconds = seconds(t0, tAudio);
 
     size_t end = frames.size();
     if (opt.numFrames >= 0 && static_cast<size_t>(opt.numFrames) < end) end = static_cast<size_t>(opt.numFrames);
-    if (end == 0) return 0;
+    if (end == 0) {
+        if (stats) stats->totalSeconds = seconds(t0, Clock::now());
+        return 0;
+    }
     const DngWriter writer(containerMetadata);
     const size_t batch = static_cast<size_t>(opt.batch > 0 ? opt.batch : 1);
     const size_t nthreads = static_cast<size_t>(opt.writerThreads > 0 ? opt.writerThreads : 1);
 
-    // Two batches in flight: the writers drain one while the GPU decodes the next.
+    // Two batches in flight: the writers stream batch k straight out of one of the Decoder's pinned result buffers
+    // while the GPU decodes batch k+1 into the other (Decoder::loadFramesPinned) -- no host copy between the D2H copy
+    // and the file.
     struct InFlight {
-        std::vector<std::vector<uint8_t>> data;
+        std::vector<FrameView> frames;
         std::vector<nlohmann::json> metadata;
         std::vector<std::future<void>> writers;
         void drain() {
@@ -417,13 +431,22 @@ size_t exportClip(const std::string& inputPath, const std::string& outputDir, co
     } inflight[2];
 
     size_t which = 0;
+    Clock::time_point tFirstBatch = tAudio;
     try {
         for (size_t first = 0; first < end; first += batch, which ^= 1) {
             InFlight& b = inflight[which];
-            b.drain();
+            Clock::time_point t = Clock::now();
+            b.drain();                                   // its pinned buffer is about to be reused
+            if (stats) stats->writerWaitSeconds += seconds(t, Clock::now());
             const size_t n = std::min(batch, end - first);
             const std::vector<Timestamp> stamps(frames.begin() + static_cast<ptrdiff_t>(first), frames.begin() + static_cast<ptrdiff_t>(first + n));
-            decoder.loadFrames(stamps, b.data, b.metadata);
+            t = Clock::now();
+            decoder.loadFramesPinned(stamps, b.frames, b.metadata);
+            if (stats) stats->decodeSeconds += seconds(t, Clock::now());
+            if (first == 0) {
+                tFirstBatch = Clock::now();
+                if (stats) stats->firstBatchSeconds = seconds(t, tFirstBatch);
+            }
             if (log)
                 for (size_t i = 0; i < n; i++) std::fprintf(log, "Writing frame_%06zu.dng\n", first + i);
             for (size_t t = 0; t < std::min(nthreads, n); t++) {
@@ -431,13 +454,15 @@ size_t exportClip(const std::string& inputPath, const std::string& outputDir, co
                     char name[40];
                     for (size_t i = t; i < n; i += nthreads) {
                         std::snprintf(name, sizeof(name), "frame_%06zu.dng", first + i);
-                        writer.write(dir + name, b.data[i].data(), b.data[i].size(), b.metadata[i]);
+                        writer.write(dir + name, b.frames[i].data, b.frames[i].size, b.metadata[i]);
                     }
                 }));
             }
         }
+        const Clock::time_point t = Clock::now();
         inflight[0].drain();
         inflight[1].drain();
+        if (stats) stats->writerWaitSeconds += seconds(t, Clock::now());
     } catch (...) {
         for (auto& b : inflight) {
             try {
@@ -446,6 +471,14 @@ size_t exportClip(const std::string& inputPath, const std::string& outputDir, co
             }
         }
         throw;
+    }
+    if (stats) {
+        const Clock::time_point tEnd = Clock::now();
+        stats->frames = end;
+        stats->totalSeconds = seconds(t0, tEnd);
+        // everything after the first batch has been decoded (context creation, pinned allocations and first touches are
+        // in that batch): the first batch's writes and all later batches
+        stats->steadySeconds = seconds(tFirstBatch, tEnd);
     }
     return end;
 }

@@ -81,16 +81,24 @@ int mcb200_write_audio(const char* path, int sample_rate_hz, int channels, const
 }
 
 // The example program's loop (audio.wav + frame_%06d.dng into out_dir) on the batched B200 decode.
-// Returns the number of frames written, or -1 (text in err).
+// Returns the number of frames written, or -1 (text in err).  stats (may be null) receives 6 doubles: total, open+audio,
+// decode, first batch, writer wait, steady seconds (motioncam::ExportStats).
 int64_t mcb200_export_clip(const char* input_path, const char* out_dir, int num_frames, int batch, int writer_threads,
-                           int write_audio, char* err, size_t errcap) {
+                           int write_audio, double* stats, char* err, size_t errcap) {
     try {
         motioncam::ExportOptions opt;
         opt.numFrames = num_frames;
         if (batch > 0) opt.batch = batch;
         if (writer_threads > 0) opt.writerThreads = writer_threads;
         opt.writeAudio = write_audio != 0;
-        return static_cast<int64_t>(motioncam::exportClip(input_path, out_dir, opt, nullptr));
+        motioncam::ExportStats st;
+        const size_t n = motioncam::exportClip(input_path, out_dir, opt, nullptr, &st);
+        if (stats) {
+            const double v[6] = {st.totalSeconds, st.openAndAudioSeconds, st.decodeSeconds, st.firstBatchSeconds,
+                                 st.writerWaitSeconds, st.steadySeconds};
+            std::memcpy(stats, v, sizeof v);
+        }
+        return static_cast<int64_t>(n);
     } catch (const std::exception& e) {
         copy_out(e.what(), err, errcap);
         return -1;

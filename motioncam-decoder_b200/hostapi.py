@@ -50,7 +50,7 @@ def _bind(c, prefix):
     f("write_audio").argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(i64), i64, ctypes.c_char_p, sz]
     if prefix == "mcb200_":
         c.mcb200_export_clip.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                         ctypes.c_int, ctypes.c_char_p, sz]
+                                         ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_char_p, sz]
         c.mcb200_export_clip.restype = i64
         c.mcb200_decoder_load_frames.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(vp), ctypes.POINTER(i64)]
         c.mcb200_decoder_load_frames.restype = i64
@@ -110,14 +110,18 @@ def write_audio(path, sample_rate_hz, channels, chunks, lib=None, prefix="mcb200
         raise DecoderError(err.value.decode())
 
 
-def export_clip(path, out_dir, num_frames=-1, batch=16, writer_threads=4, audio=True):
-    """motioncam::exportClip: the reference's example program (audio.wav + frame_%06d.dng) on the batched B200 decode."""
+def export_clip(path, out_dir, num_frames=-1, batch=16, writer_threads=4, audio=True, stats=None):
+    """motioncam::exportClip: the reference's example program (audio.wav + frame_%06d.dng) on the batched B200 decode.
+    `stats` (a dict) receives motioncam::ExportStats."""
     c = library()
     err = ctypes.create_string_buffer(1024)
+    st = (ctypes.c_double * 6)()
     n = c.mcb200_export_clip(str(path).encode(), str(out_dir).encode(), int(num_frames), int(batch), int(writer_threads),
-                             1 if audio else 0, err, len(err))
+                             1 if audio else 0, st, err, len(err))
     if n < 0:
         raise DecoderError(err.value.decode())
+    if stats is not None:
+        stats.update(zip(("total_s", "open_audio_s", "decode_s", "first_batch_s", "writer_wait_s", "steady_s"), (round(x, 4) for x in st)))
     return int(n)
 
 
