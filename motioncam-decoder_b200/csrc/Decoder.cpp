@@ -102,11 +102,21 @@ private:
 
 struct FrameGeometry { int width, height, compressionType; };
 
+// A key the reference reads with operator[] (Decoder.cpp:161-167, :216-218).  Absent keys are undefined behaviour there
+// (an assertion inside nlohmann::json, or a null dereference with NDEBUG); here they are an IOException.  Wrong types
+// throw nlohmann's type_error on conversion, as in the reference.
+const nlohmann::json& member(const nlohmann::json& object, const char* key, const char* what) {
+    if (!object.is_object()) throw IOException(std::string("Invalid ") + what + " metadata");
+    const auto it = object.find(key);
+    if (it == object.end()) throw IOException(std::string("Invalid ") + what + " metadata (no \"" + key + "\")");
+    return *it;
+}
+
 FrameGeometry geometryOf(const nlohmann::json& meta) {
     FrameGeometry g;
-    g.width = meta["width"];                       // Decoder.cpp:216-218 (json type errors propagate)
-    g.height = meta["height"];
-    g.compressionType = meta["compressionType"];
+    g.width = member(meta, "width", "frame");      // Decoder.cpp:216-218
+    g.height = member(meta, "height", "frame");
+    g.compressionType = member(meta, "compressionType", "frame");
     return g;
 }
 
@@ -278,8 +288,12 @@ Decoder::~Decoder() = default;
 
 const std::vector<Timestamp>& Decoder::getFrames() const { return m->frameList; }
 const nlohmann::json& Decoder::getContainerMetadata() const { return m->containerMetadata; }
-int Decoder::audioSampleRateHz() const { return m->containerMetadata["extraData"]["audioSampleRate"]; }   // :161-163
-int Decoder::numAudioChannels() const { return m->containerMetadata["extraData"]["audioChannels"]; }      // :165-167
+int Decoder::audioSampleRateHz() const {          // :161-163
+    return member(member(m->containerMetadata, "extraData", "camera"), "audioSampleRate", "camera");
+}
+int Decoder::numAudioChannels() const {           // :165-167
+    return member(member(m->containerMetadata, "extraData", "camera"), "audioChannels", "camera");
+}
 
 void Decoder::loadAudio(std::vector<AudioChunk>& outAudioChunks) {
     for (const BufferOffset& o : m->audioIndex) {

@@ -92,7 +92,7 @@ def write_dng(path, pixels, frame_metadata, container_metadata, lib=None, prefix
     rc = getattr(c, prefix + "write_dng")(str(path).encode(), px.ctypes.data, px.size, json.dumps(frame_metadata).encode(),
                                           json.dumps(container_metadata).encode(), err, len(err))
     if rc != 0:
-        raise DecoderError(err.value.decode())
+        raise DecoderError(err.value.decode("utf-8", "replace"))
 
 
 def write_audio(path, sample_rate_hz, channels, chunks, lib=None, prefix="mcb200_"):
@@ -107,7 +107,7 @@ def write_audio(path, sample_rate_hz, channels, chunks, lib=None, prefix="mcb200
     rc = getattr(c, prefix + "write_audio")(str(path).encode(), int(sample_rate_hz), int(channels), flat.ctypes.data,
                                             offs.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(chunks), err, len(err))
     if rc != 0:
-        raise DecoderError(err.value.decode())
+        raise DecoderError(err.value.decode("utf-8", "replace"))
 
 
 def export_clip(path, out_dir, num_frames=-1, batch=16, writer_threads=4, audio=True, stats=None):
@@ -119,7 +119,7 @@ def export_clip(path, out_dir, num_frames=-1, batch=16, writer_threads=4, audio=
     n = c.mcb200_export_clip(str(path).encode(), str(out_dir).encode(), int(num_frames), int(batch), int(writer_threads),
                              1 if audio else 0, st, err, len(err))
     if n < 0:
-        raise DecoderError(err.value.decode())
+        raise DecoderError(err.value.decode("utf-8", "replace"))
     if stats is not None:
         stats.update(zip(("total_s", "open_audio_s", "decode_s", "first_batch_s", "writer_wait_s", "steady_s"), (round(x, 4) for x in st)))
     return int(n)
@@ -134,7 +134,7 @@ class Decoder:
         err = ctypes.create_string_buffer(1024)
         self._h = self._f("decoder_open")(str(path).encode(), err, len(err))
         if not self._h:
-            raise DecoderError(err.value.decode())
+            raise DecoderError(err.value.decode("utf-8", "replace"))
 
     def _f(self, name):
         return getattr(self._c, self._p + name)
@@ -163,7 +163,7 @@ class Decoder:
         return buf.value.decode()
 
     def _raise(self):
-        raise DecoderError(self._f("decoder_last_error")(self._h).decode())
+        raise DecoderError(self._f("decoder_last_error")(self._h).decode("utf-8", "replace"))
 
     def get_container_metadata(self):
         return json.loads(self._text("decoder_container_metadata"))

@@ -123,6 +123,23 @@ def test_error_messages_match_reference(tmp_path):
                   "Frame not found (timestamp: 42)")                                          # :185-186
 
 
+def test_missing_metadata_keys_are_exceptions(tmp_path):
+    """The reference reads these keys with json::operator[] on a const object (Decoder.cpp:161-167, :216-218): an
+    assertion / undefined behaviour when the key is absent.  Here: IOException."""
+    img = tv.gen_photon(64, 8, 1023, seed=1)
+    frame = {"timestamp": 5, "data": tv.encode_current(img), "height": 8, "compressionType": 7}      # no "width"
+    meta = {k: v for k, v in tv.DEFAULT_CONTAINER_METADATA.items() if k != "extraData"}
+    path = str(tmp_path / "nokeys.mcraw")
+    tv.write_mcraw(path, [frame], [], container_metadata=meta)
+    d = hostapi.Decoder(path)
+    with pytest.raises(hostapi.DecoderError, match='Invalid frame metadata \\(no "width"\\)'):
+        d.load_frame(5)
+    with pytest.raises(hostapi.DecoderError, match='Invalid camera metadata \\(no "extraData"\\)'):
+        d.audio_sample_rate_hz()
+    with pytest.raises(hostapi.DecoderError, match='Invalid camera metadata \\(no "extraData"\\)'):
+        d.num_audio_channels()
+
+
 def test_exports_reference_symbols():
     """The drop-in library exports the reference's mangled codec symbols (RawData.hpp:25-37)."""
     import ctypes
