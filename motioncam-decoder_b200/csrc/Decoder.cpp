@@ -52,6 +52,12 @@ public:
     void read(int64_t offset, void* dst, size_t bytes) const {
         if (!tryRead(offset, dst, bytes)) throw IOException("Failed to read data");
     }
+    // A size taken from the file must fit in the file BEFORE memory is set aside for it (the read would fail anyway,
+    // but only after a count of 2^60 index entries or a 4 GB record has been allocated and zeroed).
+    void require(int64_t offset, uint64_t bytes) const {
+        if (mSize < 0) return;                      // not a regular file: let the read decide
+        if (offset < 0 || offset > mSize || bytes > static_cast<uint64_t>(mSize - offset)) throw IOException("Failed to read data");
+    }
 
 private:
     FILE* mFile;
@@ -67,6 +73,7 @@ bool readAudioChunk(const FileView& file, const BufferOffset& where, AudioChunk&
     file.read(pos, &item, sizeof item);
     pos += sizeof item;
     if (item.type != Type::AUDIO_DATA) throw IOException("Invalid audio data");
+    file.require(pos, item.size);
     std::vector<int16_t> samples((static_cast<size_t>(item.size) + 1) / 2);
     file.read(pos, samples.data(), item.size);
     pos += item.size;
@@ -117,6 +124,10 @@ FrameGeometry geometryOf(const nlohmann::json& meta) {
     g.width = member(meta, "width", "frame");      // Decoder.cpp:216-218
     g.height = member(meta, "height", "frame");
     g.compressionType = member(meta, "compressionType", "frame");
+    // the callers size buffers with width*height (Decoder.cpp:221-222 does so unchecked)
+    if (g.width <= 0 || g.height <= 0 || g.width > 65536 || g.height > 65536 ||
+        static_cast<int64_t>(g.width) * g.height > (int64_t(1) << 30))
+        throw IOException("Invalid frame metadata (width x height)");
     return g;
 }
 
@@ -211,6 +222,7 @@ void Decoder::Impl::open() {
     Item item{};
     file.read(sizeof header, &item, sizeof item);
     if (item.type != Type::METADATA) throw IOException("Invalid camera metadata");
+    file.require(sizeof header + sizeof item, item.size);
     std::string text(item.size, '\0');
     file.read(sizeof header + sizeof item, &text[0], item.size);
     containerMetadata = nlohmann::json::parse(text);
@@ -231,6 +243,7 @@ void Decoder::Impl::readFrameIndex() {
     file.read(file.size() - static_cast<int64_t>(sizeof(BufferIndex)), &index, sizeof index);
     if (static_cast<uint32_t>(index.magicNumber) != INDEX_MAGIC_NUMBER) throw IOException("Corrupted file");
     if (index.numOffsets < 0 || index.indexDataOffset < 0) throw IOException("Invalid index");
+    file.require(index.indexDataOffset, static_cast<uint64_t>(index.numOffsets) * sizeof(BufferOffset));
     frameIndex.resize(static_cast<size_t>(index.numOffsets));
     file.read(index.indexDataOffset, frameIndex.data(), sizeof(BufferOffset) * frameIndex.size());
 
@@ -262,6 +275,8 @@ void Decoder::Impl::findAudioIndex() {
             file.read(pos, &index, sizeof index);
             pos += sizeof index;
             if (index.numOffsets < 0) throw IOException("Failed to read data");
+            if (static_cast<uint64_t>(index.numOffsets) > (1ull << 40)) throw IOException("Failed to read data");
+            file.require(pos, static_cast<uint64_t>(index.numOffsets) * sizeof(BufferOffset));
             audioIndex.resize(static_cast<size_t>(index.numOffsets));
             file.read(pos, audioIndex.data(), sizeof(BufferOffset) * audioIndex.size());
             pos += static_cast<int64_t>(sizeof(BufferOffset) * audioIndex.size());
@@ -317,6 +332,7 @@ FrameLocation Decoder::locateFrame(const Timestamp timestamp) const {
     where.timestamp = timestamp;
     where.payloadOffset = it->second.offset + static_cast<int64_t>(sizeof item);
     where.payloadSize = item.size;
+    m->file.require(where.payloadOffset, where.payloadSize);
     return where;
 }
 
@@ -327,6 +343,7 @@ void Decoder::readFrame(const FrameLocation& where, uint8_t* dst, nlohmann::json
     m->file.read(pos, &item, sizeof item);
     pos += sizeof item;
     if (item.type != Type::METADATA) throw IOException("Invalid metadata");
+    m->file.require(pos, item.size);
     std::string text(item.size, '\0');
     m->file.read(pos, &text[0], item.size);
     outMetadata = nlohmann::json::parse(text);

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from motioncam_decoder_b200 import hostapi, testvec as tv
-resource.setrlimit(resource.RLIMIT_AS, (8<<30, 8<<30))
+if not os.environ.get('MCRAW_FUZZ_NO_RLIMIT'):      # (an AddressSanitizer build needs its shadow mappings)
+    resource.setrlimit(resource.RLIMIT_AS, (8<<30, 8<<30))
 seed=int(sys.argv[1]); N=int(sys.argv[2])
 rng=np.random.default_rng(seed)
 d=sys.argv[3]
