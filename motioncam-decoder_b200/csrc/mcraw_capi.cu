@@ -268,7 +268,10 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     // A slot remembers the descriptors it was last built for: a caller that decodes into a ring of buffers presents the
     // same descriptors again and again, and then the device-side tables of the slot are still valid -- nothing to
     // validate, build or upload.
-    const bool hit = s.plan_valid && s.plan_descs.size() == n && std::memcmp(s.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
+    // (flag_uses bound: the per-frame meta_done counters k_units compares with 2 * flag_uses are 32 bits wide and only
+    // zeroed when a plan is uploaded, so a plan that has been reused 2^30 times is uploaded afresh.)
+    const bool hit = s.plan_valid && s.flag_uses < (1u << 30) && s.plan_descs.size() == n &&
+                     std::memcmp(s.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
     if (!hit) {
         s.plan_valid = false;
         std::vector<FrameDev>& frames = ctx->tmp_frames;     // reused across calls: no allocation in steady state
