@@ -221,3 +221,31 @@ def test_reference_program_files_equal_our_writers(tmp_path, legacy):
         hostapi.write_dng(out, px, fm, container)
         assert open(out, "rb").read() == open(ref_dir / f"frame_{i:06d}.dng", "rb").read(), i
     assert json.loads(json.dumps(container)) == cm
+
+
+# ---- committed fixtures (tests/golden/export_golden.json, made by tests/golden/make_export_golden.py from the compiled
+# ---- reference program): the pin that holds where neither /root/reference nor oracle/_ref exists
+def _golden():
+    import base64
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "export_golden.json")) as f:
+        g = json.load(f)
+    return g, base64.b64decode
+
+
+@pytest.mark.parametrize("prefix", ["mcb200_", "mcref_"])
+def test_golden_dng_and_wav(tmp_path, prefix):
+    if prefix == "mcref_" and not ol.have_ref():
+        pytest.skip("compiled reference not present")
+    lib = _ref_lib() if prefix == "mcref_" else None
+    g, dec = _golden()
+    assert len(g["dng"]) == 6 and len(g["wav"]) == 5
+    for c in g["dng"]:
+        px = np.frombuffer(dec(c["pixels"]), np.uint16).reshape(c["frame"]["height"], c["frame"]["width"])
+        path = str(tmp_path / (c["name"] + ".dng"))
+        hostapi.write_dng(path, px, c["frame"], c["container"], lib=lib, prefix=prefix)
+        assert open(path, "rb").read() == dec(c["file"]), c["name"]
+    for c in g["wav"]:
+        chunks = [np.frombuffer(dec(x), np.int16) for x in c["chunks"]]
+        path = str(tmp_path / (c["name"] + ".wav"))
+        hostapi.write_audio(path, c["rate"], c["channels"], chunks, lib=lib, prefix=prefix)
+        assert open(path, "rb").read() == dec(c["file"]), c["name"]
