@@ -65,6 +65,12 @@ struct mcraw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_streams[kCopyStreams] = {nullptr, nullptr};
+    // EXPERIMENT (off unless MCRAW_CROSS_BATCH=<CTAs> is set): k_units holds back that many of its resident CTAs and k_meta of
+    // the NEXT batch runs in the gap, on a stream of its own, while k_units of the current batch streams pixels; the two
+    // only meet through the per-frame meta_done counters.  Valid when the compressed frames are already in device
+    // memory when mcraw_decode_batch is called (k_meta no longer waits for earlier work on the caller's stream).
+    cudaStream_t meta_stream = nullptr;
+    uint32_t cross_ctas = 0;
     Slot slots[kSlots];
     int cur = -1;
     Stage stages[kStage];
@@ -313,6 +319,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
 
     // descriptor + work list upload and the index kernels between e0 and e1, the pixel kernels between e1 and e2
     const bool timed = ctx->timing_every && (ctx->chunk_seq++ % ctx->timing_every) == 0;
+    const bool cross = ctx->cross_ctas > 0 && hit && any7 && !any6 && !timed;
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e0, st));
     if (!hit) {
         CU_TRY(ctx, cudaMemcpyAsync(s.d_up, s.h_up, s.plan_bytes, cudaMemcpyHostToDevice, st));
@@ -321,7 +328,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         s.flag_uses = 0;
         s.plan_valid = true;
     }
-    if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
+    if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, cross ? ctx->meta_stream : st>>>(d_frames, d_states); ctx->launches += 1; }
     if (any6) {
         k_legacy_maps<<<dim3(s.max_ltiles, n), LG_MAPS_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
         k_legacy_scan<<<n, LG_THREADS, 0, st>>>(d_frames, d_states, d_results);
@@ -331,11 +338,12 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
     if (any7) {
         const uint32_t want = (s.nitems + KU_WARPS - 1) / KU_WARPS;
-        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(ctx->resident_ctas, 1), want));
+        const uint32_t room = cross && ctx->resident_ctas > ctx->cross_ctas ? ctx->resident_ctas - ctx->cross_ctas : ctx->resident_ctas;
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(room, 1), want));
         // Programmatic dependent launch: k_units becomes resident while k_meta's last wave is still running and synchronises
         // per frame (see k_units).  Timed batches are launched the ordinary way, so that the events bracket one kernel each.
         s.flag_uses += 1;
-        const bool pdl = ctx->overlap && !timed;
+        const bool pdl = ctx->overlap && !timed && !cross;
         cudaLaunchConfig_t cfg;
         std::memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(KD_THREADS); cfg.dynamicSmemBytes = KU_SMEM; cfg.stream = st;
@@ -345,7 +353,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
         CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems, d_counter,
-                                       pdl ? 2u * s.flag_uses : 0u));
+                                       (pdl || cross) ? 2u * s.flag_uses : 0u));
         ctx->launches += 1;
     }
     if (any6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
@@ -420,6 +428,14 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
     for (auto& cs : ctx->copy_streams)
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
+    if (const char* e = getenv("MCRAW_CROSS_BATCH")) {
+        ctx->cross_ctas = (uint32_t)std::max(0, atoi(e));
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (ctx->cross_ctas && cudaStreamCreateWithPriority(&ctx->meta_stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
+            ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA);
+        }
+    }
     if (cudaFuncSetAttribute(k_meta, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_legacy_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_MAPS_SMEM) != cudaSuccess ||
@@ -432,6 +448,8 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
             ctx->err = "k_units does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
+        // k_units spins on counters that k_meta bumps: in the cross-batch experiment k_meta must always find room beside it
+        ctx->cross_ctas = std::min(ctx->cross_ctas, ctx->resident_ctas / 2);
     }
     for (auto& s : ctx->slots) {
         if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&s.e0) != cudaSuccess ||
@@ -475,6 +493,7 @@ void mcraw_ctx_destroy(mcraw_ctx* ctx) {
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
     for (auto& cs : ctx->copy_streams) if (cs) cudaStreamDestroy(cs);
+    if (ctx->meta_stream) cudaStreamDestroy(ctx->meta_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""c2_steps.py -- torch-free A/B timer for the device-resident C2 step (240 frames 1920x1080, 16 distinct, type 7):
+wall clock over many back-to-back mcraw_decode_batch calls on one context (the GPU runs them back to back, the host
+stays ahead), outputs checked against the source images afterwards.  Used to compare builds / environment switches
+(e.g. MCRAW_CROSS_BATCH, MCRAW_NO_OVERLAP) in seconds; bench.py stays the number of record.
+
+    python tools/c2_steps.py [--steps 400] [--frames 240]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from motioncam_decoder_b200 import capi, testvec as tv  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--frames", type=int, default=240)
+    ap.add_argument("--label", default="")
+    a = ap.parse_args()
+    w, h = 1920, 1080
+    images = [tv.gen_photon(w, h, 4095, seed=s + 1) for s in range(16)]
+    streams = [tv.encode_current(img) for img in images]
+    ctx = capi.Context(0)
+    items = []
+    for i in range(a.frames):
+        s = streams[i % 16]
+        sp = ctx.device_alloc(len(s) + 256)
+        dp = ctx.device_alloc(w * h * 2 + 256)
+        ctx.h2d(sp, s)
+        items.append((sp, len(s), w, h, capi.COMPRESSION_CURRENT, dp, w * h))
+    descs, n = capi.Context.make_descs(items)
+    for _ in range(24):                       # every slot of the context has seen this plan
+        ctx.decode_batch(descs, n)
+    ctx.batch_wait(n)
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            ctx.decode_batch(descs, n)
+        written, status = ctx.batch_wait(n)
+        best = min(best, (time.perf_counter() - t0) / a.steps)
+    ok = all(x == w * h for x in written) and not any(status)
+    out = np.empty((h, w), np.uint16)
+    for i in list(range(16)) + [a.frames - 1]:
+        ctx.d2h(out, items[i][5])
+        ok = ok and bool(np.array_equal(out, images[i % 16]))
+    print(json.dumps({"label": a.label, "env": {k: v for k, v in os.environ.items() if k.startswith("MCRAW_")},
+                      "ms_per_step": round(best * 1e3, 4), "tpix_per_s": round(a.frames * w * h / best / 1e12, 3), "outputs_ok": ok}))
+
+
+if __name__ == "__main__":
+    main()
