@@ -90,3 +90,21 @@ def test_export_without_reference(tmp_path):
             assert len(blob) > 8 + data.size + 300
     with pytest.raises(hostapi.DecoderError):
         hostapi.export_clip(str(tmp_path / "missing.mcraw"), out)
+
+
+RELINKED = os.path.join(os.path.dirname(ol.REF_SO), "ref_example_relinked")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_EXAMPLE) and os.path.exists(RELINKED)), reason="reference programs not built")
+def test_relinked_reference_program(tmp_path):
+    """the reference's own example.cpp + lib/Decoder.cpp, unchanged, linked against this repo's
+    library instead of lib/RawData*.cpp (oracle/Makefile `relinked`) -- every frame goes through the mangled
+    motioncam::raw::Decode / DecodeLegacy symbols onto the GPU; output files identical to the all-CPU reference program."""
+    clip, n = _clip(tmp_path)
+    ref_dir, ref_out = _reference_run(tmp_path, clip)
+    out = tmp_path / "relinked"
+    out.mkdir()
+    r = subprocess.run([RELINKED, clip], cwd=out, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == ref_out
+    assert len(_same_files(ref_dir, out)) == n + 1
