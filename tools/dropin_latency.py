@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Latency of the reference-shaped single-frame call (motioncam::raw::Decode: host bytes in, host uint16 out, synchronous)
 through this repo's drop-in library, next to the compiled reference on one host core.  BASELINE config 1."""
-import ctypes
 import os
 import sys
 import time

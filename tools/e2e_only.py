@@ -1,6 +1,5 @@
 import os, sys, time
 sys.path.insert(0, '/root/repo')
-import numpy as np
 import bench
 from motioncam_decoder_b200 import capi
 desc, w, h, ct, frames, streams = bench.make_streams('c2')
