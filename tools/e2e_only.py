@@ -1,5 +1,6 @@
+"""e2e_only.py -- micro-benchmark of the host-input pipeline alone (pinned ring -> staged H2D -> decode), C2."""
 import os, sys, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from motioncam_decoder_b200 import capi
 desc, w, h, ct, frames, streams = bench.make_streams('c2')
