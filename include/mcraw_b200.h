@@ -96,6 +96,12 @@ int mcraw_device_alloc(mcraw_ctx* ctx, size_t bytes, void** out);
 int mcraw_device_free(mcraw_ctx* ctx, void* p);
 int mcraw_host_alloc_pinned(mcraw_ctx* ctx, size_t bytes, void** out);
 int mcraw_host_free_pinned(mcraw_ctx* ctx, void* p);
+/* Page-lock memory the caller already owns (e.g. a read-only mmap of the .mcraw file), so that mcraw_decode_batch_host
+ * can copy frames to the device straight from it -- the "GPU-direct feed" of SURVEY.md section 8f-3, in place of the
+ * page-cache -> pinned-ring copy in front of the reference's fread (Decoder.cpp:203-209).  read_only != 0 is required
+ * for PROT_READ mappings.  Fails (MCRAW_ERR_CUDA, text in mcraw_last_error) where the platform cannot pin the range. */
+int mcraw_host_register(mcraw_ctx* ctx, void* p, size_t bytes, int read_only);
+int mcraw_host_unregister(mcraw_ctx* ctx, void* p);
 int mcraw_memcpy_h2d(mcraw_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, void* stream);
 int mcraw_memcpy_d2h(mcraw_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, void* stream);
 int mcraw_stream_sync(mcraw_ctx* ctx, void* stream);

@@ -71,7 +71,7 @@ public:
     // ---- additions (batched, B200) -------------------------------------------------------------------
     // Locate a frame's compressed bytes; throws IOException like loadFrame for unknown timestamps.
     FrameLocation locateFrame(const Timestamp timestamp) const;
-    // Read the frame's compressed bytes into dst (payloadSize bytes, e.g. pinned memory) and parse its JSON.
+    // Read the frame's compressed bytes into dst (payloadSize bytes, e.g. pinned memory; nullptr = skip) and parse its JSON.
     void readFrame(const FrameLocation& where, uint8_t* dst, nlohmann::json& outMetadata) const;
     // loadFrame for many timestamps: one overlapped H2D + batched decode + D2H.  outData[i] / outMetadata[i]
     // are what loadFrame(timestamps[i], ...) would have produced; the same exceptions are thrown.
@@ -88,6 +88,10 @@ public:
     // Decoder and reused) -> staged H2D on side streams -> kernels; nothing is copied back.  Device: MCRAW_B200_DEVICE.
     void loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint16_t* const* dst, const uint64_t* dstCapacityElems,
                             std::vector<nlohmann::json>& outMetadata);
+    // How loadFramesToDevice gets the compressed bytes to the GPU: "pread -> pinned ring" (default) or, with
+    // MCRAW_FEED=mmap in the environment, the file mapped read-only and page-locked so that the H2D copies read the
+    // page cache directly (falls back to the ring, with the reason in this text, where the platform refuses).
+    const char* feedDescription() const;
 
 private:
     struct Impl;

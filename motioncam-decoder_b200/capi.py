@@ -40,6 +40,7 @@ EXPORTED = [
     "mcraw_device_alloc", "mcraw_device_free", "mcraw_host_alloc_pinned", "mcraw_host_free_pinned",
     "mcraw_memcpy_h2d", "mcraw_memcpy_d2h", "mcraw_stream_sync", "mcraw_kernel_launches",
     "mcraw_last_batch_kernel_ms", "mcraw_kernel_time_totals", "mcraw_set_kernel_timing",
+    "mcraw_host_register", "mcraw_host_unregister",
 ]
 
 _c = None
@@ -66,6 +67,8 @@ def lib():
         c.mcraw_device_free.argtypes = [vp, vp]
         c.mcraw_host_alloc_pinned.argtypes = [vp, sz, ctypes.POINTER(vp)]
         c.mcraw_host_free_pinned.argtypes = [vp, vp]
+        c.mcraw_host_register.argtypes = [vp, vp, sz, ctypes.c_int]
+        c.mcraw_host_unregister.argtypes = [vp, vp]
         c.mcraw_memcpy_h2d.argtypes = [vp, vp, vp, sz, vp]
         c.mcraw_memcpy_d2h.argtypes = [vp, vp, vp, sz, vp]
         c.mcraw_stream_sync.argtypes = [vp, vp]

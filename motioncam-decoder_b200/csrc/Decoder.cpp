@@ -8,11 +8,13 @@
 #include <motioncam/Decoder.hpp>
 #include <motioncam/RawData.hpp>
 
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <cstdlib>
 #include <cstring>
 #include <exception>
@@ -40,6 +42,7 @@ public:
         if (mFile) std::fclose(mFile);
     }
     int64_t size() const { return mSize; }
+    int fd() const { return mFd; }
     bool tryRead(int64_t offset, void* dst, size_t bytes) const {
         uint8_t* p = static_cast<uint8_t*>(dst);
         while (bytes) {
@@ -203,7 +206,52 @@ struct Decoder::Impl {
             pinnedOutBytes[outFlip] = out + out / 8;
         }
     }
+    // ---- mapped feed (opt-in: MCRAW_FEED=mmap).  The whole file is mapped read-only and
+    // page-locked once, and loadFramesToDevice hands the frames' addresses INSIDE the mapping to the H2D pipeline: the
+    // DMA engine reads the page cache directly, the pread copy into the pinned ring disappears.  Falls back to the ring
+    // (and says why in feedNote) when the mapping or the registration is refused, or the file is larger than
+    // MCRAW_FEED_MMAP_MAX_MB (default 8192: registering pins every page of the file).
+    void* map = nullptr;
+    size_t mapBytes = 0;
+    mcraw_ctx* mapCtx = nullptr;
+    bool mapTried = false;
+    std::string feedNote = "pread -> pinned ring";
+    const uint8_t* mappedFile(mcraw_ctx* ctx) {
+        if (mapTried) return static_cast<const uint8_t*>(map);
+        mapTried = true;
+        const char* mode = std::getenv("MCRAW_FEED");
+        if (!mode || std::string(mode) != "mmap") return nullptr;
+        int64_t limitMb = 8192;
+        if (const char* e = std::getenv("MCRAW_FEED_MMAP_MAX_MB")) limitMb = std::atoll(e);
+        if (file.size() <= 0 || file.size() > limitMb * (int64_t(1) << 20)) {
+            feedNote = "pread -> pinned ring (mmap feed: file size outside the limit)";
+            return nullptr;
+        }
+        void* p = ::mmap(nullptr, static_cast<size_t>(file.size()), PROT_READ, MAP_SHARED, file.fd(), 0);
+        if (p == MAP_FAILED) {
+            feedNote = std::string("pread -> pinned ring (mmap failed: ") + std::strerror(errno) + ")";
+            return nullptr;
+        }
+        if (mcraw_host_register(ctx, p, static_cast<size_t>(file.size()), 1) != MCRAW_OK) {
+            feedNote = std::string("pread -> pinned ring (cudaHostRegister refused the mapping: ") + mcraw_last_error(ctx) + ")";
+            ::munmap(p, static_cast<size_t>(file.size()));
+            return nullptr;
+        }
+        map = p;
+        mapBytes = static_cast<size_t>(file.size());
+        mapCtx = ctx;
+        feedNote = "mmap + cudaHostRegister (read-only): H2D straight from the page cache";
+        return static_cast<const uint8_t*>(map);
+    }
+    void releaseMap() {
+        if (!map) return;
+        mcraw_host_unregister(mapCtx, map);
+        ::munmap(map, mapBytes);
+        map = nullptr;
+        mapBytes = 0;
+    }
     ~Impl() {
+        releaseMap();
         releaseStaging();
         if (batchCtx) mcraw_ctx_destroy(batchCtx);
     }
@@ -337,7 +385,7 @@ FrameLocation Decoder::locateFrame(const Timestamp timestamp) const {
 }
 
 void Decoder::readFrame(const FrameLocation& where, uint8_t* dst, nlohmann::json& outMetadata) const {
-    m->file.read(where.payloadOffset, dst, where.payloadSize);
+    if (dst) m->file.read(where.payloadOffset, dst, where.payloadSize);     // dst == nullptr: metadata only
     int64_t pos = where.payloadOffset + where.payloadSize;
     Item item{};
     m->file.read(pos, &item, sizeof item);
@@ -479,6 +527,8 @@ void Decoder::loadFramesPinned(const std::vector<Timestamp>& timestamps, std::ve
     }
 }
 
+const char* Decoder::feedDescription() const { return m->feedNote.c_str(); }
+
 void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint16_t* const* dst, const uint64_t* dstCapacityElems,
                                  std::vector<nlohmann::json>& outMetadata) {
     const size_t n = timestamps.size();
@@ -495,17 +545,25 @@ void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint1
         off[i] = bytes;
         bytes += (static_cast<size_t>(where[i].payloadSize) + 255) & ~static_cast<size_t>(255);
     }
-    m->reserveStaging(ctx, bytes + 256, 0);
-    uint8_t* ring = static_cast<uint8_t*>(m->ring);
+    const uint8_t* mapped = m->mappedFile(ctx);
+    uint8_t* ring = nullptr;
+    if (!mapped) {
+        m->reserveStaging(ctx, bytes + 256, 0);
+        ring = static_cast<uint8_t*>(m->ring);
+    }
     std::vector<mcraw_frame_desc> descs(n);
-    readFramesParallel(*this, where, ring, off, outMetadata);
+    if (mapped) {
+        for (size_t i = 0; i < n; i++) readFrame(where[i], nullptr, outMetadata[i]);
+    } else {
+        readFramesParallel(*this, where, ring, off, outMetadata);
+    }
     for (size_t i = 0; i < n; i++) {
         const FrameGeometry g = geometryOf(outMetadata[i]);
         if (g.compressionType != kCompressionCurrent && g.compressionType != kCompressionLegacy)
             throw IOException("Invalid compression type");
         mcraw_frame_desc& d = descs[i];
         std::memset(&d, 0, sizeof d);
-        d.src = ring + off[i];
+        d.src = mapped ? mapped + where[i].payloadOffset : ring + off[i];
         d.len = where[i].payloadSize;
         d.width = g.width;
         d.height = g.height;

@@ -47,6 +47,10 @@ int64_t mcb200_decoder_load_frames_to_device(void* hv, const int64_t* timestamps
     }
 }
 
+size_t mcb200_decoder_feed(void* hv, char* buf, size_t cap) {
+    return copy_out(static_cast<HandleT*>(hv)->dec->feedDescription(), buf, cap);
+}
+
 size_t mcb200_decoder_frame_metadata_at(int64_t i, char* buf, size_t cap) {
     if (i < 0 || static_cast<size_t>(i) >= g_meta_text.size()) return 0;
     return copy_out(g_meta_text[static_cast<size_t>(i)], buf, cap);

@@ -683,6 +683,17 @@ int mcraw_host_free_pinned(mcraw_ctx* ctx, void* p) {
     CU_TRY(ctx, cudaFreeHost(p));
     return MCRAW_OK;
 }
+int mcraw_host_register(mcraw_ctx* ctx, void* p, size_t bytes, int read_only) {
+    if (!ctx || !p || !bytes) return MCRAW_ERR_ARG;
+    if (bind(ctx)) return MCRAW_ERR_CUDA;
+    CU_TRY(ctx, cudaHostRegister(p, bytes, cudaHostRegisterPortable | (read_only ? cudaHostRegisterReadOnly : 0)));
+    return MCRAW_OK;
+}
+int mcraw_host_unregister(mcraw_ctx* ctx, void* p) {
+    if (!ctx || !p) return MCRAW_ERR_ARG;
+    CU_TRY(ctx, cudaHostUnregister(p));
+    return MCRAW_OK;
+}
 int mcraw_memcpy_h2d(mcraw_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
     if (bind(ctx)) return MCRAW_ERR_CUDA;

@@ -57,6 +57,8 @@ def _bind(c, prefix):
         c.mcb200_decoder_load_frames_to_device.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64)]
         c.mcb200_decoder_load_frames_to_device.restype = i64
         c.mcb200_decoder_frame_metadata_at.argtypes = [i64, ctypes.c_char_p, sz]
+        c.mcb200_decoder_feed.argtypes = [vp, ctypes.c_char_p, sz]
+        c.mcb200_decoder_feed.restype = sz
         c.mcb200_decoder_frame_metadata_at.restype = sz
     return c
 
@@ -212,6 +214,12 @@ class Decoder:
             self._c.mcb200_decoder_frame_metadata_at(i, buf, k + 1)
             out.append(json.loads(buf.value.decode()))
         return out
+
+    def feed_description(self):
+        """How load_frames_to_device moves the compressed bytes (Decoder::feedDescription)."""
+        buf = ctypes.create_string_buffer(512)
+        self._c.mcb200_decoder_feed(self._h, buf, len(buf))
+        return buf.value.decode("utf-8", "replace")
 
     def audio_sample_rate_hz(self):
         v = self._f("decoder_audio_sample_rate")(self._h)

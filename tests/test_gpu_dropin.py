@@ -129,3 +129,33 @@ def test_load_frames_to_device(tmp_path):
     for p in ptrs:
         ctx.device_free(p)
     ctx.close()
+
+
+def test_mapped_feed(tmp_path, monkeypatch):
+    """MCRAW_FEED=mmap: loadFramesToDevice copies the frames to the GPU straight out of a page-locked read-only
+    mapping of the file (no pread into the pinned ring).  Where the platform refuses to pin the mapping the Decoder
+    falls back to the ring and says so; the decoded frames are the same either way."""
+    from motioncam_decoder_b200 import capi
+    monkeypatch.setenv("MCRAW_FEED", "mmap")
+    path, frames, images, _ = _clip(tmp_path, n=9)
+    ours = hostapi.Decoder(path)
+    assert ours.feed_description() == "pread -> pinned ring"          # decided at the first device load
+    stamps = ours.get_frames()
+    ctx = capi.Context(0)
+    ptrs = [ctx.device_alloc(images[ts].size * 2) for ts in stamps]
+    caps = [images[ts].size for ts in stamps]
+    for _ in range(2):
+        for p, ts in zip(ptrs, stamps):
+            ctx.h2d(p, np.zeros(images[ts].shape, np.uint16))
+        ours.load_frames_to_device(stamps, ptrs, caps)
+        for ts, p in zip(stamps, ptrs):
+            out = np.empty(images[ts].shape, dtype=np.uint16)
+            ctx.d2h(out, p)
+            assert np.array_equal(out, images[ts]), ts
+    feed = ours.feed_description()
+    print("feed:", feed)
+    assert "mmap" in feed or "cudaHostRegister" in feed               # active, or the stated reason for the fallback
+    ours.close()
+    for p in ptrs:
+        ctx.device_free(p)
+    ctx.close()
