@@ -106,6 +106,7 @@ namespace {
         cudaError_t e_ = (call);                                                               \
         if (e_ != cudaSuccess) {                                                               \
             (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+            (void)cudaGetLastError(); /* reported here: must not resurface at the next launch check */ \
             return MCRAW_ERR_CUDA;                                                             \
         }                                                                                      \
     } while (0)
@@ -686,7 +687,28 @@ int mcraw_host_free_pinned(mcraw_ctx* ctx, void* p) {
 int mcraw_host_register(mcraw_ctx* ctx, void* p, size_t bytes, int read_only) {
     if (!ctx || !p || !bytes) return MCRAW_ERR_ARG;
     if (bind(ctx)) return MCRAW_ERR_CUDA;
-    CU_TRY(ctx, cudaHostRegister(p, bytes, cudaHostRegisterPortable | (read_only ? cudaHostRegisterReadOnly : 0)));
+    if (read_only) {
+        int supported = 0;
+        cudaDeviceGetAttribute(&supported, cudaDevAttrHostRegisterReadOnlySupported, ctx->device);
+        if (!supported) {
+            ctx->err = "cudaHostRegister: read-only registration is not supported on this device/driver";
+            return MCRAW_ERR_CUDA;
+        }
+    }
+    // the range is pinned in whole pages
+    const size_t page = 4096;
+    const size_t span = (bytes + page - 1) / page * page;
+    cudaError_t e = cudaHostRegister(p, span, cudaHostRegisterPortable | (read_only ? cudaHostRegisterReadOnly : 0));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        const cudaError_t first = e;
+        e = cudaHostRegister(p, span, read_only ? cudaHostRegisterReadOnly : cudaHostRegisterDefault);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            ctx->err = std::string("cudaHostRegister: ") + cudaGetErrorString(first) + " (portable), " + cudaGetErrorString(e) + " (default)";
+            return MCRAW_ERR_CUDA;
+        }
+    }
     return MCRAW_OK;
 }
 int mcraw_host_unregister(mcraw_ctx* ctx, void* p) {
