@@ -50,6 +50,7 @@ def test_open_index_metadata(tmp_path):
     assert ours.get_frames() == sorted(f["timestamp"] for f in frames)      # Decoder.cpp:266-279
     assert ours.get_container_metadata() == tv.DEFAULT_CONTAINER_METADATA
     assert ours.audio_sample_rate_hz() == 48000 and ours.num_audio_channels() == 2
+    assert ours.feed_description() == "pread -> pinned ring"
     if ref:
         assert ours.get_frames() == ref.get_frames()
         assert ours.get_container_metadata() == ref.get_container_metadata()
