@@ -42,7 +42,7 @@ extern "C" {
 #define MCRAW_ERR_NO_DEVICE (-3)
 #define MCRAW_ERR_STATE (-4)    /* e.g. results requested with no batch in flight */
 
-/* Per-frame failure reasons reported by mcraw_batch_status() (0 = decoded). */
+/* Per-frame failure reasons reported through mcraw_batch_wait's status[] (0 = decoded). */
 #define MCRAW_FRAME_OK 0u
 #define MCRAW_FRAME_BAD_HEADER 1u      /* offsets > len, encodedWidth % 64, encodedWidth < width (RawData.cpp:547-554) */
 #define MCRAW_FRAME_TRUNCATED 2u       /* a block or metadata block runs past len (reference: stale data, RawData.cpp:419) */
@@ -74,7 +74,12 @@ int mcraw_ctx_device(const mcraw_ctx* ctx);
 
 /* ---- batched device entry point -------------------------------------------------------------------- */
 /* Enqueue the decode of n frames on `stream` (a cudaStream_t passed as void*; NULL = the context's own
- * stream).  Asynchronous: returns once the work is enqueued.  Frames may mix sizes and compression types. */
+ * stream).  Asynchronous: returns once the work is enqueued.  Frames may mix sizes and compression types.
+ * The work is ordered after everything enqueued on `stream` before the call (so descs[i].src may be produced there).
+ * Experiment, off by default: with MCRAW_CROSS_BATCH=<CTAs> in the environment when the context is created, the index
+ * kernel of a batch whose descriptors the context has seen before runs on a stream of the context's own, beside the
+ * previous batch's pixel kernel, and is NOT ordered after `stream`: the compressed frames must then be complete in device
+ * memory when this function is called (profiles/README.md). */
 int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);
 
 /* Same, but descs[i].src are HOST buffers: the context copies them to device staging on its side streams in
