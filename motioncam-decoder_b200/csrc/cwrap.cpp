@@ -47,6 +47,20 @@ int64_t mcb200_decoder_load_frames_to_device(void* hv, const int64_t* timestamps
     }
 }
 
+// Decoder::locateFrame: 0 and the location, or -1 with decoder_last_error() set.
+int mcb200_decoder_locate(void* hv, int64_t timestamp, int64_t* payload_offset, uint32_t* payload_size) {
+    HandleT* h = static_cast<HandleT*>(hv);
+    try {
+        const motioncam::FrameLocation w = h->dec->locateFrame(timestamp);
+        if (payload_offset) *payload_offset = w.payloadOffset;
+        if (payload_size) *payload_size = w.payloadSize;
+        return 0;
+    } catch (const std::exception& e) {
+        h->error = e.what();
+        return -1;
+    }
+}
+
 size_t mcb200_decoder_feed(void* hv, char* buf, size_t cap) {
     return copy_out(static_cast<HandleT*>(hv)->dec->feedDescription(), buf, cap);
 }

@@ -22,6 +22,8 @@ def _bind(c, prefix):
         f(name).restype = sz
     f("decoder_open").argtypes = [ctypes.c_char_p, ctypes.c_char_p, sz]
     f("decoder_open").restype = vp
+    f("decoder_open_fp").argtypes = [ctypes.c_char_p, ctypes.c_char_p, sz]
+    f("decoder_open_fp").restype = vp
     f("decoder_close").argtypes = [vp]
     f("decoder_close").restype = None
     f("decoder_last_error").argtypes = [vp]
@@ -58,6 +60,7 @@ def _bind(c, prefix):
         c.mcb200_decoder_load_frames_to_device.restype = i64
         c.mcb200_decoder_frame_metadata_at.argtypes = [i64, ctypes.c_char_p, sz]
         c.mcb200_decoder_feed.argtypes = [vp, ctypes.c_char_p, sz]
+        c.mcb200_decoder_locate.argtypes = [vp, i64, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_uint32)]
         c.mcb200_decoder_feed.restype = sz
         c.mcb200_decoder_frame_metadata_at.restype = sz
     return c
@@ -130,11 +133,15 @@ def export_clip(path, out_dir, num_frames=-1, batch=16, writer_threads=4, audio=
 class Decoder:
     """motioncam::Decoder (Decoder.hpp:47-73)."""
 
-    def __init__(self, path, lib=None, prefix="mcb200_"):
+    def __init__(self, path, lib=None, prefix="mcb200_", via_file_handle=False):
+        """via_file_handle: construct through Decoder(FILE*) (the wrapper fopens `path`; path=None passes a null handle)."""
         self._c = lib or library()
         self._p = prefix
         err = ctypes.create_string_buffer(1024)
-        self._h = self._f("decoder_open")(str(path).encode(), err, len(err))
+        if via_file_handle:
+            self._h = self._f("decoder_open_fp")(None if path is None else str(path).encode(), err, len(err))
+        else:
+            self._h = self._f("decoder_open")(str(path).encode(), err, len(err))
         if not self._h:
             raise DecoderError(err.value.decode("utf-8", "replace"))
 
@@ -214,6 +221,13 @@ class Decoder:
             self._c.mcb200_decoder_frame_metadata_at(i, buf, k + 1)
             out.append(json.loads(buf.value.decode()))
         return out
+
+    def locate_frame(self, timestamp):
+        """Decoder::locateFrame -> (file offset of the compressed bytes, their size)."""
+        off, size = ctypes.c_int64(), ctypes.c_uint32()
+        if self._c.mcb200_decoder_locate(self._h, int(timestamp), ctypes.byref(off), ctypes.byref(size)) != 0:
+            self._raise()
+        return off.value, size.value
 
     def feed_description(self):
         """How load_frames_to_device moves the compressed bytes (Decoder::feedDescription)."""

@@ -141,6 +141,59 @@ def test_missing_metadata_keys_are_exceptions(tmp_path):
         d.num_audio_channels()
 
 
+def test_file_handle_constructor(tmp_path):
+    """Decoder(FILE*) (Decoder.cpp:97-102): same view of the file as Decoder(path); a null handle is "Invalid file";
+    the Decoder owns the handle (closed with it)."""
+    path, frames, audio = _clip(tmp_path)
+    fds_before = len(os.listdir("/proc/self/fd"))
+    ours = hostapi.Decoder(path, via_file_handle=True)
+    assert ours.get_frames() == sorted(f["timestamp"] for f in frames)
+    assert len(ours.load_audio()) == len(audio)
+    assert len(os.listdir("/proc/self/fd")) == fds_before + 1
+    ours.close()
+    assert len(os.listdir("/proc/self/fd")) == fds_before
+    with pytest.raises(hostapi.DecoderError) as e:
+        hostapi.Decoder(None, via_file_handle=True)
+    assert str(e.value) == "Invalid file"
+    bad = str(tmp_path / "bad.mcraw")
+    with open(bad, "wb") as f:
+        f.write(b"NOTION " + open(path, "rb").read()[7:])
+    with pytest.raises(hostapi.DecoderError, match="Invalid header id"):
+        hostapi.Decoder(bad, via_file_handle=True)
+    assert len(os.listdir("/proc/self/fd")) == fds_before          # a failed open gives the handle back too
+    if ol.have_ref():
+        ref = hostapi.Decoder(path, lib=_ref_lib(), prefix="mcref_", via_file_handle=True)
+        assert ref.get_frames() == sorted(f["timestamp"] for f in frames)
+        ref.close()
+        with pytest.raises(hostapi.DecoderError) as e:
+            hostapi.Decoder(None, lib=_ref_lib(), prefix="mcref_", via_file_handle=True)
+        assert str(e.value) == "Invalid file"
+
+
+def test_duplicate_timestamps(tmp_path):
+    """getFrames() lists every index entry, duplicates included, in timestamp order (Decoder.cpp:266-279)."""
+    frames = []
+    for i, ts in enumerate([30, 10, 30, 20, 10]):
+        img = tv.gen_photon(64, 4 + 4 * i, 1023, seed=i)
+        frames.append({"timestamp": ts, "data": tv.encode_current(img), "width": 64, "height": 4 + 4 * i, "compressionType": 7})
+    path = str(tmp_path / "dup.mcraw")
+    tv.write_mcraw(path, frames, [])
+    ours, ref = _open_both(path)
+    assert ours.get_frames() == [10, 10, 20, 30, 30]
+    # loadFrame finds the FIRST entry of a timestamp; here "first" is index order (stable sort), in the reference it is
+    # whatever std::sort left in front (unspecified), so only the documented rule is checked on this side
+    raw = open(path, "rb").read()
+    for ts, first in ((30, frames[0]), (10, frames[1]), (20, frames[3])):
+        off, size = ours.locate_frame(ts)
+        assert size == len(first["data"]) and raw[off:off + size] == bytes(first["data"].tobytes()), ts
+    with pytest.raises(hostapi.DecoderError, match="Frame not found"):
+        ours.locate_frame(11)
+    if ref:
+        assert ref.get_frames() == ours.get_frames()
+        data, meta = ref.load_frame(20)                      # the reference decodes on the CPU
+        assert data.size == 2 * 64 * frames[3]["height"]
+
+
 def test_exports_reference_symbols():
     """The drop-in library exports the reference's mangled codec symbols (RawData.hpp:25-37)."""
     import ctypes
