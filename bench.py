@@ -223,6 +223,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cross-batch", type=int, default=0,
+                    help="experiment (profiles/README.md): CTAs the pixel kernel leaves to the next batch's index kernel; 0 = off")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -295,6 +297,9 @@ def main():
         ctx.decode_batch(descs, n, sh)
     ctx.batch_wait(n)
 
+    if args.cross_batch:
+        # the sources of the device-resident leg are complete in HBM before any timed call: the promise this switch needs
+        ctx.set_sources_resident(args.cross_batch)
     for _ in range(args.warmup):
         ctx.decode_batch(descs, n, sh)
     ctx.batch_wait(n)
@@ -398,7 +403,8 @@ def main():
                        "compressed_bytes_per_pixel": comp_bytes / pix, "algorithmic_bytes_per_pixel": (comp_bytes + out_bytes) / pix,
                        "l2": f"every frame has its own input and output buffer: {(comp_bytes + out_bytes) / 1e6:.0f} MB touched per step "
                              f"(> 126 MB L2), no flush needed",
-                       "parallelism": f"frame-parallel, {world} rank(s), no collective"},
+                       "parallelism": f"frame-parallel, {world} rank(s), no collective",
+                       "cross_batch_ctas": args.cross_batch},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_units" if ct == 7 else "k_legacy_decode",
                          "algorithmic_bytes_per_launch": alg_main, "kernel_ms_per_launch": main_ms,

@@ -82,6 +82,12 @@ int mcraw_ctx_device(const mcraw_ctx* ctx);
  * memory when this function is called (profiles/README.md). */
 int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);
 
+/* Opt in to the cross-batch experiment described above for this context (same effect as MCRAW_CROSS_BATCH at creation):
+ * holdback_ctas = resident CTAs the pixel kernel leaves to the next batch's index kernel (16..32 measured best on B200;
+ * 0 = off, the default).  By calling this with a non-zero value the caller promises that the compressed frames of every
+ * later mcraw_decode_batch call are complete in device memory at the time of the call. */
+int mcraw_set_sources_resident(mcraw_ctx* ctx, uint32_t holdback_ctas);
+
 /* Same, but descs[i].src are HOST buffers: the context copies them to device staging on its side streams in
  * chunks (double-buffered) so transfer overlaps decode, then decodes into descs[i].dst (device). */
 int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);

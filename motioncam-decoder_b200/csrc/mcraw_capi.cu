@@ -265,7 +265,8 @@ void build_items(const std::vector<FrameDev>& frames, uint32_t resident_ctas, st
 // Enqueue one chunk (device-resident sources) of the current logical batch on `st`.  Everything stays on that one
 // stream: on this platform a cross-stream event dependency costs tens of microseconds, more than the index kernels it
 // could hide (measured: profiles/README.md).
-int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st) {
+int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st,
+                  bool sources_resident) {
     if (n == 0) return MCRAW_OK;
     ctx->cur = (ctx->cur + 1) % kSlots;
     Slot& s = ctx->slots[ctx->cur];
@@ -320,7 +321,9 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
 
     // descriptor + work list upload and the index kernels between e0 and e1, the pixel kernels between e1 and e2
     const bool timed = ctx->timing_every && (ctx->chunk_seq++ % ctx->timing_every) == 0;
-    const bool cross = ctx->cross_ctas > 0 && hit && any7 && !any6 && !timed;
+    // (never for chunks whose sources are still on their way: mcraw_decode_batch_host orders the decode after its H2D copies
+    // through `st`, which k_meta on its own stream would not see)
+    const bool cross = sources_resident && ctx->cross_ctas > 0 && hit && any7 && !any6 && !timed;
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e0, st));
     if (!hit) {
         CU_TRY(ctx, cudaMemcpyAsync(s.d_up, s.h_up, s.plan_bytes, cudaMemcpyHostToDevice, st));
@@ -366,13 +369,13 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     return MCRAW_OK;
 }
 
-int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStream_t st) {
+int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStream_t st, bool sources_resident) {
     if (!descs && n) return fail_arg(ctx, "descs is null");
     int rc = bind(ctx);
     if (rc) return rc;
     begin_batch(ctx, descs, n);
     for (uint32_t base = 0; base < n; base += kMaxGridY) {
-        rc = enqueue_chunk(ctx, descs + base, std::min(kMaxGridY, n - base), base, st);
+        rc = enqueue_chunk(ctx, descs + base, std::min(kMaxGridY, n - base), base, st, sources_resident);
         if (rc) return rc;
     }
     return MCRAW_OK;
@@ -510,6 +513,20 @@ int mcraw_set_kernel_timing(mcraw_ctx* ctx, uint32_t every_n_chunks) {
     return MCRAW_OK;
 }
 
+int mcraw_set_sources_resident(mcraw_ctx* ctx, uint32_t holdback_ctas) {
+    if (!ctx) return MCRAW_ERR_ARG;
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (holdback_ctas && !ctx->meta_stream) {
+        int lo = 0, hi = 0;
+        CU_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU_TRY(ctx, cudaStreamCreateWithPriority(&ctx->meta_stream, cudaStreamNonBlocking, hi));
+    }
+    // batches already enqueued keep the mode they were enqueued with; the switch applies from the next call on
+    ctx->cross_ctas = std::min(holdback_ctas, ctx->resident_ctas / 2);
+    return MCRAW_OK;
+}
+
 int mcraw_kernel_time_totals(mcraw_ctx* ctx, double* meta_ms, double* main_ms, uint64_t* chunks) {
     if (!ctx) return MCRAW_ERR_ARG;
     int rc = bind(ctx);
@@ -523,7 +540,7 @@ int mcraw_kernel_time_totals(mcraw_ctx* ctx, double* meta_ms, double* main_ms, u
 
 int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
-    return enqueue(ctx, descs, n, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+    return enqueue(ctx, descs, n, stream ? static_cast<cudaStream_t>(stream) : ctx->stream, true);
 }
 
 int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
@@ -587,7 +604,7 @@ int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint3
         CU_TRY(ctx, cudaEventRecord(g.copied, cs));
         // ---- decode on the main stream after the copy; then the buffer is free again
         CU_TRY(ctx, cudaStreamWaitEvent(st, g.copied, 0));
-        rc = enqueue_chunk(ctx, chunk.data(), j - i, i, st);
+        rc = enqueue_chunk(ctx, chunk.data(), j - i, i, st, false);
         if (rc) return rc;
         CU_TRY(ctx, cudaEventRecord(g.freed, st));
         g.used = true;
@@ -637,7 +654,7 @@ size_t mcraw_decode_host(mcraw_ctx* ctx, uint16_t* output, int width, int height
     std::memset(&d, 0, sizeof d);
     d.src = ctx->d_in; d.len = len; d.width = width; d.height = height; d.compression_type = compression_type;
     d.dst = ctx->d_out; d.dst_capacity_elems = out_elems;
-    if (enqueue(ctx, &d, 1, ctx->stream)) return 0;
+    if (enqueue(ctx, &d, 1, ctx->stream, false)) return 0;   // the H2D copy above is still in flight on the stream
     // the transfers back are queued behind the kernels right away (16-byte aligned pieces)
     auto part_begin = [&](int k) { return (out_bytes * k / out_parts) & ~(size_t)15; };
     for (int k = 0; k < out_parts; k++) {
