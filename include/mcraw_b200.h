@@ -48,8 +48,10 @@ extern "C" {
 #define MCRAW_FRAME_TRUNCATED 2u       /* a block or metadata block runs past len (reference: stale data, RawData.cpp:419) */
 #define MCRAW_FRAME_BAD_BITS 4u        /* bits[] value > 16 (reference: out-of-bounds table read) */
 #define MCRAW_FRAME_BAD_META_COUNT 8u  /* metadata count smaller than the number of blocks */
-#define MCRAW_FRAME_GEOMETRY 16u       /* encoded size larger than width/height in the descriptor allow */
+#define MCRAW_FRAME_GEOMETRY 16u       /* encodedHeight larger than the descriptor's height allows, dst too small (legacy), or the
+                                        * header's encodedWidth is not what the descriptor planned for (see encoded_width) */
 #define MCRAW_FRAME_BAD_TYPE 32u       /* compression_type not 6 or 7 (Decoder.cpp:233) */
+#define MCRAW_FRAME_INTERNAL 64u       /* a device-side wait gave up (never expected; reported instead of hanging the GPU) */
 
 typedef struct mcraw_ctx mcraw_ctx; /* opaque; owns scratch, streams, staging rings on one device */
 
@@ -61,7 +63,12 @@ typedef struct mcraw_frame_desc {
     int32_t width;               /* frame JSON "width"  (Decoder.cpp:216) */
     int32_t height;              /* frame JSON "height" (Decoder.cpp:217) */
     int32_t compression_type;    /* frame JSON "compressionType": 7 or 6 (Decoder.cpp:218) */
-    int32_t reserved;
+    int32_t encoded_width;       /* current format only.  0 = the frame header's encodedWidth is width rounded up to 64 (what every
+                                  * known encoder writes).  Otherwise: the encodedWidth the caller has read from bytes 0..3 of the
+                                  * frame (RawData.cpp:500-524) -- any multiple of 64 >= width is a valid frame for the reference
+                                  * (RawData.cpp:550-554), and the work list is planned from it.  The kernels check the header
+                                  * against it; a mismatch fails the frame with MCRAW_FRAME_GEOMETRY.  The host-source entry
+                                  * points (mcraw_decode_batch_host, mcraw_decode_host) read the header themselves when this is 0. */
     uint16_t* dst;               /* DEVICE output, width*height uint16, row-major (Decoder.cpp:221-222) */
     uint64_t dst_capacity_elems; /* capacity of dst in uint16 elements */
 } mcraw_frame_desc;
@@ -87,6 +94,11 @@ int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n
  * 0 = off, the default).  By calling this with a non-zero value the caller promises that the compressed frames of every
  * later mcraw_decode_batch call are complete in device memory at the time of the call. */
 int mcraw_set_sources_resident(mcraw_ctx* ctx, uint32_t holdback_ctas);
+
+/* For callers that upload compressed frames themselves: the value to put into mcraw_frame_desc.encoded_width for a
+ * compressionType 7 frame whose first bytes are at `frame` in HOST memory (0 when the header is the usual width rounded
+ * up to 64, or is one no valid frame can carry -- the kernels then reject the frame by their own checks). */
+int32_t mcraw_frame_encoded_width(const uint8_t* frame, uint64_t len, int32_t width, int32_t height);
 
 /* Same, but descs[i].src are HOST buffers: the context copies them to device staging on its side streams in
  * chunks (double-buffered) so transfer overlaps decode, then decodes into descs[i].dst (device). */

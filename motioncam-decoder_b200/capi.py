@@ -28,7 +28,7 @@ class FrameDesc(ctypes.Structure):
         ("width", ctypes.c_int32),
         ("height", ctypes.c_int32),
         ("compression_type", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("encoded_width", ctypes.c_int32),
         ("dst", ctypes.c_void_p),
         ("dst_capacity_elems", ctypes.c_uint64),
     ]
@@ -40,7 +40,7 @@ EXPORTED = [
     "mcraw_device_alloc", "mcraw_device_free", "mcraw_host_alloc_pinned", "mcraw_host_free_pinned",
     "mcraw_memcpy_h2d", "mcraw_memcpy_d2h", "mcraw_stream_sync", "mcraw_kernel_launches",
     "mcraw_last_batch_kernel_ms", "mcraw_kernel_time_totals", "mcraw_set_kernel_timing",
-    "mcraw_host_register", "mcraw_host_unregister", "mcraw_set_sources_resident",
+    "mcraw_host_register", "mcraw_host_unregister", "mcraw_set_sources_resident", "mcraw_frame_encoded_width",
 ]
 
 _c = None
@@ -80,8 +80,16 @@ def lib():
                                                ctypes.POINTER(u64)]
         c.mcraw_set_kernel_timing.argtypes = [vp, u32]
         c.mcraw_set_sources_resident.argtypes = [vp, u32]
+        c.mcraw_frame_encoded_width.argtypes = [vp, u64, ctypes.c_int32, ctypes.c_int32]
+        c.mcraw_frame_encoded_width.restype = ctypes.c_int32
         _c = c
     return _c
+
+
+def frame_encoded_width(stream, width, height):
+    """mcraw_frame_encoded_width: what a caller who uploads a compressionType 7 frame puts into FrameDesc.encoded_width."""
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    return int(lib().mcraw_frame_encoded_width(stream.ctypes.data, stream.size, width, height))
 
 
 class McrawError(RuntimeError):
@@ -158,12 +166,14 @@ class Context:
     # -- decode -------------------------------------------------------------------------------------
     @staticmethod
     def make_descs(frames):
-        """frames: iterable of (src_ptr, len, width, height, compression_type, dst_ptr, dst_capacity_elems)."""
+        """frames: iterable of (src_ptr, len, width, height, compression_type, dst_ptr, dst_capacity_elems[, encoded_width])."""
         frames = list(frames)
         arr = (FrameDesc * max(1, len(frames)))()
-        for i, (src, ln, w, h, ct, dst, cap) in enumerate(frames):
+        for i, fr in enumerate(frames):
+            src, ln, w, h, ct, dst, cap = fr[:7]
             arr[i].src, arr[i].len, arr[i].width, arr[i].height = src, ln, w, h
-            arr[i].compression_type, arr[i].reserved, arr[i].dst, arr[i].dst_capacity_elems = ct, 0, dst, cap
+            arr[i].compression_type, arr[i].dst, arr[i].dst_capacity_elems = ct, dst, cap
+            arr[i].encoded_width = fr[7] if len(fr) > 7 else 0
         return arr, len(frames)
 
     def decode_batch(self, descs, n, stream=None):
@@ -219,14 +229,16 @@ class DeviceBatch:
         self.frames = frames
         self.src_ptrs, self.dst_ptrs = [], []
         items = []
-        for stream, w, h, ct in frames:
+        for stream, w, h, ct, *rest in frames:
             stream = np.ascontiguousarray(stream, dtype=np.uint8)
             sp = ctx.device_alloc(stream.size + 16)
             dp = ctx.device_alloc(w * h * 2 + 16)
             ctx.h2d(sp, stream)
             self.src_ptrs.append(sp)
             self.dst_ptrs.append(dp)
-            items.append((sp, stream.size, w, h, ct, dp, w * h))
+            # the uploader has seen the frame header: it tells the decoder which encodedWidth to plan for
+            ew = rest[0] if rest else (frame_encoded_width(stream, w, h) if ct == COMPRESSION_CURRENT else 0)
+            items.append((sp, stream.size, w, h, ct, dp, w * h, ew))
         self.descs, self.n = Context.make_descs(items)
 
     def decode(self, stream=None):
@@ -234,14 +246,14 @@ class DeviceBatch:
         return self.ctx.batch_wait(self.n)
 
     def fetch(self, i, fill=None):
-        _, w, h, _ = self.frames[i]
+        w, h = self.frames[i][1], self.frames[i][2]
         out = np.empty(w * h, dtype=np.uint16)
         self.ctx.d2h(out, self.dst_ptrs[i])
         return out.reshape(h, w)
 
     def fill_outputs(self, value=0xA5A5):
-        for (_, w, h, _), dp in zip(self.frames, self.dst_ptrs):
-            self.ctx.h2d(dp, np.full(w * h, value, dtype=np.uint16))
+        for fr, dp in zip(self.frames, self.dst_ptrs):
+            self.ctx.h2d(dp, np.full(fr[1] * fr[2], value, dtype=np.uint16))
 
     def free(self):
         for p in self.src_ptrs + self.dst_ptrs:

@@ -50,6 +50,10 @@ struct Slot {
     uint32_t max_ltiles = 0, nitems = 0;
     size_t items_off = 0, plan_bytes = 0;
     uint32_t flag_uses = 0;         // k_meta launches on this plan since its counters were zeroed
+    uint32_t lg_nwork = 0;          // (frame, tile) tickets of the legacy frames of the plan
+    size_t lg_work_off = 0;
+    uint32_t lg_epoch = 0;          // k_legacy_fused launches on this plan since its status words were zeroed
+    size_t plan_scratch = 0;        // scratch bytes the plan uses
 };
 
 struct Stage {
@@ -78,6 +82,9 @@ struct mcraw_ctx {
     uint64_t launches = 0;
     std::vector<FrameDev> tmp_frames;
     std::vector<WorkItem> tmp_items;
+    std::vector<LgWork> tmp_lgwork;
+    bool legacy_split = getenv("MCRAW_LEGACY_SPLIT") != nullptr;   // A/B switch: the round-1 four-kernel legacy path
+    uint32_t lgf_resident_ctas = 0; // CTAs of k_legacy_fused the device holds at once
     bool overlap = getenv("MCRAW_NO_OVERLAP") == nullptr;   // k_units as a programmatic dependent of k_meta
     uint32_t timing_every = 0;      // record kernel-timing events on every n-th chunk (0 = never)
     uint64_t chunk_seq = 0;
@@ -185,7 +192,8 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
         FrameDev f;
         std::memset(&f, 0, sizeof f);
         if (!d.src || !d.dst) return fail_arg(ctx, who() + ": null src/dst");
-        if (d.width <= 0 || d.height <= 0 || d.width > 65536 || d.height > 65536)
+        if (d.width <= 0 || d.height <= 0 || d.width > 65536 || d.height > 65536 ||
+            (uint64_t)d.width * (uint64_t)d.height > (1ull << 30))        // payload offsets are 32 bits wide on the device
             return fail_arg(ctx, who() + ": unsupported width/height");
         if (((uintptr_t)d.src & 15) || ((uintptr_t)d.dst & 1))
             return fail_arg(ctx, who() + ": src must be 16-byte aligned, dst 2-byte aligned");
@@ -193,6 +201,12 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
         f.width = d.width; f.height = d.height; f.type = d.compression_type;
         f.tiles_x = (uint32_t)(d.width + 63) / 64;
         f.tile_rows = (uint32_t)(d.height + 3) / 4;
+        if (d.compression_type == MCRAW_COMPRESSION_CURRENT && d.encoded_width != 0) {
+            // the caller has seen the frame header: plan for its encodedWidth (RawData.cpp:550-554 accepts any multiple of 64 >= width)
+            if (d.encoded_width < d.width || (d.encoded_width % 64) != 0 || d.encoded_width > (1 << 24))
+                return fail_arg(ctx, who() + ": encoded_width must be a multiple of 64, >= width");
+            f.tiles_x = (uint32_t)d.encoded_width / 64;
+        }
         f.flags = ((d.width % 8) == 0 && ((uintptr_t)d.dst & 15) == 0) ? FLAG_VEC_STORE : 0;
         if (d.compression_type == MCRAW_COMPRESSION_CURRENT) {
             any7 = true;
@@ -222,12 +236,27 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
             scratch += (size_t)ntile * LG_TILE_WORDS * 4;
             f.lg_merge = reinterpret_cast<uint16_t*>(scratch);
             scratch += ((size_t)ntile * LG_STATES * 2 + 15) & ~(size_t)15;
+            f.lg_status = reinterpret_cast<unsigned long long*>(scratch);
+            scratch += ((size_t)ntile * 8 + 15) & ~(size_t)15;
             scratch = (scratch + 127) & ~(size_t)127;
             max_ltiles = std::max<uint32_t>(max_ltiles, (uint32_t)ntile);
         }   // any other type: no work is queued, mcraw_batch_wait reports MCRAW_FRAME_BAD_TYPE
         out[i] = f;
     }
     return MCRAW_OK;
+}
+
+// Host-source entry points: the frame header is in reach, so the descriptor's encoded_width is filled in from it (when
+// the caller left it 0 and the header value is one a valid frame can carry; anything else is left to the kernels' checks).
+void peek_encoded_width(mcraw_frame_desc& d) {
+    if (d.compression_type != MCRAW_COMPRESSION_CURRENT || d.encoded_width != 0 || !d.src || d.len < 16 || d.width <= 0 || d.height <= 0) return;
+    uint32_t ew;
+    std::memcpy(&ew, d.src, 4);                                   // little-endian u32 (RawData.cpp:500-524); hosts here are little-endian
+    if (ew % 64u || ew < (uint32_t)d.width || ew > (1u << 24)) return;
+    // every unit (64 blocks) costs at least two 2-byte metadata block headers: a frame of len bytes cannot hold more
+    const uint64_t units = ((uint64_t)(ew / 64u) * (uint64_t)((d.height + 3) / 4) + 15) / 16;
+    if (units * 4 > d.len) return;
+    d.encoded_width = (int32_t)ew;
 }
 
 // Start a new logical batch of n frames: earlier batches' unharvested chunks only keep their timing.
@@ -278,7 +307,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     // validate, build or upload.
     // (flag_uses bound: the per-frame meta_done counters k_units compares with 2 * flag_uses are 32 bits wide and only
     // zeroed when a plan is uploaded, so a plan that has been reused 2^30 times is uploaded afresh.)
-    const bool hit = s.plan_valid && s.flag_uses < (1u << 30) && s.plan_descs.size() == n &&
+    const bool hit = s.plan_valid && s.flag_uses < (1u << 30) && s.lg_epoch < 0xFFFFF0u && s.plan_descs.size() == n &&
                      std::memcmp(s.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
     if (!hit) {
         s.plan_valid = false;
@@ -291,7 +320,23 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         if (s.any7) build_items(frames, ctx->resident_ctas, items);
         s.items_off = (sizeof(FrameDev) * n + 15) & ~(size_t)15;
         s.nitems = (uint32_t)items.size();
-        s.plan_bytes = (s.items_off + sizeof(WorkItem) * items.size() + 15) & ~(size_t)15;
+        // legacy tickets: tile index major, frame minor -- neighbouring tickets belong to different frames, so the look-back
+        // chain of every frame only has to advance a few tiles per generation of resident CTAs (k_legacy_fused)
+        std::vector<LgWork>& lgwork = ctx->tmp_lgwork;
+        lgwork.clear();
+        if (s.any6) {
+            std::vector<std::pair<uint32_t, uint32_t>> lf;      // (frame, tiles)
+            for (uint32_t i = 0; i < n; i++)
+                if (frames[i].type == MCRAW_COMPRESSION_LEGACY)
+                    lf.emplace_back(i, (uint32_t)std::max<uint64_t>(1, (frames[i].len + LG_TILE - 1) / LG_TILE));
+            for (uint32_t t = 0; t < s.max_ltiles; t++)
+                for (const auto& fr : lf)
+                    if (t < fr.second) lgwork.push_back(LgWork{fr.first, t});
+        }
+        s.lg_work_off = (s.items_off + sizeof(WorkItem) * items.size() + 15) & ~(size_t)15;
+        s.lg_nwork = (uint32_t)lgwork.size();
+        s.plan_bytes = (s.lg_work_off + sizeof(LgWork) * lgwork.size() + 15) & ~(size_t)15;
+        s.plan_scratch = scratch;
         rc = slot_reserve(ctx, s, n, s.plan_bytes, scratch);
         if (rc) return rc;
         FrameDev* h_frames = reinterpret_cast<FrameDev*>(s.h_up);
@@ -305,10 +350,12 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
                 f.lg_tilestate = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilestate));
                 f.lg_bitmap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_bitmap));
                 f.lg_merge = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_merge));
+                f.lg_status = reinterpret_cast<unsigned long long*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_status));
             }
             h_frames[i] = f;
         }
         if (!items.empty()) std::memcpy(s.h_up + s.items_off, items.data(), sizeof(WorkItem) * items.size());
+        if (!lgwork.empty()) std::memcpy(s.h_up + s.lg_work_off, lgwork.data(), sizeof(LgWork) * lgwork.size());
         s.plan_descs.assign(descs, descs + n);
     }
     uint32_t* d_counter = reinterpret_cast<uint32_t*>(s.d_dyn);
@@ -331,9 +378,13 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         CU_TRY(ctx, cudaMemsetAsync(s.d_dyn, 0, 16 + sizeof(FrameState) * n, st));
         s.flag_uses = 0;
         s.plan_valid = true;
+        // k_legacy_fused: the tiles' status words are tagged with the launch epoch of the plan, which starts over here
+        if (any6 && s.plan_scratch) CU_TRY(ctx, cudaMemsetAsync(s.d_scratch, 0, s.plan_scratch, st));
+        s.lg_epoch = 0;
     }
     if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, cross ? ctx->meta_stream : st>>>(d_frames, d_states); ctx->launches += 1; }
-    if (any6) {
+    const bool split6 = any6 && ctx->legacy_split;
+    if (split6) {
         k_legacy_maps<<<dim3(s.max_ltiles, n), LG_MAPS_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
         k_legacy_scan<<<n, LG_THREADS, 0, st>>>(d_frames, d_states, d_results);
         k_legacy_fix<<<dim3((s.max_ltiles + LG_THREADS - 1) / LG_THREADS, n), LG_THREADS, 0, st>>>(d_frames, d_states);
@@ -360,7 +411,15 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
                                        (pdl || cross) ? 2u * s.flag_uses : 0u));
         ctx->launches += 1;
     }
-    if (any6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
+    if (split6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
+    else if (any6) {
+        // one pass over the stream: transfer maps, decoupled look-back and the pixel work in one persistent kernel
+        s.lg_epoch += 1;
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(ctx->lgf_resident_ctas, s.lg_nwork));
+        k_legacy_fused<<<grid, LGF_THREADS, LGF_SMEM, st>>>(d_frames, d_results, reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off),
+                                                           s.lg_nwork, d_counter, s.lg_epoch);
+        ctx->launches += 1;
+    }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e2, st));
     s.timed = timed && (any7 || any6);
     CU_TRY(ctx, cudaGetLastError());
@@ -443,7 +502,8 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     if (cudaFuncSetAttribute(k_meta, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_legacy_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_MAPS_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_legacy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_DEC_SMEM) != cudaSuccess) {
+        cudaFuncSetAttribute(k_legacy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_DEC_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_legacy_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, LGF_SMEM) != cudaSuccess) {
         ctx->err = "cudaFuncSetAttribute(smem) failed"; return bail(MCRAW_ERR_CUDA);
     }
     {
@@ -454,6 +514,11 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
         // k_units spins on counters that k_meta bumps: in the cross-batch experiment k_meta must always find room beside it
         ctx->cross_ctas = std::min(ctx->cross_ctas, ctx->resident_ctas / 2);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_fused, LGF_THREADS, LGF_SMEM) != cudaSuccess || per_sm < 1) {
+            ctx->err = "k_legacy_fused does not fit on this device"; return bail(MCRAW_ERR_CUDA);
+        }
+        if (const char* e = getenv("MCRAW_LGF_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        ctx->lgf_resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
     }
     for (auto& s : ctx->slots) {
         if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&s.e0) != cudaSuccess ||
@@ -543,6 +608,14 @@ int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n
     return enqueue(ctx, descs, n, stream ? static_cast<cudaStream_t>(stream) : ctx->stream, true);
 }
 
+int32_t mcraw_frame_encoded_width(const uint8_t* frame, uint64_t len, int32_t width, int32_t height) {
+    mcraw_frame_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.src = frame; d.len = len; d.width = width; d.height = height; d.compression_type = MCRAW_COMPRESSION_CURRENT;
+    peek_encoded_width(d);
+    return d.encoded_width == ((width + 63) / 64) * 64 ? 0 : d.encoded_width;
+}
+
 int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
     if (!descs && n) return fail_arg(ctx, "descs is null");
@@ -581,6 +654,7 @@ int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint3
         // ---- H2D on a side stream once the previous user of this staging buffer has been decoded
         if (g.used) CU_TRY(ctx, cudaStreamWaitEvent(cs, g.freed, 0));
         chunk.assign(descs + i, descs + j);
+        for (mcraw_frame_desc& c : chunk) peek_encoded_width(c);
         // frames that lie back to back in host memory at the same 256-byte pitch (a pinned ring filled by a container
         // reader) travel in ONE copy: per-copy overhead is ~3 us, a 2 MB frame is ~40 us of PCIe time
         size_t off = 0;
@@ -654,6 +728,12 @@ size_t mcraw_decode_host(mcraw_ctx* ctx, uint16_t* output, int width, int height
     std::memset(&d, 0, sizeof d);
     d.src = ctx->d_in; d.len = len; d.width = width; d.height = height; d.compression_type = compression_type;
     d.dst = ctx->d_out; d.dst_capacity_elems = out_elems;
+    {
+        mcraw_frame_desc h = d;
+        h.src = input;
+        peek_encoded_width(h);
+        d.encoded_width = h.encoded_width;
+    }
     if (enqueue(ctx, &d, 1, ctx->stream, false)) return 0;   // the H2D copy above is still in flight on the stream
     // the transfers back are queued behind the kernels right away (16-byte aligned pieces)
     auto part_begin = [&](int k) { return (out_bytes * k / out_parts) & ~(size_t)15; };

@@ -37,7 +37,7 @@ struct FrameDev {
     uint16_t* dst;                 // device
     unsigned long long dst_cap;    // elements
     int width, height, type;
-    unsigned tiles_x;              // expected encodedWidth/64   = ceil(width/64)
+    unsigned tiles_x;              // planned encodedWidth/64: ceil(width/64), or the descriptor's encoded_width / 64
     unsigned tile_rows;            // expected ceil(encodedHeight/4) upper bound = ceil(height/4)
     unsigned flags;                // FLAG_*
     unsigned inv_tiles_x;          // ceil(2^32 / tiles_x) when tile / tiles_x may use mulhi, else 0
@@ -49,6 +49,7 @@ struct FrameDev {
     uint32_t* lg_tilestate;        // legacy scratch [tiles][2]    entry offset (| LG_SLOW) / first block ordinal of every tile
     uint32_t* lg_bitmap;           // legacy scratch [tiles][512]  block starts of every tile (one bit per 2 bytes)
     uint16_t* lg_merge;            // legacy scratch [tiles][17]   where the chain of entry e meets the chain of entry 0
+    unsigned long long* lg_status; // legacy scratch [tiles]       k_legacy_fused: epoch-tagged look-back status of every tile
 };
 
 // Per-frame words written by the index kernels and read by the pixel kernels.  Every word is written on every path
@@ -244,6 +245,11 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -251,12 +257,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // grid = 2 * frames, block = K1_THREADS, dynamic smem = K1_SMEM
-// Publish everything this CTA wrote for (frame, stream): every thread fences its own writes, then one thread bumps the
-// frame's counter.  k_units may be running already (programmatic dependent launch) and polls the counter.
+// Publish everything this CTA wrote for (frame, stream): the barrier orders every thread's writes before thread 0, whose
+// fence (cumulative) and counter bump form the release; k_units may be running already (programmatic dependent launch)
+// and polls the counter, ending the poll with an acquire load.
 __device__ __forceinline__ void meta_publish(FrameState& S) {
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(&S.meta_done, 1u);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&S.meta_done, 1u);
+    }
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restrict__ frames, FrameState* __restrict__ states) {
@@ -290,8 +299,6 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
             const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));                // RawData.cpp:500-524 (little-endian u32 x 4)
             ew = h.x; eh = h.y; boff = h.z; roff = h.w;
             if (boff > len || roff > len) err |= MCRAW_FRAME_BAD_HEADER;            // :547
-            if ((boff | roff) & 1u) err |= MCRAW_FRAME_BAD_HEADER;                  // every encoder output has even offsets (16 + 8k,
-                                                                                    // then blocks of 2 + 8m bytes); 16-bit loads rely on it
             if (ew % 64u) err |= MCRAW_FRAME_BAD_HEADER;                            // :550
             if (F.width <= 0 || ew < (uint32_t)F.width) err |= MCRAW_FRAME_BAD_HEADER;  // :553
             if (ew == 0 || eh == 0) err |= MCRAW_FRAME_BAD_HEADER;
@@ -328,14 +335,18 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
     const uint32_t ntiles = tiles_x * tile_rows;
     const uint32_t need_mb = (ntiles * 4u + 63u) / 64u;  // = number of units
     unsigned long long pos = (unsigned long long)sh_hdr[2 + stream] + 4;
+    const unsigned long long par = pos & 1ull;
 
     uint32_t* __restrict__ unitoff = F.unitoff;
     uint32_t done = 0;            // meta blocks (= units) finished
     uint32_t carry = 16;          // running payload offset, METADATA_OFFSET (RawData.cpp:25,562)
 
     while (done < need_mb) {
-        // ---- stage [base, base + K1_CHUNK + 32) of the frame buffer in shared memory (zero past len)
-        const unsigned long long base = pos & ~15ull;
+        // ---- stage [base, base + K1_CHUNK + 32) of the frame buffer in shared memory (zero past len).  Block lengths are
+        //      even (2 + 8m), so every position of a chain has the parity of its start: the candidates of the window are the
+        //      even offsets from `base`, which is 16-byte aligned for streams that start at an even offset (every encoder
+        //      output) and one byte further for the others (the reference reads bytes, RawData.cpp:463-498: any offset goes).
+        const unsigned long long base = ((pos - par) & ~15ull) + par;
         {
             uint4 q[5];
 #pragma unroll
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
                 const unsigned long long o = base + (unsigned long long)v * 16;
                 q[k] = make_uint4(0, 0, 0, 0);
                 if (v < (K1_CHUNK + 32) / 16) {
-                    if (o + 16 <= len) q[k] = __ldg(reinterpret_cast<const uint4*>(src + o));
+                    if (!par && o + 16 <= len) q[k] = __ldg(reinterpret_cast<const uint4*>(src + o));
                     else if (o < len) {
                         uint32_t t4[4] = {0, 0, 0, 0};
                         for (int e = 0; e < 16; e++)
@@ -638,16 +649,20 @@ __device__ __forceinline__ uint32_t meta_values(const uint32_t blk, const uint32
     const uint32_t hb = (hdr >> 4) & 15u;
     const uint32_t ref = ((hdr & 15u) << 8) | ((hdr >> 8) & 0xFFu);                // RawData.cpp:106-110
     const uint32_t pay = blk + (pos & 15u) + 2u;
+    // a stream that starts at an odd offset (never written by an encoder, accepted by the reference) puts every byte pair
+    // at an odd address: two byte loads instead of one 16-bit load, decided once per block (warp-uniform)
+    const bool odd = (pos & 1u) != 0u;
+    auto pair_at = [&](const uint32_t a) { return odd ? (lds_u8(a) | (lds_u8(a + 1u) << 8)) : lds_u16(a); };
     uint32_t v = 0;
     if (hb > 10u) {                                                               // RawData.cpp:376-408
-        v = lds_u16(pay + 4u * lane) | (lds_u16(pay + 4u * lane + 2u) << 16);
+        v = pair_at(pay + 4u * lane) | (pair_at(pay + 4u * lane + 2u) << 16);
     } else {
         const uint32_t* row = s_terms + (hb * 8u + (lane >> 2)) * 3u;
         const uint32_t b = 2u * (lane & 3u);
 #pragma unroll
         for (int t = 0; t < 3; t++) {
             const uint32_t term = row[t];
-            if (term >> 16) v |= mcraw_meta_term_pair(term, lds_u16(pay + 8u * mcraw_meta_term_group(term) + b));
+            if (term >> 16) v |= mcraw_meta_term_pair(term, pair_at(pay + 8u * mcraw_meta_term_group(term) + b));
         }
     }
     return __vadd2(v, ref | (ref << 16));
@@ -803,9 +818,9 @@ constexpr int KD_THREADS = 32 * KU_WARPS;
 
 // counters[0]: next item; counters[1]: warps that have left the kernel (the last one resets both for the next launch).
 // flag_target != 0: launched as a programmatic dependent of k_meta, i.e. possibly while k_meta's last wave is still
-// running -- before touching a frame, lane 0 polls the frame's meta_done counter (relaxed loads served by L2).  The
-// loads that follow are issued only after the loop has seen the value (no speculation past the branch; the other lanes
-// wait at the warp barrier) and read L2 as well, so they see everything k_meta fenced before bumping the counter.
+// running -- before touching a frame, lane 0 polls the frame's meta_done counter (relaxed loads served by L2) and closes
+// the wait with one acquire load; the other lanes wait at the warp barrier.  The per-unit records are then read with
+// ld.global.cg (L2), so they see everything k_meta released before bumping the counter.
 // Three CTAs per SM (168 registers): the fourth buys 2 % of bandwidth and leaves no room for this logic without spills.
 __global__ void __launch_bounds__(KD_THREADS, 3)
 k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states, Result* __restrict__ results,
@@ -832,6 +847,9 @@ k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ stat
                     if (v >= flag_target) break;
                     __nanosleep(256);
                 }
+                // the counter is monotone: one acquire load now pairs with k_meta's release (relaxed polls keep the L1
+                // invalidations of an acquire out of the wait loop); the warp barrier below extends the order to the other lanes
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
             }
         }
         __syncwarp();

@@ -526,4 +526,436 @@ __global__ void __launch_bounds__(LG_THREADS, 9) k_legacy_decode(const FrameDev*
     }
 }
 
+// =========================================================================================================
+// k_legacy_fused: the whole legacy decode in ONE pass over the stream (replaces maps + scan + fix + decode).
+//
+// Persistent CTAs take (frame, tile) tickets in a host-built order (tile index major, frame minor: neighbouring
+// tickets belong to different frames, so every frame's chain only has to advance a few tiles per generation of CTAs).
+// Per tile:
+//   1. stage the tile (+ overrun) in shared memory -- the only time the stream is read;
+//   2. warp 0 resolves chain C0 (entry offset 0) with the self-synchronising segment walk, then the other 16 entry
+//      offsets up to their merge point with C0: the tile's transfer map  entry -> (exit offset, block count);
+//   3. publish the map (LOCAL), then DECOUPLED LOOK-BACK over the previous tiles of the frame: the nearest predecessor
+//      whose inclusive state (exit offset, blocks so far) is known, composed with the maps of the tiles in between
+//      (a window of 32 status words per poll; one lane chases the concrete entry state through the staged maps);
+//      publish this tile's inclusive state (INCL) before doing anything else, so that successors can go on;
+//   4. patch the bitmap for the true entry (the few blocks before the merge point; a chain that never meets C0 is
+//      re-walked with the segment walk from its entry), turn it into the list of block pairs, decode from shared memory.
+// Ticket order guarantees that every predecessor a tile waits for has been started by a resident CTA (which never waits
+// for a successor), so the waits always end; they are bounded all the same (MCRAW_FRAME_INTERNAL instead of a hang).
+// Status words carry the launch epoch of the slot, so nothing has to be zeroed between launches.
+// =========================================================================================================
+struct LgWork { uint32_t frame, tile; };
+
+constexpr int LGF_THREADS = 128;
+constexpr int LGF_DATA = LG_TILE + LG_OVERRUN;
+constexpr int LGF_LB = 32;                              // look-back window: status words read per poll
+constexpr int LGF_SCRATCH = (LGF_LB * LG_STATES * 4 > LG_PAIR_CHUNK * 2) ? LGF_LB * LG_STATES * 4 : LG_PAIR_CHUNK * 2;
+constexpr int LGF_SMEM = LGF_DATA + LG_TILE_WORDS * 4 + LGF_SCRATCH;
+constexpr uint32_t LGF_ST_LOCAL = 1u, LGF_ST_INCL = 2u;
+constexpr uint32_t LGF_ERR_BIT = 1u << 5;               // sticky: a wait gave up somewhere up the chain
+constexpr uint32_t LGF_SPIN_LIMIT = 1u << 22;
+static_assert(LGF_DATA % 16 == 0, "tile staging works in 16-byte granules");
+
+// status word of a tile: blocks up to the end of the tile << 32 | epoch (24 bits) << 8 | state << 6 | error << 5 | exit offset / 2
+__device__ __forceinline__ unsigned long long lgf_pack(uint32_t count, uint32_t epoch, uint32_t st, uint32_t low6) {
+    return ((unsigned long long)count << 32) | ((unsigned long long)(epoch & 0xFFFFFFu) << 8) | (st << 6) | low6;
+}
+__device__ __forceinline__ void lgf_store_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lgf_load_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One lane, one segment of the staged tile: walk from tile-relative byte offset p to the end of segment `seg`.  Block
+// starts go into bm[] (one word per 64 bytes of the segment).  With MERGE the walk stops at the first position already
+// marked in bm[] -- from there on the old marks are this chain's own -- and older marks before it are dropped.
+// rel: bytes from the tile start to the end of the buffer (a block is decoded only if it ends before the last byte,
+// RawData_Legacy.cpp:387,398).  Returns true if the chain ended at an undecodable block.
+template <bool MERGE>
+__device__ __forceinline__ bool lgf_walk_segment(const uint8_t* data, const uint32_t seg, uint32_t& p, uint32_t (&bm)[LG_SEG_WORDS], const uint32_t rel) {
+    bool merged = false, dead = false;
+    const uint32_t seg0 = seg * LG_SEG;
+#pragma unroll
+    for (int wd = 0; wd < LG_SEG_WORDS; wd++) {
+        if (merged) continue;
+        const uint32_t stop = seg0 + 64u * (wd + 1);
+        if (dead || p >= stop) { bm[wd] = 0; continue; }
+        const uint32_t old = bm[wd];
+        uint32_t acc = 0;
+        while (p < stop) {
+            const uint32_t bit = 1u << ((p >> 1) & 31u);
+            if (MERGE && (old & bit)) { merged = true; acc |= old & ~(bit - 1u); break; }
+            const uint32_t q = p + leg_step(data[p]);
+            if (q >= rel) { dead = true; break; }
+            acc |= bit;
+            p = q;
+        }
+        bm[wd] = acc;
+    }
+    return dead;
+}
+
+// Warp-wide: the exact chain that enters the tile at byte offset entry0 (even, < LG_SEG), as a bitmap of block starts in
+// shared memory.  Lane s owns segment s: a guessed chain from the segment start first, then re-walks from the left
+// neighbour's real exit until the lane's own marks are met, repeated until no entry changes.
+// Returns (all lanes) the chain's exit from the tile: byte offset into the next tile, or 0xFFFFFFFF if the chain died.
+__device__ __forceinline__ uint32_t lgf_chain(const uint8_t* data, uint32_t* bitmap, const uint32_t entry0, const uint32_t tile_rel,
+                                              const uint32_t lane, uint32_t& total) {
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    uint32_t bm[LG_SEG_WORDS];
+#pragma unroll
+    for (int wd = 0; wd < LG_SEG_WORDS; wd++) bm[wd] = 0;
+    const uint32_t seg0 = lane * LG_SEG;
+    uint32_t entry = lane == 0 ? entry0 : seg0;          // tile-relative position where this lane's walk starts
+    uint32_t p = entry;
+    bool dead = lgf_walk_segment<false>(data, lane, p, bm, tile_rel);
+    uint32_t exitv = dead ? NONE : p;                    // tile-relative position in (or beyond) the next segment
+    for (;;) {
+        uint32_t e = __shfl_up_sync(0xFFFFFFFFu, exitv, 1);
+        if (lane == 0) e = entry0;
+        // an exit that jumps over this whole segment (impossible: steps are <= 34 bytes) is not handled: LG_SEG >= 64
+        const bool upd = e != entry;
+        if (upd) {
+            entry = e;
+            if (e == NONE) {
+#pragma unroll
+                for (int wd = 0; wd < LG_SEG_WORDS; wd++) bm[wd] = 0;
+                exitv = NONE;
+            } else {
+                p = e;
+                dead = lgf_walk_segment<true>(data, lane, p, bm, tile_rel);
+                if (dead) exitv = NONE;
+                else if (p >= seg0 + (uint32_t)LG_SEG) exitv = p;      // walked to the end without meeting the old chain
+                // else: merged -> the old exit stands
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, upd)) break;
+    }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int wd = 0; wd < LG_SEG_WORDS; wd++) { bitmap[lane * LG_SEG_WORDS + wd] = bm[wd]; cnt += __popc(bm[wd]); }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+    total = cnt;
+    const uint32_t ex = __shfl_sync(0xFFFFFFFFu, exitv, 31);
+    __syncwarp();
+    return ex == NONE ? NONE : ex - (uint32_t)LG_TILE;
+}
+
+// OR the 16 samples of the block at byte offset o (header nibble `bits`) into px[], at bit ADJ of each word (0: even-column
+// block, 16: odd-column block, RawData_Legacy.cpp:483-486).  d32: the staged tile as words.  The payload is a contiguous
+// MSB-first bit stream (:38-358), so 8 samples are exactly `bits` bytes: per group of 8 the bytes are fetched as
+// big-endian words (PRMT with a runtime selector does alignment and byte order in one go) and every sample is one
+// rotate + one mask.  Three lane-uniform formulations instead of one code path per width: widths 0..8 (two 4-sample
+// windows per group), 9..10 (four 2-sample windows), and 16-bit big-endian samples (:360-370, nibbles 11..15, :395).
+template <int ADJ>
+__device__ __forceinline__ void lgf_block(const uint32_t* __restrict__ d32, const uint32_t o, const uint32_t bits, uint32_t (&px)[16]) {
+    const uint32_t a = o + 2u;
+    if (bits <= 8u) {
+        const uint32_t w = bits;
+        const uint32_t mask = ((1u << w) - 1u) << ADJ;
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) r[j] = (32u - ADJ - (uint32_t)(j + 1) * w) & 31u;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            const uint32_t ag = a + g * w;
+            const uint32_t i = ag >> 2, sel = 0x0123u + 0x1111u * (ag & 3u);
+            const uint32_t W0 = d32[i], W1 = d32[i + 1], W2 = d32[i + 2];
+            const uint32_t G0 = __byte_perm(W0, W1, sel), G1 = __byte_perm(W1, W2, sel);
+            const uint32_t A1 = __funnelshift_lc(G1, G0, 4u * w);                      // the window of samples 4..7
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                px[8 * g + j] |= __funnelshift_r(G0, G0, r[j]) & mask;
+                px[8 * g + 4 + j] |= __funnelshift_r(A1, A1, r[j]) & mask;
+            }
+        }
+    } else if (bits <= 10u) {
+        const uint32_t w = bits;
+        const uint32_t mask = ((1u << w) - 1u) << ADJ;
+        const uint32_t r0 = (32u - ADJ - w) & 31u, r1 = (32u - ADJ - 2u * w) & 31u;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            const uint32_t ag = a + g * w;
+            const uint32_t i = ag >> 2, sel = 0x0123u + 0x1111u * (ag & 3u);
+            const uint32_t W0 = d32[i], W1 = d32[i + 1], W2 = d32[i + 2], W3 = d32[i + 3];
+            const uint32_t G0 = __byte_perm(W0, W1, sel), G1 = __byte_perm(W1, W2, sel), G2 = __byte_perm(W2, W3, sel);
+            uint32_t win[4];
+            win[0] = G0;                                                               // samples 2m, 2m+1 start at bit 2mw
+            win[1] = __funnelshift_l(G1, G0, 2u * w);
+            win[2] = __funnelshift_l(G2, G1, 4u * w - 32u);
+            win[3] = __funnelshift_l(G2, G1, 6u * w - 32u);
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                px[8 * g + 2 * m] |= __funnelshift_r(win[m], win[m], r0) & mask;
+                px[8 * g + 2 * m + 1] |= __funnelshift_r(win[m], win[m], r1) & mask;
+            }
+        }
+    } else {
+        const uint32_t i = a >> 2, k0 = a & 3u;                                        // the payload starts 2-byte aligned
+        // sample k = bytes (2k, 2k+1), big-endian: byte index (k0 + 2 (k & 1)) of the word pair (k / 2, k / 2 + 1)
+        const uint32_t selA = ((k0 + 1u) | (k0 << 4)) << (ADJ / 4), selB = ((k0 + 3u) | ((k0 + 2u) << 4)) << (ADJ / 4);
+        uint32_t lo = d32[i];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const uint32_t hi = d32[i + m + 1];
+            px[2 * m] |= __byte_perm(lo, hi, selA) & (0xFFFFu << ADJ);
+            px[2 * m + 1] |= __byte_perm(lo, hi, selB) & (0xFFFFu << ADJ);
+            lo = hi;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LGF_THREADS) k_legacy_fused(const FrameDev* __restrict__ frames, Result* __restrict__ results,
+                                                              const LgWork* __restrict__ work, const uint32_t nwork,
+                                                              uint32_t* __restrict__ counters, const uint32_t epoch) {
+    extern __shared__ __align__(16) uint8_t lg_smem[];
+    uint8_t* data = lg_smem;
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LGF_DATA);                             // [LG_TILE_WORDS]
+    uint32_t* lbmaps = reinterpret_cast<uint32_t*>(lg_smem + LGF_DATA + LG_TILE_WORDS * 4);         // look-back: [LGF_LB][LG_STATES]
+    uint16_t* plist = reinterpret_cast<uint16_t*>(lbmaps);                                          // later: the pair list
+    __shared__ uint32_t sh_ticket, sh_entry, sh_base, sh_total, sh_err;
+    __shared__ uint32_t sh_map[LG_STATES], sh_merge[LG_STATES], warp_sums[LGF_THREADS / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (;;) {
+        __syncthreads();                                     // the previous tile's shared memory is no longer in use
+        if (tid == 0) sh_ticket = atomicAdd(&counters[2], 1u);
+        __syncthreads();
+        const uint32_t ticket = sh_ticket;
+        if (ticket >= nwork) break;
+        const LgWork wk = work[ticket];
+        const FrameDev& F = frames[wk.frame];
+        const unsigned long long len = F.len;
+        const uint32_t ntile = (uint32_t)max((len + LG_TILE - 1) / LG_TILE, 1ull);
+        const uint32_t tile = wk.tile;
+        const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
+        const uint32_t tile_rel = (uint32_t)min(len > tile_off ? len - tile_off : 0ull, (unsigned long long)(1u << 30));
+        const bool last_tile = tile + 1 == ntile;
+        const uint32_t ppr = ((uint32_t)F.width + 31u) / 32u;                            // pairs per row (RawData_Legacy.cpp:34-36)
+        const unsigned long long need = 2ull * ppr * (unsigned long long)F.height;       // blocks of the image (:478-482)
+        const bool fits = F.dst_cap >= (unsigned long long)F.width * (unsigned long long)F.height;
+
+        // ---- 1. stage
+        lg_stage<LGF_THREADS>(data, F.src, len, tile_off, LGF_DATA, tid);
+        __syncthreads();
+
+        // ---- 2./3. transfer map, publication, look-back (warp 0)
+        if (warp == 0) {
+            uint32_t total0;
+            const uint32_t ex0 = lgf_chain(data, bitmap, 0u, tile_rel, lane, total0);
+            const uint32_t exit0 = (ex0 == 0xFFFFFFFFu || last_tile) ? LG_DEAD : ex0 >> 1;
+            uint32_t mapv = 0, mergev = LG_NO_MERGE;
+            if (lane < LG_STATES) {
+                uint32_t q = 2u * lane, pre = 0, m = LG_NO_MERGE, ex = exit0, count;
+                bool d2 = false;
+                if (lane == 0) { m = 0; count = total0; }
+                else {
+                    for (;;) {
+                        if (q >= (uint32_t)LG_TILE) { ex = (q - LG_TILE) >> 1; break; }                 // never met C0 in this tile
+                        if ((bitmap[q >> 6] >> ((q >> 1) & 31u)) & 1u) { m = q >> 1; break; }
+                        const uint32_t nq = q + leg_step(data[q]);
+                        if (nq >= tile_rel) { d2 = true; break; }
+                        q = nq;
+                        pre++;
+                    }
+                    if (m != LG_NO_MERGE) {
+                        uint32_t before = 0;                    // blocks of C0 from the merge point on = total0 - (marks before it)
+                        for (uint32_t w = 0; w < (m >> 5); w++) before += __popc(bitmap[w]);
+                        before += __popc(bitmap[m >> 5] & ((1u << (m & 31u)) - 1u));
+                        count = pre + total0 - before;
+                    } else {
+                        count = pre;
+                        if (d2 || last_tile) ex = LG_DEAD;
+                    }
+                }
+                mapv = ex | (count << 5);
+                mergev = m;
+                sh_map[lane] = mapv;
+                sh_merge[lane] = mergev;
+                F.lg_tilemap[(size_t)tile * LG_STATES + lane] = mapv;
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();                                 // release: the map before the status word
+                lgf_store_status(F.lg_status + tile, lgf_pack(0u, epoch, LGF_ST_LOCAL, 0u));
+            }
+            // look-back
+            uint32_t entry = 0, base = 0, errbit = 0;
+            if (tile > 0) {
+                const uint32_t jhi = tile - 1;
+                uint32_t spins = 0;
+                for (;;) {
+                    const int j = (int)jhi - lane;
+                    unsigned long long sw = 0;
+                    if (j >= 0) sw = lgf_load_status(F.lg_status + j);
+                    const uint32_t lo32 = (uint32_t)sw;
+                    const uint32_t st = ((lo32 >> 8) & 0xFFFFFFu) == (epoch & 0xFFFFFFu) ? (lo32 >> 6) & 3u : 0u;
+                    const unsigned incl = __ballot_sync(0xFFFFFFFFu, st == LGF_ST_INCL);
+                    const unsigned any = __ballot_sync(0xFFFFFFFFu, st != 0u);
+                    if (incl) {
+                        const int d = __ffs(incl) - 1;            // nearest predecessor with a known inclusive state: tile jhi - d
+                        const unsigned between = (1u << d) - 1u;  // tiles jhi - d + 1 .. jhi must have published their maps
+                        if ((any & between) == between) {
+                            uint32_t state = __shfl_sync(0xFFFFFFFFu, lo32 & 31u, d);
+                            uint32_t count = __shfl_sync(0xFFFFFFFFu, (uint32_t)(sw >> 32), d);
+                            errbit = __shfl_sync(0xFFFFFFFFu, lo32 & LGF_ERR_BIT, d);
+                            const uint32_t first = jhi - (uint32_t)d + 1u;                          // maps of tiles first .. jhi
+                            __syncwarp();                        // every lane's acquire load before any lane's map loads
+                            for (uint32_t idx = lane; idx < (uint32_t)d * LG_STATES; idx += 32)
+                                lbmaps[idx] = __ldcg(F.lg_tilemap + (size_t)first * LG_STATES + idx);
+                            __syncwarp();
+                            if (lane == 0) {
+                                for (int m = 0; m < d; m++) {
+                                    if (state == LG_DEAD) break;
+                                    const uint32_t v = lbmaps[m * LG_STATES + state];
+                                    count += v >> 5;
+                                    state = v & 31u;
+                                }
+                            }
+                            entry = __shfl_sync(0xFFFFFFFFu, state, 0);
+                            base = __shfl_sync(0xFFFFFFFFu, count, 0);
+                            break;
+                        }
+                    }
+                    if (++spins > LGF_SPIN_LIMIT) { entry = LG_DEAD; errbit = LGF_ERR_BIT; break; }   // never expected
+                    __nanosleep(spins < 16 ? 32 : 200);
+                }
+            }
+            // this tile's inclusive state, published before the pixel work
+            uint32_t exitv = LG_DEAD, total = base;
+            if (entry != LG_DEAD) {
+                const uint32_t v = sh_map[entry];
+                exitv = v & 31u;
+                total = base + (v >> 5);
+            }
+            if (lane == 0) {
+                lgf_store_status(F.lg_status + tile, lgf_pack(total, epoch, LGF_ST_INCL, exitv | errbit));
+                sh_entry = entry; sh_base = base; sh_total = total; sh_err = errbit;
+            }
+            // ---- 4a. the bitmap for the true entry
+            if (entry != 0 && entry != LG_DEAD) {
+                const uint32_t m = sh_merge[entry];
+                if (m == LG_NO_MERGE) {
+                    uint32_t t2;
+                    __syncwarp();
+                    lgf_chain(data, bitmap, 2u * entry, tile_rel, lane, t2);       // blocks of one constant width: walk it again from its entry
+                } else {
+                    __syncwarp();
+                    for (uint32_t w = lane; w < (m >> 5); w += 32) bitmap[w] = 0;  // C0's marks before the merge point go
+                    __syncwarp();
+                    if (lane == 0) {
+                        bitmap[m >> 5] &= ~((1u << (m & 31u)) - 1u);
+                        uint32_t p = 2u * entry;
+                        while (p < 2u * m) {
+                            bitmap[p >> 6] |= 1u << ((p >> 1) & 31u);
+                            p += leg_step(data[p]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t entry = sh_entry, tile_base = sh_base;
+        if (last_tile && tid == 0) {
+            unsigned status = 0;
+            if (!fits) status |= MCRAW_FRAME_GEOMETRY;
+            if ((unsigned long long)sh_total < need) status |= MCRAW_FRAME_TRUNCATED;     // reference: stale samples (:387,398)
+            if (sh_err) status |= MCRAW_FRAME_INTERNAL;
+            Result r;
+            r.written = status ? 0ull : (unsigned long long)F.width * (unsigned long long)F.height;   // :494
+            r.status = status;
+            r.pad = 0;
+            results[wk.frame] = r;
+        }
+        if (entry == LG_DEAD || !fits || (unsigned long long)tile_base >= need) continue;   // nothing of the image starts here
+
+        // ---- 4b. pair list of the tile: every block with an even ordinal leads a pair (even-column block, then odd-column
+        //      block, RawData_Legacy.cpp:480-481); plist[q] = (tile-relative offset of the leader) / 2 for pair ordinal
+        //      p_first + q.  Ordinals come from prefix popcounts of the bitmap: thread t owns words 2t and 2t+1.
+        const uint32_t w0 = bitmap[2 * tid], w1 = bitmap[2 * tid + 1];
+        const uint32_t c = __popc(w0) + __popc(w1);
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < LGF_THREADS / 32; w++) {
+            const uint32_t v = warp_sums[w];
+            if (w < warp) before += v;
+            total += v;
+        }
+        const uint32_t p_first = (tile_base + 1u) >> 1;
+        uint32_t npairs = ((tile_base + total + 1u) >> 1) - p_first;
+        npairs = (uint32_t)min((unsigned long long)npairs, (need >> 1) - (unsigned long long)p_first);
+        const int width = F.width;
+        uint16_t* __restrict__ dst = F.dst;
+        const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
+        const uint32_t ord0 = tile_base + before + incl - c;     // ordinal of the first block start in this thread's words
+        const uint32_t* d32 = reinterpret_cast<const uint32_t*>(data);
+        for (uint32_t c0 = 0; c0 < npairs; c0 += LG_PAIR_CHUNK) {
+            const uint32_t cn = min((uint32_t)LG_PAIR_CHUNK, npairs - c0);
+            {
+                uint32_t ord = ord0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    uint32_t wv = h ? w1 : w0;
+                    while (wv) {
+                        const uint32_t b = __ffs(wv) - 1;
+                        wv &= wv - 1;
+                        const uint32_t q = (ord >> 1) - p_first - c0;       // wraps to a huge value for earlier passes' pairs
+                        if (!(ord & 1u) && q < cn) plist[q] = (uint16_t)(32u * (2u * tid + h) + b);
+                        ord++;
+                    }
+                }
+            }
+            __syncthreads();
+            uint32_t P = p_first + c0 + (uint32_t)tid;
+            uint32_t y = P / ppr, xq = P - y * ppr;
+            for (uint32_t q = tid; q < cn; q += LGF_THREADS) {
+                const uint32_t oE = 2u * (uint32_t)plist[q];
+                const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
+                const uint32_t oO = oE + 2u + leg_len(bitsE);
+                const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
+                uint32_t px[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) px[k] = 0;
+                lgf_block<0>(d32, oE, bitsE, px);
+                lgf_block<16>(d32, oO, bitsO, px);
+                const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
+#pragma unroll
+                for (int k = 0; k < 16; k++) px[k] = __vadd2(px[k], refs);                    // :483-486, + reference mod 2^16
+                const int x = (int)(32u * xq);
+                uint16_t* orow = dst + (size_t)y * (size_t)width + x;
+                if (vec && x + 32 <= width) {
+                    uint4* o4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) o4[k] = make_uint4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {                                            // crop at width (:490)
+                        if (x + 2 * k < width) orow[2 * k] = (uint16_t)px[k];
+                        if (x + 2 * k + 1 < width) orow[2 * k + 1] = (uint16_t)(px[k] >> 16);
+                    }
+                }
+                xq += LGF_THREADS;                                                            // the pair LGF_THREADS further on
+                while (xq >= ppr) { xq -= ppr; y++; }
+            }
+            __syncthreads();
+        }
+    }
+    // the last CTA to leave resets the ticket counters for the next launch
+    if (tid == 0 && atomicAdd(&counters[3], 1u) == gridDim.x - 1u) { counters[2] = 0; counters[3] = 0; }
+}
+
 }  // namespace mcraw

@@ -116,6 +116,25 @@ def assemble_current(enc_width, enc_height, bits, refs, seed=1):
     return out[:n].copy()
 
 
+def pad_meta_current(stream, pad_bits=0, pad_refs=0, fill=0xEE):
+    """Insert pad_bits filler bytes in front of the "bits" metadata stream and pad_refs in front of the "refs" stream of a
+    compressionType 7 frame and patch bitsOffset / refsOffset (bytes 8..15) accordingly.  The result decodes to the same
+    image in the reference (RawData.cpp:547-560 only needs the offsets to be <= len); odd pads give metadata streams at
+    odd byte offsets, which no known encoder writes."""
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    ew, eh, boff, roff = (int(v) for v in np.frombuffer(stream[:16].tobytes(), dtype="<u4"))
+    assert 16 <= boff <= roff <= stream.size, "expected payload | bits stream | refs stream"
+    out = np.concatenate([stream[:boff], np.full(pad_bits, fill, np.uint8), stream[boff:roff],
+                          np.full(pad_refs, fill, np.uint8), stream[roff:]])
+    out[8:16] = np.frombuffer(np.array([boff + pad_bits, roff + pad_bits + pad_refs], dtype="<u4").tobytes(), dtype=np.uint8)
+    return out
+
+
+def encoded_width_of(stream):
+    """encodedWidth from the header of a compressionType 7 frame (RawData.cpp:500-524)."""
+    return int(np.frombuffer(np.ascontiguousarray(stream[:4], dtype=np.uint8).tobytes(), dtype="<u4")[0])
+
+
 def encode_legacy(img, policy=POLICY_MINIMAL, policy_arg=0, trailer_records=0, seed=1):
     """compressionType 6 stream for a (height, width) uint16 image -> np.uint8 array."""
     img = np.ascontiguousarray(img, dtype=np.uint16)

@@ -48,6 +48,13 @@ def build():
     bits = rng.integers(0, 17, 12).astype(np.uint16)
     refs = rng.integers(0, 65536, 12).astype(np.uint16)
     add("cur_random_stream", tv.assemble_current(192, 4, bits, refs, seed=3), 150, 4, False)
+    # metadata streams at odd offsets; a frame encoded wider than it is decoded (encodedWidth >= width + 64)
+    img = tv.gen_photon(320, 8, 4095, seed=74)
+    enc = tv.encode_current(img, policy=tv.POLICY_ALIASES, seed=5)
+    add("cur_meta_pad_1_0", tv.pad_meta_current(enc, 1, 0), 320, 8, False)
+    add("cur_meta_pad_3_2", tv.pad_meta_current(enc, 3, 2), 320, 8, False)
+    wide = tv.gen_photon(256, 8, 1023, seed=75)
+    add("cur_wide_256_as_100", tv.encode_current(wide, seed=6), 100, 8, False)
     # legacy format: every header nibble 0..15 on one row of 64 px
     for nib in range(16):
         w_needed = nib if nib <= 10 else 16

@@ -10,7 +10,7 @@ import oracle_lib as ol
 def test_golden_fixture_is_complete():
     g = golden_lib.load()
     names = [v[0] for v in g]
-    assert len(g) == 38
+    assert len(g) == 41
     assert sum(n.startswith("cur_hdr") for n in names) == 17 and sum(n.startswith("leg_nib") for n in names) == 16
 
 

@@ -176,3 +176,28 @@ def test_host_batch_pipeline(ctx):
     for dp in dsts:
         ctx.device_free(dp)
     ctx.pinned_free(ring_ptr)
+
+
+def test_encoded_width_wider_than_width(ctx):
+    """RawData.cpp:550-554 accepts any encodedWidth that is a multiple of 64 and >= width, and crops the rows to width
+    (:598-608).  Device-resident sources: the caller names the header's encodedWidth in the descriptor
+    (mcraw_frame_encoded_width); host sources: the library reads the header itself."""
+    from motioncam_decoder_b200 import capi, testvec as tv
+    wide = tv.gen_photon(320, 12, 1023, seed=77)
+    s = tv.encode_current(wide, policy=tv.POLICY_ALIASES, seed=78)          # encodedWidth 320
+    for w in (60, 128, 200, 256):                                            # planned default would be 64 / 128 / 256 / 256
+        n_or, want = ol.oracle_decode(s, w, 12)
+        assert n_or == w * 12 and np.array_equal(want, wide[:, :w])
+        hint = capi.frame_encoded_width(s, w, 12)
+        assert hint == 320
+        batch = capi.DeviceBatch(ctx, [(s, w, 12, capi.COMPRESSION_CURRENT, hint), (s, w, 12, capi.COMPRESSION_CURRENT, 0)])
+        batch.fill_outputs(0xA5A5)
+        written, status = batch.decode()
+        assert written[0] == w * 12 and status[0] == 0, (w, written, status)
+        assert np.array_equal(batch.fetch(0), want), w
+        # without the hint the work list was planned for width rounded up to 64: reported, never decoded wrongly
+        assert written[1] == 0 and status[1] & capi.FRAME_GEOMETRY, (w, written, status)
+        batch.free()
+        n, got = ctx.decode_host(s, w, 12, capi.COMPRESSION_CURRENT)        # host source: header read by the library
+        assert n == w * 12 and np.array_equal(got, want), w
+    assert capi.frame_encoded_width(s, 320, 12) == 0 and capi.frame_encoded_width(s, 300, 12) == 0

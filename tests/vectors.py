@@ -38,6 +38,24 @@ def current_vectors(small=True):
         bits = rng.integers(0, 17, nb).astype(np.uint16)
         refs = rng.integers(0, 65536, nb).astype(np.uint16)
         out.append((f"random_stream_{k}", tv.assemble_current(ew, eh, bits, refs, seed=50 + k), w, eh, None))
+    # metadata streams at odd byte offsets (RawData.cpp:463-498 reads bytes: any offset is valid for the reference)
+    img = tv.gen_photon(1000, 16, 4095, seed=31)
+    base = tv.encode_current(img, policy=tv.POLICY_ALIASES, seed=31)
+    for pb, pr in [(1, 0), (0, 1), (1, 1), (3, 2), (5, 7), (2, 6)]:
+        out.append((f"meta_pad_{pb}_{pr}", tv.pad_meta_current(base, pb, pr), 1000, 16, img))
+    img16 = tv.gen_uniform(512, 8, 0, 65535, seed=32)                     # 16-bit metadata blocks at odd addresses
+    out.append(("meta_pad_wrap16_1_1", tv.pad_meta_current(tv.encode_current(img16, ref_wrap=True, seed=33), 1, 1), 512, 8, img16))
+    rngp = np.random.default_rng(34)
+    nbp = 1024 * 16 // 64
+    out.append(("meta_pad_random_stream_3_1", tv.pad_meta_current(
+        tv.assemble_current(1024, 16, rngp.integers(0, 17, nbp).astype(np.uint16), rngp.integers(0, 65536, nbp).astype(np.uint16), seed=35),
+        3, 1), 1000, 16, None))
+    # encodedWidth larger than width rounded up to 64 (RawData.cpp:550-554 accepts any multiple of 64 >= width;
+    # the rows are cropped to width, :598-608): frames encoded wider than they are decoded
+    for (ew, w, h, seed) in [(128, 50, 8, 41), (192, 100, 8, 42), (1024, 520, 12, 43), (4096, 1928, 4, 44), (256, 8, 16, 45)]:
+        wide = tv.gen_photon(ew, h, 1023, seed=seed)
+        out.append((f"wide_enc_{ew}_as_{w}", tv.encode_current(wide, policy=tv.POLICY_ALIASES, seed=seed), w, h,
+                    np.ascontiguousarray(wide[:, :w])))
     if not small:
         img = tv.gen_photon(1920, 1080, 4095, seed=21)
         out.append(("photon_1080p", tv.encode_current(img), 1920, 1080, img))
