@@ -104,6 +104,13 @@ int32_t mcraw_frame_encoded_width(const uint8_t* frame, uint64_t len, int32_t wi
  * chunks (double-buffered) so transfer overlaps decode, then decodes into descs[i].dst (device). */
 int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);
 
+/* Host in, HOST OUT -- the reference's own contract for a decoded frame (Decoder.cpp:221-230: outData is a host vector),
+ * batched: like mcraw_decode_batch_host, and the pixels of frame i (width*height uint16) are also copied to host_dst[i]
+ * (pinned for overlap) as soon as the chunk that holds the frame has been decoded -- the device->host copy of chunk c runs
+ * beside the host->device copy and the decode of chunk c+1.  descs[i].dst still names the DEVICE buffer the frame is
+ * decoded into.  mcraw_batch_wait returns once the host buffers are complete. */
+int mcraw_decode_batch_host_out(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t n, void* stream);
+
 /* Wait for the most recently enqueued batch and fetch its per-frame results: written_elems[i] is the number
  * of uint16 elements written for frame i (0 = failed), status[i] the MCRAW_FRAME_* bits.  Either may be NULL. */
 int mcraw_batch_wait(mcraw_ctx* ctx, uint64_t* written_elems, uint32_t* status, uint32_t n);
@@ -128,6 +135,14 @@ int mcraw_host_unregister(mcraw_ctx* ctx, void* p);
 int mcraw_memcpy_h2d(mcraw_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, void* stream);
 int mcraw_memcpy_d2h(mcraw_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, void* stream);
 int mcraw_stream_sync(mcraw_ctx* ctx, void* stream);
+
+/* ---- integrity ---------------------------------------------------------------------------------------- */
+/* Position-weighted 64-bit checksum of n decoded frames in DEVICE memory, computed on the device (one kernel over all
+ * frames, synchronous):  out[f] = sum over i < elems[f] of (frame_f[i] + 1) * ((i + 1) * 0x9E3779B97F4A7C15)  mod 2^64.
+ * The multiplier is odd, so any single changed sample changes the sum; numpy restates it in one line (capi.checksum_u16).
+ * bench.py uses it to check every pixel of every timed batch against the source images without copying 1-25 GB back. */
+int mcraw_checksum_frames(mcraw_ctx* ctx, const uint16_t* const* frames_dev, const uint64_t* elems, uint32_t n, uint64_t* out,
+                          void* stream);
 
 /* ---- introspection ---------------------------------------------------------------------------------- */
 /* Kernels of this library launched through ctx since creation (bench.py reports the per-step delta). */

@@ -41,6 +41,7 @@ EXPORTED = [
     "mcraw_memcpy_h2d", "mcraw_memcpy_d2h", "mcraw_stream_sync", "mcraw_kernel_launches",
     "mcraw_last_batch_kernel_ms", "mcraw_kernel_time_totals", "mcraw_set_kernel_timing",
     "mcraw_host_register", "mcraw_host_unregister", "mcraw_set_sources_resident", "mcraw_frame_encoded_width",
+    "mcraw_checksum_frames", "mcraw_decode_batch_host_out",
 ]
 
 _c = None
@@ -60,6 +61,7 @@ def lib():
         c.mcraw_ctx_device.argtypes = [vp]
         c.mcraw_decode_batch.argtypes = [vp, ctypes.POINTER(FrameDesc), u32, vp]
         c.mcraw_decode_batch_host.argtypes = [vp, ctypes.POINTER(FrameDesc), u32, vp]
+        c.mcraw_decode_batch_host_out.argtypes = [vp, ctypes.POINTER(FrameDesc), ctypes.POINTER(vp), u32, vp]
         c.mcraw_batch_wait.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u32), u32]
         c.mcraw_decode_host.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, sz, ctypes.c_int]
         c.mcraw_decode_host.restype = sz
@@ -82,6 +84,7 @@ def lib():
         c.mcraw_set_sources_resident.argtypes = [vp, u32]
         c.mcraw_frame_encoded_width.argtypes = [vp, u64, ctypes.c_int32, ctypes.c_int32]
         c.mcraw_frame_encoded_width.restype = ctypes.c_int32
+        c.mcraw_checksum_frames.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64), u32, ctypes.POINTER(u64), vp]
         _c = c
     return _c
 
@@ -90,6 +93,17 @@ def frame_encoded_width(stream, width, height):
     """mcraw_frame_encoded_width: what a caller who uploads a compressionType 7 frame puts into FrameDesc.encoded_width."""
     stream = np.ascontiguousarray(stream, dtype=np.uint8)
     return int(lib().mcraw_frame_encoded_width(stream.ctypes.data, stream.size, width, height))
+
+
+CHECKSUM_K = 0x9E3779B97F4A7C15
+
+
+def checksum_u16(img):
+    """The checksum of mcraw_checksum_frames, restated with numpy (uint64 arithmetic wraps mod 2^64)."""
+    v = np.ascontiguousarray(img, dtype=np.uint16).reshape(-1).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        m = (np.arange(1, v.size + 1, dtype=np.uint64)) * np.uint64(CHECKSUM_K)
+        return int(((v + np.uint64(1)) * m).sum(dtype=np.uint64))
 
 
 class McrawError(RuntimeError):
@@ -182,11 +196,24 @@ class Context:
     def decode_batch_host(self, descs, n, stream=None):
         self._check(self._c.mcraw_decode_batch_host(self._h, descs, n, stream), "mcraw_decode_batch_host")
 
+    def decode_batch_host_out(self, descs, host_dst_ptrs, n, stream=None):
+        """Host in, host out (mcraw_decode_batch_host_out); host_dst_ptrs: ctypes array of n host pointers."""
+        self._check(self._c.mcraw_decode_batch_host_out(self._h, descs, host_dst_ptrs, n, stream), "mcraw_decode_batch_host_out")
+
     def batch_wait(self, n):
         written = (ctypes.c_uint64 * max(1, n))()
         status = (ctypes.c_uint32 * max(1, n))()
         self._check(self._c.mcraw_batch_wait(self._h, written, status, n), "mcraw_batch_wait")
         return list(written[:n]), list(status[:n])
+
+    def checksum_frames(self, ptrs, elems, stream=None):
+        """mcraw_checksum_frames over device frames -> list of 64-bit sums (see checksum_u16)."""
+        n = len(ptrs)
+        pa = (ctypes.c_void_p * max(1, n))(*ptrs)
+        ea = (ctypes.c_uint64 * max(1, n))(*elems)
+        out = (ctypes.c_uint64 * max(1, n))()
+        self._check(self._c.mcraw_checksum_frames(self._h, pa, ea, n, out, stream), "mcraw_checksum_frames")
+        return list(out[:n])
 
     def decode_host(self, stream_bytes, width, height, compression_type, fill=0xA5A5):
         """Reference-shaped call: host bytes in, host uint16 image out -> (elements_written, image)."""

@@ -16,6 +16,50 @@
 
 using namespace mcraw;
 
+// ---------------------------------------------------------------------------------------------------------
+// k_checksum: position-weighted 64-bit checksum of decoded frames (mcraw_checksum_frames), so that a caller -- bench.py
+// after every timed loop, a pipeline that wants an integrity tag -- can check EVERY pixel of a batch without moving it:
+//   sum over i of (v[i] + 1) * ((i + 1) * K)  mod 2^64,  K = 0x9E3779B97F4A7C15 (odd: any single changed sample changes the sum)
+// grid = (blocks per frame, frames)
+// ---------------------------------------------------------------------------------------------------------
+namespace mcraw {
+constexpr unsigned long long CK_K = 0x9E3779B97F4A7C15ull;
+constexpr int CK_THREADS = 256;
+__global__ void __launch_bounds__(CK_THREADS) k_checksum(const uint16_t* const* __restrict__ frames, const unsigned long long* __restrict__ elems,
+                                                         unsigned long long* __restrict__ out) {
+    const uint16_t* __restrict__ p = frames[blockIdx.y];
+    const unsigned long long n = elems[blockIdx.y];
+    unsigned long long acc = 0;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * CK_THREADS + threadIdx.x, nthr = (unsigned long long)gridDim.x * CK_THREADS;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const unsigned long long n8 = n / 8;
+        for (unsigned long long g = tid; g < n8; g += nthr) {
+            const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p) + g);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            unsigned long long m = (8 * g + 1) * CK_K;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                acc += (unsigned long long)((w[k] & 0xFFFFu) + 1u) * m; m += CK_K;
+                acc += (unsigned long long)((w[k] >> 16) + 1u) * m; m += CK_K;
+            }
+        }
+        for (unsigned long long i = 8 * n8 + tid; i < n; i += nthr) acc += (unsigned long long)(p[i] + 1u) * ((i + 1) * CK_K);
+    } else {
+        for (unsigned long long i = tid; i < n; i += nthr) acc += (unsigned long long)(p[i] + 1u) * ((i + 1) * CK_K);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    __shared__ unsigned long long part[CK_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < CK_THREADS / 32; k++) t += part[k];
+        atomicAdd(out + blockIdx.y, t);
+    }
+}
+}  // namespace mcraw
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -73,6 +117,9 @@ struct mcraw_ctx {
     // the NEXT batch runs in the gap, on a stream of its own, while k_units of the current batch streams pixels; the two
     // only meet through the per-frame meta_done counters.  Valid when the compressed frames are already in device
     // memory when mcraw_decode_batch is called (k_meta no longer waits for earlier work on the caller's stream).
+    cudaStream_t d2h_stream = nullptr;      // mcraw_decode_batch_host_out: device -> host copies of decoded chunks
+    cudaEvent_t d2h_done = nullptr;
+    bool d2h_pending = false;
     cudaStream_t meta_stream = nullptr;
     uint32_t cross_ctas = 0;
     Slot slots[kSlots];
@@ -563,6 +610,8 @@ void mcraw_ctx_destroy(mcraw_ctx* ctx) {
     if (ctx->d_out) cudaFree(ctx->d_out);
     for (auto& cs : ctx->copy_streams) if (cs) cudaStreamDestroy(cs);
     if (ctx->meta_stream) cudaStreamDestroy(ctx->meta_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->d2h_done) cudaEventDestroy(ctx->d2h_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -616,12 +665,27 @@ int32_t mcraw_frame_encoded_width(const uint8_t* frame, uint64_t len, int32_t wi
     return d.encoded_width == ((width + 63) / 64) * 64 ? 0 : d.encoded_width;
 }
 
+static int decode_batch_host_impl(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t n, void* stream);
+
 int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
+    return decode_batch_host_impl(ctx, descs, nullptr, n, stream);
+}
+
+int mcraw_decode_batch_host_out(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t n, void* stream) {
+    if (ctx && n && !host_dst) return fail_arg(ctx, "host_dst is null");
+    return decode_batch_host_impl(ctx, descs, host_dst, n, stream);
+}
+
+static int decode_batch_host_impl(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t n, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
     if (!descs && n) return fail_arg(ctx, "descs is null");
     int rc = bind(ctx);
     if (rc) return rc;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (host_dst && !ctx->d2h_stream) {
+        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->d2h_done, cudaEventDisableTiming));
+    }
     begin_batch(ctx, descs, n);
     std::vector<mcraw_frame_desc> chunk;
     uint32_t i = 0;
@@ -682,6 +746,24 @@ int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint3
         if (rc) return rc;
         CU_TRY(ctx, cudaEventRecord(g.freed, st));
         g.used = true;
+        if (host_dst) {
+            // pixels of this chunk go back while the next chunk is copied in and decoded (PCIe is full duplex); frames that
+            // lie back to back on both sides travel in one copy
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, g.freed, 0));
+            for (uint32_t k = i; k < j;) {
+                size_t elems = 0;
+                uint32_t m = k;
+                for (; m < j; m++) {
+                    if (!host_dst[m] || !descs[m].dst) return fail_arg(ctx, "frame " + std::to_string(m) + ": null dst");
+                    if (m > k && (descs[m].dst != descs[k].dst + elems || host_dst[m] != host_dst[k] + elems)) break;
+                    elems += (size_t)descs[m].width * (size_t)descs[m].height;
+                }
+                CU_TRY(ctx, cudaMemcpyAsync(host_dst[k], descs[k].dst, elems * 2, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                k = m;
+            }
+            CU_TRY(ctx, cudaEventRecord(ctx->d2h_done, ctx->d2h_stream));
+            ctx->d2h_pending = true;
+        }
         i = j;
     }
     return MCRAW_OK;
@@ -693,6 +775,10 @@ int mcraw_batch_wait(mcraw_ctx* ctx, uint64_t* written_elems, uint32_t* status, 
     int rc = bind(ctx);
     if (rc) return rc;
     for (auto& s : ctx->slots) { rc = harvest(ctx, s); if (rc) return rc; }
+    if (ctx->d2h_pending) {           // mcraw_decode_batch_host_out: the pixels have landed in the caller's host buffers
+        CU_TRY(ctx, cudaEventSynchronize(ctx->d2h_done));
+        ctx->d2h_pending = false;
+    }
     const uint32_t m = std::min(n, ctx->batch_n);
     for (uint32_t i = 0; i < m; i++) {
         uint64_t w = ctx->res_written[i];
@@ -756,6 +842,35 @@ size_t mcraw_decode_host(mcraw_ctx* ctx, uint16_t* output, int width, int height
         if (b > a) std::memcpy(reinterpret_cast<uint8_t*>(output) + a, reinterpret_cast<uint8_t*>(ctx->h_out) + a, b - a);
     });
     return ok ? (size_t)written : 0;
+}
+
+int mcraw_checksum_frames(mcraw_ctx* ctx, const uint16_t* const* frames_dev, const uint64_t* elems, uint32_t n, uint64_t* out,
+                          void* stream) {
+    if (!ctx || (n && (!frames_dev || !elems || !out))) return MCRAW_ERR_ARG;
+    if (n == 0) return MCRAW_OK;
+    if (bind(ctx)) return MCRAW_ERR_CUDA;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    // [pointers | element counts | sums] in one device allocation (not a hot path: allocated per call)
+    uint8_t* d = nullptr;
+    const size_t bytes = (size_t)n * 24;
+    CU_TRY(ctx, cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemcpyAsync(d, frames_dev, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + (size_t)n * 8, elems, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d + (size_t)n * 16, 0, (size_t)n * 8, st);
+    if (e == cudaSuccess) {
+        for (uint32_t base = 0; base < n && e == cudaSuccess; base += kMaxGridY) {
+            const uint32_t m = std::min(kMaxGridY, n - base);
+            k_checksum<<<dim3(64, m), CK_THREADS, 0, st>>>(reinterpret_cast<const uint16_t* const*>(d) + base,
+                                                           reinterpret_cast<const unsigned long long*>(d + (size_t)n * 8) + base,
+                                                           reinterpret_cast<unsigned long long*>(d + (size_t)n * 16) + base);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + (size_t)n * 16, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) { ctx->err = std::string("mcraw_checksum_frames: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return MCRAW_ERR_CUDA; }
+    return MCRAW_OK;
 }
 
 int mcraw_device_alloc(mcraw_ctx* ctx, size_t bytes, void** out) {
