@@ -55,7 +55,9 @@ struct FrameView {
 class Decoder {
 public:
     Decoder(const std::string& path);
-    Decoder(FILE* file);       // takes ownership: the handle is closed by the destructor
+    Decoder(FILE* file);       // takes ownership once constructed: the handle is closed by the destructor; if the constructor
+                               // throws, the handle stays open and the caller's (Decoder.cpp:97-114).  The container is read
+                               // from the handle's current position, like the reference's init() (Decoder.cpp:116-141)
     ~Decoder();
     Decoder(const Decoder&) = delete;
     Decoder& operator=(const Decoder&) = delete;

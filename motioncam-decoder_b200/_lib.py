@@ -6,7 +6,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 
-LIB_CAPI = os.path.join(PKG_DIR, "libmcraw_b200.so")           # kernels + C-ABI (needs a GPU to run)
+# kernels + C-ABI (needs a GPU to run); MCRAW_B200_LIB names an A/B build of the same sources (csrc/Makefile `variants`)
+LIB_CAPI = os.path.join(PKG_DIR, os.environ.get("MCRAW_B200_LIB", "libmcraw_b200.so"))
 LIB_TOOLS = os.path.join(PKG_DIR, "libmcraw_tools.so")         # CPU encoder / generators
 LIB_DROPIN = os.path.join(PKG_DIR, "libmotioncam_decoder_b200.so")  # drop-in C++ API + flat wrappers
 

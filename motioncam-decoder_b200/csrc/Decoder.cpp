@@ -37,10 +37,18 @@ public:
     explicit FileView(FILE* f) : mFile(f), mFd(fileno(f)) {
         struct stat st;
         mSize = (mFd >= 0 && fstat(mFd, &st) == 0) ? static_cast<int64_t>(st.st_size) : -1;
+        // the reference reads the container header from wherever the handle stands (Decoder.cpp:116-141 never seeks);
+        // everything after it is addressed by absolute offsets (:188,:239,:258,:284)
+        const off_t at = ftello(f);
+        mStart = at > 0 ? static_cast<int64_t>(at) : 0;
     }
     ~FileView() {
         if (mFile) std::fclose(mFile);
     }
+    // give the handle back to whoever passed it in (a constructor that throws must not close the caller's FILE:
+    // the reference leaves it open on that path, and the caller's own fclose would then be a double close)
+    void release() { mFile = nullptr; }
+    int64_t start() const { return mStart; }
     int64_t size() const { return mSize; }
     int fd() const { return mFd; }
     bool tryRead(int64_t offset, void* dst, size_t bytes) const {
@@ -66,6 +74,7 @@ private:
     FILE* mFile;
     int mFd;
     int64_t mSize;
+    int64_t mStart = 0;
 };
 
 // One audio chunk (Decoder.cpp:42-75).  false = unreachable offset (the reference's failed seek).
@@ -185,7 +194,10 @@ struct Decoder::Impl {
     // make room for `in` bytes of compressed frames and (loadFrames only) `out` bytes of decoded frames
     void reserveStaging(mcraw_ctx* ctx, size_t in, size_t out) {
         if (ringCtx != ctx) { releaseStaging(); ringCtx = ctx; }
-        auto fail = [&] { throw IOException(mcraw_last_error(ctx)); };
+        auto fail = [&] {
+            throw IOException(std::string("Cannot reserve staging memory for this many frames in one call (") + mcraw_last_error(ctx) +
+                              "); request fewer frames per call");
+        };
         if (in > ringBytes) {
             if (ring) mcraw_host_free_pinned(ctx, ring);
             ring = nullptr; ringBytes = 0;
@@ -263,16 +275,17 @@ struct Decoder::Impl {
 
 void Decoder::Impl::open() {
     // Decoder.cpp:116-151
+    const int64_t at = file.start();
     Header header{};
-    file.read(0, &header, sizeof header);
+    file.read(at, &header, sizeof header);
     if (header.version != CONTAINER_VERSION) throw IOException("Invalid container version");
     if (std::memcmp(header.ident, CONTAINER_ID, sizeof CONTAINER_ID) != 0) throw IOException("Invalid header id");
     Item item{};
-    file.read(sizeof header, &item, sizeof item);
+    file.read(at + sizeof header, &item, sizeof item);
     if (item.type != Type::METADATA) throw IOException("Invalid camera metadata");
-    file.require(sizeof header + sizeof item, item.size);
+    file.require(at + sizeof header + sizeof item, item.size);
     std::string text(item.size, '\0');
-    file.read(sizeof header + sizeof item, &text[0], item.size);
+    file.read(at + sizeof header + sizeof item, &text[0], item.size);
     containerMetadata = nlohmann::json::parse(text);
 
     readFrameIndex();
@@ -337,7 +350,12 @@ void Decoder::Impl::findAudioIndex() {
 Decoder::Decoder(FILE* file) {
     if (!file) throw IOException("Invalid file");
     m.reset(new Impl(file));
-    m->open();
+    try {
+        m->open();
+    } catch (...) {
+        m->file.release();      // ownership passes to the Decoder only once it exists (Decoder.hpp)
+        throw;
+    }
 }
 
 Decoder::Decoder(const std::string& path) {
@@ -453,12 +471,30 @@ void Decoder::loadFrame(const Timestamp timestamp, std::vector<uint8_t>& outData
 
 void Decoder::loadFrames(const std::vector<Timestamp>& timestamps, std::vector<std::vector<uint8_t>>& outData,
                          std::vector<nlohmann::json>& outMetadata) {
+    // The caller owns the result vectors, so the pinned / device staging behind loadFramesPinned only ever has to hold a
+    // bounded sub-batch: a whole clip (loadFrames(getFrames(), ...), tens of GB decoded) goes through ~1 GB at a time.
+    const size_t n = timestamps.size();
+    outData.assign(n, std::vector<uint8_t>());
+    outMetadata.assign(n, nlohmann::json());
+    constexpr size_t kSubBatchBytes = size_t(1) << 30;
+    std::vector<Timestamp> part;
     std::vector<FrameView> views;
-    loadFramesPinned(timestamps, views, outMetadata);
-    outData.resize(views.size());
-    for (size_t i = 0; i < views.size(); i++) {
-        outData[i].resize(views[i].size);
-        std::memcpy(outData[i].data(), views[i].data, views[i].size);
+    std::vector<nlohmann::json> meta;
+    for (size_t i = 0; i < n;) {
+        // decoded size is only known from the frame's JSON; the compressed size (>= ~1/4 of it for real data) bounds the count
+        part.clear();
+        size_t bytes = 0;
+        size_t j = i;
+        for (; j < n && (j == i || bytes < kSubBatchBytes / 4) && j - i < 4096; j++) {
+            bytes += locateFrame(timestamps[j]).payloadSize;
+            part.push_back(timestamps[j]);
+        }
+        loadFramesPinned(part, views, meta);
+        for (size_t k = 0; k < views.size(); k++) {
+            outData[i + k].assign(views[k].data, views[k].data + views[k].size);
+            outMetadata[i + k] = std::move(meta[k]);
+        }
+        i = j;
     }
 }
 
@@ -468,6 +504,7 @@ void Decoder::loadFramesPinned(const std::vector<Timestamp>& timestamps, std::ve
     outFrames.assign(n, FrameView{nullptr, 0});
     outMetadata.assign(n, nlohmann::json());
     if (n == 0) return;
+    if (n > 0xFFFFFFFFull) throw IOException("Too many frames in one call");
     mcraw_ctx* ctx = m->batchContext();
     m->outFlip ^= 1;                                   // the previous call's frames stay where they are
 
@@ -508,8 +545,12 @@ void Decoder::loadFramesPinned(const std::vector<Timestamp>& timestamps, std::ve
         d.dst = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(m->devOut) + outOff[i]);
         d.dst_capacity_elems = static_cast<uint64_t>(geo[i].width) * static_cast<uint64_t>(geo[i].height);
     }
+    // host in, host out: the pixels of a decoded chunk travel back while the next chunk is copied in and decoded
+    uint8_t* const result = static_cast<uint8_t*>(m->pinnedOut[m->outFlip]);
+    std::vector<uint16_t*> hostDst(n);
+    for (size_t i = 0; i < n; i++) hostDst[i] = reinterpret_cast<uint16_t*>(result + outOff[i]);
     std::vector<uint64_t> written(n);
-    if (mcraw_decode_batch_host(ctx, descs.data(), static_cast<uint32_t>(n), nullptr) != MCRAW_OK ||
+    if (mcraw_decode_batch_host_out(ctx, descs.data(), hostDst.data(), static_cast<uint32_t>(n), nullptr) != MCRAW_OK ||
         mcraw_batch_wait(ctx, written.data(), nullptr, static_cast<uint32_t>(n)) != MCRAW_OK)
         throw IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(ctx));
     for (size_t i = 0; i < n; i++) {
@@ -517,10 +558,6 @@ void Decoder::loadFramesPinned(const std::vector<Timestamp>& timestamps, std::ve
             throw IOException(geo[i].compressionType == kCompressionCurrent ? "Failed to uncompress frame"
                                                                              : "Failed to uncompress legacy frame");
     }
-    uint8_t* const result = static_cast<uint8_t*>(m->pinnedOut[m->outFlip]);
-    if (mcraw_memcpy_d2h(ctx, result, m->devOut, outBytes, nullptr) != MCRAW_OK ||
-        mcraw_stream_sync(ctx, nullptr) != MCRAW_OK)
-        throw IOException(mcraw_last_error(ctx));
     for (size_t i = 0; i < n; i++) {
         const size_t bytes = sizeof(uint16_t) * static_cast<size_t>(geo[i].width) * static_cast<size_t>(geo[i].height);
         outFrames[i] = FrameView{result + outOff[i], bytes};
@@ -534,6 +571,7 @@ void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint1
     const size_t n = timestamps.size();
     outMetadata.assign(n, nlohmann::json());
     if (n == 0) return;
+    if (n > 0xFFFFFFFFull) throw IOException("Too many frames in one call");
     mcraw_ctx* ctx = m->batchContext();
 
     // ---- locate every frame and lay the ring out (256-byte aligned slots, back to back: one H2D copy per chunk)

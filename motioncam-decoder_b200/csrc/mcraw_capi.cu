@@ -94,6 +94,12 @@ struct Slot {
     uint32_t max_ltiles = 0, nitems = 0;
     size_t items_off = 0, plan_bytes = 0;
     uint32_t flag_uses = 0;         // k_meta launches on this plan since its counters were zeroed
+    // completion through a word in pinned host memory (see k_units) instead of the `done` event
+    unsigned* h_done = nullptr;     // pinned, one word
+    unsigned done_seq = 0;
+    bool flag_wait = false;
+    cudaStream_t stream = nullptr;  // the stream the chunk was enqueued on
+    uintptr_t dst_lo = 0, dst_hi = 0;   // address range spanned by the plan's output buffers
     uint32_t lg_nwork = 0;          // (frame, tile) tickets of the legacy frames of the plan
     size_t lg_work_off = 0;
     uint32_t lg_epoch = 0;          // k_legacy_fused launches on this plan since its status words were zeroed
@@ -122,6 +128,15 @@ struct mcraw_ctx {
     bool d2h_pending = false;
     cudaStream_t meta_stream = nullptr;
     uint32_t cross_ctas = 0;
+    // CHAIN (MCRAW_CHAIN=<CTAs>, 0 = off): back-to-back batches on one stream are linked by programmatic dependent launches
+    // all the way -- k_meta of batch i+1 is a programmatic dependent of k_units of batch i, so it runs in the room k_units
+    // leaves (chain_ctas resident CTAs held back) while batch i streams pixels.  Stream order is kept for everything the
+    // caller can observe: it is only used when batch i+1 presents the descriptors of batch i again or writes a disjoint
+    // range of output addresses, and anything else enqueued on the stream in between ends the overlap by itself.
+    uint32_t chain_ctas = 0;
+    bool done_flag_mode = false;    // MCRAW_DONE_FLAG: completion word in pinned memory instead of an event behind k_units
+    int prev_slot = -1;             // slot of the previous enqueue_chunk call
+    unsigned done_counter = 0;
     Slot slots[kSlots];
     int cur = -1;
     Stage stages[kStage];
@@ -182,6 +197,10 @@ int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t up_bytes, size_t sc
         if (s.d_dyn) cudaFree(s.d_dyn);
         s.h_results = nullptr; s.d_dyn = nullptr; s.cap_frames = 0;
         CU_TRY(ctx, cudaMallocHost(&s.h_results, sizeof(Result) * cap));
+        if (!s.h_done) {
+            CU_TRY(ctx, cudaMallocHost(&s.h_done, 64));
+            *s.h_done = 0;
+        }
         CU_TRY(ctx, cudaMalloc(&s.d_dyn, 16 + sizeof(FrameState) * cap));
         s.cap_frames = cap;
     }
@@ -208,7 +227,29 @@ int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t up_bytes, size_t sc
 // one) and its kernel times into the context totals.
 int harvest(mcraw_ctx* ctx, Slot& s) {
     if (!s.in_flight) return MCRAW_OK;
-    CU_TRY(ctx, cudaEventSynchronize(s.done));
+    if (s.flag_wait) {
+        // the last warp of k_units writes the chunk's sequence number into pinned memory; a kernel that died never does,
+        // so the stream is asked now and then
+        const volatile unsigned* flag = s.h_done;
+        for (uint64_t spins = 0; *flag != s.done_seq; spins++) {
+            if (spins < 2000) continue;
+            if ((spins & 1023) == 0) {
+                const cudaError_t q = cudaStreamQuery(s.stream);
+                if (q != cudaErrorNotReady) {
+                    if (q != cudaSuccess || *flag != s.done_seq) {
+                        ctx->err = std::string("decode did not complete: ") + (q == cudaSuccess ? "completion word missing" : cudaGetErrorString(q));
+                        (void)cudaGetLastError();
+                        s.in_flight = false;
+                        return MCRAW_ERR_CUDA;
+                    }
+                }
+            }
+            std::this_thread::yield();
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+        CU_TRY(ctx, cudaEventSynchronize(s.done));
+    }
     s.in_flight = false;
     if (s.timed) {
         float a = 0.f, b = 0.f;
@@ -404,6 +445,12 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         if (!items.empty()) std::memcpy(s.h_up + s.items_off, items.data(), sizeof(WorkItem) * items.size());
         if (!lgwork.empty()) std::memcpy(s.h_up + s.lg_work_off, lgwork.data(), sizeof(LgWork) * lgwork.size());
         s.plan_descs.assign(descs, descs + n);
+        s.dst_lo = ~(uintptr_t)0; s.dst_hi = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(descs[i].dst);
+            s.dst_lo = std::min(s.dst_lo, a);
+            s.dst_hi = std::max(s.dst_hi, a + 2 * (uintptr_t)descs[i].dst_capacity_elems);
+        }
     }
     uint32_t* d_counter = reinterpret_cast<uint32_t*>(s.d_dyn);
     FrameState* d_states = reinterpret_cast<FrameState*>(s.d_dyn + 16);
@@ -418,6 +465,16 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     // (never for chunks whose sources are still on their way: mcraw_decode_batch_host orders the decode after its H2D copies
     // through `st`, which k_meta on its own stream would not see)
     const bool cross = sources_resident && ctx->cross_ctas > 0 && hit && any7 && !any6 && !timed;
+    bool chain = false;
+    if (ctx->overlap && ctx->chain_ctas && !cross && hit && any7 && !any6 && !timed && ctx->prev_slot >= 0 && ctx->prev_slot != ctx->cur) {
+        const Slot& p = ctx->slots[ctx->prev_slot];
+        // the previous chunk ended with k_units on this stream, and whatever it still writes cannot collide with this chunk
+        if (p.plan_valid && p.any7 && !p.any6 && p.stream == st && !p.timed) {
+            const bool same = p.plan_descs.size() == n && std::memcmp(p.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
+            chain = same || p.dst_hi <= s.dst_lo || s.dst_hi <= p.dst_lo;
+        }
+    }
+    s.stream = st;
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e0, st));
     if (!hit) {
         CU_TRY(ctx, cudaMemcpyAsync(s.d_up, s.h_up, s.plan_bytes, cudaMemcpyHostToDevice, st));
@@ -429,7 +486,18 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         if (any6 && s.plan_scratch) CU_TRY(ctx, cudaMemsetAsync(s.d_scratch, 0, s.plan_scratch, st));
         s.lg_epoch = 0;
     }
-    if (any7) { k_meta<<<2 * n, K1_THREADS, K1_SMEM, cross ? ctx->meta_stream : st>>>(d_frames, d_states); ctx->launches += 1; }
+    if (any7) {
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(2 * n); cfg.blockDim = dim3(K1_THREADS); cfg.dynamicSmemBytes = K1_SMEM; cfg.stream = cross ? ctx->meta_stream : st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = chain ? 1 : 0;
+        CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta, d_frames, d_states));
+        ctx->launches += 1;
+    }
     const bool split6 = any6 && ctx->legacy_split;
     if (split6) {
         k_legacy_maps<<<dim3(s.max_ltiles, n), LG_MAPS_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
@@ -440,7 +508,8 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
     if (any7) {
         const uint32_t want = (s.nitems + KU_WARPS - 1) / KU_WARPS;
-        const uint32_t room = cross && ctx->resident_ctas > ctx->cross_ctas ? ctx->resident_ctas - ctx->cross_ctas : ctx->resident_ctas;
+        const uint32_t hold = cross ? ctx->cross_ctas : chain ? ctx->chain_ctas : 0u;
+        const uint32_t room = ctx->resident_ctas > hold ? ctx->resident_ctas - hold : ctx->resident_ctas;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(room, 1), want));
         // Programmatic dependent launch: k_units becomes resident while k_meta's last wave is still running and synchronises
         // per frame (see k_units).  Timed batches are launched the ordinary way, so that the events bracket one kernel each.
@@ -454,9 +523,14 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
+        // completion word instead of an event: only where k_units is the chunk's last kernel and nothing else needs the event
+        s.flag_wait = ctx->done_flag_mode && !any6 && !timed && s.h_done != nullptr;
+        if (s.flag_wait) s.done_seq = ++ctx->done_counter ? ctx->done_counter : ++ctx->done_counter;
         CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems, d_counter,
-                                       (pdl || cross) ? 2u * s.flag_uses : 0u));
+                                       (pdl || cross) ? 2u * s.flag_uses : 0u, s.flag_wait ? s.h_done : (unsigned*)nullptr, s.done_seq));
         ctx->launches += 1;
+    } else {
+        s.flag_wait = false;
     }
     if (split6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
     else if (any6) {
@@ -470,8 +544,9 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e2, st));
     s.timed = timed && (any7 || any6);
     CU_TRY(ctx, cudaGetLastError());
-    CU_TRY(ctx, cudaEventRecord(s.done, st));
+    if (!s.flag_wait) CU_TRY(ctx, cudaEventRecord(s.done, st));
     s.in_flight = true;
+    ctx->prev_slot = ctx->cur;
     return MCRAW_OK;
 }
 
@@ -538,6 +613,8 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
     for (auto& cs : ctx->copy_streams)
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
+    if (const char* e = getenv("MCRAW_CHAIN")) ctx->chain_ctas = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("MCRAW_DONE_FLAG")) ctx->done_flag_mode = atoi(e) != 0;
     if (const char* e = getenv("MCRAW_CROSS_BATCH")) {
         ctx->cross_ctas = (uint32_t)std::max(0, atoi(e));
         int lo = 0, hi = 0;
@@ -561,6 +638,7 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
         // k_units spins on counters that k_meta bumps: in the cross-batch experiment k_meta must always find room beside it
         ctx->cross_ctas = std::min(ctx->cross_ctas, ctx->resident_ctas / 2);
+        ctx->chain_ctas = std::min(ctx->chain_ctas, ctx->resident_ctas / 2);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_fused, LGF_THREADS, LGF_SMEM) != cudaSuccess || per_sm < 1) {
             ctx->err = "k_legacy_fused does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
@@ -591,6 +669,7 @@ void mcraw_ctx_destroy(mcraw_ctx* ctx) {
         if (s.h_up) cudaFreeHost(s.h_up);
         if (s.d_up) cudaFree(s.d_up);
         if (s.h_results) cudaFreeHost(s.h_results);
+        if (s.h_done) cudaFreeHost(s.h_done);
         if (s.d_dyn) cudaFree(s.d_dyn);
         if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.done) cudaEventDestroy(s.done);

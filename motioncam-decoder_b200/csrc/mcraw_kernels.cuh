@@ -542,13 +542,25 @@ constexpr int KU_ROW_PITCH = 16 * KU_SLOT_PITCH + 64;   // 2368: (pitch/16) % 8 
 constexpr int KU_OUT_BYTES = 2 * KU_ROW_PITCH;    // two rows at a time (planes 0..3, then planes 4..7)
 constexpr int KU_META_BLOCK = 160;                // a staged metadata block: <= 15 bytes of alignment + 2 + 128, in 16-byte chunks
 constexpr int KU_META_BYTES = 2 * 2 * KU_META_BLOCK;   // (this unit, next unit) x (bits block, refs block)
-constexpr int KU_WARP_SMEM = ((KU_IN_BYTES + KU_OUT_BYTES + KU_META_BYTES + 127) / 128) * 128;
+#ifdef MCRAW_KU_BULK
+// EXPERIMENT (profiles/README.md, "bulk staging"): the unit payload arrives by ONE cp.async.bulk (TMA, 1-D) per unit,
+// issued by lane 0 and tracked by an mbarrier, instead of 16-byte cp.async per lane.  A bulk copy is linear, so the
+// XOR swizzle of the staged payload is gone: the decode reads meet whatever bank conflicts the block lengths produce.
+constexpr int KU_BAR_BYTES = 128;                 // the warp's mbarrier (8 bytes used)
+#else
+constexpr int KU_BAR_BYTES = 0;
+#endif
+constexpr int KU_WARP_SMEM = ((KU_IN_BYTES + KU_OUT_BYTES + KU_META_BYTES + KU_BAR_BYTES + 127) / 128) * 128;
 constexpr int KU_SMEM = KU_WARPS * KU_WARP_SMEM;
 static_assert(KU_IN_BYTES % 128 == 0 && KU_WARP_SMEM % 128 == 0, "swizzle rows are 128 bytes");
 static_assert((KU_ROW_PITCH / 16) % 8 == 4, "row pitch must skew pair rows by four 16-byte bank groups");
 
 // 128-byte rows, 16-byte chunks XOR-ed with the row index: lanes reading at a 128-byte stride stay (nearly) conflict free
+#ifdef MCRAW_KU_BULK
+__device__ __forceinline__ uint32_t swz(uint32_t o) { return o; }
+#else
 __device__ __forceinline__ uint32_t swz(uint32_t o) { return o ^ ((o >> 3) & 0x70u); }
+#endif
 
 struct SwzFetch {
     uint32_t base;   // shared-window address of the staged unit (128-byte aligned)
@@ -669,7 +681,8 @@ __device__ __forceinline__ uint32_t meta_values(const uint32_t blk, const uint32
 }
 
 __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& S, Result* __restrict__ result,
-                                           const uint32_t u0, const uint32_t upw, uint8_t* smem_warp, const uint32_t* s_terms) {
+                                           const uint32_t u0, const uint32_t upw, uint8_t* smem_warp, const uint32_t* s_terms,
+                                           uint32_t& bulk_phase) {
     const uint32_t lane = threadIdx.x & 31;
     const unsigned status = __ldcg(&S.status[0]) | __ldcg(&S.status[1]);
     const uint32_t rows_fit = __ldcg(&S.rows_fit);
@@ -719,13 +732,27 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
 
+#ifdef MCRAW_KU_BULK
+    const uint32_t bar = meta_base + KU_META_BYTES;
+#endif
     // stage unit payload [a0, a1) (rounded out to 16 bytes) with swizzled 16-byte cp.async
     auto stage_unit = [&](uint32_t a0, uint32_t a1) {
         const uint32_t s0 = a0 & ~15u;
         const uint32_t nchunks = (a1 - s0 + 15u) >> 4;                            // <= (8192 + 8 + 15) / 16
         if ((unsigned long long)s0 + 16ull * nchunks <= len) {
+#ifdef MCRAW_KU_BULK
+            if (nchunks == 0) {
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+            } else if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(16u * nchunks) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                             ::"r"(in_base), "l"(src + s0), "r"(16u * nchunks), "r"(bar) : "memory");
+            }
+            return;
+#else
             const uint8_t* g = src + s0 + 16u * lane;
             for (uint32_t c = lane; c < nchunks; c += 32, g += 512) cp_async16(in_base + swz(16u * c), g);
+#endif
         } else {                                                                   // tail of the buffer: bytes, zero filled
             for (uint32_t c = lane; c < nchunks; c += 32) {
                 const unsigned long long o = (unsigned long long)s0 + 16ull * c;
@@ -734,6 +761,12 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
                     if (o + k < len) t4[k >> 2] |= (uint32_t)src[o + k] << (8 * (k & 3));
                 sts128(in_base + swz(16u * c), t4[0], t4[1], t4[2], t4[3]);
             }
+#ifdef MCRAW_KU_BULK
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");          // the next bulk copy overwrites these generic stores
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+            return;
+#endif
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
@@ -746,7 +779,11 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
     for (uint32_t i = 0; i < nu; i++) {
         const uint32_t unit = u0 + i;
         // ---- this lane's block pair: header bits values, references, payload offset inside the unit
+#ifdef MCRAW_KU_BULK
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");                    // only the metadata travels in cp.async groups
+#else
         asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+#endif
         __syncwarp();
         const uint32_t mb = meta_base + (i & 1u) * 2u * KU_META_BLOCK;
         const uint32_t vb = meta_values(mb, rec.x, rec.z, s_terms, lane);
@@ -777,7 +814,18 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
             co.ptr[k] = dst + (size_t)(4u * ty) * (size_t)width + xpix;
         }
 
+#ifdef MCRAW_KU_BULK
+        {
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(ok) : "r"(bar), "r"(bulk_phase & 1u) : "memory");
+            }
+            bulk_phase++;
+        }
+#else
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
         __syncwarp();
 
         // ---- decode the even-column and the odd-column block of the pair
@@ -824,13 +872,25 @@ constexpr int KD_THREADS = 32 * KU_WARPS;
 // Three CTAs per SM (168 registers): the fourth buys 2 % of bandwidth and leaves no room for this logic without spills.
 __global__ void __launch_bounds__(KD_THREADS, 3)
 k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states, Result* __restrict__ results,
-        const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target) {
+        const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target,
+        unsigned* __restrict__ done_flag, const unsigned done_value) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint32_t s_terms[MCRAW_META_ROWS * 8 * 3];
+    // The NEXT batch's k_meta may be launched as a programmatic dependent of this kernel (mcraw_capi.cu, "chain"): it touches
+    // nothing this kernel uses (its own slot's scratch, its own frames), so it may start as soon as it finds room.
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     for (int i = threadIdx.x; i < MCRAW_META_ROWS * 8 * 3; i += KD_THREADS) s_terms[i] = (&c_meta_terms[0][0][0])[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     uint8_t* smem_warp = smem_raw + (threadIdx.x >> 5) * KU_WARP_SMEM;
+    uint32_t bulk_phase = 0;
+#ifdef MCRAW_KU_BULK
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(smem_warp) + KU_IN_BYTES + KU_OUT_BYTES + KU_META_BYTES) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+#endif
     uint32_t it = 0;
     if (lane == 0) it = atomicAdd(&counters[0], 1u);
     it = __shfl_sync(0xFFFFFFFFu, it, 0);
@@ -853,11 +913,24 @@ k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ stat
             }
         }
         __syncwarp();
-        units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 31u) + 1u, smem_warp, s_terms);
+        units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 31u) + 1u, smem_warp, s_terms,
+                   bulk_phase);
         __syncwarp();
         it = __shfl_sync(0xFFFFFFFFu, nxt, 0);
     }
-    if (lane == 0 && atomicAdd(&counters[1], 1u) == gridDim.x * KU_WARPS - 1u) { counters[0] = 0; counters[1] = 0; }
+    // done_flag != nullptr: completion is signalled through a word in pinned host memory instead of a CUDA event behind the
+    // kernel (an event record between this kernel and the next batch's k_meta would undo the programmatic overlap): every
+    // warp orders its result records (pinned host memory too) before its exit count, the last one out writes the word.
+    if (lane == 0) {
+        if (done_flag) __threadfence_system();
+        if (atomicAdd(&counters[1], 1u) == gridDim.x * KU_WARPS - 1u) {
+            counters[0] = 0; counters[1] = 0;
+            if (done_flag) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned*>(done_flag) = done_value;
+            }
+        }
+    }
 }
 
 }  // namespace mcraw

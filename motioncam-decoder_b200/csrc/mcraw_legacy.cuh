@@ -531,31 +531,44 @@ __global__ void __launch_bounds__(LG_THREADS, 9) k_legacy_decode(const FrameDev*
 //
 // Persistent CTAs take (frame, tile) tickets in a host-built order (tile index major, frame minor: neighbouring
 // tickets belong to different frames, so every frame's chain only has to advance a few tiles per generation of CTAs).
-// Per tile:
-//   1. stage the tile (+ overrun) in shared memory -- the only time the stream is read;
-//   2. warp 0 resolves chain C0 (entry offset 0) with the self-synchronising segment walk, then the other 16 entry
-//      offsets up to their merge point with C0: the tile's transfer map  entry -> (exit offset, block count);
+// A CTA is a two-stage pipeline over two shared-memory buffers, handed back and forth with mbarriers:
+//
+//   INDEX WARP (warp 0), one tile ahead of the others:
+//   1. stage the tile (+ overrun) with ONE bulk copy (cp.async.bulk, TMA 1-D; mbarrier transaction count) -- the only time
+//      the stream is read;
+//   2. resolve chain C0 (entry offset 0) with the self-synchronising segment walk, then the other 16 entry offsets up to
+//      their merge point with C0: the tile's transfer map  entry -> (exit offset, block count);
 //   3. publish the map (LOCAL), then DECOUPLED LOOK-BACK over the previous tiles of the frame: the nearest predecessor
 //      whose inclusive state (exit offset, blocks so far) is known, composed with the maps of the tiles in between
 //      (a window of 32 status words per poll; one lane chases the concrete entry state through the staged maps);
-//      publish this tile's inclusive state (INCL) before doing anything else, so that successors can go on;
+//      publish this tile's inclusive state (INCL) right away, so that successors can go on;
 //   4. patch the bitmap for the true entry (the few blocks before the merge point; a chain that never meets C0 is
-//      re-walked with the segment walk from its entry), turn it into the list of block pairs, decode from shared memory.
+//      re-walked with the segment walk from its entry) and hand the buffer to the decode warps.
+//   DECODE WARPS (warps 1..4): prefix popcounts over the bitmap give every thread the ordinal of the first block start
+//      in its own 128 bytes of the stream; it decodes the block PAIRS led from there (even-column block + odd-column
+//      block, RawData_Legacy.cpp:480-481) straight from shared memory and gives the buffer back.
+//
 // Ticket order guarantees that every predecessor a tile waits for has been started by a resident CTA (which never waits
 // for a successor), so the waits always end; they are bounded all the same (MCRAW_FRAME_INTERNAL instead of a hang).
 // Status words carry the launch epoch of the slot, so nothing has to be zeroed between launches.
 // =========================================================================================================
 struct LgWork { uint32_t frame, tile; };
 
-constexpr int LGF_THREADS = 128;
+constexpr int LGF_DEC_WARPS = 4;
+constexpr int LGF_DEC_THREADS = 32 * LGF_DEC_WARPS;     // thread t of the decode warps owns bitmap words 2t and 2t+1
+constexpr int LGF_THREADS = 32 + LGF_DEC_THREADS;       // warp 0: index warp
 constexpr int LGF_DATA = LG_TILE + LG_OVERRUN;
+constexpr int LGF_BUF = LGF_DATA + LG_TILE_WORDS * 4;   // one pipeline stage: tile bytes, then the bitmap of block starts
 constexpr int LGF_LB = 32;                              // look-back window: status words read per poll
-constexpr int LGF_SCRATCH = (LGF_LB * LG_STATES * 4 > LG_PAIR_CHUNK * 2) ? LGF_LB * LG_STATES * 4 : LG_PAIR_CHUNK * 2;
-constexpr int LGF_SMEM = LGF_DATA + LG_TILE_WORDS * 4 + LGF_SCRATCH;
+constexpr int LGF_SMEM = 2 * LGF_BUF + LGF_LB * LG_STATES * 4;
 constexpr uint32_t LGF_ST_LOCAL = 1u, LGF_ST_INCL = 2u;
 constexpr uint32_t LGF_ERR_BIT = 1u << 5;               // sticky: a wait gave up somewhere up the chain
 constexpr uint32_t LGF_SPIN_LIMIT = 1u << 22;
-static_assert(LGF_DATA % 16 == 0, "tile staging works in 16-byte granules");
+constexpr uint32_t LGF_STAGE_DONE = 1u, LGF_STAGE_SKIP = 2u;
+static_assert(LGF_DATA % 16 == 0 && LGF_BUF % 16 == 0, "bulk copies work in 16-byte granules");
+static_assert(LG_TILE_WORDS == 2 * LGF_DEC_THREADS, "every decode thread owns two bitmap words");
+
+struct LgfStage { uint32_t frame, tile, base, flags; };
 
 // status word of a tile: blocks up to the end of the tile << 32 | epoch (24 bits) << 8 | state << 6 | error << 5 | exit offset / 2
 __device__ __forceinline__ unsigned long long lgf_pack(uint32_t count, uint32_t epoch, uint32_t st, uint32_t low6) {
@@ -568,6 +581,19 @@ __device__ __forceinline__ unsigned long long lgf_load_status(const unsigned lon
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
 }
 
 // One lane, one segment of the staged tile: walk from tile-relative byte offset p to the end of segment `seg`.  Block
@@ -613,11 +639,10 @@ __device__ __forceinline__ uint32_t lgf_chain(const uint8_t* data, uint32_t* bit
     uint32_t entry = lane == 0 ? entry0 : seg0;          // tile-relative position where this lane's walk starts
     uint32_t p = entry;
     bool dead = lgf_walk_segment<false>(data, lane, p, bm, tile_rel);
-    uint32_t exitv = dead ? NONE : p;                    // tile-relative position in (or beyond) the next segment
+    uint32_t exitv = dead ? NONE : p;                    // tile-relative position in the next segment (steps are <= 34 bytes)
     for (;;) {
         uint32_t e = __shfl_up_sync(0xFFFFFFFFu, exitv, 1);
         if (lane == 0) e = entry0;
-        // an exit that jumps over this whole segment (impossible: steps are <= 34 bytes) is not handled: LG_SEG >= 64
         const bool upd = e != entry;
         if (upd) {
             entry = e;
@@ -697,8 +722,9 @@ __device__ __forceinline__ void lgf_block(const uint32_t* __restrict__ d32, cons
         }
     } else {
         const uint32_t i = a >> 2, k0 = a & 3u;                                        // the payload starts 2-byte aligned
-        // sample k = bytes (2k, 2k+1), big-endian: byte index (k0 + 2 (k & 1)) of the word pair (k / 2, k / 2 + 1)
-        const uint32_t selA = ((k0 + 1u) | (k0 << 4)) << (ADJ / 4), selB = ((k0 + 3u) | ((k0 + 2u) << 4)) << (ADJ / 4);
+        // sample k = bytes (2k, 2k+1), big-endian: byte index (k0 + 2 (k & 1)) of the word pair (k / 2, k / 2 + 1);
+        // the selector puts (high byte, low byte) at result bytes (1, 0) for ADJ 0 and (3, 2) for ADJ 16
+        const uint32_t selA = ((k0 + 1u) | (k0 << 4)) << (ADJ / 2), selB = ((k0 + 3u) | ((k0 + 2u) << 4)) << (ADJ / 2);
         uint32_t lo = d32[i];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
@@ -713,43 +739,66 @@ __device__ __forceinline__ void lgf_block(const uint32_t* __restrict__ d32, cons
 __global__ void __launch_bounds__(LGF_THREADS) k_legacy_fused(const FrameDev* __restrict__ frames, Result* __restrict__ results,
                                                               const LgWork* __restrict__ work, const uint32_t nwork,
                                                               uint32_t* __restrict__ counters, const uint32_t epoch) {
-    extern __shared__ __align__(16) uint8_t lg_smem[];
-    uint8_t* data = lg_smem;
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LGF_DATA);                             // [LG_TILE_WORDS]
-    uint32_t* lbmaps = reinterpret_cast<uint32_t*>(lg_smem + LGF_DATA + LG_TILE_WORDS * 4);         // look-back: [LGF_LB][LG_STATES]
-    uint16_t* plist = reinterpret_cast<uint16_t*>(lbmaps);                                          // later: the pair list
-    __shared__ uint32_t sh_ticket, sh_entry, sh_base, sh_total, sh_err;
-    __shared__ uint32_t sh_map[LG_STATES], sh_merge[LG_STATES], warp_sums[LGF_THREADS / 32];
+    extern __shared__ __align__(128) uint8_t lg_smem[];
+    uint32_t* lbmaps = reinterpret_cast<uint32_t*>(lg_smem + 2 * LGF_BUF);                          // look-back: [LGF_LB][LG_STATES]
+    __shared__ __align__(8) unsigned long long bars[6];              // per buffer: loaded (bulk copy), full (index -> decode), empty (decode -> index)
+    __shared__ LgfStage stage[2];
+    __shared__ uint32_t sh_map[LG_STATES], sh_merge[LG_STATES], warp_sums[LGF_DEC_WARPS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) mbar_init(bar0 + 8u * i, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
 
-    for (;;) {
-        __syncthreads();                                     // the previous tile's shared memory is no longer in use
-        if (tid == 0) sh_ticket = atomicAdd(&counters[2], 1u);
-        __syncthreads();
-        const uint32_t ticket = sh_ticket;
-        if (ticket >= nwork) break;
-        const LgWork wk = work[ticket];
-        const FrameDev& F = frames[wk.frame];
-        const unsigned long long len = F.len;
-        const uint32_t ntile = (uint32_t)max((len + LG_TILE - 1) / LG_TILE, 1ull);
-        const uint32_t tile = wk.tile;
-        const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
-        const uint32_t tile_rel = (uint32_t)min(len > tile_off ? len - tile_off : 0ull, (unsigned long long)(1u << 30));
-        const bool last_tile = tile + 1 == ntile;
-        const uint32_t ppr = ((uint32_t)F.width + 31u) / 32u;                            // pairs per row (RawData_Legacy.cpp:34-36)
-        const unsigned long long need = 2ull * ppr * (unsigned long long)F.height;       // blocks of the image (:478-482)
-        const bool fits = F.dst_cap >= (unsigned long long)F.width * (unsigned long long)F.height;
+    if (warp == 0) {
+        // ======================================== index warp ========================================
+        for (uint32_t k = 0;; k++) {
+            const uint32_t b = k & 1u, par = (k >> 1) & 1u;
+            uint8_t* data = lg_smem + b * LGF_BUF;
+            uint32_t* bitmap = reinterpret_cast<uint32_t*>(data + LGF_DATA);
+            const uint32_t bar_ld = bar0 + 8u * b, bar_full = bar0 + 16u + 8u * b, bar_empty = bar0 + 32u + 8u * b;
+            uint32_t ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&counters[2], 1u);
+            ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+            mbar_wait(bar_empty, par ^ 1u);                   // the decode warps are done with this buffer (passes at once the first time)
+            if (ticket >= nwork) {
+                if (lane == 0) { stage[b].flags = LGF_STAGE_DONE; mbar_arrive(bar_full); }
+                break;
+            }
+            const LgWork wk = work[ticket];
+            const FrameDev& F = frames[wk.frame];
+            const unsigned long long len = F.len;
+            const uint32_t ntile = (uint32_t)max((len + LG_TILE - 1) / LG_TILE, 1ull);
+            const uint32_t tile = wk.tile;
+            const unsigned long long tile_off = (unsigned long long)tile * LG_TILE;
+            const uint32_t tile_rel = (uint32_t)min(len > tile_off ? len - tile_off : 0ull, (unsigned long long)(1u << 30));
+            const bool last_tile = tile + 1 == ntile;
+            const uint32_t ppr = ((uint32_t)F.width + 31u) / 32u;                            // pairs per row (RawData_Legacy.cpp:34-36)
+            const unsigned long long need = 2ull * ppr * (unsigned long long)F.height;       // blocks of the image (:478-482)
+            const bool fits = F.dst_cap >= (unsigned long long)F.width * (unsigned long long)F.height;
 
-        // ---- 1. stage
-        lg_stage<LGF_THREADS>(data, F.src, len, tile_off, LGF_DATA, tid);
-        __syncthreads();
+            // ---- 1. stage: one bulk copy for a tile that lies wholly inside the buffer, else 16-byte granules with zero fill
+            if (tile_off + (unsigned long long)LGF_DATA <= len) {
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_ld), "r"((uint32_t)LGF_DATA) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                 ::"r"(smem_u32(data)), "l"(F.src + tile_off), "r"((uint32_t)LGF_DATA), "r"(bar_ld) : "memory");
+                }
+            } else {
+                lg_stage<32>(data, F.src, len, tile_off, LGF_DATA, lane);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // a later bulk copy overwrites these generic stores
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ld);
+            }
+            mbar_wait(bar_ld, par);
 
-        // ---- 2./3. transfer map, publication, look-back (warp 0)
-        if (warp == 0) {
+            // ---- 2. transfer map
             uint32_t total0;
             const uint32_t ex0 = lgf_chain(data, bitmap, 0u, tile_rel, lane, total0);
             const uint32_t exit0 = (ex0 == 0xFFFFFFFFu || last_tile) ? LG_DEAD : ex0 >> 1;
-            uint32_t mapv = 0, mergev = LG_NO_MERGE;
             if (lane < LG_STATES) {
                 uint32_t q = 2u * lane, pre = 0, m = LG_NO_MERGE, ex = exit0, count;
                 bool d2 = false;
@@ -773,19 +822,18 @@ __global__ void __launch_bounds__(LGF_THREADS) k_legacy_fused(const FrameDev* __
                         if (d2 || last_tile) ex = LG_DEAD;
                     }
                 }
-                mapv = ex | (count << 5);
-                mergev = m;
+                const uint32_t mapv = ex | (count << 5);
                 sh_map[lane] = mapv;
-                sh_merge[lane] = mergev;
+                sh_merge[lane] = m;
                 F.lg_tilemap[(size_t)tile * LG_STATES + lane] = mapv;
                 __threadfence();
             }
             __syncwarp();
+            // ---- 3. publish, look back, publish again
             if (lane == 0) {
                 __threadfence();                                 // release: the map before the status word
                 lgf_store_status(F.lg_status + tile, lgf_pack(0u, epoch, LGF_ST_LOCAL, 0u));
             }
-            // look-back
             uint32_t entry = 0, base = 0, errbit = 0;
             if (tile > 0) {
                 const uint32_t jhi = tile - 1;
@@ -827,7 +875,6 @@ __global__ void __launch_bounds__(LGF_THREADS) k_legacy_fused(const FrameDev* __
                     __nanosleep(spins < 16 ? 32 : 200);
                 }
             }
-            // this tile's inclusive state, published before the pixel work
             uint32_t exitv = LG_DEAD, total = base;
             if (entry != LG_DEAD) {
                 const uint32_t v = sh_map[entry];
@@ -836,17 +883,27 @@ __global__ void __launch_bounds__(LGF_THREADS) k_legacy_fused(const FrameDev* __
             }
             if (lane == 0) {
                 lgf_store_status(F.lg_status + tile, lgf_pack(total, epoch, LGF_ST_INCL, exitv | errbit));
-                sh_entry = entry; sh_base = base; sh_total = total; sh_err = errbit;
+                if (last_tile) {
+                    unsigned status = 0;
+                    if (!fits) status |= MCRAW_FRAME_GEOMETRY;
+                    if ((unsigned long long)total < need) status |= MCRAW_FRAME_TRUNCATED;     // reference: stale samples (:387,398)
+                    if (errbit) status |= MCRAW_FRAME_INTERNAL;
+                    Result r;
+                    r.written = status ? 0ull : (unsigned long long)F.width * (unsigned long long)F.height;   // :494
+                    r.status = status;
+                    r.pad = 0;
+                    results[wk.frame] = r;
+                }
             }
-            // ---- 4a. the bitmap for the true entry
-            if (entry != 0 && entry != LG_DEAD) {
+            // ---- 4. the bitmap for the true entry, then over to the decode warps
+            const bool skip = entry == LG_DEAD || !fits || (unsigned long long)base >= need;     // nothing of the image starts here
+            if (!skip && entry != 0) {
                 const uint32_t m = sh_merge[entry];
+                __syncwarp();
                 if (m == LG_NO_MERGE) {
                     uint32_t t2;
-                    __syncwarp();
                     lgf_chain(data, bitmap, 2u * entry, tile_rel, lane, t2);       // blocks of one constant width: walk it again from its entry
                 } else {
-                    __syncwarp();
                     for (uint32_t w = lane; w < (m >> 5); w += 32) bitmap[w] = 0;  // C0's marks before the merge point go
                     __syncwarp();
                     if (lane == 0) {
@@ -859,103 +916,96 @@ __global__ void __launch_bounds__(LGF_THREADS) k_legacy_fused(const FrameDev* __
                     }
                 }
             }
-        }
-        __syncthreads();
-        const uint32_t entry = sh_entry, tile_base = sh_base;
-        if (last_tile && tid == 0) {
-            unsigned status = 0;
-            if (!fits) status |= MCRAW_FRAME_GEOMETRY;
-            if ((unsigned long long)sh_total < need) status |= MCRAW_FRAME_TRUNCATED;     // reference: stale samples (:387,398)
-            if (sh_err) status |= MCRAW_FRAME_INTERNAL;
-            Result r;
-            r.written = status ? 0ull : (unsigned long long)F.width * (unsigned long long)F.height;   // :494
-            r.status = status;
-            r.pad = 0;
-            results[wk.frame] = r;
-        }
-        if (entry == LG_DEAD || !fits || (unsigned long long)tile_base >= need) continue;   // nothing of the image starts here
-
-        // ---- 4b. pair list of the tile: every block with an even ordinal leads a pair (even-column block, then odd-column
-        //      block, RawData_Legacy.cpp:480-481); plist[q] = (tile-relative offset of the leader) / 2 for pair ordinal
-        //      p_first + q.  Ordinals come from prefix popcounts of the bitmap: thread t owns words 2t and 2t+1.
-        const uint32_t w0 = bitmap[2 * tid], w1 = bitmap[2 * tid + 1];
-        const uint32_t c = __popc(w0) + __popc(w1);
-        uint32_t incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < LGF_THREADS / 32; w++) {
-            const uint32_t v = warp_sums[w];
-            if (w < warp) before += v;
-            total += v;
-        }
-        const uint32_t p_first = (tile_base + 1u) >> 1;
-        uint32_t npairs = ((tile_base + total + 1u) >> 1) - p_first;
-        npairs = (uint32_t)min((unsigned long long)npairs, (need >> 1) - (unsigned long long)p_first);
-        const int width = F.width;
-        uint16_t* __restrict__ dst = F.dst;
-        const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
-        const uint32_t ord0 = tile_base + before + incl - c;     // ordinal of the first block start in this thread's words
-        const uint32_t* d32 = reinterpret_cast<const uint32_t*>(data);
-        for (uint32_t c0 = 0; c0 < npairs; c0 += LG_PAIR_CHUNK) {
-            const uint32_t cn = min((uint32_t)LG_PAIR_CHUNK, npairs - c0);
-            {
-                uint32_t ord = ord0;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint32_t wv = h ? w1 : w0;
-                    while (wv) {
-                        const uint32_t b = __ffs(wv) - 1;
-                        wv &= wv - 1;
-                        const uint32_t q = (ord >> 1) - p_first - c0;       // wraps to a huge value for earlier passes' pairs
-                        if (!(ord & 1u) && q < cn) plist[q] = (uint16_t)(32u * (2u * tid + h) + b);
-                        ord++;
-                    }
-                }
+            __syncwarp();
+            if (lane == 0) {
+                LgfStage s;
+                s.frame = wk.frame; s.tile = tile; s.base = base; s.flags = skip ? LGF_STAGE_SKIP : 0u;
+                stage[b] = s;
+                mbar_arrive(bar_full);                        // release: bitmap, stage record (and the bulk copy observed above)
             }
-            __syncthreads();
-            uint32_t P = p_first + c0 + (uint32_t)tid;
+        }
+        // the last CTA to leave resets the ticket counters for the next launch
+        if (lane == 0 && atomicAdd(&counters[3], 1u) == gridDim.x - 1u) { counters[2] = 0; counters[3] = 0; }
+        return;
+    }
+
+    // ======================================== decode warps ========================================
+    const uint32_t dt = (uint32_t)tid - 32u, dwarp = (uint32_t)warp - 1u;
+    for (uint32_t k = 0;; k++) {
+        const uint32_t b = k & 1u, par = (k >> 1) & 1u;
+        const uint8_t* data = lg_smem + b * LGF_BUF;
+        const uint32_t* bitmap = reinterpret_cast<const uint32_t*>(data + LGF_DATA);
+        const uint32_t bar_full = bar0 + 16u + 8u * b, bar_empty = bar0 + 32u + 8u * b;
+        mbar_wait(bar_full, par);
+        const LgfStage st = stage[b];
+        if (st.flags & LGF_STAGE_DONE) break;
+        if (!(st.flags & LGF_STAGE_SKIP)) {
+            const FrameDev& F = frames[st.frame];
+            const uint32_t ppr = ((uint32_t)F.width + 31u) / 32u;
+            const uint32_t need_pairs = ppr * (uint32_t)F.height;               // < 2^26: width * height <= 2^30 (prepare())
+            // ordinal of the first block start in this thread's 128 bytes: prefix popcounts over the bitmap
+            const uint32_t w0 = bitmap[2 * dt], w1 = bitmap[2 * dt + 1];
+            const uint32_t c = __popc(w0) + __popc(w1);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) warp_sums[dwarp] = incl;
+            asm volatile("bar.sync 1, %0;\n" ::"n"(LGF_DEC_THREADS) : "memory");
+            uint32_t before = 0;
+#pragma unroll
+            for (int w = 0; w < LGF_DEC_WARPS; w++)
+                if ((uint32_t)w < dwarp) before += warp_sums[w];
+            const uint32_t ord0 = st.base + before + incl - c;
+            // block starts with an even ordinal lead a pair (even-column block, then odd-column block, :480-481); the
+            // partner's start is the next mark -- in these words or the next thread's, where it has an odd ordinal and is dropped
+            unsigned long long marks = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+            if ((ord0 & 1u) && marks) marks &= marks - 1;
+            uint32_t P = (ord0 >> 1) + (ord0 & 1u);                                  // ordinal of the first pair led here
             uint32_t y = P / ppr, xq = P - y * ppr;
-            for (uint32_t q = tid; q < cn; q += LGF_THREADS) {
-                const uint32_t oE = 2u * (uint32_t)plist[q];
+            const int width = F.width;
+            uint16_t* __restrict__ dst = F.dst;
+            const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
+            const uint32_t* d32 = reinterpret_cast<const uint32_t*>(data);
+            while (marks && P < need_pairs) {
+                const uint32_t bpos = (uint32_t)__ffsll((long long)marks) - 1u;
+                marks &= marks - 1;                                                   // the leader ...
+                marks &= marks - 1;                                                   // ... and its partner, if it starts in these words
+                const uint32_t oE = 256u * dt + 2u * bpos;
                 const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
                 const uint32_t oO = oE + 2u + leg_len(bitsE);
                 const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
                 uint32_t px[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) px[k] = 0;
+                for (int i = 0; i < 16; i++) px[i] = 0;
                 lgf_block<0>(d32, oE, bitsE, px);
                 lgf_block<16>(d32, oO, bitsO, px);
                 const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
 #pragma unroll
-                for (int k = 0; k < 16; k++) px[k] = __vadd2(px[k], refs);                    // :483-486, + reference mod 2^16
+                for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i], refs);                    // :483-486, + reference mod 2^16
                 const int x = (int)(32u * xq);
                 uint16_t* orow = dst + (size_t)y * (size_t)width + x;
                 if (vec && x + 32 <= width) {
                     uint4* o4 = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) o4[k] = make_uint4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+                    for (int i = 0; i < 4; i++) o4[i] = make_uint4(px[4 * i], px[4 * i + 1], px[4 * i + 2], px[4 * i + 3]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {                                            // crop at width (:490)
-                        if (x + 2 * k < width) orow[2 * k] = (uint16_t)px[k];
-                        if (x + 2 * k + 1 < width) orow[2 * k + 1] = (uint16_t)(px[k] >> 16);
+                    for (int i = 0; i < 16; i++) {                                            // crop at width (:490)
+                        if (x + 2 * i < width) orow[2 * i] = (uint16_t)px[i];
+                        if (x + 2 * i + 1 < width) orow[2 * i + 1] = (uint16_t)(px[i] >> 16);
                     }
                 }
-                xq += LGF_THREADS;                                                            // the pair LGF_THREADS further on
-                while (xq >= ppr) { xq -= ppr; y++; }
+                P++;
+                if (++xq == ppr) { xq = 0; y++; }
             }
-            __syncthreads();
         }
+        // every decode thread is done with the buffer (and with warp_sums): give it back
+        asm volatile("bar.sync 1, %0;\n" ::"n"(LGF_DEC_THREADS) : "memory");
+        if (dt == 0) mbar_arrive(bar_empty);
     }
-    // the last CTA to leave resets the ticket counters for the next launch
-    if (tid == 0 && atomicAdd(&counters[3], 1u) == gridDim.x - 1u) { counters[2] = 0; counters[3] = 0; }
 }
 
 }  // namespace mcraw

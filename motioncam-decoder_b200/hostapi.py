@@ -24,6 +24,8 @@ def _bind(c, prefix):
     f("decoder_open").restype = vp
     f("decoder_open_fp").argtypes = [ctypes.c_char_p, ctypes.c_char_p, sz]
     f("decoder_open_fp").restype = vp
+    f("decoder_open_fp_at").argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, sz]
+    f("decoder_open_fp_at").restype = vp
     f("decoder_close").argtypes = [vp]
     f("decoder_close").restype = None
     f("decoder_last_error").argtypes = [vp]
@@ -133,13 +135,14 @@ def export_clip(path, out_dir, num_frames=-1, batch=16, writer_threads=4, audio=
 class Decoder:
     """motioncam::Decoder (Decoder.hpp:47-73)."""
 
-    def __init__(self, path, lib=None, prefix="mcb200_", via_file_handle=False):
-        """via_file_handle: construct through Decoder(FILE*) (the wrapper fopens `path`; path=None passes a null handle)."""
+    def __init__(self, path, lib=None, prefix="mcb200_", via_file_handle=False, handle_offset=0):
+        """via_file_handle: construct through Decoder(FILE*) (the wrapper fopens `path` and seeks to handle_offset;
+        path=None passes a null handle)."""
         self._c = lib or library()
         self._p = prefix
         err = ctypes.create_string_buffer(1024)
         if via_file_handle:
-            self._h = self._f("decoder_open_fp")(None if path is None else str(path).encode(), err, len(err))
+            self._h = self._f("decoder_open_fp_at")(None if path is None else str(path).encode(), handle_offset, err, len(err))
         else:
             self._h = self._f("decoder_open")(str(path).encode(), err, len(err))
         if not self._h:

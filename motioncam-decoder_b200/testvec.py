@@ -187,7 +187,7 @@ def _item(t, size):
     return struct.pack("<II", t, size)
 
 
-def write_mcraw(path, frames, audio_chunks=(), container_metadata=None, index_order=None):
+def write_mcraw(path, frames, audio_chunks=(), container_metadata=None, index_order=None, prefix=b""):
     """Write a version-3 ``.mcraw`` file.
 
     frames        list of dicts {timestamp, data (bytes/np.uint8), width, height, compressionType, [extra json keys]}
@@ -195,6 +195,7 @@ def write_mcraw(path, frames, audio_chunks=(), container_metadata=None, index_or
     audio_chunks  list of (timestamp_ns_or_None, np.int16 array); None -> no AUDIO_DATA_METADATA item follows
                   (older files, Decoder.cpp:58-70)
     index_order   optional permutation for the BufferOffset array
+    prefix        bytes written in front of the container header
     Layout: Header, METADATA json, frame items (BUFFER + METADATA each), audio items, AUDIO_INDEX,
     BUFFER_INDEX_DATA, BUFFER_INDEX (last 24 bytes, Decoder.cpp:237-264).  The audio index must be reachable by
     walking items forward from the frame with the largest timestamp (Decoder.cpp:281-315), which holds for this
@@ -204,6 +205,8 @@ def write_mcraw(path, frames, audio_chunks=(), container_metadata=None, index_or
     offsets = []
     audio_offsets = []
     with open(path, "wb") as f:
+        f.write(prefix)        # foreign bytes in front of the container: Decoder(FILE*) starts at the handle's position, and
+                               # every offset stored in the file is absolute (Decoder.cpp:116-141 vs :188,239,258,284)
         f.write(b"MOTION " + bytes([3]))
         mj = json.dumps(meta).encode()
         f.write(_item(T_METADATA, len(mj)))

@@ -160,7 +160,20 @@ def test_file_handle_constructor(tmp_path):
         f.write(b"NOTION " + open(path, "rb").read()[7:])
     with pytest.raises(hostapi.DecoderError, match="Invalid header id"):
         hostapi.Decoder(bad, via_file_handle=True)
-    assert len(os.listdir("/proc/self/fd")) == fds_before          # a failed open gives the handle back too
+    # a constructor that throws leaves the handle with the caller (the reference never closes it on that path): the
+    # wrapper, being the caller, closes it -- a Decoder that had closed it as well would have made this a double close
+    assert len(os.listdir("/proc/self/fd")) == fds_before
+    # the container header is read from the handle's position (Decoder.cpp:116-141 never seeks), everything else by absolute offset
+    shifted = str(tmp_path / "shifted.mcraw")
+    tv.write_mcraw(shifted, frames, audio, prefix=b"\x00" * 4096 + b"junk in front")
+    for kw in ([dict()] + ([dict(lib=_ref_lib(), prefix="mcref_")] if ol.have_ref() else [])):
+        with pytest.raises(hostapi.DecoderError):
+            hostapi.Decoder(shifted, via_file_handle=True, **kw)                       # position 0: not a container header
+        d = hostapi.Decoder(shifted, via_file_handle=True, handle_offset=4096 + 13, **kw)
+        assert d.get_frames() == sorted(f["timestamp"] for f in frames)
+        assert len(d.load_audio()) == len(audio)
+        d.close()
+    assert len(os.listdir("/proc/self/fd")) == fds_before
     if ol.have_ref():
         ref = hostapi.Decoder(path, lib=_ref_lib(), prefix="mcref_", via_file_handle=True)
         assert ref.get_frames() == sorted(f["timestamp"] for f in frames)
