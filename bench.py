@@ -620,8 +620,6 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="run only this workload as the headline (default: c2 headline + c1/c3/c4/c5 legs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cross-batch", type=int, default=0,
-                    help="experiment (profiles/README.md): CTAs the pixel kernel leaves to the next batch's index kernel; 0 = off")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -638,9 +636,6 @@ def main():
     sampler = ClockSampler(env.local)
     sampler.start()
     head_wl = args.workload or "c2"
-    if args.cross_batch:
-        # the sources of the device-resident legs are complete in HBM before any timed call: the promise this switch needs
-        env.ctx.set_sources_resident(args.cross_batch)
     head, head_streams = run_leg(env, head_wl, args.steps, args.warmup, headline=True)
     peak_h2d = h2d_ceiling(env)
     for key in ("e2e", "e2e_host_out"):
@@ -679,7 +674,7 @@ def main():
             "e2e": head["e2e"], "e2e_host_out": head["e2e_host_out"],
             "pixels_verified": head["pixels_verified"], "verified_frames_total": head["verified_frames_total"],
             "cold_plan_ms_per_step": head.get("cold_plan_ms_per_step"),
-            "cross_batch_ctas": args.cross_batch,
+            "chain": os.environ.get("MCRAW_CHAIN", "default (24 CTAs held back for the next batch's index kernel)"),
             "gpu_launches": head["gpu_launches"],
             "clocks": clocks,
         }

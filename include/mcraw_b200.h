@@ -83,17 +83,11 @@ int mcraw_ctx_device(const mcraw_ctx* ctx);
 /* Enqueue the decode of n frames on `stream` (a cudaStream_t passed as void*; NULL = the context's own
  * stream).  Asynchronous: returns once the work is enqueued.  Frames may mix sizes and compression types.
  * The work is ordered after everything enqueued on `stream` before the call (so descs[i].src may be produced there).
- * Experiment, off by default: with MCRAW_CROSS_BATCH=<CTAs> in the environment when the context is created, the index
- * kernel of a batch whose descriptors the context has seen before runs on a stream of the context's own, beside the
- * previous batch's pixel kernel, and is NOT ordered after `stream`: the compressed frames must then be complete in device
- * memory when this function is called (profiles/README.md). */
+ * Back-to-back calls on one stream overlap where that cannot be observed: when a call presents the descriptors of the
+ * previous call again, or writes a disjoint range of output addresses, its index kernel is launched as a programmatic
+ * dependent of the previous call's pixel kernel and resolves the metadata while those pixels still stream
+ * (MCRAW_CHAIN=0 in the environment switches this off). */
 int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);
-
-/* Opt in to the cross-batch experiment described above for this context (same effect as MCRAW_CROSS_BATCH at creation):
- * holdback_ctas = resident CTAs the pixel kernel leaves to the next batch's index kernel (16..32 measured best on B200;
- * 0 = off, the default).  By calling this with a non-zero value the caller promises that the compressed frames of every
- * later mcraw_decode_batch call are complete in device memory at the time of the call. */
-int mcraw_set_sources_resident(mcraw_ctx* ctx, uint32_t holdback_ctas);
 
 /* For callers that upload compressed frames themselves: the value to put into mcraw_frame_desc.encoded_width for a
  * compressionType 7 frame whose first bytes are at `frame` in HOST memory (0 when the header is the usual width rounded
@@ -110,6 +104,14 @@ int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint3
  * beside the host->device copy and the decode of chunk c+1.  descs[i].dst still names the DEVICE buffer the frame is
  * decoded into.  mcraw_batch_wait returns once the host buffers are complete. */
 int mcraw_decode_batch_host_out(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t n, void* stream);
+
+/* One logical batch enqueued in pieces, for feeders that produce frames while earlier ones already travel and decode
+ * (Decoder::loadFramesToDevice reads chunk c+1 of the file while chunk c is on the bus): mcraw_batch_begin announces
+ * n_total frames, every mcraw_batch_append_host call enqueues frames [first_index, first_index + count) (descs[0] is
+ * frame first_index; host sources, as mcraw_decode_batch_host), mcraw_batch_wait then reports all n_total frames --
+ * frames that were never appended come back as failed with MCRAW_FRAME_BAD_TYPE. */
+int mcraw_batch_begin(mcraw_ctx* ctx, uint32_t n_total);
+int mcraw_batch_append_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t first_index, uint32_t count, void* stream);
 
 /* Wait for the most recently enqueued batch and fetch its per-frame results: written_elems[i] is the number
  * of uint16 elements written for frame i (0 = failed), status[i] the MCRAW_FRAME_* bits.  Either may be NULL. */

@@ -40,8 +40,9 @@ EXPORTED = [
     "mcraw_device_alloc", "mcraw_device_free", "mcraw_host_alloc_pinned", "mcraw_host_free_pinned",
     "mcraw_memcpy_h2d", "mcraw_memcpy_d2h", "mcraw_stream_sync", "mcraw_kernel_launches",
     "mcraw_last_batch_kernel_ms", "mcraw_kernel_time_totals", "mcraw_set_kernel_timing",
-    "mcraw_host_register", "mcraw_host_unregister", "mcraw_set_sources_resident", "mcraw_frame_encoded_width",
+    "mcraw_host_register", "mcraw_host_unregister", "mcraw_frame_encoded_width",
     "mcraw_checksum_frames", "mcraw_decode_batch_host_out",
+    "mcraw_batch_begin", "mcraw_batch_append_host",
 ]
 
 _c = None
@@ -81,7 +82,6 @@ def lib():
         c.mcraw_kernel_time_totals.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                                ctypes.POINTER(u64)]
         c.mcraw_set_kernel_timing.argtypes = [vp, u32]
-        c.mcraw_set_sources_resident.argtypes = [vp, u32]
         c.mcraw_frame_encoded_width.argtypes = [vp, u64, ctypes.c_int32, ctypes.c_int32]
         c.mcraw_frame_encoded_width.restype = ctypes.c_int32
         c.mcraw_checksum_frames.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64), u32, ctypes.POINTER(u64), vp]
@@ -233,10 +233,6 @@ class Context:
         self._check(self._c.mcraw_kernel_time_totals(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)),
                     "mcraw_kernel_time_totals")
         return a.value, b.value, n.value
-
-    def set_sources_resident(self, holdback_ctas):
-        """Cross-batch experiment (include/mcraw_b200.h): promise that sources are complete in device memory at call time."""
-        self._check(self._c.mcraw_set_sources_resident(self._h, holdback_ctas), "mcraw_set_sources_resident")
 
     def set_kernel_timing(self, every_n_chunks):
         """Bracket the kernels of every n-th chunk with CUDA events (0 = off, the default)."""

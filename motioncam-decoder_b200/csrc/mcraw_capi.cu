@@ -94,10 +94,6 @@ struct Slot {
     uint32_t max_ltiles = 0, nitems = 0;
     size_t items_off = 0, plan_bytes = 0;
     uint32_t flag_uses = 0;         // k_meta launches on this plan since its counters were zeroed
-    // completion through a word in pinned host memory (see k_units) instead of the `done` event
-    unsigned* h_done = nullptr;     // pinned, one word
-    unsigned done_seq = 0;
-    bool flag_wait = false;
     cudaStream_t stream = nullptr;  // the stream the chunk was enqueued on
     uintptr_t dst_lo = 0, dst_hi = 0;   // address range spanned by the plan's output buffers
     uint32_t lg_nwork = 0;          // (frame, tile) tickets of the legacy frames of the plan
@@ -119,28 +115,23 @@ struct mcraw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_streams[kCopyStreams] = {nullptr, nullptr};
-    // EXPERIMENT (off unless MCRAW_CROSS_BATCH=<CTAs> is set): k_units holds back that many of its resident CTAs and k_meta of
-    // the NEXT batch runs in the gap, on a stream of its own, while k_units of the current batch streams pixels; the two
-    // only meet through the per-frame meta_done counters.  Valid when the compressed frames are already in device
-    // memory when mcraw_decode_batch is called (k_meta no longer waits for earlier work on the caller's stream).
     cudaStream_t d2h_stream = nullptr;      // mcraw_decode_batch_host_out: device -> host copies of decoded chunks
     cudaEvent_t d2h_done = nullptr;
     bool d2h_pending = false;
-    cudaStream_t meta_stream = nullptr;
-    uint32_t cross_ctas = 0;
-    // CHAIN (MCRAW_CHAIN=<CTAs>, 0 = off): back-to-back batches on one stream are linked by programmatic dependent launches
-    // all the way -- k_meta of batch i+1 is a programmatic dependent of k_units of batch i, so it runs in the room k_units
-    // leaves (chain_ctas resident CTAs held back) while batch i streams pixels.  Stream order is kept for everything the
-    // caller can observe: it is only used when batch i+1 presents the descriptors of batch i again or writes a disjoint
-    // range of output addresses, and anything else enqueued on the stream in between ends the overlap by itself.
-    uint32_t chain_ctas = 0;
-    bool done_flag_mode = false;    // MCRAW_DONE_FLAG: completion word in pinned memory instead of an event behind k_units
+    // CHAIN: back-to-back batches on one stream are linked by programmatic dependent launches all the way -- k_meta of
+    // batch i+1 is a programmatic dependent of k_units of batch i, so it resolves the next batch's metadata in the room
+    // k_units leaves (chain_ctas of its resident CTAs held back) while batch i still streams pixels; the kernels only meet
+    // through the per-frame meta_done counters.  Stream order is kept for everything the caller can observe: the link is
+    // only made when batch i+1 presents the descriptors of batch i again or writes a disjoint range of output addresses,
+    // and anything else enqueued on the stream in between ends the overlap by itself (a programmatic edge only relaxes
+    // kernel -> kernel).  MCRAW_CHAIN=<CTAs> overrides the hold-back (0 = no chaining); 24 measured best on B200.
+    uint32_t chain_ctas = 24;
     int prev_slot = -1;             // slot of the previous enqueue_chunk call
-    unsigned done_counter = 0;
     Slot slots[kSlots];
     int cur = -1;
     Stage stages[kStage];
     int stage_cur = 0;
+    int copy_rr = 0;
     uint64_t launches = 0;
     std::vector<FrameDev> tmp_frames;
     std::vector<WorkItem> tmp_items;
@@ -197,10 +188,6 @@ int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t up_bytes, size_t sc
         if (s.d_dyn) cudaFree(s.d_dyn);
         s.h_results = nullptr; s.d_dyn = nullptr; s.cap_frames = 0;
         CU_TRY(ctx, cudaMallocHost(&s.h_results, sizeof(Result) * cap));
-        if (!s.h_done) {
-            CU_TRY(ctx, cudaMallocHost(&s.h_done, 64));
-            *s.h_done = 0;
-        }
         CU_TRY(ctx, cudaMalloc(&s.d_dyn, 16 + sizeof(FrameState) * cap));
         s.cap_frames = cap;
     }
@@ -227,29 +214,7 @@ int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t up_bytes, size_t sc
 // one) and its kernel times into the context totals.
 int harvest(mcraw_ctx* ctx, Slot& s) {
     if (!s.in_flight) return MCRAW_OK;
-    if (s.flag_wait) {
-        // the last warp of k_units writes the chunk's sequence number into pinned memory; a kernel that died never does,
-        // so the stream is asked now and then
-        const volatile unsigned* flag = s.h_done;
-        for (uint64_t spins = 0; *flag != s.done_seq; spins++) {
-            if (spins < 2000) continue;
-            if ((spins & 1023) == 0) {
-                const cudaError_t q = cudaStreamQuery(s.stream);
-                if (q != cudaErrorNotReady) {
-                    if (q != cudaSuccess || *flag != s.done_seq) {
-                        ctx->err = std::string("decode did not complete: ") + (q == cudaSuccess ? "completion word missing" : cudaGetErrorString(q));
-                        (void)cudaGetLastError();
-                        s.in_flight = false;
-                        return MCRAW_ERR_CUDA;
-                    }
-                }
-            }
-            std::this_thread::yield();
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
-    } else {
-        CU_TRY(ctx, cudaEventSynchronize(s.done));
-    }
+    CU_TRY(ctx, cudaEventSynchronize(s.done));
     s.in_flight = false;
     if (s.timed) {
         float a = 0.f, b = 0.f;
@@ -353,8 +318,9 @@ int begin_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n) {
     ctx->batch_n = n;
     ctx->res_written.assign(n, 0);
     ctx->res_status.assign(n, 0);
-    ctx->res_type.resize(n);
-    for (uint32_t i = 0; i < n; i++) ctx->res_type[i] = descs[i].compression_type;
+    ctx->res_type.assign(n, 0);        // frames that are never appended report MCRAW_FRAME_BAD_TYPE
+    if (descs)
+        for (uint32_t i = 0; i < n; i++) ctx->res_type[i] = descs[i].compression_type;
     return MCRAW_OK;
 }
 
@@ -382,8 +348,7 @@ void build_items(const std::vector<FrameDev>& frames, uint32_t resident_ctas, st
 // Enqueue one chunk (device-resident sources) of the current logical batch on `st`.  Everything stays on that one
 // stream: on this platform a cross-stream event dependency costs tens of microseconds, more than the index kernels it
 // could hide (measured: profiles/README.md).
-int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st,
-                  bool sources_resident) {
+int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st) {
     if (n == 0) return MCRAW_OK;
     ctx->cur = (ctx->cur + 1) % kSlots;
     Slot& s = ctx->slots[ctx->cur];
@@ -462,11 +427,8 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
 
     // descriptor + work list upload and the index kernels between e0 and e1, the pixel kernels between e1 and e2
     const bool timed = ctx->timing_every && (ctx->chunk_seq++ % ctx->timing_every) == 0;
-    // (never for chunks whose sources are still on their way: mcraw_decode_batch_host orders the decode after its H2D copies
-    // through `st`, which k_meta on its own stream would not see)
-    const bool cross = sources_resident && ctx->cross_ctas > 0 && hit && any7 && !any6 && !timed;
     bool chain = false;
-    if (ctx->overlap && ctx->chain_ctas && !cross && hit && any7 && !any6 && !timed && ctx->prev_slot >= 0 && ctx->prev_slot != ctx->cur) {
+    if (ctx->overlap && ctx->chain_ctas && hit && any7 && !any6 && !timed && ctx->prev_slot >= 0 && ctx->prev_slot != ctx->cur) {
         const Slot& p = ctx->slots[ctx->prev_slot];
         // the previous chunk ended with k_units on this stream, and whatever it still writes cannot collide with this chunk
         if (p.plan_valid && p.any7 && !p.any6 && p.stream == st && !p.timed) {
@@ -489,7 +451,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (any7) {
         cudaLaunchConfig_t cfg;
         std::memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(2 * n); cfg.blockDim = dim3(K1_THREADS); cfg.dynamicSmemBytes = K1_SMEM; cfg.stream = cross ? ctx->meta_stream : st;
+        cfg.gridDim = dim3(2 * n); cfg.blockDim = dim3(K1_THREADS); cfg.dynamicSmemBytes = K1_SMEM; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -508,13 +470,13 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
     if (any7) {
         const uint32_t want = (s.nitems + KU_WARPS - 1) / KU_WARPS;
-        const uint32_t hold = cross ? ctx->cross_ctas : chain ? ctx->chain_ctas : 0u;
+        const uint32_t hold = chain ? ctx->chain_ctas : 0u;
         const uint32_t room = ctx->resident_ctas > hold ? ctx->resident_ctas - hold : ctx->resident_ctas;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(std::max<uint32_t>(room, 1), want));
         // Programmatic dependent launch: k_units becomes resident while k_meta's last wave is still running and synchronises
         // per frame (see k_units).  Timed batches are launched the ordinary way, so that the events bracket one kernel each.
         s.flag_uses += 1;
-        const bool pdl = ctx->overlap && !timed && !cross;
+        const bool pdl = ctx->overlap && !timed;
         cudaLaunchConfig_t cfg;
         std::memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(KD_THREADS); cfg.dynamicSmemBytes = KU_SMEM; cfg.stream = st;
@@ -523,14 +485,9 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
-        // completion word instead of an event: only where k_units is the chunk's last kernel and nothing else needs the event
-        s.flag_wait = ctx->done_flag_mode && !any6 && !timed && s.h_done != nullptr;
-        if (s.flag_wait) s.done_seq = ++ctx->done_counter ? ctx->done_counter : ++ctx->done_counter;
         CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems, d_counter,
-                                       (pdl || cross) ? 2u * s.flag_uses : 0u, s.flag_wait ? s.h_done : (unsigned*)nullptr, s.done_seq));
+                                       pdl ? 2u * s.flag_uses : 0u));
         ctx->launches += 1;
-    } else {
-        s.flag_wait = false;
     }
     if (split6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
     else if (any6) {
@@ -544,19 +501,19 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e2, st));
     s.timed = timed && (any7 || any6);
     CU_TRY(ctx, cudaGetLastError());
-    if (!s.flag_wait) CU_TRY(ctx, cudaEventRecord(s.done, st));
+    CU_TRY(ctx, cudaEventRecord(s.done, st));
     s.in_flight = true;
     ctx->prev_slot = ctx->cur;
     return MCRAW_OK;
 }
 
-int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStream_t st, bool sources_resident) {
+int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStream_t st) {
     if (!descs && n) return fail_arg(ctx, "descs is null");
     int rc = bind(ctx);
     if (rc) return rc;
     begin_batch(ctx, descs, n);
     for (uint32_t base = 0; base < n; base += kMaxGridY) {
-        rc = enqueue_chunk(ctx, descs + base, std::min(kMaxGridY, n - base), base, st, sources_resident);
+        rc = enqueue_chunk(ctx, descs + base, std::min(kMaxGridY, n - base), base, st);
         if (rc) return rc;
     }
     return MCRAW_OK;
@@ -614,15 +571,6 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     for (auto& cs : ctx->copy_streams)
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
     if (const char* e = getenv("MCRAW_CHAIN")) ctx->chain_ctas = (uint32_t)std::max(0, atoi(e));
-    if (const char* e = getenv("MCRAW_DONE_FLAG")) ctx->done_flag_mode = atoi(e) != 0;
-    if (const char* e = getenv("MCRAW_CROSS_BATCH")) {
-        ctx->cross_ctas = (uint32_t)std::max(0, atoi(e));
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (ctx->cross_ctas && cudaStreamCreateWithPriority(&ctx->meta_stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
-            ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA);
-        }
-    }
     if (cudaFuncSetAttribute(k_meta, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_legacy_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_MAPS_SMEM) != cudaSuccess ||
@@ -636,8 +584,6 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
             ctx->err = "k_units does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
-        // k_units spins on counters that k_meta bumps: in the cross-batch experiment k_meta must always find room beside it
-        ctx->cross_ctas = std::min(ctx->cross_ctas, ctx->resident_ctas / 2);
         ctx->chain_ctas = std::min(ctx->chain_ctas, ctx->resident_ctas / 2);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_fused, LGF_THREADS, LGF_SMEM) != cudaSuccess || per_sm < 1) {
             ctx->err = "k_legacy_fused does not fit on this device"; return bail(MCRAW_ERR_CUDA);
@@ -669,7 +615,6 @@ void mcraw_ctx_destroy(mcraw_ctx* ctx) {
         if (s.h_up) cudaFreeHost(s.h_up);
         if (s.d_up) cudaFree(s.d_up);
         if (s.h_results) cudaFreeHost(s.h_results);
-        if (s.h_done) cudaFreeHost(s.h_done);
         if (s.d_dyn) cudaFree(s.d_dyn);
         if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.done) cudaEventDestroy(s.done);
@@ -688,7 +633,6 @@ void mcraw_ctx_destroy(mcraw_ctx* ctx) {
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
     for (auto& cs : ctx->copy_streams) if (cs) cudaStreamDestroy(cs);
-    if (ctx->meta_stream) cudaStreamDestroy(ctx->meta_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->d2h_done) cudaEventDestroy(ctx->d2h_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -706,20 +650,6 @@ int mcraw_set_kernel_timing(mcraw_ctx* ctx, uint32_t every_n_chunks) {
     return MCRAW_OK;
 }
 
-int mcraw_set_sources_resident(mcraw_ctx* ctx, uint32_t holdback_ctas) {
-    if (!ctx) return MCRAW_ERR_ARG;
-    int rc = bind(ctx);
-    if (rc) return rc;
-    if (holdback_ctas && !ctx->meta_stream) {
-        int lo = 0, hi = 0;
-        CU_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU_TRY(ctx, cudaStreamCreateWithPriority(&ctx->meta_stream, cudaStreamNonBlocking, hi));
-    }
-    // batches already enqueued keep the mode they were enqueued with; the switch applies from the next call on
-    ctx->cross_ctas = std::min(holdback_ctas, ctx->resident_ctas / 2);
-    return MCRAW_OK;
-}
-
 int mcraw_kernel_time_totals(mcraw_ctx* ctx, double* meta_ms, double* main_ms, uint64_t* chunks) {
     if (!ctx) return MCRAW_ERR_ARG;
     int rc = bind(ctx);
@@ -733,7 +663,7 @@ int mcraw_kernel_time_totals(mcraw_ctx* ctx, double* meta_ms, double* main_ms, u
 
 int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
-    return enqueue(ctx, descs, n, stream ? static_cast<cudaStream_t>(stream) : ctx->stream, true);
+    return enqueue(ctx, descs, n, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
 }
 
 int32_t mcraw_frame_encoded_width(const uint8_t* frame, uint64_t len, int32_t width, int32_t height) {
@@ -744,20 +674,39 @@ int32_t mcraw_frame_encoded_width(const uint8_t* frame, uint64_t len, int32_t wi
     return d.encoded_width == ((width + 63) / 64) * 64 ? 0 : d.encoded_width;
 }
 
-static int decode_batch_host_impl(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t n, void* stream);
+// Frames [first, first + n) of the current logical batch, sources in host memory (descs / host_dst point at frame `first`).
+static int append_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t first, uint32_t n, void* stream);
 
 int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
-    return decode_batch_host_impl(ctx, descs, nullptr, n, stream);
+    if (!ctx) return MCRAW_ERR_ARG;
+    if (!descs && n) return fail_arg(ctx, "descs is null");
+    begin_batch(ctx, descs, n);
+    return append_host(ctx, descs, nullptr, 0, n, stream);
 }
 
 int mcraw_decode_batch_host_out(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t n, void* stream) {
-    if (ctx && n && !host_dst) return fail_arg(ctx, "host_dst is null");
-    return decode_batch_host_impl(ctx, descs, host_dst, n, stream);
-}
-
-static int decode_batch_host_impl(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t n, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
     if (!descs && n) return fail_arg(ctx, "descs is null");
+    if (n && !host_dst) return fail_arg(ctx, "host_dst is null");
+    begin_batch(ctx, descs, n);
+    return append_host(ctx, descs, host_dst, 0, n, stream);
+}
+
+int mcraw_batch_begin(mcraw_ctx* ctx, uint32_t n_total) {
+    if (!ctx) return MCRAW_ERR_ARG;
+    begin_batch(ctx, nullptr, n_total);
+    return MCRAW_OK;
+}
+
+int mcraw_batch_append_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t first_index, uint32_t count, void* stream) {
+    if (!ctx) return MCRAW_ERR_ARG;
+    if (!descs && count) return fail_arg(ctx, "descs is null");
+    if (ctx->batch_id == 0 || (uint64_t)first_index + count > ctx->batch_n) return fail_arg(ctx, "append outside the batch announced by mcraw_batch_begin");
+    for (uint32_t i = 0; i < count; i++) ctx->res_type[first_index + i] = descs[i].compression_type;
+    return append_host(ctx, descs, nullptr, first_index, count, stream);
+}
+
+static int append_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* const* host_dst, uint32_t first, uint32_t n, void* stream) {
     int rc = bind(ctx);
     if (rc) return rc;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
@@ -765,16 +714,15 @@ static int decode_batch_host_impl(mcraw_ctx* ctx, const mcraw_frame_desc* descs,
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
         CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->d2h_done, cudaEventDisableTiming));
     }
-    begin_batch(ctx, descs, n);
     std::vector<mcraw_frame_desc> chunk;
     uint32_t i = 0;
-    int copy_rr = 0;
+    int copy_rr = ctx->copy_rr;
     while (i < n) {
         // ---- pick the frames of this chunk: as many as fit one staging buffer (at least one)
         size_t bytes = 0;
         uint32_t j = i;
         while (j < n && j - i < kMaxGridY) {
-            if (!descs[j].src) return fail_arg(ctx, "frame " + std::to_string(j) + ": null src");
+            if (!descs[j].src) return fail_arg(ctx, "frame " + std::to_string(first + j) + ": null src");
             size_t need = (descs[j].len + 255) & ~(size_t)255;
             if (j > i && bytes + need > kStageBytes) break;
             bytes += need;
@@ -821,7 +769,7 @@ static int decode_batch_host_impl(mcraw_ctx* ctx, const mcraw_frame_desc* descs,
         CU_TRY(ctx, cudaEventRecord(g.copied, cs));
         // ---- decode on the main stream after the copy; then the buffer is free again
         CU_TRY(ctx, cudaStreamWaitEvent(st, g.copied, 0));
-        rc = enqueue_chunk(ctx, chunk.data(), j - i, i, st, false);
+        rc = enqueue_chunk(ctx, chunk.data(), j - i, first + i, st);
         if (rc) return rc;
         CU_TRY(ctx, cudaEventRecord(g.freed, st));
         g.used = true;
@@ -845,6 +793,7 @@ static int decode_batch_host_impl(mcraw_ctx* ctx, const mcraw_frame_desc* descs,
         }
         i = j;
     }
+    ctx->copy_rr = copy_rr;
     return MCRAW_OK;
 }
 
@@ -899,7 +848,7 @@ size_t mcraw_decode_host(mcraw_ctx* ctx, uint16_t* output, int width, int height
         peek_encoded_width(h);
         d.encoded_width = h.encoded_width;
     }
-    if (enqueue(ctx, &d, 1, ctx->stream, false)) return 0;   // the H2D copy above is still in flight on the stream
+    if (enqueue(ctx, &d, 1, ctx->stream)) return 0;   // the H2D copy above is still in flight on the stream
     // the transfers back are queued behind the kernels right away (16-byte aligned pieces)
     auto part_begin = [&](int k) { return (out_bytes * k / out_parts) & ~(size_t)15; };
     for (int k = 0; k < out_parts; k++) {

@@ -872,8 +872,7 @@ constexpr int KD_THREADS = 32 * KU_WARPS;
 // Three CTAs per SM (168 registers): the fourth buys 2 % of bandwidth and leaves no room for this logic without spills.
 __global__ void __launch_bounds__(KD_THREADS, 3)
 k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states, Result* __restrict__ results,
-        const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target,
-        unsigned* __restrict__ done_flag, const unsigned done_value) {
+        const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint32_t s_terms[MCRAW_META_ROWS * 8 * 3];
     // The NEXT batch's k_meta may be launched as a programmatic dependent of this kernel (mcraw_capi.cu, "chain"): it touches
@@ -918,19 +917,7 @@ k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ stat
         __syncwarp();
         it = __shfl_sync(0xFFFFFFFFu, nxt, 0);
     }
-    // done_flag != nullptr: completion is signalled through a word in pinned host memory instead of a CUDA event behind the
-    // kernel (an event record between this kernel and the next batch's k_meta would undo the programmatic overlap): every
-    // warp orders its result records (pinned host memory too) before its exit count, the last one out writes the word.
-    if (lane == 0) {
-        if (done_flag) __threadfence_system();
-        if (atomicAdd(&counters[1], 1u) == gridDim.x * KU_WARPS - 1u) {
-            counters[0] = 0; counters[1] = 0;
-            if (done_flag) {
-                __threadfence_system();
-                *reinterpret_cast<volatile unsigned*>(done_flag) = done_value;
-            }
-        }
-    }
+    if (lane == 0 && atomicAdd(&counters[1], 1u) == gridDim.x * KU_WARPS - 1u) { counters[0] = 0; counters[1] = 0; }
 }
 
 }  // namespace mcraw

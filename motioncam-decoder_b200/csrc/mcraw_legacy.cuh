@@ -739,7 +739,7 @@ __device__ __forceinline__ void lgf_block(const uint32_t* __restrict__ d32, cons
 __global__ void __launch_bounds__(LGF_THREADS) k_legacy_fused(const FrameDev* __restrict__ frames, Result* __restrict__ results,
                                                               const LgWork* __restrict__ work, const uint32_t nwork,
                                                               uint32_t* __restrict__ counters, const uint32_t epoch) {
-    extern __shared__ __align__(128) uint8_t lg_smem[];
+    extern __shared__ __align__(16) uint8_t lg_smem[];
     uint32_t* lbmaps = reinterpret_cast<uint32_t*>(lg_smem + 2 * LGF_BUF);                          // look-back: [LGF_LB][LG_STATES]
     __shared__ __align__(8) unsigned long long bars[6];              // per buffer: loaded (bulk copy), full (index -> decode), empty (decode -> index)
     __shared__ LgfStage stage[2];
@@ -973,7 +973,7 @@ __global__ void __launch_bounds__(LGF_THREADS) k_legacy_fused(const FrameDev* __
                 const uint32_t bpos = (uint32_t)__ffsll((long long)marks) - 1u;
                 marks &= marks - 1;                                                   // the leader ...
                 marks &= marks - 1;                                                   // ... and its partner, if it starts in these words
-                const uint32_t oE = 256u * dt + 2u * bpos;
+                const uint32_t oE = 128u * dt + 2u * bpos;                               // two bitmap words = 128 bytes of the tile
                 const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
                 const uint32_t oO = oE + 2u + leg_len(bitsE);
                 const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
