@@ -90,10 +90,13 @@ public:
     // Decoder and reused) -> staged H2D on side streams -> kernels; nothing is copied back.  Device: MCRAW_B200_DEVICE.
     void loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint16_t* const* dst, const uint64_t* dstCapacityElems,
                             std::vector<nlohmann::json>& outMetadata);
-    // How loadFramesToDevice gets the compressed bytes to the GPU: "pread -> pinned ring" (default) or, with
-    // MCRAW_FEED=mmap in the environment, the file mapped read-only and page-locked so that the H2D copies read the
-    // page cache directly (falls back to the ring, with the reason in this text, where the platform refuses).
+    // How loadFramesToDevice gets the compressed bytes to the GPU.  Default: reader threads pread into the pinned ring while
+    // the chunks already read travel and decode.  MCRAW_FEED in the environment asks for another feed: "direct" (O_DIRECT
+    // reads into the ring), "cufile" (cuFileRead into device memory: GPUDirect Storage), "mmap" (H2D straight from a
+    // page-locked mapping of the file); each falls back to the ring, with the reason in this text, where the platform refuses.
     const char* feedDescription() const;
+
+    struct Feed;    // state of the optional feeds (Decoder.cpp)
 
 private:
     struct Impl;

@@ -8,12 +8,17 @@
 #include <motioncam/Decoder.hpp>
 #include <motioncam/RawData.hpp>
 
+#include <dlfcn.h>
+#include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cufile.h>      // types and prototypes only: libcufile is looked up with dlopen when MCRAW_FEED=cufile asks for it
+
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cerrno>
 #include <cstdlib>
 #include <cstring>
@@ -228,6 +233,7 @@ struct Decoder::Impl {
     mcraw_ctx* mapCtx = nullptr;
     bool mapTried = false;
     std::string feedNote = "pread -> pinned ring";
+    std::unique_ptr<Decoder::Feed> feed;
     const uint8_t* mappedFile(mcraw_ctx* ctx) {
         if (mapTried) return static_cast<const uint8_t*>(map);
         mapTried = true;
@@ -566,6 +572,63 @@ void Decoder::loadFramesPinned(const std::vector<Timestamp>& timestamps, std::ve
 
 const char* Decoder::feedDescription() const { return m->feedNote.c_str(); }
 
+// ---- feeds of loadFramesToDevice ------------------------------------------------------------------------------------
+// "ring" (default)  reader threads pread the frames into the pinned ring while the chunks already read travel to the device
+//                    and decode: the file read of chunk c+1 overlaps the H2D copy and the kernels of chunk c.
+// "direct"           the same, but the payload reads go through a second descriptor opened with O_DIRECT (the page cache is
+//                    bypassed; every read covers the 4 KiB-aligned range around the frame and lands at the same misalignment
+//                    in the ring).  Falls back to buffered reads where the filesystem refuses.
+// "cufile"           GPUDirect Storage: cuFileRead straight into device memory, then the device-resident decode.  Needs
+//                    libcufile and a driver / filesystem that take it; otherwise the reason is reported and the ring is used.
+// "mmap"             H2D straight from a page-locked mapping of the file (see mappedFile()).
+namespace {
+
+struct CuFileApi {
+    void* lib = nullptr;
+    CUfileError_t (*driverOpen)() = nullptr;
+    CUfileError_t (*handleRegister)(CUfileHandle_t*, CUfileDescr_t*) = nullptr;
+    void (*handleDeregister)(CUfileHandle_t) = nullptr;
+    ssize_t (*read)(CUfileHandle_t, void*, size_t, off_t, off_t) = nullptr;
+    std::string why;
+    bool load() {
+        if (lib) return true;
+        for (const char* name : {"libcufile.so.0", "libcufile.so", "/usr/local/cuda/lib64/libcufile.so.0"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) { why = "libcufile not found"; return false; }
+        driverOpen = reinterpret_cast<decltype(driverOpen)>(dlsym(lib, "cuFileDriverOpen"));
+        handleRegister = reinterpret_cast<decltype(handleRegister)>(dlsym(lib, "cuFileHandleRegister"));
+        handleDeregister = reinterpret_cast<decltype(handleDeregister)>(dlsym(lib, "cuFileHandleDeregister"));
+        read = reinterpret_cast<decltype(read)>(dlsym(lib, "cuFileRead"));
+        if (!driverOpen || !handleRegister || !handleDeregister || !read) { why = "libcufile lacks the expected symbols"; dlclose(lib); lib = nullptr; return false; }
+        return true;
+    }
+};
+
+std::string cufileText(const CUfileError_t& e) {
+    return std::string(cufileop_status_error(e.err)) + " (" + std::to_string(static_cast<int>(e.err)) + ")";
+}
+
+}  // namespace
+
+struct Decoder::Feed {
+    // O_DIRECT descriptor of the same file (feed "direct" / "cufile"), -1 when not open
+    int directFd = -1;
+    bool directTried = false;
+    CuFileApi cufile;
+    CUfileHandle_t cufileHandle{};
+    bool cufileReady = false, cufileTried = false;
+    void* devIn = nullptr;          // device copy of the compressed frames (feed "cufile")
+    size_t devInBytes = 0;
+    mcraw_ctx* devCtx = nullptr;
+    ~Feed() {
+        if (cufileReady) cufile.handleDeregister(cufileHandle);
+        if (devIn && devCtx) mcraw_device_free(devCtx, devIn);
+        if (directFd >= 0) ::close(directFd);
+    }
+};
+
 void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint16_t* const* dst, const uint64_t* dstCapacityElems,
                                  std::vector<nlohmann::json>& outMetadata) {
     const size_t n = timestamps.size();
@@ -573,50 +636,227 @@ void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint1
     if (n == 0) return;
     if (n > 0xFFFFFFFFull) throw IOException("Too many frames in one call");
     mcraw_ctx* ctx = m->batchContext();
+    if (!m->feed) m->feed.reset(new Feed());
+    Feed& feed = *m->feed;
+    const char* modeEnv = std::getenv("MCRAW_FEED");
+    const std::string mode = modeEnv ? modeEnv : "ring";
 
-    // ---- locate every frame and lay the ring out (256-byte aligned slots, back to back: one H2D copy per chunk)
     std::vector<FrameLocation> where(n);
-    std::vector<size_t> off(n);
-    size_t bytes = 0;
-    for (size_t i = 0; i < n; i++) {
-        where[i] = locateFrame(timestamps[i]);
-        off[i] = bytes;
-        bytes += (static_cast<size_t>(where[i].payloadSize) + 255) & ~static_cast<size_t>(255);
-    }
-    const uint8_t* mapped = m->mappedFile(ctx);
-    uint8_t* ring = nullptr;
-    if (!mapped) {
-        m->reserveStaging(ctx, bytes + 256, 0);
-        ring = static_cast<uint8_t*>(m->ring);
-    }
-    std::vector<mcraw_frame_desc> descs(n);
-    if (mapped) {
-        for (size_t i = 0; i < n; i++) readFrame(where[i], nullptr, outMetadata[i]);
-    } else {
-        readFramesParallel(*this, where, ring, off, outMetadata);
-    }
-    for (size_t i = 0; i < n; i++) {
+    for (size_t i = 0; i < n; i++) where[i] = locateFrame(timestamps[i]);
+    auto describe = [&](size_t i, mcraw_frame_desc& d, const uint8_t* src) {
         const FrameGeometry g = geometryOf(outMetadata[i]);
         if (g.compressionType != kCompressionCurrent && g.compressionType != kCompressionLegacy)
             throw IOException("Invalid compression type");
-        mcraw_frame_desc& d = descs[i];
         std::memset(&d, 0, sizeof d);
-        d.src = mapped ? mapped + where[i].payloadOffset : ring + off[i];
+        d.src = src;
         d.len = where[i].payloadSize;
         d.width = g.width;
         d.height = g.height;
         d.compression_type = g.compressionType;
         d.dst = dst[i];
         d.dst_capacity_elems = dstCapacityElems[i];
+    };
+    auto finish = [&](const std::vector<mcraw_frame_desc>& descs) {
+        std::vector<uint64_t> written(n);
+        if (mcraw_batch_wait(ctx, written.data(), nullptr, static_cast<uint32_t>(n)) != MCRAW_OK)
+            throw IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(ctx));
+        for (size_t i = 0; i < n; i++)
+            if (written[i] == 0)
+                throw IOException(descs[i].compression_type == kCompressionCurrent ? "Failed to uncompress frame"
+                                                                                   : "Failed to uncompress legacy frame");
+    };
+    std::vector<mcraw_frame_desc> descs(n);
+
+    // ---- mapped feed: nothing to read, the DMA engine takes the frames out of the page cache
+    if (const uint8_t* mapped = m->mappedFile(ctx)) {
+        for (size_t i = 0; i < n; i++) {
+            readFrame(where[i], nullptr, outMetadata[i]);
+            describe(i, descs[i], mapped + where[i].payloadOffset);
+        }
+        if (mcraw_decode_batch_host(ctx, descs.data(), static_cast<uint32_t>(n), nullptr) != MCRAW_OK)
+            throw IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(ctx));
+        finish(descs);
+        return;
     }
-    std::vector<uint64_t> written(n);
-    if (mcraw_decode_batch_host(ctx, descs.data(), static_cast<uint32_t>(n), nullptr) != MCRAW_OK ||
-        mcraw_batch_wait(ctx, written.data(), nullptr, static_cast<uint32_t>(n)) != MCRAW_OK)
-        throw IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(ctx));
-    for (size_t i = 0; i < n; i++)
-        if (written[i] == 0)
-            throw IOException(descs[i].compression_type == kCompressionCurrent ? "Failed to uncompress frame"
-                                                                               : "Failed to uncompress legacy frame");
+
+    // ---- O_DIRECT descriptor (feeds "direct" and "cufile")
+    if ((mode == "direct" || mode == "cufile") && !feed.directTried) {
+        feed.directTried = true;
+        const std::string link = "/proc/self/fd/" + std::to_string(m->file.fd());
+        feed.directFd = ::open(link.c_str(), O_RDONLY | O_DIRECT);
+        if (feed.directFd < 0) m->feedNote = std::string("pread -> pinned ring (O_DIRECT open refused: ") + std::strerror(errno) + ")";
+    }
+
+    // ---- cuFile feed: file -> device memory, device-resident decode
+    if (mode == "cufile" && !feed.cufileTried) {
+        feed.cufileTried = true;
+        if (feed.directFd < 0) {
+            // feedNote already says why
+        } else if (!feed.cufile.load()) {
+            m->feedNote = "pread -> pinned ring (cuFile: " + feed.cufile.why + ")";
+        } else {
+            CUfileError_t e = feed.cufile.driverOpen();
+            if (e.err != CU_FILE_SUCCESS) {
+                m->feedNote = "pread -> pinned ring (cuFileDriverOpen: " + cufileText(e) + ")";
+            } else {
+                CUfileDescr_t descr;
+                std::memset(&descr, 0, sizeof descr);
+                descr.handle.fd = feed.directFd;
+                descr.type = CU_FILE_HANDLE_TYPE_OPAQUE_FD;
+                e = feed.cufile.handleRegister(&feed.cufileHandle, &descr);
+                if (e.err != CU_FILE_SUCCESS) m->feedNote = "pread -> pinned ring (cuFileHandleRegister: " + cufileText(e) + ")";
+                else { feed.cufileReady = true; m->feedNote = "cuFileRead -> device memory (GPUDirect Storage or its compatibility mode)"; }
+            }
+        }
+    }
+    if (mode == "cufile" && feed.cufileReady) {
+        std::vector<size_t> off(n);
+        size_t bytes = 0;
+        for (size_t i = 0; i < n; i++) { off[i] = bytes; bytes += (static_cast<size_t>(where[i].payloadSize) + 4095) & ~static_cast<size_t>(4095); }
+        if (bytes > feed.devInBytes || feed.devCtx != ctx) {
+            if (feed.devIn && feed.devCtx) mcraw_device_free(feed.devCtx, feed.devIn);
+            feed.devIn = nullptr; feed.devInBytes = 0; feed.devCtx = ctx;
+            if (mcraw_device_alloc(ctx, bytes + bytes / 4, &feed.devIn) != MCRAW_OK) throw IOException(mcraw_last_error(ctx));
+            feed.devInBytes = bytes + bytes / 4;
+        }
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        auto work = [&] {
+            for (size_t i = next.fetch_add(1); i < n && !bad; i = next.fetch_add(1)) {
+                const ssize_t got = feed.cufile.read(feed.cufileHandle, feed.devIn, where[i].payloadSize,
+                                                     static_cast<off_t>(where[i].payloadOffset), static_cast<off_t>(off[i]));
+                if (got != static_cast<ssize_t>(where[i].payloadSize)) bad = true;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < std::min<size_t>(n, 8); t++) pool.emplace_back(work);
+        work();
+        for (std::thread& t : pool) t.join();
+        if (bad) {
+            feed.cufileReady = false;          // from now on: the ring
+            m->feedNote = "pread -> pinned ring (cuFileRead failed)";
+        } else {
+            for (size_t i = 0; i < n; i++) {
+                readFrame(where[i], nullptr, outMetadata[i]);
+                describe(i, descs[i], static_cast<const uint8_t*>(feed.devIn) + off[i]);
+            }
+            if (mcraw_decode_batch(ctx, descs.data(), static_cast<uint32_t>(n), nullptr) != MCRAW_OK)
+                throw IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(ctx));
+            finish(descs);
+            return;
+        }
+    }
+
+    // ---- ring feeds: lay the ring out (256-byte aligned slots back to back -- one H2D copy per chunk; O_DIRECT reads need
+    //      4 KiB slots and keep the frame's misalignment), cut it into chunks, read and enqueue chunk by chunk
+    const bool direct = mode == "direct" && feed.directFd >= 0;
+    std::vector<size_t> off(n);
+    size_t bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (direct) {
+            const size_t mis = static_cast<size_t>(where[i].payloadOffset) & 4095;
+            off[i] = bytes + mis;
+            bytes += (mis + static_cast<size_t>(where[i].payloadSize) + 4095) & ~static_cast<size_t>(4095);
+        } else {
+            off[i] = bytes;
+            bytes += (static_cast<size_t>(where[i].payloadSize) + 255) & ~static_cast<size_t>(255);
+        }
+    }
+    m->reserveStaging(ctx, bytes + 8192, 0);
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(m->ring) + 4095) & ~static_cast<uintptr_t>(4095));
+    size_t kChunkBytes = size_t(32) << 20;                // a chunk is handed to the device as soon as it has been read
+    if (const char* e = std::getenv("MCRAW_FEED_CHUNK_KB")) kChunkBytes = static_cast<size_t>(std::max(1, std::atoi(e))) << 10;
+    std::vector<size_t> chunkFirst{0};
+    {
+        size_t acc = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (acc >= kChunkBytes) { chunkFirst.push_back(i); acc = 0; }
+            acc += where[i].payloadSize;
+        }
+        chunkFirst.push_back(n);
+    }
+    const size_t nchunks = chunkFirst.size() - 1;
+    std::vector<std::atomic<size_t>> remaining(nchunks);
+    std::vector<uint32_t> chunkOf(n);
+    for (size_t c = 0; c < nchunks; c++) {
+        remaining[c].store(chunkFirst[c + 1] - chunkFirst[c]);
+        for (size_t i = chunkFirst[c]; i < chunkFirst[c + 1]; i++) chunkOf[i] = static_cast<uint32_t>(c);
+    }
+    std::mutex lock;
+    std::condition_variable ready;
+    std::exception_ptr failure;
+    std::atomic<size_t> next{0};
+    std::atomic<bool> directFailed{false};
+    auto readOne = [&](size_t i) {
+        bool done = false;
+        if (direct && !directFailed) {
+            const int64_t a = where[i].payloadOffset & ~int64_t(4095);
+            const size_t span = (static_cast<size_t>(where[i].payloadOffset - a) + where[i].payloadSize + 4095) & ~static_cast<size_t>(4095);
+            uint8_t* p = ring + off[i] - static_cast<size_t>(where[i].payloadOffset - a);
+            size_t got = 0;
+            while (got < span) {
+                const ssize_t r = ::pread(feed.directFd, p + got, span - got, static_cast<off_t>(a + static_cast<int64_t>(got)));
+                if (r <= 0) break;
+                got += static_cast<size_t>(r);
+            }
+            // the last block of the file may be short: enough is what covers the frame
+            done = got >= static_cast<size_t>(where[i].payloadOffset - a) + where[i].payloadSize;
+            if (!done) directFailed = true;
+        }
+        readFrame(where[i], done ? nullptr : ring + off[i], outMetadata[i]);
+    };
+    auto work = [&] {
+        try {
+            for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+                readOne(i);
+                if (remaining[chunkOf[i]].fetch_sub(1) == 1) {
+                    std::lock_guard<std::mutex> g(lock);
+                    ready.notify_all();
+                }
+            }
+        } catch (...) {
+            std::lock_guard<std::mutex> g(lock);
+            if (!failure) failure = std::current_exception();
+            next.store(n);
+            ready.notify_all();
+        }
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    size_t cap = 8;
+    if (const char* e = std::getenv("MCRAW_READ_THREADS")) cap = std::max(1, std::atoi(e));
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>({n, cap, hw}));
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nthreads; t++) pool.emplace_back(work);
+    struct Joiner {
+        std::vector<std::thread>& p;
+        ~Joiner() { for (std::thread& t : p) if (t.joinable()) t.join(); }
+    } joiner{pool};
+
+    if (mcraw_batch_begin(ctx, static_cast<uint32_t>(n)) != MCRAW_OK) throw IOException(mcraw_last_error(ctx));
+    for (size_t c = 0; c < nchunks; c++) {
+        {
+            std::unique_lock<std::mutex> g(lock);
+            ready.wait(g, [&] { return failure || remaining[c].load() == 0; });
+            if (failure) break;
+        }
+        const size_t a = chunkFirst[c], b = chunkFirst[c + 1];
+        for (size_t i = a; i < b; i++) describe(i, descs[i], ring + off[i]);
+        if (mcraw_batch_append_host(ctx, descs.data() + a, static_cast<uint32_t>(a), static_cast<uint32_t>(b - a), nullptr) != MCRAW_OK) {
+            std::lock_guard<std::mutex> g(lock);
+            if (!failure) failure = std::make_exception_ptr(IOException(std::string("Failed to uncompress frame: ") + mcraw_last_error(ctx)));
+            next.store(n);
+            break;
+        }
+    }
+    for (std::thread& t : pool) t.join();
+    if (failure) {
+        mcraw_batch_wait(ctx, nullptr, nullptr, 0);      // whatever was enqueued still reads the ring: let it finish
+        std::rethrow_exception(failure);
+    }
+    if (direct) m->feedNote = directFailed ? "pread -> pinned ring (O_DIRECT read refused by the filesystem; buffered reads)"
+                                           : "O_DIRECT pread -> pinned ring, read of chunk c+1 overlapping H2D + decode of chunk c";
+    else if (mode == "ring" || mode == "") m->feedNote = "pread -> pinned ring, read of chunk c+1 overlapping H2D + decode of chunk c";
+    finish(descs);
 }
 
 }  // namespace motioncam

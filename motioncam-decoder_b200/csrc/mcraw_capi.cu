@@ -98,7 +98,7 @@ struct Slot {
     uintptr_t dst_lo = 0, dst_hi = 0;   // address range spanned by the plan's output buffers
     uint32_t lg_nwork = 0;          // (frame, tile) tickets of the legacy frames of the plan
     size_t lg_work_off = 0;
-    uint32_t lg_epoch = 0;          // k_legacy_fused launches on this plan since its status words were zeroed
+    uint32_t lg_epoch = 0;          // k_legacy_warp launches on this plan since its status words were zeroed
     size_t plan_scratch = 0;        // scratch bytes the plan uses
 };
 
@@ -136,8 +136,7 @@ struct mcraw_ctx {
     std::vector<FrameDev> tmp_frames;
     std::vector<WorkItem> tmp_items;
     std::vector<LgWork> tmp_lgwork;
-    bool legacy_split = getenv("MCRAW_LEGACY_SPLIT") != nullptr;   // A/B switch: the round-1 four-kernel legacy path
-    uint32_t lgf_resident_ctas = 0; // CTAs of k_legacy_fused the device holds at once
+    uint32_t lgw_resident_ctas = 0; // CTAs (= warps) of k_legacy_warp the device holds at once
     bool overlap = getenv("MCRAW_NO_OVERLAP") == nullptr;   // k_units as a programmatic dependent of k_meta
     uint32_t timing_every = 0;      // record kernel-timing events on every n-th chunk (0 = never)
     uint64_t chunk_seq = 0;
@@ -278,17 +277,11 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
         } else if (d.compression_type == MCRAW_COMPRESSION_LEGACY) {
             any6 = true;
             if (d.len >= ((uint64_t)1 << 40)) return fail_arg(ctx, who() + ": legacy frame buffer too large");
-            const uint64_t ntile = std::max<uint64_t>(1, (d.len + LG_TILE - 1) / LG_TILE);
+            const uint64_t ntile = std::max<uint64_t>(1, (d.len + LGW_TILE - 1) / LGW_TILE);
             if (ntile > 0x7FFFFFFFull) return fail_arg(ctx, who() + ": legacy frame buffer too large");
-            // scratch layout (offsets for now): tile maps | tile states | bitmaps | merge points
+            // scratch layout (offsets for now): transfer maps | look-back status words of every tile
             f.lg_tilemap = reinterpret_cast<uint32_t*>(scratch);
             scratch += ((size_t)ntile * LG_STATES * 4 + 15) & ~(size_t)15;
-            f.lg_tilestate = reinterpret_cast<uint32_t*>(scratch);
-            scratch += ((size_t)ntile * 2 * 4 + 15) & ~(size_t)15;
-            f.lg_bitmap = reinterpret_cast<uint32_t*>(scratch);
-            scratch += (size_t)ntile * LG_TILE_WORDS * 4;
-            f.lg_merge = reinterpret_cast<uint16_t*>(scratch);
-            scratch += ((size_t)ntile * LG_STATES * 2 + 15) & ~(size_t)15;
             f.lg_status = reinterpret_cast<unsigned long long*>(scratch);
             scratch += ((size_t)ntile * 8 + 15) & ~(size_t)15;
             scratch = (scratch + 127) & ~(size_t)127;
@@ -374,14 +367,14 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         s.items_off = (sizeof(FrameDev) * n + 15) & ~(size_t)15;
         s.nitems = (uint32_t)items.size();
         // legacy tickets: tile index major, frame minor -- neighbouring tickets belong to different frames, so the look-back
-        // chain of every frame only has to advance a few tiles per generation of resident CTAs (k_legacy_fused)
+        // chain of every frame only has to advance a few tiles per generation of resident CTAs (k_legacy_warp)
         std::vector<LgWork>& lgwork = ctx->tmp_lgwork;
         lgwork.clear();
         if (s.any6) {
             std::vector<std::pair<uint32_t, uint32_t>> lf;      // (frame, tiles)
             for (uint32_t i = 0; i < n; i++)
                 if (frames[i].type == MCRAW_COMPRESSION_LEGACY)
-                    lf.emplace_back(i, (uint32_t)std::max<uint64_t>(1, (frames[i].len + LG_TILE - 1) / LG_TILE));
+                    lf.emplace_back(i, (uint32_t)std::max<uint64_t>(1, (frames[i].len + LGW_TILE - 1) / LGW_TILE));
             for (uint32_t t = 0; t < s.max_ltiles; t++)
                 for (const auto& fr : lf)
                     if (t < fr.second) lgwork.push_back(LgWork{fr.first, t});
@@ -400,9 +393,6 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
                 f.metarec = reinterpret_cast<uint4*>(s.d_scratch + reinterpret_cast<size_t>(f.metarec));
             } else if (f.type == MCRAW_COMPRESSION_LEGACY) {
                 f.lg_tilemap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilemap));
-                f.lg_tilestate = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilestate));
-                f.lg_bitmap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_bitmap));
-                f.lg_merge = reinterpret_cast<uint16_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_merge));
                 f.lg_status = reinterpret_cast<unsigned long long*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_status));
             }
             h_frames[i] = f;
@@ -444,7 +434,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         CU_TRY(ctx, cudaMemsetAsync(s.d_dyn, 0, 16 + sizeof(FrameState) * n, st));
         s.flag_uses = 0;
         s.plan_valid = true;
-        // k_legacy_fused: the tiles' status words are tagged with the launch epoch of the plan, which starts over here
+        // k_legacy_warp: the tiles' status words are tagged with the launch epoch of the plan, which starts over here
         if (any6 && s.plan_scratch) CU_TRY(ctx, cudaMemsetAsync(s.d_scratch, 0, s.plan_scratch, st));
         s.lg_epoch = 0;
     }
@@ -459,13 +449,6 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         cfg.numAttrs = chain ? 1 : 0;
         CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta, d_frames, d_states));
         ctx->launches += 1;
-    }
-    const bool split6 = any6 && ctx->legacy_split;
-    if (split6) {
-        k_legacy_maps<<<dim3(s.max_ltiles, n), LG_MAPS_THREADS, LG_MAPS_SMEM, st>>>(d_frames);
-        k_legacy_scan<<<n, LG_THREADS, 0, st>>>(d_frames, d_states, d_results);
-        k_legacy_fix<<<dim3((s.max_ltiles + LG_THREADS - 1) / LG_THREADS, n), LG_THREADS, 0, st>>>(d_frames, d_states);
-        ctx->launches += 3;
     }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
     if (any7) {
@@ -489,13 +472,12 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
                                        pdl ? 2u * s.flag_uses : 0u));
         ctx->launches += 1;
     }
-    if (split6) { k_legacy_decode<<<dim3(s.max_ltiles, n), LG_THREADS, LG_DEC_SMEM, st>>>(d_frames, d_states); ctx->launches += 1; }
-    else if (any6) {
+    if (any6) {
         // one pass over the stream: transfer maps, decoupled look-back and the pixel work in one persistent kernel
         s.lg_epoch += 1;
-        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(ctx->lgf_resident_ctas, s.lg_nwork));
-        k_legacy_fused<<<grid, LGF_THREADS, LGF_SMEM, st>>>(d_frames, d_results, reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off),
-                                                           s.lg_nwork, d_counter, s.lg_epoch);
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(ctx->lgw_resident_ctas, s.lg_nwork));
+        k_legacy_warp<<<grid, 32, LGW_SMEM, st>>>(d_frames, d_results, reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off),
+                                                 s.lg_nwork, d_counter, s.lg_epoch);
         ctx->launches += 1;
     }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e2, st));
@@ -573,9 +555,7 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     if (const char* e = getenv("MCRAW_CHAIN")) ctx->chain_ctas = (uint32_t)std::max(0, atoi(e));
     if (cudaFuncSetAttribute(k_meta, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_legacy_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_MAPS_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_legacy_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_DEC_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_legacy_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, LGF_SMEM) != cudaSuccess) {
+        cudaFuncSetAttribute(k_legacy_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, LGW_SMEM) != cudaSuccess) {
         ctx->err = "cudaFuncSetAttribute(smem) failed"; return bail(MCRAW_ERR_CUDA);
     }
     {
@@ -585,11 +565,11 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         }
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
         ctx->chain_ctas = std::min(ctx->chain_ctas, ctx->resident_ctas / 2);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_fused, LGF_THREADS, LGF_SMEM) != cudaSuccess || per_sm < 1) {
-            ctx->err = "k_legacy_fused does not fit on this device"; return bail(MCRAW_ERR_CUDA);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp, 32, LGW_SMEM) != cudaSuccess || per_sm < 1) {
+            ctx->err = "k_legacy_warp does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
-        if (const char* e = getenv("MCRAW_LGF_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
-        ctx->lgf_resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
+        if (const char* e = getenv("MCRAW_LGW_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        ctx->lgw_resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
     }
     for (auto& s : ctx->slots) {
         if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&s.e0) != cudaSuccess ||

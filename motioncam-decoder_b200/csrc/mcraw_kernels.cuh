@@ -45,15 +45,12 @@ struct FrameDev {
     uint32_t* unitoff;             // scratch [nunits + 1]   payload offset of each unit (+ end)
     uint4* metarec;                // scratch [nunits]  where the unit's two metadata blocks are: {offset of the bits block,
                                    //                   offset of the refs block, header of the bits block, header of the refs block}
-    uint32_t* lg_tilemap;          // legacy scratch [tiles][17]   transfer map of every 32 KiB tile: exit | blocks << 5
-    uint32_t* lg_tilestate;        // legacy scratch [tiles][2]    entry offset (| LG_SLOW) / first block ordinal of every tile
-    uint32_t* lg_bitmap;           // legacy scratch [tiles][512]  block starts of every tile (one bit per 2 bytes)
-    uint16_t* lg_merge;            // legacy scratch [tiles][17]   where the chain of entry e meets the chain of entry 0
-    unsigned long long* lg_status; // legacy scratch [tiles]       k_legacy_fused: epoch-tagged look-back status of every tile
+    uint32_t* lg_tilemap;          // legacy scratch [tiles][17]   transfer map of every tile: exit | blocks << 5
+    unsigned long long* lg_status; // legacy scratch [tiles]       epoch-tagged look-back status of every tile (k_legacy_warp)
 };
 
 // Per-frame words written by the index kernels and read by the pixel kernels.  Every word is written on every path
-// (no host-side zeroing): status[s] by the CTA of metadata stream s (legacy: [0] by k_legacy_scan, [1] = 0).
+// (no host-side zeroing): status[s] by the CTA of metadata stream s (not used by the legacy kernel).
 struct FrameState {
     unsigned status[2];            // MCRAW_FRAME_* bits
     unsigned tile_rows_dev;        // ceil(encodedHeight/4) from the frame header

@@ -1,5 +1,8 @@
 """GPU: the drop-in C++ API (motioncam::Decoder::loadFrame / loadFrames, motioncam::raw::Decode*) of this repo
 against the compiled reference and the oracle, on synthetic .mcraw files."""
+import ctypes
+import os
+
 import numpy as np
 import pytest
 
@@ -131,12 +134,48 @@ def test_load_frames_to_device(tmp_path):
     ctx.close()
 
 
-def test_mapped_feed(tmp_path, monkeypatch):
-    """MCRAW_FEED=mmap: loadFramesToDevice copies the frames to the GPU straight out of a page-locked read-only
-    mapping of the file (no pread into the pinned ring).  Where the platform refuses to pin the mapping the Decoder
-    falls back to the ring and says so; the decoded frames are the same either way."""
+def _platform_takes(mode, path):
+    """What this box allows, found out independently of the Decoder: O_DIRECT reads of the file, page-locking a mapping."""
+    import mmap
     from motioncam_decoder_b200 import capi
-    monkeypatch.setenv("MCRAW_FEED", "mmap")
+    if mode == "direct":
+        try:
+            fd = os.open(path, os.O_RDONLY | os.O_DIRECT)
+        except OSError:
+            return False
+        try:
+            buf = mmap.mmap(-1, 8192)                     # page-aligned
+            return os.preadv(fd, [memoryview(buf)[:4096]], 0) > 0
+        except OSError:
+            return False
+        finally:
+            os.close(fd)
+    if mode == "mmap":
+        ctx = capi.Context(0)
+        with open(path, "rb") as f:
+            m = mmap.mmap(f.fileno(), 0, prot=mmap.PROT_READ)
+            arr = np.frombuffer(m, dtype=np.uint8)
+            addr = arr.ctypes.data
+            ok = ctx._c.mcraw_host_register(ctx._h, addr, arr.size, 1) == 0
+            if ok:
+                ctx._c.mcraw_host_unregister(ctx._h, addr)
+            del arr
+            m.close()
+        ctx.close()
+        return ok
+    return None
+
+
+@pytest.mark.parametrize("mode", ["ring", "direct", "cufile", "mmap"])
+def test_feeds(tmp_path, monkeypatch, mode):
+    """The feeds of Decoder::loadFramesToDevice (MCRAW_FEED): pipelined pread into the pinned ring (default), O_DIRECT
+    reads, cuFile (GPUDirect Storage) into device memory, H2D from a page-locked mapping.  Every feed must deliver the
+    same frames; a feed the platform refuses falls back to the ring and says why -- and which of the two it is on
+    this box is established independently (no assertion that cannot fail)."""
+    from motioncam_decoder_b200 import capi
+    if mode != "ring":
+        monkeypatch.setenv("MCRAW_FEED", mode)
+    monkeypatch.setenv("MCRAW_FEED_CHUNK_KB", "16")                    # several chunks even for this small clip
     path, frames, images, _ = _clip(tmp_path, n=9)
     ours = hostapi.Decoder(path)
     assert ours.feed_description() == "pread -> pinned ring"          # decided at the first device load
@@ -153,8 +192,23 @@ def test_mapped_feed(tmp_path, monkeypatch):
             ctx.d2h(out, p)
             assert np.array_equal(out, images[ts]), ts
     feed = ours.feed_description()
-    print("feed:", feed)
-    assert "mmap" in feed or "cudaHostRegister" in feed               # active, or the stated reason for the fallback
+    print(f"feed[{mode}]:", feed)
+    if mode == "ring":
+        assert feed == "pread -> pinned ring, read of chunk c+1 overlapping H2D + decode of chunk c"
+    elif mode == "direct":
+        if _platform_takes("direct", path):
+            assert feed.startswith("O_DIRECT pread -> pinned ring")
+        else:
+            assert feed.startswith("pread -> pinned ring (O_DIRECT")
+    elif mode == "mmap":
+        if _platform_takes("mmap", path):
+            assert feed.startswith("mmap + cudaHostRegister")
+        else:
+            assert feed.startswith("pread -> pinned ring (cudaHostRegister refused the mapping")
+    else:
+        # cuFile cannot be probed without cuFile: the text must name the feed or the call that refused it
+        assert feed.startswith("cuFileRead -> device memory") or feed.startswith("pread -> pinned ring (cuFile") or \
+            feed.startswith("pread -> pinned ring (O_DIRECT open refused")
     ours.close()
     for p in ptrs:
         ctx.device_free(p)
