@@ -98,6 +98,25 @@ int32_t mcraw_frame_encoded_width(const uint8_t* frame, uint64_t len, int32_t wi
  * chunks (double-buffered) so transfer overlaps decode, then decodes into descs[i].dst (device). */
 int mcraw_decode_batch_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);
 
+/* ---- optional epilogue: black / white level -------------------------------------------------------- */
+/* What the reference's consumer side does with a decoded frame starts from the container's blackLevel[4] / whiteLevel
+ * (example.cpp:66-67, handed to the DNG at :89-91).  mcraw_decode_batch_levels fuses that first step into the pixel
+ * kernels, where the samples are in registers anyway: levels[i] applies to descs[i]; black[] is indexed by the CFA
+ * position (y & 1) * 2 + (x & 1).  The output keeps 16 bits per pixel, same layout, same `written` counts.
+ *   MCRAW_OUT_RAW        the raw values (what the reference delivers; same as mcraw_decode_batch)
+ *   MCRAW_OUT_BLACK_SUB  uint16: min(max(v - b, 0), w - b) with b = lrintf(black[c]), w = lrintf(white)  (exact integers)
+ *   MCRAW_OUT_NORM_F16   IEEE half: clamp(((float)v - black[c]) * (1.0f / (white - black[c])), 0, 1), fp32 arithmetic,
+ *                        one rounding to half (round to nearest even); white <= black[c] gives scale 0 */
+#define MCRAW_OUT_RAW 0u
+#define MCRAW_OUT_BLACK_SUB 1u
+#define MCRAW_OUT_NORM_F16 2u
+typedef struct mcraw_levels {
+    float black[4];
+    float white;
+    uint32_t mode; /* MCRAW_OUT_* */
+} mcraw_levels;
+int mcraw_decode_batch_levels(mcraw_ctx* ctx, const mcraw_frame_desc* descs, const mcraw_levels* levels, uint32_t n, void* stream);
+
 /* Host in, HOST OUT -- the reference's own contract for a decoded frame (Decoder.cpp:221-230: outData is a host vector),
  * batched: like mcraw_decode_batch_host, and the pixels of frame i (width*height uint16) are also copied to host_dst[i]
  * (pinned for overlap) as soon as the chunk that holds the frame has been decoded -- the device->host copy of chunk c runs

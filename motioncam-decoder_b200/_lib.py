@@ -9,7 +9,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 # kernels + C-ABI (needs a GPU to run); MCRAW_B200_LIB names an A/B build of the same sources (csrc/Makefile `variants`)
 LIB_CAPI = os.path.join(PKG_DIR, os.environ.get("MCRAW_B200_LIB", "libmcraw_b200.so"))
 LIB_TOOLS = os.path.join(PKG_DIR, "libmcraw_tools.so")         # CPU encoder / generators
-LIB_DROPIN = os.path.join(PKG_DIR, "libmotioncam_decoder_b200.so")  # drop-in C++ API + flat wrappers
+# drop-in C++ API + flat wrappers; MCRAW_DROPIN_LIB: another build of it (tools/asan_host_fuzz.sh: AddressSanitizer + UBSan)
+LIB_DROPIN = os.path.join(PKG_DIR, os.environ.get("MCRAW_DROPIN_LIB", "libmotioncam_decoder_b200.so"))
 
 
 def load(path):

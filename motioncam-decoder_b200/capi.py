@@ -34,6 +34,35 @@ class FrameDesc(ctypes.Structure):
     ]
 
 
+OUT_RAW, OUT_BLACK_SUB, OUT_NORM_F16 = 0, 1, 2
+
+
+class Levels(ctypes.Structure):
+    _fields_ = [("black", ctypes.c_float * 4), ("white", ctypes.c_float), ("mode", ctypes.c_uint32)]
+
+
+def apply_levels(img, black, white, mode):
+    """numpy restatement of the fused epilogue (include/mcraw_b200.h, MCRAW_OUT_*) on a decoded (height, width) uint16 image:
+    returns uint16 for OUT_BLACK_SUB and the BIT PATTERNS (uint16 view) of the IEEE halves for OUT_NORM_F16."""
+    img = np.ascontiguousarray(img, dtype=np.uint16)
+    h, w = img.shape
+    cfa = (np.arange(h)[:, None] & 1) * 2 + (np.arange(w)[None, :] & 1)
+    if mode == OUT_RAW:
+        return img
+    if mode == OUT_BLACK_SUB:
+        rint = lambda v: int(min(65535, max(0, np.rint(np.float32(v)))))     # noqa: E731  (lrintf: round half to even)
+        b = np.array([rint(v) for v in black], dtype=np.int64)[cfa]
+        rng = np.maximum(rint(white) - b, 0)
+        return np.minimum(np.maximum(img.astype(np.int64) - b, 0), rng).astype(np.uint16)
+    bl = np.array(black, dtype=np.float32)
+    wh = np.float32(white)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = np.where(wh > bl, np.float32(1.0) / (wh - bl), np.float32(0.0)).astype(np.float32)
+    x = (img.astype(np.float32) - bl[cfa]) * scale[cfa]          # float32 throughout, like the kernel
+    x = np.minimum(np.maximum(x, np.float32(0.0)), np.float32(1.0)) + np.float32(0.0)      # saturation yields +0.0, never -0.0
+    return x.astype(np.float16).view(np.uint16)
+
+
 EXPORTED = [
     "mcraw_version", "mcraw_ctx_create", "mcraw_ctx_destroy", "mcraw_last_error", "mcraw_ctx_device",
     "mcraw_decode_batch", "mcraw_decode_batch_host", "mcraw_batch_wait", "mcraw_decode_host",
@@ -42,7 +71,7 @@ EXPORTED = [
     "mcraw_last_batch_kernel_ms", "mcraw_kernel_time_totals", "mcraw_set_kernel_timing",
     "mcraw_host_register", "mcraw_host_unregister", "mcraw_frame_encoded_width",
     "mcraw_checksum_frames", "mcraw_decode_batch_host_out",
-    "mcraw_batch_begin", "mcraw_batch_append_host",
+    "mcraw_batch_begin", "mcraw_batch_append_host", "mcraw_decode_batch_levels",
 ]
 
 _c = None
@@ -63,6 +92,7 @@ def lib():
         c.mcraw_decode_batch.argtypes = [vp, ctypes.POINTER(FrameDesc), u32, vp]
         c.mcraw_decode_batch_host.argtypes = [vp, ctypes.POINTER(FrameDesc), u32, vp]
         c.mcraw_decode_batch_host_out.argtypes = [vp, ctypes.POINTER(FrameDesc), ctypes.POINTER(vp), u32, vp]
+        c.mcraw_decode_batch_levels.argtypes = [vp, ctypes.POINTER(FrameDesc), ctypes.POINTER(Levels), u32, vp]
         c.mcraw_batch_wait.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u32), u32]
         c.mcraw_decode_host.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, sz, ctypes.c_int]
         c.mcraw_decode_host.restype = sz
@@ -192,6 +222,14 @@ class Context:
 
     def decode_batch(self, descs, n, stream=None):
         self._check(self._c.mcraw_decode_batch(self._h, descs, n, stream), "mcraw_decode_batch")
+
+    def decode_batch_levels(self, descs, levels, n, stream=None):
+        """mcraw_decode_batch_levels; levels: list of (black[4], white, mode) per frame."""
+        arr = (Levels * max(1, n))()
+        for i, (black, white, mode) in enumerate(levels):
+            arr[i].black[:] = [float(v) for v in black]
+            arr[i].white, arr[i].mode = float(white), int(mode)
+        self._check(self._c.mcraw_decode_batch_levels(self._h, descs, arr, n, stream), "mcraw_decode_batch_levels")
 
     def decode_batch_host(self, descs, n, stream=None):
         self._check(self._c.mcraw_decode_batch_host(self._h, descs, n, stream), "mcraw_decode_batch_host")

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cerrno>
 #include <cstdlib>
@@ -622,6 +623,10 @@ struct Decoder::Feed {
     void* devIn = nullptr;          // device copy of the compressed frames (feed "cufile")
     size_t devInBytes = 0;
     mcraw_ctx* devCtx = nullptr;
+    static int deadlineSeconds() {
+        if (const char* e = std::getenv("MCRAW_CUFILE_DEADLINE_S")) return std::max(1, std::atoi(e));
+        return 10;
+    }
     ~Feed() {
         if (cufileReady) cufile.handleDeregister(cufileHandle);
         if (devIn && devCtx) mcraw_device_free(devCtx, devIn);
@@ -687,25 +692,48 @@ void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint1
         if (feed.directFd < 0) m->feedNote = std::string("pread -> pinned ring (O_DIRECT open refused: ") + std::strerror(errno) + ")";
     }
 
-    // ---- cuFile feed: file -> device memory, device-resident decode
+    // ---- cuFile feed: file -> device memory, device-resident decode.  Everything that calls into libcufile runs on a helper
+    //      thread under a deadline: on platforms without the nvidia-fs driver the library's compatibility mode has been seen
+    //      to block for good (profiles/README.md), and a feed that was asked for must never cost more than its deadline.
     if (mode == "cufile" && !feed.cufileTried) {
         feed.cufileTried = true;
-        if (feed.directFd < 0) {
-            // feedNote already says why
-        } else if (!feed.cufile.load()) {
-            m->feedNote = "pread -> pinned ring (cuFile: " + feed.cufile.why + ")";
-        } else {
-            CUfileError_t e = feed.cufile.driverOpen();
-            if (e.err != CU_FILE_SUCCESS) {
-                m->feedNote = "pread -> pinned ring (cuFileDriverOpen: " + cufileText(e) + ")";
+        if (feed.directFd >= 0) {
+            struct Probe { std::mutex m; std::condition_variable cv; bool done = false, ok = false; std::string note; CuFileApi api; CUfileHandle_t h{}; };
+            auto probe = std::make_shared<Probe>();
+            const int fd = feed.directFd;
+            std::thread([probe, fd, ctx] {
+                std::string note;
+                bool ok = false;
+                mcraw_stream_sync(ctx, nullptr);                       // binds the device to this thread
+                if (!probe->api.load()) note = "cuFile: " + probe->api.why;
+                else {
+                    CUfileError_t e = probe->api.driverOpen();
+                    if (e.err != CU_FILE_SUCCESS) note = "cuFileDriverOpen: " + cufileText(e);
+                    else {
+                        CUfileDescr_t descr;
+                        std::memset(&descr, 0, sizeof descr);
+                        descr.handle.fd = fd;
+                        descr.type = CU_FILE_HANDLE_TYPE_OPAQUE_FD;
+                        e = probe->api.handleRegister(&probe->h, &descr);
+                        if (e.err != CU_FILE_SUCCESS) note = "cuFileHandleRegister: " + cufileText(e);
+                        else ok = true;
+                    }
+                }
+                std::lock_guard<std::mutex> g(probe->m);
+                probe->ok = ok; probe->note = note; probe->done = true;
+                probe->cv.notify_all();
+            }).detach();
+            std::unique_lock<std::mutex> g(probe->m);
+            if (!probe->cv.wait_for(g, std::chrono::seconds(feed.deadlineSeconds()), [&] { return probe->done; })) {
+                m->feedNote = "pread -> pinned ring (cuFile: no answer from cuFileDriverOpen / cuFileHandleRegister within " +
+                              std::to_string(feed.deadlineSeconds()) + " s)";
+            } else if (!probe->ok) {
+                m->feedNote = "pread -> pinned ring (" + probe->note + ")";
             } else {
-                CUfileDescr_t descr;
-                std::memset(&descr, 0, sizeof descr);
-                descr.handle.fd = feed.directFd;
-                descr.type = CU_FILE_HANDLE_TYPE_OPAQUE_FD;
-                e = feed.cufile.handleRegister(&feed.cufileHandle, &descr);
-                if (e.err != CU_FILE_SUCCESS) m->feedNote = "pread -> pinned ring (cuFileHandleRegister: " + cufileText(e) + ")";
-                else { feed.cufileReady = true; m->feedNote = "cuFileRead -> device memory (GPUDirect Storage or its compatibility mode)"; }
+                feed.cufile = probe->api;
+                feed.cufileHandle = probe->h;
+                feed.cufileReady = true;
+                m->feedNote = "cuFileRead -> device memory (GPUDirect Storage or its compatibility mode)";
             }
         }
     }
@@ -719,22 +747,36 @@ void Decoder::loadFramesToDevice(const std::vector<Timestamp>& timestamps, uint1
             if (mcraw_device_alloc(ctx, bytes + bytes / 4, &feed.devIn) != MCRAW_OK) throw IOException(mcraw_last_error(ctx));
             feed.devInBytes = bytes + bytes / 4;
         }
-        std::atomic<size_t> next{0};
-        std::atomic<bool> bad{false};
-        auto work = [&] {
-            for (size_t i = next.fetch_add(1); i < n && !bad; i = next.fetch_add(1)) {
-                const ssize_t got = feed.cufile.read(feed.cufileHandle, feed.devIn, where[i].payloadSize,
-                                                     static_cast<off_t>(where[i].payloadOffset), static_cast<off_t>(off[i]));
-                if (got != static_cast<ssize_t>(where[i].payloadSize)) bad = true;
-            }
-        };
-        std::vector<std::thread> pool;
-        for (size_t t = 1; t < std::min<size_t>(n, 8); t++) pool.emplace_back(work);
-        work();
-        for (std::thread& t : pool) t.join();
-        if (bad) {
-            feed.cufileReady = false;          // from now on: the ring
-            m->feedNote = "pread -> pinned ring (cuFileRead failed)";
+        struct Reads { std::mutex m; std::condition_variable cv; bool done = false, ok = false; };
+        auto reads = std::make_shared<Reads>();
+        {
+            const CuFileApi api = feed.cufile;
+            const CUfileHandle_t h = feed.cufileHandle;
+            void* devIn = feed.devIn;
+            std::vector<FrameLocation> w = where;
+            std::vector<size_t> o = off;
+            std::thread([reads, api, h, devIn, w, o, ctx] {
+                mcraw_stream_sync(ctx, nullptr);
+                bool ok = true;
+                for (size_t i = 0; i < w.size() && ok; i++)
+                    ok = api.read(h, devIn, w[i].payloadSize, static_cast<off_t>(w[i].payloadOffset), static_cast<off_t>(o[i])) ==
+                         static_cast<ssize_t>(w[i].payloadSize);
+                std::lock_guard<std::mutex> g(reads->m);
+                reads->ok = ok; reads->done = true;
+                reads->cv.notify_all();
+            }).detach();
+        }
+        bool good = false;
+        {
+            std::unique_lock<std::mutex> g(reads->m);
+            const bool answered = reads->cv.wait_for(g, std::chrono::seconds(feed.deadlineSeconds() + static_cast<int>(bytes >> 28)), [&] { return reads->done; });
+            good = answered && reads->ok;
+            if (!answered) m->feedNote = "pread -> pinned ring (cuFileRead: no answer within the deadline)";
+            else if (!reads->ok) m->feedNote = "pread -> pinned ring (cuFileRead failed)";
+        }
+        if (!good) {
+            feed.cufileReady = false;          // from now on: the ring.  (A helper that never answers keeps its own copies of what it uses.)
+            if (feed.devIn) { feed.devIn = nullptr; feed.devInBytes = 0; }   // still the helper's target: never reused, never freed
         } else {
             for (size_t i = 0; i < n; i++) {
                 readFrame(where[i], nullptr, outMetadata[i]);

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -90,6 +91,7 @@ struct Slot {
     uint64_t batch_id = 0;
     // the plan this slot's device tables were built for (see enqueue_chunk)
     std::vector<mcraw_frame_desc> plan_descs;
+    std::vector<mcraw_levels> plan_levels;   // empty: raw output
     bool plan_valid = false, any7 = false, any6 = false;
     uint32_t max_ltiles = 0, nitems = 0;
     size_t items_off = 0, plan_bytes = 0;
@@ -136,6 +138,8 @@ struct mcraw_ctx {
     std::vector<FrameDev> tmp_frames;
     std::vector<WorkItem> tmp_items;
     std::vector<LgWork> tmp_lgwork;
+    uint32_t sm_count = 0;
+    bool meta_small_only = getenv("MCRAW_META_SMALL") != nullptr;   // A/B switch: never use the big-window shape of k_meta
     uint32_t lgw_resident_ctas = 0; // CTAs (= warps) of k_legacy_warp the device holds at once
     bool overlap = getenv("MCRAW_NO_OVERLAP") == nullptr;   // k_units as a programmatic dependent of k_meta
     uint32_t timing_every = 0;      // record kernel-timing events on every n-th chunk (0 = never)
@@ -234,7 +238,7 @@ int harvest(mcraw_ctx* ctx, Slot& s) {
 }
 
 // Validate descriptors and build the device-side frame records; tilemeta holds an OFFSET until rebased.
-int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t first_index, std::vector<FrameDev>& out,
+int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, const mcraw_levels* levels, uint32_t n, uint32_t first_index, std::vector<FrameDev>& out,
             size_t& scratch, uint32_t& max_tile_rows, uint32_t& max_units, uint32_t& max_ltiles, bool& any7, bool& any6) {
     out.resize(n);
     scratch = 0; max_tile_rows = 0; max_units = 0; max_ltiles = 0; any7 = any6 = false;
@@ -260,6 +264,21 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t 
             f.tiles_x = (uint32_t)d.encoded_width / 64;
         }
         f.flags = ((d.width % 8) == 0 && ((uintptr_t)d.dst & 15) == 0) ? FLAG_VEC_STORE : 0;
+        if (levels && levels[i].mode != MCRAW_OUT_RAW) {
+            const mcraw_levels& L = levels[i];
+            if (L.mode != MCRAW_OUT_BLACK_SUB && L.mode != MCRAW_OUT_NORM_F16) return fail_arg(ctx, who() + ": unknown output mode");
+            f.epi_mode = L.mode;
+            auto u16 = [](float v) { return (uint32_t)std::min(65535l, std::max(0l, lrintf(v))); };
+            const uint32_t w = u16(L.white);
+            for (int c = 0; c < 4; c++) {
+                if (!std::isfinite(L.black[c]) || !std::isfinite(L.white)) return fail_arg(ctx, who() + ": black / white level is not a number");
+                const uint32_t b = u16(L.black[c]);
+                f.epi_black2[c >> 1] |= b << (16 * (c & 1));
+                f.epi_range2[c >> 1] |= (w > b ? w - b : 0u) << (16 * (c & 1));
+                f.epi_blackf[c] = L.black[c];
+                f.epi_scalef[c] = L.white > L.black[c] ? 1.0f / (L.white - L.black[c]) : 0.0f;
+            }
+        }
         if (d.compression_type == MCRAW_COMPRESSION_CURRENT) {
             any7 = true;
             const uint64_t ntiles = (uint64_t)f.tiles_x * f.tile_rows;
@@ -341,7 +360,8 @@ void build_items(const std::vector<FrameDev>& frames, uint32_t resident_ctas, st
 // Enqueue one chunk (device-resident sources) of the current logical batch on `st`.  Everything stays on that one
 // stream: on this platform a cross-stream event dependency costs tens of microseconds, more than the index kernels it
 // could hide (measured: profiles/README.md).
-int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st) {
+int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st,
+                  const mcraw_levels* levels = nullptr) {
     if (n == 0) return MCRAW_OK;
     ctx->cur = (ctx->cur + 1) % kSlots;
     Slot& s = ctx->slots[ctx->cur];
@@ -353,14 +373,16 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     // validate, build or upload.
     // (flag_uses bound: the per-frame meta_done counters k_units compares with 2 * flag_uses are 32 bits wide and only
     // zeroed when a plan is uploaded, so a plan that has been reused 2^30 times is uploaded afresh.)
-    const bool hit = s.plan_valid && s.flag_uses < (1u << 30) && s.lg_epoch < 0xFFFFF0u && s.plan_descs.size() == n &&
+    const bool same_levels = levels ? (s.plan_levels.size() == n && std::memcmp(s.plan_levels.data(), levels, sizeof(mcraw_levels) * n) == 0)
+                                    : s.plan_levels.empty();
+    const bool hit = s.plan_valid && same_levels && s.flag_uses < (1u << 30) && s.lg_epoch < 0xFFFFF0u && s.plan_descs.size() == n &&
                      std::memcmp(s.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
     if (!hit) {
         s.plan_valid = false;
         std::vector<FrameDev>& frames = ctx->tmp_frames;     // reused across calls: no allocation in steady state
         std::vector<WorkItem>& items = ctx->tmp_items;
         size_t scratch; uint32_t max_tile_rows, max_units;
-        rc = prepare(ctx, descs, n, result_offset, frames, scratch, max_tile_rows, max_units, s.max_ltiles, s.any7, s.any6);
+        rc = prepare(ctx, descs, levels, n, result_offset, frames, scratch, max_tile_rows, max_units, s.max_ltiles, s.any7, s.any6);
         if (rc) return rc;
         items.clear();
         if (s.any7) build_items(frames, ctx->resident_ctas, items);
@@ -400,6 +422,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         if (!items.empty()) std::memcpy(s.h_up + s.items_off, items.data(), sizeof(WorkItem) * items.size());
         if (!lgwork.empty()) std::memcpy(s.h_up + s.lg_work_off, lgwork.data(), sizeof(LgWork) * lgwork.size());
         s.plan_descs.assign(descs, descs + n);
+        if (levels) s.plan_levels.assign(levels, levels + n); else s.plan_levels.clear();
         s.dst_lo = ~(uintptr_t)0; s.dst_hi = 0;
         for (uint32_t i = 0; i < n; i++) {
             const uintptr_t a = reinterpret_cast<uintptr_t>(descs[i].dst);
@@ -441,13 +464,17 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (any7) {
         cudaLaunchConfig_t cfg;
         std::memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(2 * n); cfg.blockDim = dim3(K1_THREADS); cfg.dynamicSmemBytes = K1_SMEM; cfg.stream = st;
+        // a handful of frames: one stream's chain is the critical path -> big windows, one CTA per SM (k_meta)
+        const bool few = 2 * n <= ctx->sm_count && !ctx->meta_small_only;
+        cfg.gridDim = dim3(2 * n); cfg.blockDim = dim3(few ? K1Few::K1_THREADS : K1Batch::K1_THREADS);
+        cfg.dynamicSmemBytes = few ? K1Few::K1_SMEM : K1Batch::K1_SMEM; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = chain ? 1 : 0;
-        CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta, d_frames, d_states));
+        if (few) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Few>, d_frames, d_states));
+        else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Batch>, d_frames, d_states));
         ctx->launches += 1;
     }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
@@ -476,7 +503,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         // one pass over the stream: transfer maps, decoupled look-back and the pixel work in one persistent kernel
         s.lg_epoch += 1;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(ctx->lgw_resident_ctas, s.lg_nwork));
-        k_legacy_warp<<<grid, 32, LGW_SMEM, st>>>(d_frames, d_results, reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off),
+        k_legacy_warp<<<grid, LGW_THREADS, LGW_SMEM, st>>>(d_frames, d_results, reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off),
                                                  s.lg_nwork, d_counter, s.lg_epoch);
         ctx->launches += 1;
     }
@@ -489,13 +516,13 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     return MCRAW_OK;
 }
 
-int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStream_t st) {
+int enqueue(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, cudaStream_t st, const mcraw_levels* levels = nullptr) {
     if (!descs && n) return fail_arg(ctx, "descs is null");
     int rc = bind(ctx);
     if (rc) return rc;
     begin_batch(ctx, descs, n);
     for (uint32_t base = 0; base < n; base += kMaxGridY) {
-        rc = enqueue_chunk(ctx, descs + base, std::min(kMaxGridY, n - base), base, st);
+        rc = enqueue_chunk(ctx, descs + base, std::min(kMaxGridY, n - base), base, st, levels ? levels + base : nullptr);
         if (rc) return rc;
     }
     return MCRAW_OK;
@@ -553,7 +580,8 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     for (auto& cs : ctx->copy_streams)
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
     if (const char* e = getenv("MCRAW_CHAIN")) ctx->chain_ctas = (uint32_t)std::max(0, atoi(e));
-    if (cudaFuncSetAttribute(k_meta, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_meta<K1Batch>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Batch::K1_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_meta<K1Few>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Few::K1_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_legacy_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, LGW_SMEM) != cudaSuccess) {
         ctx->err = "cudaFuncSetAttribute(smem) failed"; return bail(MCRAW_ERR_CUDA);
@@ -564,8 +592,9 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
             ctx->err = "k_units does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
+        ctx->sm_count = (uint32_t)prop.multiProcessorCount;
         ctx->chain_ctas = std::min(ctx->chain_ctas, ctx->resident_ctas / 2);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp, 32, LGW_SMEM) != cudaSuccess || per_sm < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm < 1) {
             ctx->err = "k_legacy_warp does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
         if (const char* e = getenv("MCRAW_LGW_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
@@ -644,6 +673,11 @@ int mcraw_kernel_time_totals(mcraw_ctx* ctx, double* meta_ms, double* main_ms, u
 int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream) {
     if (!ctx) return MCRAW_ERR_ARG;
     return enqueue(ctx, descs, n, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
+}
+
+int mcraw_decode_batch_levels(mcraw_ctx* ctx, const mcraw_frame_desc* descs, const mcraw_levels* levels, uint32_t n, void* stream) {
+    if (!ctx) return MCRAW_ERR_ARG;
+    return enqueue(ctx, descs, n, stream ? static_cast<cudaStream_t>(stream) : ctx->stream, levels);
 }
 
 int32_t mcraw_frame_encoded_width(const uint8_t* frame, uint64_t len, int32_t width, int32_t height) {

@@ -11,8 +11,9 @@
 //            whole 64-value block (same width-specialised SWAR routine as the pixel kernel) to turn the reference's running
 //            `offset +=` (RawData.cpp:562,576-579) into prefix sums: the payload offset of every unit.
 //   k_units  persistent, launched as a programmatic dependent of k_meta; every WARP takes items (a few consecutive units of
-//            one frame) from a queue and decodes one unit at a time.  The unit's payload (contiguous, <= 8 KiB) and its two
-//            metadata blocks are staged in shared memory with 16-byte cp.async (payload XOR-swizzled); every lane pulls
+//            one frame) from a queue and decodes one unit at a time.  The unit's payload (contiguous, <= 8 KiB) arrives in
+//            shared memory by ONE bulk copy (cp.async.bulk, TMA 1-D, tracked by the warp's mbarrier), its two metadata
+//            blocks by 16-byte cp.async with zero fill; every lane pulls
 //            the two bits values and the two references of ITS block pair out of the metadata blocks (table-driven,
 //            mcraw_meta_table.h), a warp scan gives the pair's payload offset, and the lane decodes the pair: a `switch`
 //            on the header bits value selects straight-line code with immediate shifts/masks (lanes that share
@@ -23,6 +24,7 @@
 //
 // Legacy format (compressionType 6; reference: /root/reference/lib/RawData_Legacy.cpp:445-495): mcraw_legacy.cuh.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -45,6 +47,12 @@ struct FrameDev {
     uint32_t* unitoff;             // scratch [nunits + 1]   payload offset of each unit (+ end)
     uint4* metarec;                // scratch [nunits]  where the unit's two metadata blocks are: {offset of the bits block,
                                    //                   offset of the refs block, header of the bits block, header of the refs block}
+    // optional epilogue fused into the pixel kernels (mcraw_decode_batch_levels): 0 = raw values (the reference's output)
+    unsigned epi_mode;             // MCRAW_OUT_*
+    unsigned epi_black2[2];        // per row parity: black level of the even column | odd column << 16 (integers)
+    unsigned epi_range2[2];        // per row parity: white - black, packed the same way
+    float epi_blackf[4];           // black level per CFA position (row parity * 2 + column parity)
+    float epi_scalef[4];           // 1 / (white - black)
     uint32_t* lg_tilemap;          // legacy scratch [tiles][17]   transfer map of every tile: exit | blocks << 5
     unsigned long long* lg_status; // legacy scratch [tiles]       epoch-tagged look-back status of every tile (k_legacy_warp)
 };
@@ -218,9 +226,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // --------------------------------------------------------------------------------------------------------
 // k_meta
 // --------------------------------------------------------------------------------------------------------
-constexpr int K1_THREADS = 256;
-constexpr int K1_CHUNK = 16384;   // bytes of the stream staged in shared memory per round
-constexpr int K1_MB = 256;        // meta blocks per round (= threads: one lane decodes one meta block)
+// Two shapes of the kernel: windows of 16 KiB worked by 256 threads (three CTAs per SM: batches, where throughput counts),
+// and windows of 48 KiB worked by 1024 threads (one CTA per SM: a handful of frames, where the latency of one stream's
+// chain counts -- a third of the windows, each as fast as a small one).  Window offsets are 16 bits wide: < 64 KiB.
+template <int CHUNK, int THREADS>
+struct K1 {
+    static constexpr int K1_THREADS = THREADS;
+    static constexpr int K1_CHUNK = CHUNK;        // bytes of the stream staged in shared memory per round
+    static constexpr int K1_MB = THREADS;         // meta blocks per round (= threads: one lane decodes one meta block)
+    static constexpr int K1_NXT_BYTES = K1_CHUNK + 16;                       // u16 per even offset, byte offset == stream offset
+    static constexpr int K1_SMEM = (K1_CHUNK + 32) + 2 * K1_NXT_BYTES + 2 * (K1_MB + 8) + 2 * (K1_MB / 4 + 8);   // stage, nxt1, nxt4, ends, anchors
+    static constexpr int K1_STAGE_PER_THREAD = ((K1_CHUNK + 32) / 16 + K1_THREADS - 1) / K1_THREADS;
+    static_assert(K1_CHUNK % (16 * K1_THREADS) == 0 && K1_CHUNK < 65536, "window shape");
+};
+using K1Batch = K1<16384, 256>;
+using K1Few = K1<49152, 1024>;
 
 // group fetch from the staged stream at a 2-byte aligned position (meta block payloads follow a 2-byte header)
 struct StageFetch {
@@ -234,8 +254,6 @@ struct StageFetch {
     }
 };
 
-constexpr int K1_NXT_BYTES = K1_CHUNK + 16;                       // u16 per even offset, byte offset == stream offset
-constexpr int K1_SMEM = (K1_CHUNK + 32) + 2 * K1_NXT_BYTES + 2 * (K1_MB + 8) + 2 * (K1_MB / 4 + 8);   // stage, nxt1, nxt4, ends, anchors
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint32_t v;
@@ -253,7 +271,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
-// grid = 2 * frames, block = K1_THREADS, dynamic smem = K1_SMEM
+// grid = 2 * frames, block = Shape::K1_THREADS, dynamic smem = Shape::K1_SMEM
 // Publish everything this CTA wrote for (frame, stream): the barrier orders every thread's writes before thread 0, whose
 // fence (cumulative) and counter bump form the release; k_units may be running already (programmatic dependent launch)
 // and polls the counter, ending the poll with an acquire load.
@@ -265,7 +283,10 @@ __device__ __forceinline__ void meta_publish(FrameState& S) {
     }
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restrict__ frames, FrameState* __restrict__ states) {
+template <class Shape>
+__global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 3 : 1) k_meta(const FrameDev* __restrict__ frames, FrameState* __restrict__ states) {
+    constexpr int K1_THREADS = Shape::K1_THREADS, K1_CHUNK = Shape::K1_CHUNK, K1_MB = Shape::K1_MB, K1_NXT_BYTES = Shape::K1_NXT_BYTES;
+    constexpr int K1_STAGE = Shape::K1_STAGE_PER_THREAD;
     extern __shared__ __align__(16) uint8_t k1_smem[];
     uint8_t* stage = k1_smem;                                                        // K1_CHUNK + 32 bytes of the stream
     const uint32_t stage_s = smem_u32(stage);
@@ -345,9 +366,9 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
         //      output) and one byte further for the others (the reference reads bytes, RawData.cpp:463-498: any offset goes).
         const unsigned long long base = ((pos - par) & ~15ull) + par;
         {
-            uint4 q[5];
+            uint4 q[K1_STAGE];
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
+            for (int k = 0; k < K1_STAGE; k++) {
                 const int v = tid + k * K1_THREADS;
                 const unsigned long long o = base + (unsigned long long)v * 16;
                 q[k] = make_uint4(0, 0, 0, 0);
@@ -362,7 +383,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k_meta(const FrameDev* __restri
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
+            for (int k = 0; k < K1_STAGE; k++) {
                 const int v = tid + k * K1_THREADS;
                 if (v < (K1_CHUNK + 32) / 16) *reinterpret_cast<uint4*>(stage + v * 16) = q[k];
             }
@@ -539,10 +560,14 @@ constexpr int KU_ROW_PITCH = 16 * KU_SLOT_PITCH + 64;   // 2368: (pitch/16) % 8 
 constexpr int KU_OUT_BYTES = 2 * KU_ROW_PITCH;    // two rows at a time (planes 0..3, then planes 4..7)
 constexpr int KU_META_BLOCK = 160;                // a staged metadata block: <= 15 bytes of alignment + 2 + 128, in 16-byte chunks
 constexpr int KU_META_BYTES = 2 * 2 * KU_META_BLOCK;   // (this unit, next unit) x (bits block, refs block)
+// Payload staging: ONE cp.async.bulk (TMA, 1-D) per unit, issued by lane 0 and tracked by the warp's mbarrier.  A bulk copy
+// is linear, so the staged payload is not swizzled: the decode reads meet whatever bank conflicts the block lengths
+// produce -- measured faster all the same (profiles/README.md: k_units 260.6 -> 251.3 us on C2).  -DMCRAW_KU_LDGSTS builds
+// the round-1 staging (16-byte cp.async per lane into an XOR-swizzled buffer) for the A/B.
+#ifndef MCRAW_KU_LDGSTS
+#define MCRAW_KU_BULK 1
+#endif
 #ifdef MCRAW_KU_BULK
-// EXPERIMENT (profiles/README.md, "bulk staging"): the unit payload arrives by ONE cp.async.bulk (TMA, 1-D) per unit,
-// issued by lane 0 and tracked by an mbarrier, instead of 16-byte cp.async per lane.  A bulk copy is linear, so the
-// XOR swizzle of the staged payload is gone: the decode reads meet whatever bank conflicts the block lengths produce.
 constexpr int KU_BAR_BYTES = 128;                 // the warp's mbarrier (8 bytes used)
 #else
 constexpr int KU_BAR_BYTES = 0;
@@ -599,6 +624,21 @@ __device__ __forceinline__ void emit_half(const uint32_t (&LE)[16], const uint32
     }
 }
 
+// Optional epilogue on one word = two horizontally adjacent pixels (even column | odd column << 16) of a row with parity
+// `rowpar`: what the reference's consumer does with the container's blackLevel[4] / whiteLevel (example.cpp:66-67,89-91 hands
+// them to the DNG; a raw processor subtracts and scales).  mode 1: integers, min(max(v - black, 0), white - black);
+// mode 2: IEEE half, ((float)v - black) * (1 / (white - black)) clamped to [0, 1], fp32 arithmetic, round to nearest.
+__device__ __forceinline__ uint32_t epilogue_word(const uint32_t v, const unsigned mode, const FrameDev& F, const int rowpar) {
+    if (mode == MCRAW_OUT_BLACK_SUB) {
+        const uint32_t b = F.epi_black2[rowpar];
+        return __vminu2(__vsub2(__vmaxu2(v, b), b), F.epi_range2[rowpar]);
+    }
+    const float x = __saturatef((__uint2float_rn(v & 0xFFFFu) - F.epi_blackf[2 * rowpar]) * F.epi_scalef[2 * rowpar]);
+    const float y = __saturatef((__uint2float_rn(v >> 16) - F.epi_blackf[2 * rowpar + 1]) * F.epi_scalef[2 * rowpar + 1]);
+    const __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 // Copy-out role of a lane: 16-byte chunk (lane & 7) of the 128-byte row segments of tile slots (lane >> 3) + 4k.
 struct CopyOut {
     uint16_t* ptr[4];    // address of the lane's chunk in row 4*ty of the tile of slot group k
@@ -606,7 +646,8 @@ struct CopyOut {
 };
 
 template <bool VEC, int HALF>
-__device__ __forceinline__ void copy_half(const CopyOut& co, const uint32_t out_base, const uint32_t lane, const int width) {
+__device__ __forceinline__ void copy_half(const CopyOut& co, const uint32_t out_base, const uint32_t lane, const int width,
+                                          const FrameDev& F, const unsigned epi) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t s = out_base + ((lane >> 3) + 4u * k) * KU_SLOT_PITCH + (lane & 7u) * 16u;
@@ -616,6 +657,10 @@ __device__ __forceinline__ void copy_half(const CopyOut& co, const uint32_t out_
             if (r < (VEC ? co.nrows[k] : (co.nrows[k] & 0xFFu))) {
                 uint4 v;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s + qq * KU_ROW_PITCH));
+                if (epi) {                                   // output row 4 ty + r: its parity is qq; the chunk starts at an even column
+                    v.x = epilogue_word(v.x, epi, F, qq); v.y = epilogue_word(v.y, epi, F, qq);
+                    v.z = epilogue_word(v.z, epi, F, qq); v.w = epilogue_word(v.w, epi, F, qq);
+                }
                 uint16_t* orow = co.ptr[k] + (size_t)r * (size_t)width;
                 if (VEC) *reinterpret_cast<uint4*>(orow) = v;
                 else {
@@ -633,15 +678,16 @@ __device__ __forceinline__ void copy_half(const CopyOut& co, const uint32_t out_
 template <bool VEC>
 __device__ __forceinline__ void emit_and_copy(const uint32_t (&LE)[16], const uint32_t (&HE)[16], const uint32_t (&LO)[16],
                                               const uint32_t (&HO)[16], const uint32_t refs, const bool with_h, const CopyOut& co,
-                                              const uint32_t out_base, const uint32_t lane, const int width) {
+                                              const uint32_t out_base, const uint32_t lane, const int width, const FrameDev& F,
+                                              const unsigned epi) {
     const uint32_t out_lane = out_base + (lane & 1u) * KU_ROW_PITCH + (lane >> 1) * KU_SLOT_PITCH;
     if (with_h) emit_half<true, 0>(LE, HE, LO, HO, refs, out_lane); else emit_half<false, 0>(LE, HE, LO, HO, refs, out_lane);
     __syncwarp();
-    copy_half<VEC, 0>(co, out_base, lane, width);
+    copy_half<VEC, 0>(co, out_base, lane, width, F, epi);
     __syncwarp();
     if (with_h) emit_half<true, 1>(LE, HE, LO, HO, refs, out_lane); else emit_half<false, 1>(LE, HE, LO, HO, refs, out_lane);
     __syncwarp();
-    copy_half<VEC, 1>(co, out_base, lane, width);
+    copy_half<VEC, 1>(co, out_base, lane, width, F, epi);
     __syncwarp();
 }
 
@@ -704,6 +750,7 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
     const unsigned long long len = F.len;
     const uint32_t inv = F.inv_tiles_x;
     const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
+    const unsigned epi = F.epi_mode;
     uint16_t* __restrict__ dst = F.dst;
 
     // payload offsets of this warp's units (+ end): lane i holds unitoff[u0 + i]; and their metadata records
@@ -732,7 +779,7 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
 #ifdef MCRAW_KU_BULK
     const uint32_t bar = meta_base + KU_META_BYTES;
 #endif
-    // stage unit payload [a0, a1) (rounded out to 16 bytes) with swizzled 16-byte cp.async
+    // stage unit payload [a0, a1) (rounded out to 16 bytes)
     auto stage_unit = [&](uint32_t a0, uint32_t a1) {
         const uint32_t s0 = a0 & ~15u;
         const uint32_t nchunks = (a1 - s0 + 15u) >> 4;                            // <= (8192 + 8 + 15) / 16
@@ -841,8 +888,8 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
         }
 
         const bool with_h = __any_sync(0xFFFFFFFFu, (bE > 8u) | (bO > 8u));
-        if (vec) emit_and_copy<true>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width);
-        else emit_and_copy<false>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width);
+        if (vec) emit_and_copy<true>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width, F, epi);
+        else emit_and_copy<false>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width, F, epi);
     }
 }
 

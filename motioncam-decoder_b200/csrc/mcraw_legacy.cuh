@@ -39,24 +39,31 @@
 namespace mcraw {
 
 #ifndef MCRAW_LGW_SEG
-#define MCRAW_LGW_SEG 128
+#define MCRAW_LGW_SEG 512
 #endif
-constexpr int LGW_SEG = MCRAW_LGW_SEG;         // bytes per segment (one lane)
-constexpr int LGW_TILE = 32 * LGW_SEG;         // bytes per tile (one warp)
+#ifndef MCRAW_LGW_WARPS
+#define MCRAW_LGW_WARPS 4
+#endif
+constexpr int LGW_SEG = MCRAW_LGW_SEG;         // bytes per segment (one lane of the index warp)
+constexpr int LGW_WARPS = MCRAW_LGW_WARPS;     // warps per CTA: warp 0 resolves the chain, all of them decode
+constexpr int LGW_THREADS = 32 * LGW_WARPS;
+constexpr int LGW_TILE = 32 * LGW_SEG;         // bytes per tile (one CTA at a time)
 constexpr int LGW_SEG_WORDS = LGW_SEG / 64;    // bitmap words per segment: one bit per even offset
 constexpr int LGW_TILE_WORDS = 32 * LGW_SEG_WORDS;
+constexpr int LGW_DEC_WORDS = LGW_TILE_WORDS / LGW_THREADS;   // bitmap words (64 bytes of the stream each) a thread decodes
+constexpr int LGW_PRE = 192;                   // bytes a lane's guessed chain runs in front of its segment to fall in step
 constexpr int LG_STATES = 17;                  // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;               // exit code of a chain that ran into the end of the buffer
 constexpr uint32_t LG_NO_MERGE = 0xFFFFu;      // merge point of an entry whose chain never meets C0 inside the tile
 constexpr int LG_OVERRUN = 80;                 // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it (+ word reads)
 constexpr int LGW_DATA = LGW_TILE + LG_OVERRUN;
-constexpr int LGW_LB = 16;                     // look-back window: status words read per poll
+constexpr int LGW_LB = 32;                     // look-back window: status words read per poll
 constexpr int LGW_SMEM = LGW_DATA + LGW_TILE_WORDS * 4 + LGW_LB * LG_STATES * 4;
-constexpr int LGW_CTAS_PER_SM = (LGW_SEG == 128) ? 32 : 21;
 constexpr uint32_t LGW_ST_LOCAL = 1u, LGW_ST_INCL = 2u;
 constexpr uint32_t LGW_ERR_BIT = 1u << 5;      // sticky: a wait gave up somewhere up the chain
-constexpr uint32_t LGW_SPIN_LIMIT = 1u << 22;
-static_assert(LGW_SEG == 128 || LGW_SEG == 256, "a lane owns one or two 64-bit groups of marks");
+constexpr uint32_t LGW_SPIN_LIMIT = 1u << 18;  // polls of ~0.2 us: a wait that long means something is broken, not slow
+static_assert(LGW_SEG >= 2 * LGW_PRE || LGW_SEG >= 256, "the run-up of a guessed chain stays inside the previous segment or two");
+static_assert(LGW_DEC_WORDS >= 2 && LGW_DEC_WORDS % 2 == 0, "a thread owns whole 64-bit groups of marks");
 static_assert(LGW_DATA % 16 == 0, "bulk copies work in 16-byte granules");
 
 struct LgWork { uint32_t frame, tile; };
@@ -79,8 +86,8 @@ __device__ __forceinline__ uint32_t leg_hdr_ref(uint32_t h) { return ((h & 15u) 
 
 // stage [tile_off, tile_off + nbytes) of the frame into shared memory, zero past len (16-byte granules): the tail of a buffer
 __device__ __forceinline__ void lg_stage_tail(uint8_t* sm, const uint8_t* __restrict__ src, unsigned long long len,
-                                              unsigned long long tile_off, int nbytes, int lane) {
-    for (int v = lane; v < nbytes / 16; v += 32) {
+                                              unsigned long long tile_off, int nbytes, int tid) {
+    for (int v = tid; v < nbytes / 16; v += LGW_THREADS) {
         const unsigned long long o = tile_off + 16ull * (unsigned)v;
         uint4 q = make_uint4(0, 0, 0, 0);
         if (o + 16 <= len) q = __ldg(reinterpret_cast<const uint4*>(src + o));
@@ -149,8 +156,16 @@ __device__ __forceinline__ uint32_t lgw_chain(const uint8_t* data, uint32_t* bit
 #pragma unroll
     for (int wd = 0; wd < LGW_SEG_WORDS; wd++) bm[wd] = 0;
     const uint32_t seg0 = lane * LGW_SEG;
-    uint32_t entry = lane == 0 ? entry0 : seg0;          // tile-relative position where this lane's walk starts
-    uint32_t p = entry;
+    // Lane 0 knows where its chain starts.  The others guess -- but not blindly: a chain started anywhere falls in step
+    // with the true one within a few blocks, so the guess runs LGW_PRE bytes in front of the segment first (no marks, five
+    // instructions a block) and nearly always enters the segment where the true chain does: then the left neighbour's
+    // exit below confirms the entry and nothing has to be walked twice.
+    uint32_t p = entry0;
+    if (lane != 0) {
+        p = seg0 - (uint32_t)LGW_PRE;
+        while (p < seg0) p += leg_step(data[p]);
+    }
+    uint32_t entry = p;                                  // tile-relative position where this lane's marked walk starts
     bool dead = lgw_walk_segment<false>(data, lane, p, bm, tile_rel);
     uint32_t exitv = dead ? NONE : p;                    // tile-relative position in the next segment (steps are <= 34 bytes)
     for (;;) {
@@ -249,28 +264,48 @@ __device__ __forceinline__ void lgw_block(const uint32_t* __restrict__ d32, cons
     }
 }
 
-__global__ void __launch_bounds__(32, LGW_CTAS_PER_SM) k_legacy_warp(const FrameDev* __restrict__ frames, Result* __restrict__ results,
-                                                                    const LgWork* __restrict__ work, const uint32_t nwork,
-                                                                    uint32_t* __restrict__ counters, const uint32_t epoch) {
+__device__ __forceinline__ void lgw_cta_sync() {
+    if (LGW_WARPS == 1) __syncwarp(); else __syncthreads();
+}
+
+__global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __restrict__ frames, Result* __restrict__ results,
+                                                             const LgWork* __restrict__ work, const uint32_t nwork,
+                                                             uint32_t* __restrict__ counters, const uint32_t epoch) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     uint8_t* data = lg_smem;
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LGW_DATA);                     // [LGW_TILE_WORDS]
     uint32_t* lbmaps = bitmap + LGW_TILE_WORDS;                                             // look-back: [LGW_LB][LG_STATES]
     __shared__ __align__(8) unsigned long long bar_storage;
-    __shared__ uint32_t sh_map[LG_STATES], sh_merge[LG_STATES];
-    const uint32_t lane = threadIdx.x;
+    __shared__ uint32_t sh_map[LG_STATES], sh_merge[LG_STATES], warp_sums[LGW_WARPS];
+    __shared__ uint32_t sh_ticket, sh_base, sh_skip;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t bar = smem_u32(&bar_storage);
-    if (lane == 0) {
+    if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    __syncwarp();
     const uint32_t* d32 = reinterpret_cast<const uint32_t*>(data);
+    uint32_t bulk_uses = 0;                                  // bulk copies this CTA has waited for: the mbarrier's phase
 
-    for (uint32_t k = 0;; k++) {
-        uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&counters[2], 1u);
-        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+    for (;;) {
+        lgw_cta_sync();                                       // every thread is done with the previous tile's shared memory
+        // ---- 1. ticket; stage: ONE bulk copy for a tile that lies wholly inside the buffer
+        if (tid == 0) {
+            const uint32_t t = atomicAdd(&counters[2], 1u);
+            sh_ticket = t;
+            if (t < nwork) {
+                const LgWork w0 = work[t];
+                const FrameDev& F0 = frames[w0.frame];
+                const unsigned long long off0 = (unsigned long long)w0.tile * LGW_TILE;
+                if (off0 + (unsigned long long)LGW_DATA <= F0.len) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)LGW_DATA) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                 ::"r"(smem_u32(data)), "l"(F0.src + off0), "r"((uint32_t)LGW_DATA), "r"(bar) : "memory");
+                }
+            }
+        }
+        lgw_cta_sync();
+        const uint32_t ticket = sh_ticket;
         if (ticket >= nwork) break;
         const LgWork wk = work[ticket];
         const FrameDev& F = frames[wk.frame];
@@ -284,181 +319,186 @@ __global__ void __launch_bounds__(32, LGW_CTAS_PER_SM) k_legacy_warp(const Frame
         const uint32_t need_pairs = ppr * (uint32_t)F.height;                            // < 2^26: width * height <= 2^30 (prepare())
         const unsigned long long need = 2ull * need_pairs;                               // blocks of the image (:478-482)
         const bool fits = F.dst_cap >= (unsigned long long)F.width * (unsigned long long)F.height;
-
-        // ---- 1. stage: one bulk copy for a tile that lies wholly inside the buffer, else 16-byte granules with zero fill
-        __syncwarp();                                         // every lane is done with the previous tile's shared memory
         if (tile_off + (unsigned long long)LGW_DATA <= len) {
-            if (lane == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)LGW_DATA) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                             ::"r"(smem_u32(data)), "l"(F.src + tile_off), "r"((uint32_t)LGW_DATA), "r"(bar) : "memory");
-            }
-        } else {
-            lg_stage_tail(data, F.src, len, tile_off, LGW_DATA, (int)lane);
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");           // a later bulk copy overwrites these generic stores
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-        }
-        {
-            uint32_t ok = 0;
             for (;;) {
+                uint32_t ok;
                 asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                             : "=r"(ok) : "r"(bar), "r"(k & 1u) : "memory");
+                             : "=r"(ok) : "r"(bar), "r"(bulk_uses & 1u) : "memory");
                 if (ok) break;
                 __nanosleep(32);                              // the issue slots belong to the warps that have their data
             }
+            bulk_uses++;
+        } else {                                              // the tail of the buffer: 16-byte granules with zero fill
+            lg_stage_tail(data, F.src, len, tile_off, LGW_DATA, (int)tid);
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");           // a later bulk copy overwrites these generic stores
+            lgw_cta_sync();
         }
 
-        // ---- 2. transfer map
-        uint32_t total0;
-        const uint32_t ex0 = lgw_chain(data, bitmap, 0u, tile_rel, lane, total0);
-        const uint32_t exit0 = (ex0 == 0xFFFFFFFFu || last_tile) ? LG_DEAD : ex0 >> 1;
-        if (lane < LG_STATES) {
-            uint32_t q = 2u * lane, pre = 0, m = LG_NO_MERGE, ex = exit0, count;
-            bool d2 = false;
-            if (lane == 0) { m = 0; count = total0; }
-            else {
+        if (warp == 0) {
+            // ---- 2. transfer map
+            uint32_t total0;
+            const uint32_t ex0 = lgw_chain(data, bitmap, 0u, tile_rel, lane, total0);
+            const uint32_t exit0 = (ex0 == 0xFFFFFFFFu || last_tile) ? LG_DEAD : ex0 >> 1;
+            if (lane < LG_STATES) {
+                uint32_t q = 2u * lane, pre = 0, m = LG_NO_MERGE, ex = exit0, count;
+                bool d2 = false;
+                if (lane == 0) { m = 0; count = total0; }
+                else {
+                    for (;;) {
+                        if (q >= (uint32_t)LGW_TILE) { ex = (q - LGW_TILE) >> 1; break; }               // never met C0 in this tile
+                        if ((bitmap[q >> 6] >> ((q >> 1) & 31u)) & 1u) { m = q >> 1; break; }
+                        const uint32_t nq = q + leg_step(data[q]);
+                        if (nq >= tile_rel) { d2 = true; break; }
+                        q = nq;
+                        pre++;
+                    }
+                    if (m != LG_NO_MERGE) {
+                        uint32_t before = 0;                    // blocks of C0 from the merge point on = total0 - (marks before it)
+                        for (uint32_t w = 0; w < (m >> 5); w++) before += __popc(bitmap[w]);
+                        before += __popc(bitmap[m >> 5] & ((1u << (m & 31u)) - 1u));
+                        count = pre + total0 - before;
+                    } else {
+                        count = pre;
+                        if (d2 || last_tile) ex = LG_DEAD;
+                    }
+                }
+                const uint32_t mapv = ex | (count << 5);
+                sh_map[lane] = mapv;
+                sh_merge[lane] = m;
+                F.lg_tilemap[(size_t)tile * LG_STATES + lane] = mapv;
+            }
+            __syncwarp();
+            // ---- 3. publish (release: the map entries the other lanes wrote are ordered before it by the warp barrier), look back
+            if (lane == 0) lgw_store_release(F.lg_status + tile, lgw_pack(0u, epoch, LGW_ST_LOCAL, 0u));
+            uint32_t entry = 0, base = 0, errbit = 0;
+            if (tile > 0) {
+                const uint32_t jhi = tile - 1;
+                uint32_t spins = 0;
                 for (;;) {
-                    if (q >= (uint32_t)LGW_TILE) { ex = (q - LGW_TILE) >> 1; break; }               // never met C0 in this tile
-                    if ((bitmap[q >> 6] >> ((q >> 1) & 31u)) & 1u) { m = q >> 1; break; }
-                    const uint32_t nq = q + leg_step(data[q]);
-                    if (nq >= tile_rel) { d2 = true; break; }
-                    q = nq;
-                    pre++;
-                }
-                if (m != LG_NO_MERGE) {
-                    uint32_t before = 0;                    // blocks of C0 from the merge point on = total0 - (marks before it)
-                    for (uint32_t w = 0; w < (m >> 5); w++) before += __popc(bitmap[w]);
-                    before += __popc(bitmap[m >> 5] & ((1u << (m & 31u)) - 1u));
-                    count = pre + total0 - before;
-                } else {
-                    count = pre;
-                    if (d2 || last_tile) ex = LG_DEAD;
-                }
-            }
-            const uint32_t mapv = ex | (count << 5);
-            sh_map[lane] = mapv;
-            sh_merge[lane] = m;
-            F.lg_tilemap[(size_t)tile * LG_STATES + lane] = mapv;
-        }
-        __syncwarp();
-        // ---- 3. publish (release: the map entries the other lanes wrote are ordered before it by the warp barrier), look back
-        if (lane == 0) lgw_store_release(F.lg_status + tile, lgw_pack(0u, epoch, LGW_ST_LOCAL, 0u));
-        uint32_t entry = 0, base = 0, errbit = 0;
-        if (tile > 0) {
-            const uint32_t jhi = tile - 1;
-            uint32_t spins = 0;
-            for (;;) {
-                const int j = (int)jhi - (int)lane;
-                unsigned long long sw = 0;
-                if (lane < (uint32_t)LGW_LB && j >= 0) sw = lgw_load_acquire(F.lg_status + j);
-                const uint32_t lo32 = (uint32_t)sw;
-                const uint32_t st = ((lo32 >> 8) & 0xFFFFFFu) == (epoch & 0xFFFFFFu) ? (lo32 >> 6) & 3u : 0u;
-                const unsigned incl = __ballot_sync(0xFFFFFFFFu, st == LGW_ST_INCL);
-                const unsigned any = __ballot_sync(0xFFFFFFFFu, st != 0u);
-                if (incl) {
-                    const int d = __ffs(incl) - 1;            // nearest predecessor with a known inclusive state: tile jhi - d
-                    const unsigned between = (1u << d) - 1u;  // tiles jhi - d + 1 .. jhi must have published their maps
-                    if ((any & between) == between) {
-                        uint32_t state = __shfl_sync(0xFFFFFFFFu, lo32 & 31u, d);
-                        uint32_t count = __shfl_sync(0xFFFFFFFFu, (uint32_t)(sw >> 32), d);
-                        errbit = __shfl_sync(0xFFFFFFFFu, lo32 & LGW_ERR_BIT, d);
-                        const uint32_t first = jhi - (uint32_t)d + 1u;                          // maps of tiles first .. jhi
-                        __syncwarp();                        // every lane's acquire load before any lane's map loads
-                        for (uint32_t idx = lane; idx < (uint32_t)d * LG_STATES; idx += 32)
-                            lbmaps[idx] = __ldcg(F.lg_tilemap + (size_t)first * LG_STATES + idx);
-                        __syncwarp();
-                        if (lane == 0) {
-                            for (int m = 0; m < d; m++) {
-                                if (state == LG_DEAD) break;
-                                const uint32_t v = lbmaps[m * LG_STATES + state];
-                                count += v >> 5;
-                                state = v & 31u;
+                    const int j = (int)jhi - (int)lane;
+                    unsigned long long sw = 0;
+                    if (lane < (uint32_t)LGW_LB && j >= 0) sw = lgw_load_acquire(F.lg_status + j);
+                    const uint32_t lo32 = (uint32_t)sw;
+                    const uint32_t st = ((lo32 >> 8) & 0xFFFFFFu) == (epoch & 0xFFFFFFu) ? (lo32 >> 6) & 3u : 0u;
+                    const unsigned incl = __ballot_sync(0xFFFFFFFFu, st == LGW_ST_INCL);
+                    const unsigned any = __ballot_sync(0xFFFFFFFFu, st != 0u);
+                    if (incl) {
+                        const int d = __ffs(incl) - 1;            // nearest predecessor with a known inclusive state: tile jhi - d
+                        const unsigned between = (1u << d) - 1u;  // tiles jhi - d + 1 .. jhi must have published their maps
+                        if ((any & between) == between) {
+                            uint32_t state = __shfl_sync(0xFFFFFFFFu, lo32 & 31u, d);
+                            uint32_t count = __shfl_sync(0xFFFFFFFFu, (uint32_t)(sw >> 32), d);
+                            errbit = __shfl_sync(0xFFFFFFFFu, lo32 & LGW_ERR_BIT, d);
+                            const uint32_t first = jhi - (uint32_t)d + 1u;                          // maps of tiles first .. jhi
+                            __syncwarp();                        // every lane's acquire load before any lane's map loads
+                            for (uint32_t idx = lane; idx < (uint32_t)d * LG_STATES; idx += 32)
+                                lbmaps[idx] = __ldcg(F.lg_tilemap + (size_t)first * LG_STATES + idx);
+                            __syncwarp();
+                            if (lane == 0) {
+                                for (int m = 0; m < d; m++) {
+                                    if (state == LG_DEAD) break;
+                                    const uint32_t v = lbmaps[m * LG_STATES + state];
+                                    count += v >> 5;
+                                    state = v & 31u;
+                                }
                             }
+                            entry = __shfl_sync(0xFFFFFFFFu, state, 0);
+                            base = __shfl_sync(0xFFFFFFFFu, count, 0);
+                            break;
                         }
-                        entry = __shfl_sync(0xFFFFFFFFu, state, 0);
-                        base = __shfl_sync(0xFFFFFFFFu, count, 0);
-                        break;
                     }
+                    if (++spins > LGW_SPIN_LIMIT) { entry = LG_DEAD; errbit = LGW_ERR_BIT; break; }   // never expected
+                    __nanosleep(spins < 8 ? 40 : 200);
                 }
-                if (++spins > LGW_SPIN_LIMIT) { entry = LG_DEAD; errbit = LGW_ERR_BIT; break; }   // never expected
-                __nanosleep(spins < 8 ? 40 : 200);
             }
-        }
-        uint32_t exitv = LG_DEAD, total = base;
-        if (entry != LG_DEAD) {
-            const uint32_t v = sh_map[entry];
-            exitv = v & 31u;
-            total = base + (v >> 5);
-        }
-        if (lane == 0) {
-            lgw_store_relaxed(F.lg_status + tile, lgw_pack(total, epoch, LGW_ST_INCL, exitv | errbit));   // self-contained word
-            if (last_tile) {
-                unsigned status = 0;
-                if (!fits) status |= MCRAW_FRAME_GEOMETRY;
-                if ((unsigned long long)total < need) status |= MCRAW_FRAME_TRUNCATED;     // reference: stale samples (:387,398)
-                if (errbit) status |= MCRAW_FRAME_INTERNAL;
-                Result r;
-                r.written = status ? 0ull : (unsigned long long)F.width * (unsigned long long)F.height;   // :494
-                r.status = status;
-                r.pad = 0;
-                results[wk.frame] = r;
+            uint32_t exitv = LG_DEAD, total = base;
+            if (entry != LG_DEAD) {
+                const uint32_t v = sh_map[entry];
+                exitv = v & 31u;
+                total = base + (v >> 5);
             }
-        }
-        if (entry == LG_DEAD || !fits || (unsigned long long)base >= need) continue;           // nothing of the image starts here
-
-        // ---- 4. the bitmap for the true entry
-        if (entry != 0) {
-            const uint32_t m = sh_merge[entry];
-            __syncwarp();
-            if (m == LG_NO_MERGE) {
-                uint32_t t2;
-                lgw_chain(data, bitmap, 2u * entry, tile_rel, lane, t2);       // blocks of one constant width: walk it again from its entry
-            } else {
-                for (uint32_t w = lane; w < (m >> 5); w += 32) bitmap[w] = 0;  // C0's marks before the merge point go
+            const bool skip = entry == LG_DEAD || !fits || (unsigned long long)base >= need;     // nothing of the image starts here
+            if (lane == 0) {
+                lgw_store_relaxed(F.lg_status + tile, lgw_pack(total, epoch, LGW_ST_INCL, exitv | errbit));   // self-contained word
+                if (last_tile) {
+                    unsigned status = 0;
+                    if (!fits) status |= MCRAW_FRAME_GEOMETRY;
+                    if ((unsigned long long)total < need) status |= MCRAW_FRAME_TRUNCATED;     // reference: stale samples (:387,398)
+                    if (errbit) status |= MCRAW_FRAME_INTERNAL;
+                    Result r;
+                    r.written = status ? 0ull : (unsigned long long)F.width * (unsigned long long)F.height;   // :494
+                    r.status = status;
+                    r.pad = 0;
+                    results[wk.frame] = r;
+                }
+                sh_base = base;
+                sh_skip = skip ? 1u : 0u;
+            }
+            // ---- 4. the bitmap for the true entry
+            if (!skip && entry != 0) {
+                const uint32_t m = sh_merge[entry];
                 __syncwarp();
-                if (lane == 0) {
-                    bitmap[m >> 5] &= ~((1u << (m & 31u)) - 1u);
-                    uint32_t p = 2u * entry;
-                    while (p < 2u * m) {
-                        bitmap[p >> 6] |= 1u << ((p >> 1) & 31u);
-                        p += leg_step(data[p]);
+                if (m == LG_NO_MERGE) {
+                    uint32_t t2;
+                    lgw_chain(data, bitmap, 2u * entry, tile_rel, lane, t2);       // blocks of one constant width: walk it again from its entry
+                } else {
+                    for (uint32_t w = lane; w < (m >> 5); w += 32) bitmap[w] = 0;  // C0's marks before the merge point go
+                    __syncwarp();
+                    if (lane == 0) {
+                        bitmap[m >> 5] &= ~((1u << (m & 31u)) - 1u);
+                        uint32_t p = 2u * entry;
+                        while (p < 2u * m) {
+                            bitmap[p >> 6] |= 1u << ((p >> 1) & 31u);
+                            p += leg_step(data[p]);
+                        }
                     }
                 }
             }
-            __syncwarp();
         }
+        lgw_cta_sync();
+        if (sh_skip) continue;
+        const uint32_t base = sh_base;
 
-        // ---- 5. decode: ordinal of the first block start in this lane's segment, then the pairs led from there.  Block
-        //      starts with an even ordinal lead a pair (even-column block, then odd-column block, :480-481); the partner's
-        //      start is the next mark -- in this segment or the next lane's, where it has an odd ordinal and is dropped.
-        uint32_t wv[LGW_SEG_WORDS];
+        // ---- 5. decode: ordinal of the first block start in this thread's part of the stream, then the pairs led from
+        //      there.  Block starts with an even ordinal lead a pair (even-column block, then odd-column block, :480-481);
+        //      the partner's start is the next mark -- here or in the next thread's part, where it has an odd ordinal and
+        //      is dropped.
+        uint32_t wv[LGW_DEC_WORDS];
         uint32_t c = 0;
 #pragma unroll
-        for (int i = 0; i < LGW_SEG_WORDS; i++) { wv[i] = bitmap[lane * LGW_SEG_WORDS + i]; c += __popc(wv[i]); }
+        for (int i = 0; i < LGW_DEC_WORDS; i++) { wv[i] = bitmap[tid * LGW_DEC_WORDS + i]; c += __popc(wv[i]); }
         uint32_t incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= (uint32_t)d) incl += o;
         }
-        const uint32_t ord0 = base + incl - c;
+        uint32_t before = 0;
+        if (LGW_WARPS > 1) {
+            if (lane == 31) warp_sums[warp] = incl;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < LGW_WARPS; w++)
+                if ((uint32_t)w < warp) before += warp_sums[w];
+        }
+        const uint32_t ord0 = base + before + incl - c;
         uint32_t P = (ord0 >> 1) + (ord0 & 1u);                                  // ordinal of the first pair led here
         uint32_t y = P / ppr, xq = P - y * ppr;
         bool drop = (ord0 & 1u) != 0u;                                           // the first mark is a partner: not a leader
         const int width = F.width;
         uint16_t* __restrict__ dst = F.dst;
         const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
+        const unsigned epi = F.epi_mode;
 #pragma unroll
-        for (int g = 0; g < LGW_SEG_WORDS / 2; g++) {
+        for (int g = 0; g < LGW_DEC_WORDS / 2; g++) {
             unsigned long long marks = (unsigned long long)wv[2 * g] | ((unsigned long long)wv[2 * g + 1] << 32);
             if (drop && marks) { marks &= marks - 1; drop = false; }
             while (marks && P < need_pairs) {
                 const uint32_t bpos = (uint32_t)__ffsll((long long)marks) - 1u;
                 marks &= marks - 1;                                                   // the leader ...
                 if (marks) marks &= marks - 1;                                        // ... and its partner, if it starts in this group
-                else drop = true;                                                     // else it is the first mark of the next group / lane
-                const uint32_t oE = (uint32_t)LGW_SEG * lane + 128u * g + 2u * bpos;
+                else drop = true;                                                     // else it is the first mark of the next group / thread
+                const uint32_t oE = 64u * (uint32_t)LGW_DEC_WORDS * tid + 128u * g + 2u * bpos;
                 const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
                 const uint32_t oO = oE + 2u + leg_len(bitsE);
                 const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
@@ -470,6 +510,10 @@ __global__ void __launch_bounds__(32, LGW_CTAS_PER_SM) k_legacy_warp(const Frame
                 const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
 #pragma unroll
                 for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i], refs);                    // :483-486, + reference mod 2^16
+                if (epi) {                                                                    // optional black / white level epilogue
+#pragma unroll
+                    for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, F, (int)(y & 1u));
+                }
                 const int x = (int)(32u * xq);
                 uint16_t* orow = dst + (size_t)y * (size_t)width + x;
                 if (vec && x + 32 <= width) {
@@ -488,8 +532,8 @@ __global__ void __launch_bounds__(32, LGW_CTAS_PER_SM) k_legacy_warp(const Frame
             }
         }
     }
-    // the last warp to leave resets the ticket counters for the next launch
-    if (lane == 0 && atomicAdd(&counters[3], 1u) == gridDim.x - 1u) { counters[2] = 0; counters[3] = 0; }
+    // the last CTA to leave resets the ticket counters for the next launch
+    if (tid == 0 && atomicAdd(&counters[3], 1u) == gridDim.x - 1u) { counters[2] = 0; counters[3] = 0; }
 }
 
 }  // namespace mcraw

@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout; ignored when the plugin is absent)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -21,6 +22,10 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         have = False
     if have:
+        # a GPU test that hangs (a device-side wait, a third-party library that never answers) must fail, not stall the run
+        for it in items:
+            if "gpu" in it.keywords and not any(m.name == "timeout" for m in it.iter_markers()):
+                it.add_marker(pytest.mark.timeout(300))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:

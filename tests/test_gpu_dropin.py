@@ -166,7 +166,25 @@ def _platform_takes(mode, path):
     return None
 
 
-@pytest.mark.parametrize("mode", ["ring", "direct", "cufile", "mmap"])
+def test_feed_cufile(tmp_path):
+    """MCRAW_FEED=cufile (GPUDirect Storage through libcufile): the attempt runs under a deadline inside the library, so the
+    call always comes back -- with the frames decoded through cuFile, or through the ring and the reason in the text.
+    Runs in a child process (tests/helpers/feed_child.py) with a hard limit: a hang is a failure."""
+    import json
+    import subprocess
+    import sys
+    helper = os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers", "feed_child.py")
+    r = subprocess.run([sys.executable, helper, "cufile", str(tmp_path)], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    print("feed[cufile]:", out["feed"])
+    assert out["frames_ok"]
+    feed = out["feed"]
+    assert feed.startswith("cuFileRead -> device memory") or feed.startswith("pread -> pinned ring (cuFile") or \
+        feed.startswith("pread -> pinned ring (O_DIRECT open refused")
+
+
+@pytest.mark.parametrize("mode", ["ring", "direct", "mmap"])
 def test_feeds(tmp_path, monkeypatch, mode):
     """The feeds of Decoder::loadFramesToDevice (MCRAW_FEED): pipelined pread into the pinned ring (default), O_DIRECT
     reads, cuFile (GPUDirect Storage) into device memory, H2D from a page-locked mapping.  Every feed must deliver the
@@ -205,10 +223,6 @@ def test_feeds(tmp_path, monkeypatch, mode):
             assert feed.startswith("mmap + cudaHostRegister")
         else:
             assert feed.startswith("pread -> pinned ring (cudaHostRegister refused the mapping")
-    else:
-        # cuFile cannot be probed without cuFile: the text must name the feed or the call that refused it
-        assert feed.startswith("cuFileRead -> device memory") or feed.startswith("pread -> pinned ring (cuFile") or \
-            feed.startswith("pread -> pinned ring (O_DIRECT open refused")
     ours.close()
     for p in ptrs:
         ctx.device_free(p)
