@@ -92,7 +92,7 @@ struct Slot {
     // the plan this slot's device tables were built for (see enqueue_chunk)
     std::vector<mcraw_frame_desc> plan_descs;
     std::vector<mcraw_levels> plan_levels;   // empty: raw output
-    bool plan_valid = false, any7 = false, any6 = false;
+    bool plan_valid = false, any7 = false, any6 = false, any_epi = false;
     uint32_t max_ltiles = 0, nitems = 0;
     size_t items_off = 0, plan_bytes = 0;
     uint32_t flag_uses = 0;         // k_meta launches on this plan since its counters were zeroed
@@ -423,6 +423,8 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         if (!lgwork.empty()) std::memcpy(s.h_up + s.lg_work_off, lgwork.data(), sizeof(LgWork) * lgwork.size());
         s.plan_descs.assign(descs, descs + n);
         if (levels) s.plan_levels.assign(levels, levels + n); else s.plan_levels.clear();
+        s.any_epi = false;
+        for (uint32_t i = 0; i < n; i++) s.any_epi = s.any_epi || frames[i].epi_mode != 0;
         s.dst_lo = ~(uintptr_t)0; s.dst_hi = 0;
         for (uint32_t i = 0; i < n; i++) {
             const uintptr_t a = reinterpret_cast<uintptr_t>(descs[i].dst);
@@ -495,16 +497,19 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
-        CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems, d_counter,
-                                       pdl ? 2u * s.flag_uses : 0u));
+        if (s.any_epi) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units<true>, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems,
+                                                      d_counter, pdl ? 2u * s.flag_uses : 0u));
+        else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units<false>, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems,
+                                            d_counter, pdl ? 2u * s.flag_uses : 0u));
         ctx->launches += 1;
     }
     if (any6) {
         // one pass over the stream: transfer maps, decoupled look-back and the pixel work in one persistent kernel
         s.lg_epoch += 1;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(ctx->lgw_resident_ctas, s.lg_nwork));
-        k_legacy_warp<<<grid, LGW_THREADS, LGW_SMEM, st>>>(d_frames, d_results, reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off),
-                                                 s.lg_nwork, d_counter, s.lg_epoch);
+        const LgWork* d_work = reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off);
+        if (s.any_epi) k_legacy_warp<true><<<grid, LGW_THREADS, LGW_SMEM, st>>>(d_frames, d_results, d_work, s.lg_nwork, d_counter, s.lg_epoch);
+        else k_legacy_warp<false><<<grid, LGW_THREADS, LGW_SMEM, st>>>(d_frames, d_results, d_work, s.lg_nwork, d_counter, s.lg_epoch);
         ctx->launches += 1;
     }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e2, st));
@@ -582,19 +587,21 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     if (const char* e = getenv("MCRAW_CHAIN")) ctx->chain_ctas = (uint32_t)std::max(0, atoi(e));
     if (cudaFuncSetAttribute(k_meta<K1Batch>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Batch::K1_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_meta<K1Few>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Few::K1_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_units, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_legacy_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, LGW_SMEM) != cudaSuccess) {
+        cudaFuncSetAttribute(k_units<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_units<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_legacy_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LGW_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_legacy_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LGW_SMEM) != cudaSuccess) {
         ctx->err = "cudaFuncSetAttribute(smem) failed"; return bail(MCRAW_ERR_CUDA);
     }
     {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_units, KD_THREADS, KU_SMEM) != cudaSuccess || per_sm < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_units<true>, KD_THREADS, KU_SMEM) != cudaSuccess || per_sm < 1) {
             ctx->err = "k_units does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
         ctx->sm_count = (uint32_t)prop.multiProcessorCount;
         ctx->chain_ctas = std::min(ctx->chain_ctas, ctx->resident_ctas / 2);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp<true>, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm < 1) {
             ctx->err = "k_legacy_warp does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
         if (const char* e = getenv("MCRAW_LGW_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));

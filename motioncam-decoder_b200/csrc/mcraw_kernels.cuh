@@ -723,6 +723,7 @@ __device__ __forceinline__ uint32_t meta_values(const uint32_t blk, const uint32
     return __vadd2(v, ref | (ref << 16));
 }
 
+template <bool EPI>
 __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& S, Result* __restrict__ result,
                                            const uint32_t u0, const uint32_t upw, uint8_t* smem_warp, const uint32_t* s_terms,
                                            uint32_t& bulk_phase) {
@@ -750,7 +751,7 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
     const unsigned long long len = F.len;
     const uint32_t inv = F.inv_tiles_x;
     const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
-    const unsigned epi = F.epi_mode;
+    const unsigned epi = EPI ? F.epi_mode : 0u;         // EPI = false: the epilogue code is not even in the kernel
     uint16_t* __restrict__ dst = F.dst;
 
     // payload offsets of this warp's units (+ end): lane i holds unitoff[u0 + i]; and their metadata records
@@ -914,6 +915,7 @@ constexpr int KD_THREADS = 32 * KU_WARPS;
 // the wait with one acquire load; the other lanes wait at the warp barrier.  The per-unit records are then read with
 // ld.global.cg (L2), so they see everything k_meta released before bumping the counter.
 // Three CTAs per SM (168 registers): the fourth buys 2 % of bandwidth and leaves no room for this logic without spills.
+template <bool EPI>
 __global__ void __launch_bounds__(KD_THREADS, 3)
 k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states, Result* __restrict__ results,
         const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target) {
@@ -956,7 +958,7 @@ k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ stat
             }
         }
         __syncwarp();
-        units_task(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 31u) + 1u, smem_warp, s_terms,
+        units_task<EPI>(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 31u) + 1u, smem_warp, s_terms,
                    bulk_phase);
         __syncwarp();
         it = __shfl_sync(0xFFFFFFFFu, nxt, 0);

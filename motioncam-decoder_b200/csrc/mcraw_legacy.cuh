@@ -38,32 +38,26 @@
 
 namespace mcraw {
 
-#ifndef MCRAW_LGW_SEG
-#define MCRAW_LGW_SEG 512
-#endif
 #ifndef MCRAW_LGW_WARPS
 #define MCRAW_LGW_WARPS 4
 #endif
-constexpr int LGW_SEG = MCRAW_LGW_SEG;         // bytes per segment (one lane of the index warp)
-constexpr int LGW_WARPS = MCRAW_LGW_WARPS;     // warps per CTA: warp 0 resolves the chain, all of them decode
+constexpr int LGW_WARPS = MCRAW_LGW_WARPS;     // warps per CTA
 constexpr int LGW_THREADS = 32 * LGW_WARPS;
-constexpr int LGW_TILE = 32 * LGW_SEG;         // bytes per tile (one CTA at a time)
-constexpr int LGW_SEG_WORDS = LGW_SEG / 64;    // bitmap words per segment: one bit per even offset
-constexpr int LGW_TILE_WORDS = 32 * LGW_SEG_WORDS;
-constexpr int LGW_DEC_WORDS = LGW_TILE_WORDS / LGW_THREADS;   // bitmap words (64 bytes of the stream each) a thread decodes
-constexpr int LGW_PRE = 192;                   // bytes a lane's guessed chain runs in front of its segment to fall in step
+constexpr int LGW_SEG = 128;                   // bytes of the tile a thread owns: 64 candidate block starts = two bitmap words
+constexpr int LGW_TILE = LGW_THREADS * LGW_SEG;   // bytes per tile (one CTA at a time): 16 KiB for four warps
+constexpr int LGW_TILE_WORDS = LGW_TILE / 64;  // bitmap words: one bit per even offset
+constexpr int LGW_PRE = 192;                   // bytes a thread's guessed chain runs in front of its segment to fall in step
 constexpr int LG_STATES = 17;                  // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;               // exit code of a chain that ran into the end of the buffer
 constexpr uint32_t LG_NO_MERGE = 0xFFFFu;      // merge point of an entry whose chain never meets C0 inside the tile
 constexpr int LG_OVERRUN = 80;                 // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it (+ word reads)
 constexpr int LGW_DATA = LGW_TILE + LG_OVERRUN;
 constexpr int LGW_LB = 32;                     // look-back window: status words read per poll
-constexpr int LGW_SMEM = LGW_DATA + LGW_TILE_WORDS * 4 + LGW_LB * LG_STATES * 4;
+constexpr int LGW_SMEM = LGW_DATA + LGW_TILE_WORDS * 4 + LGW_LB * LG_STATES * 4 + LGW_THREADS * 4;
 constexpr uint32_t LGW_ST_LOCAL = 1u, LGW_ST_INCL = 2u;
 constexpr uint32_t LGW_ERR_BIT = 1u << 5;      // sticky: a wait gave up somewhere up the chain
 constexpr uint32_t LGW_SPIN_LIMIT = 1u << 18;  // polls of ~0.2 us: a wait that long means something is broken, not slow
-static_assert(LGW_SEG >= 2 * LGW_PRE || LGW_SEG >= 256, "the run-up of a guessed chain stays inside the previous segment or two");
-static_assert(LGW_DEC_WORDS >= 2 && LGW_DEC_WORDS % 2 == 0, "a thread owns whole 64-bit groups of marks");
+constexpr uint32_t LGW_NONE = 0xFFFFFFFFu;     // "no chain arrives here" (it ended at an undecodable block)
 static_assert(LGW_DATA % 16 == 0, "bulk copies work in 16-byte granules");
 
 struct LgWork { uint32_t frame, tile; };
@@ -117,86 +111,98 @@ __device__ __forceinline__ unsigned long long lgw_load_acquire(const unsigned lo
     return v;
 }
 
-// One lane, one segment of the staged tile: walk from tile-relative byte offset p to the end of segment `seg`.  Block
-// starts go into bm[] (one word per 64 bytes of the segment).  With MERGE the walk stops at the first position already
-// marked in bm[] -- from there on the old marks are this chain's own -- and older marks before it are dropped.
+__device__ __forceinline__ void lgw_cta_sync() {
+    if (LGW_WARPS == 1) __syncwarp(); else __syncthreads();
+}
+__device__ __forceinline__ bool lgw_cta_any(const bool v) {
+    if (LGW_WARPS == 1) return __any_sync(0xFFFFFFFFu, v) != 0;
+    return __syncthreads_or(v ? 1 : 0) != 0;
+}
+
+// One thread, its segment [seg0, seg0 + LGW_SEG) of the staged tile: walk from tile-relative byte offset p to the end of the
+// segment.  Block starts go into (m0, m1): one bit per even offset.  With MERGE the walk stops at the first position
+// already marked -- from there on the old marks are this chain's own -- and older marks before it are dropped.
 // rel: bytes from the tile start to the end of the buffer (a block is decoded only if it ends before the last byte,
 // RawData_Legacy.cpp:387,398).  Returns true if the chain ended at an undecodable block.
 template <bool MERGE>
-__device__ __forceinline__ bool lgw_walk_segment(const uint8_t* data, const uint32_t seg, uint32_t& p, uint32_t (&bm)[LGW_SEG_WORDS], const uint32_t rel) {
-    bool merged = false, dead = false;
-    const uint32_t seg0 = seg * LGW_SEG;
-#pragma unroll
-    for (int wd = 0; wd < LGW_SEG_WORDS; wd++) {
-        if (merged) continue;
-        const uint32_t stop = seg0 + 64u * (wd + 1);
-        if (dead || p >= stop) { bm[wd] = 0; continue; }
-        const uint32_t old = bm[wd];
-        uint32_t acc = 0;
-        while (p < stop) {
-            const uint32_t bit = 1u << ((p >> 1) & 31u);
-            if (MERGE && (old & bit)) { merged = true; acc |= old & ~(bit - 1u); break; }
-            const uint32_t q = p + leg_step(data[p]);
-            if (q >= rel) { dead = true; break; }
-            acc |= bit;
-            p = q;
+__device__ __forceinline__ bool lgw_walk_segment(const uint8_t* data, const uint32_t seg0, uint32_t& p, uint32_t& m0, uint32_t& m1, const uint32_t rel) {
+    const uint32_t old0 = m0, old1 = m1;
+    uint32_t a0 = 0, a1 = 0;
+    bool dead = false;
+    const uint32_t end = seg0 + (uint32_t)LGW_SEG;
+    while (p < end) {
+        const uint32_t pos = (p - seg0) >> 1;                         // 0 .. 63
+        const uint32_t bit = 1u << (pos & 31u);
+        const bool hi = pos >= 32u;
+        if (MERGE && ((hi ? old1 : old0) & bit)) {                    // met the old chain: its marks from here on stay
+            if (hi) a1 |= old1 & ~(bit - 1u);
+            else { a0 |= old0 & ~(bit - 1u); a1 = old1; }
+            break;
         }
-        bm[wd] = acc;
+        const uint32_t q = p + leg_step(data[p]);
+        if (q >= rel) { dead = true; break; }
+        if (hi) a1 |= bit; else a0 |= bit;
+        p = q;
     }
+    m0 = a0; m1 = a1;
     return dead;
 }
 
-// Warp-wide: the exact chain that enters the tile at byte offset entry0 (even, <= 32), as a bitmap of block starts in
-// shared memory.  Returns (all lanes) the chain's exit from the tile: byte offset into the next tile, or 0xFFFFFFFF if the
-// chain died; total = its block count.
-__device__ __forceinline__ uint32_t lgw_chain(const uint8_t* data, uint32_t* bitmap, const uint32_t entry0, const uint32_t tile_rel,
-                                              const uint32_t lane, uint32_t& total) {
-    constexpr uint32_t NONE = 0xFFFFFFFFu;
-    uint32_t bm[LGW_SEG_WORDS];
-#pragma unroll
-    for (int wd = 0; wd < LGW_SEG_WORDS; wd++) bm[wd] = 0;
-    const uint32_t seg0 = lane * LGW_SEG;
-    // Lane 0 knows where its chain starts.  The others guess -- but not blindly: a chain started anywhere falls in step
-    // with the true one within a few blocks, so the guess runs LGW_PRE bytes in front of the segment first (no marks, five
-    // instructions a block) and nearly always enters the segment where the true chain does: then the left neighbour's
-    // exit below confirms the entry and nothing has to be walked twice.
+// CTA-wide: the exact chain that enters the tile at byte offset entry0 (even, <= 32), as a bitmap of block starts in
+// shared memory (thread t owns words 2t, 2t+1).  Thread 0 knows where its chain starts.  The others guess -- but not
+// blindly: a chain started anywhere falls in step with the true one within a few blocks, so the guess runs LGW_PRE bytes
+// in front of the segment first (no marks, five instructions a block) and nearly always enters the segment where the
+// true chain does.  Then every thread takes its left neighbour's real exit as its entry: if that is what it guessed,
+// nothing is left to do; otherwise it re-walks only until it meets its own marks (self-synchronisation).  Repeated
+// until no entry changes.  Returns (all threads) the chain's exit from the tile -- byte offset into the next tile, or
+// LGW_NONE if the chain died -- and its block count in `total`.
+__device__ __forceinline__ uint32_t lgw_chain(const uint8_t* data, uint32_t* bitmap, uint32_t* sh_exit, uint32_t* sh_sums,
+                                              const uint32_t entry0, const uint32_t tile_rel, const uint32_t tid, uint32_t& total) {
+    const uint32_t seg0 = tid * (uint32_t)LGW_SEG;
     uint32_t p = entry0;
-    if (lane != 0) {
-        p = seg0 - (uint32_t)LGW_PRE;
+    if (tid != 0) {
+        p = seg0 > (uint32_t)LGW_PRE + entry0 ? seg0 - (uint32_t)LGW_PRE : entry0;
         while (p < seg0) p += leg_step(data[p]);
     }
-    uint32_t entry = p;                                  // tile-relative position where this lane's marked walk starts
-    bool dead = lgw_walk_segment<false>(data, lane, p, bm, tile_rel);
-    uint32_t exitv = dead ? NONE : p;                    // tile-relative position in the next segment (steps are <= 34 bytes)
+    uint32_t entry = p, m0 = 0, m1 = 0;
+    bool dead = lgw_walk_segment<false>(data, seg0, p, m0, m1, tile_rel);
+    uint32_t exitv = dead ? LGW_NONE : p;                // tile-relative position in the next segment (steps are <= 34 bytes)
     for (;;) {
-        uint32_t e = __shfl_up_sync(0xFFFFFFFFu, exitv, 1);
-        if (lane == 0) e = entry0;
+        sh_exit[tid] = exitv;
+        lgw_cta_sync();
+        const uint32_t e = tid == 0 ? entry0 : sh_exit[tid - 1];
         const bool upd = e != entry;
         if (upd) {
             entry = e;
-            if (e == NONE) {
-#pragma unroll
-                for (int wd = 0; wd < LGW_SEG_WORDS; wd++) bm[wd] = 0;
-                exitv = NONE;
-            } else {
+            if (e == LGW_NONE) { m0 = 0; m1 = 0; exitv = LGW_NONE; }
+            else {
                 p = e;
-                dead = lgw_walk_segment<true>(data, lane, p, bm, tile_rel);
-                if (dead) exitv = NONE;
+                dead = lgw_walk_segment<true>(data, seg0, p, m0, m1, tile_rel);
+                if (dead) exitv = LGW_NONE;
                 else if (p >= seg0 + (uint32_t)LGW_SEG) exitv = p;     // walked to the end without meeting the old chain
                 // else: merged -> the old exit stands
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, upd)) break;
+        if (!lgw_cta_any(upd)) break;                    // (a CTA barrier: every read of sh_exit above is done)
     }
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int wd = 0; wd < LGW_SEG_WORDS; wd++) { bitmap[lane * LGW_SEG_WORDS + wd] = bm[wd]; cnt += __popc(bm[wd]); }
+    bitmap[2 * tid] = m0;
+    bitmap[2 * tid + 1] = m1;
+    uint32_t cnt = __popc(m0) + __popc(m1);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+    if (LGW_WARPS > 1) {
+        if ((tid & 31u) == 0) sh_sums[tid >> 5] = cnt;
+        __syncthreads();
+        cnt = 0;
+#pragma unroll
+        for (int w = 0; w < LGW_WARPS; w++) cnt += sh_sums[w];
+    } else {
+        __syncwarp();
+    }
     total = cnt;
-    const uint32_t ex = __shfl_sync(0xFFFFFFFFu, exitv, 31);
-    __syncwarp();
-    return ex == NONE ? NONE : ex - (uint32_t)LGW_TILE;
+    const uint32_t ex = sh_exit[LGW_THREADS - 1];
+    lgw_cta_sync();                                      // sh_exit / sh_sums may be reused
+    return ex == LGW_NONE ? LGW_NONE : ex - (uint32_t)LGW_TILE;
 }
 
 // OR the 16 samples of the block at byte offset o (header nibble `bits`) into px[], at bit ADJ of each word (0: even-column
@@ -264,10 +270,7 @@ __device__ __forceinline__ void lgw_block(const uint32_t* __restrict__ d32, cons
     }
 }
 
-__device__ __forceinline__ void lgw_cta_sync() {
-    if (LGW_WARPS == 1) __syncwarp(); else __syncthreads();
-}
-
+template <bool EPI>
 __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __restrict__ frames, Result* __restrict__ results,
                                                              const LgWork* __restrict__ work, const uint32_t nwork,
                                                              uint32_t* __restrict__ counters, const uint32_t epoch) {
@@ -275,9 +278,10 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
     uint8_t* data = lg_smem;
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LGW_DATA);                     // [LGW_TILE_WORDS]
     uint32_t* lbmaps = bitmap + LGW_TILE_WORDS;                                             // look-back: [LGW_LB][LG_STATES]
+    uint32_t* sh_exit = lbmaps + LGW_LB * LG_STATES;                                        // chain walk: [LGW_THREADS]
     __shared__ __align__(8) unsigned long long bar_storage;
     __shared__ uint32_t sh_map[LG_STATES], sh_merge[LG_STATES], warp_sums[LGW_WARPS];
-    __shared__ uint32_t sh_ticket, sh_base, sh_skip;
+    __shared__ uint32_t sh_ticket, sh_base, sh_skip, sh_rewalk;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t bar = smem_u32(&bar_storage);
     if (tid == 0) {
@@ -334,11 +338,11 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
             lgw_cta_sync();
         }
 
+        // ---- 2. chain C0 (all threads), then the transfer map (warp 0)
+        uint32_t total0;
+        const uint32_t ex0 = lgw_chain(data, bitmap, sh_exit, warp_sums, 0u, tile_rel, tid, total0);
         if (warp == 0) {
-            // ---- 2. transfer map
-            uint32_t total0;
-            const uint32_t ex0 = lgw_chain(data, bitmap, 0u, tile_rel, lane, total0);
-            const uint32_t exit0 = (ex0 == 0xFFFFFFFFu || last_tile) ? LG_DEAD : ex0 >> 1;
+            const uint32_t exit0 = (ex0 == LGW_NONE || last_tile) ? LG_DEAD : ex0 >> 1;
             if (lane < LG_STATES) {
                 uint32_t q = 2u * lane, pre = 0, m = LG_NO_MERGE, ex = exit0, count;
                 bool d2 = false;
@@ -433,14 +437,14 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                 }
                 sh_base = base;
                 sh_skip = skip ? 1u : 0u;
+                sh_rewalk = 0;
             }
             // ---- 4. the bitmap for the true entry
             if (!skip && entry != 0) {
                 const uint32_t m = sh_merge[entry];
                 __syncwarp();
                 if (m == LG_NO_MERGE) {
-                    uint32_t t2;
-                    lgw_chain(data, bitmap, 2u * entry, tile_rel, lane, t2);       // blocks of one constant width: walk it again from its entry
+                    if (lane == 0) sh_rewalk = 2u * entry;                         // blocks of one constant width: see below
                 } else {
                     for (uint32_t w = lane; w < (m >> 5); w += 32) bitmap[w] = 0;  // C0's marks before the merge point go
                     __syncwarp();
@@ -458,15 +462,17 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
         lgw_cta_sync();
         if (sh_skip) continue;
         const uint32_t base = sh_base;
+        if (sh_rewalk) {                                      // the entry's chain never meets C0 in this tile: walk it from its entry
+            uint32_t t2;
+            lgw_chain(data, bitmap, sh_exit, warp_sums, sh_rewalk, tile_rel, tid, t2);
+        }
 
         // ---- 5. decode: ordinal of the first block start in this thread's part of the stream, then the pairs led from
         //      there.  Block starts with an even ordinal lead a pair (even-column block, then odd-column block, :480-481);
         //      the partner's start is the next mark -- here or in the next thread's part, where it has an odd ordinal and
         //      is dropped.
-        uint32_t wv[LGW_DEC_WORDS];
-        uint32_t c = 0;
-#pragma unroll
-        for (int i = 0; i < LGW_DEC_WORDS; i++) { wv[i] = bitmap[tid * LGW_DEC_WORDS + i]; c += __popc(wv[i]); }
+        const uint32_t wv0 = bitmap[2 * tid], wv1 = bitmap[2 * tid + 1];
+        const uint32_t c = __popc(wv0) + __popc(wv1);
         uint32_t incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -484,21 +490,19 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
         const uint32_t ord0 = base + before + incl - c;
         uint32_t P = (ord0 >> 1) + (ord0 & 1u);                                  // ordinal of the first pair led here
         uint32_t y = P / ppr, xq = P - y * ppr;
-        bool drop = (ord0 & 1u) != 0u;                                           // the first mark is a partner: not a leader
+        const bool drop = (ord0 & 1u) != 0u;                                     // the first mark is a partner: not a leader
         const int width = F.width;
         uint16_t* __restrict__ dst = F.dst;
         const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
-        const unsigned epi = F.epi_mode;
-#pragma unroll
-        for (int g = 0; g < LGW_DEC_WORDS / 2; g++) {
-            unsigned long long marks = (unsigned long long)wv[2 * g] | ((unsigned long long)wv[2 * g + 1] << 32);
-            if (drop && marks) { marks &= marks - 1; drop = false; }
+        const unsigned epi = EPI ? F.epi_mode : 0u;       // EPI = false: the epilogue code is not even in the kernel
+        {
+            unsigned long long marks = (unsigned long long)wv0 | ((unsigned long long)wv1 << 32);
+            if (drop && marks) marks &= marks - 1;
             while (marks && P < need_pairs) {
                 const uint32_t bpos = (uint32_t)__ffsll((long long)marks) - 1u;
                 marks &= marks - 1;                                                   // the leader ...
-                if (marks) marks &= marks - 1;                                        // ... and its partner, if it starts in this group
-                else drop = true;                                                     // else it is the first mark of the next group / thread
-                const uint32_t oE = 64u * (uint32_t)LGW_DEC_WORDS * tid + 128u * g + 2u * bpos;
+                marks &= marks - 1;                                                   // ... and its partner, if it starts in this segment
+                const uint32_t oE = (uint32_t)LGW_SEG * tid + 2u * bpos;
                 const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
                 const uint32_t oO = oE + 2u + leg_len(bitsE);
                 const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
