@@ -43,22 +43,26 @@ namespace mcraw {
 #endif
 constexpr int LGW_WARPS = MCRAW_LGW_WARPS;     // warps per CTA
 constexpr int LGW_THREADS = 32 * LGW_WARPS;
-constexpr int LGW_SEG = 128;                   // bytes of the tile a thread owns: 64 candidate block starts = two bitmap words
-constexpr int LGW_TILE = LGW_THREADS * LGW_SEG;   // bytes per tile (one CTA at a time): 16 KiB for four warps
-constexpr int LGW_TILE_WORDS = LGW_TILE / 64;  // bitmap words: one bit per even offset
-constexpr int LGW_PRE = 192;                   // bytes a thread's guessed chain runs in front of its segment to fall in step
+constexpr int LGW_SEG = 124;                   // bytes of the tile a thread owns: 62 candidate block starts, two words of marks.
+                                               // NOT a multiple of 128: threads at the same offset of their segments hit 32
+                                               // different shared-memory banks (the walks are byte loads at thread * LGW_SEG + d)
+constexpr int LGW_TILE = LGW_THREADS * LGW_SEG;   // bytes per tile (one CTA at a time): 15 872 for four warps
+constexpr int LGW_PRE = LGW_SEG;               // bytes a thread's guessed chain runs in front of its segment to fall in step
+constexpr int LGW_PAIR_CHUNK = 1024;           // pairs listed and decoded per pass (a tile holds ~700 for typical images,
+                                               // up to LGW_TILE / 4 when every block is 2 bytes: then several passes)
 constexpr int LG_STATES = 17;                  // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;               // exit code of a chain that ran into the end of the buffer
 constexpr uint32_t LG_NO_MERGE = 0xFFFFu;      // merge point of an entry whose chain never meets C0 inside the tile
 constexpr int LG_OVERRUN = 80;                 // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it (+ word reads)
 constexpr int LGW_DATA = LGW_TILE + LG_OVERRUN;
 constexpr int LGW_LB = 32;                     // look-back window: status words read per poll
-constexpr int LGW_SMEM = LGW_DATA + LGW_TILE_WORDS * 4 + LGW_LB * LG_STATES * 4 + LGW_THREADS * 4;
+constexpr int LGW_SMEM = LGW_DATA + LGW_THREADS * 8 /*marks*/ + LGW_LB * LG_STATES * 4 + LGW_THREADS * 4 /*exits, prefix*/ + LGW_PAIR_CHUNK * 2;
 constexpr uint32_t LGW_ST_LOCAL = 1u, LGW_ST_INCL = 2u;
 constexpr uint32_t LGW_ERR_BIT = 1u << 5;      // sticky: a wait gave up somewhere up the chain
 constexpr uint32_t LGW_SPIN_LIMIT = 1u << 18;  // polls of ~0.2 us: a wait that long means something is broken, not slow
 constexpr uint32_t LGW_NONE = 0xFFFFFFFFu;     // "no chain arrives here" (it ended at an undecodable block)
-static_assert(LGW_DATA % 16 == 0, "bulk copies work in 16-byte granules");
+static_assert(LGW_DATA % 16 == 0 && LGW_TILE % 16 == 0, "bulk copies work in 16-byte granules");
+static_assert(LGW_SEG % 2 == 0 && LGW_SEG / 2 <= 64 && LGW_SEG >= 34, "two words of marks per segment; a block never skips a segment");
 
 struct LgWork { uint32_t frame, tile; };
 
@@ -187,22 +191,48 @@ __device__ __forceinline__ uint32_t lgw_chain(const uint8_t* data, uint32_t* bit
     }
     bitmap[2 * tid] = m0;
     bitmap[2 * tid + 1] = m1;
-    uint32_t cnt = __popc(m0) + __popc(m1);
+    // exclusive prefix of the block counts per segment (kept in sh_exit for lgw_marks_before) and the total
+    const uint32_t c = __popc(m0) + __popc(m1);
+    uint32_t incl = c;
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
-    if (LGW_WARPS > 1) {
-        if ((tid & 31u) == 0) sh_sums[tid >> 5] = cnt;
-        __syncthreads();
-        cnt = 0;
-#pragma unroll
-        for (int w = 0; w < LGW_WARPS; w++) cnt += sh_sums[w];
-    } else {
-        __syncwarp();
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((tid & 31u) >= (uint32_t)d) incl += o;
     }
-    total = cnt;
     const uint32_t ex = sh_exit[LGW_THREADS - 1];
-    lgw_cta_sync();                                      // sh_exit / sh_sums may be reused
+    uint32_t before = 0, all = incl;
+    if (LGW_WARPS > 1) {
+        if ((tid & 31u) == 31u) sh_sums[tid >> 5] = incl;
+        __syncthreads();
+        all = 0;
+#pragma unroll
+        for (int w = 0; w < LGW_WARPS; w++) {
+            const uint32_t v = sh_sums[w];
+            if ((uint32_t)w < (tid >> 5)) before += v;
+            all += v;
+        }
+    } else {
+        all = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        __syncwarp();                                    // every lane has read the last exit
+    }
+    sh_exit[tid] = before + incl - c;
+    total = all;
+    lgw_cta_sync();
     return ex == LGW_NONE ? LGW_NONE : ex - (uint32_t)LGW_TILE;
+}
+
+// marks are kept per segment: words 2s, 2s+1 hold the block starts of segment s, one bit per even offset from its start
+__device__ __forceinline__ bool lgw_marked(const uint32_t* bitmap, const uint32_t q) {
+    const uint32_t seg = q / (uint32_t)LGW_SEG, pos = (q - seg * (uint32_t)LGW_SEG) >> 1;
+    return (bitmap[2u * seg + (pos >> 5)] >> (pos & 31u)) & 1u;
+}
+// marked block starts in front of tile-relative position q (prefix: lgw_chain's per-segment counts)
+__device__ __forceinline__ uint32_t lgw_marks_before(const uint32_t* bitmap, const uint32_t* prefix, const uint32_t q) {
+    const uint32_t seg = q / (uint32_t)LGW_SEG, pos = (q - seg * (uint32_t)LGW_SEG) >> 1;
+    uint32_t n = prefix[seg];
+    if (pos >= 32u) n += __popc(bitmap[2u * seg]) + __popc(bitmap[2u * seg + 1] & ((1u << (pos - 32u)) - 1u));
+    else n += __popc(bitmap[2u * seg] & ((1u << pos) - 1u));
+    return n;
 }
 
 // OR the 16 samples of the block at byte offset o (header nibble `bits`) into px[], at bit ADJ of each word (0: even-column
@@ -276,9 +306,10 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                                                              uint32_t* __restrict__ counters, const uint32_t epoch) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     uint8_t* data = lg_smem;
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LGW_DATA);                     // [LGW_TILE_WORDS]
-    uint32_t* lbmaps = bitmap + LGW_TILE_WORDS;                                             // look-back: [LGW_LB][LG_STATES]
-    uint32_t* sh_exit = lbmaps + LGW_LB * LG_STATES;                                        // chain walk: [LGW_THREADS]
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LGW_DATA);                     // marks: two words per segment
+    uint32_t* lbmaps = bitmap + 2 * LGW_THREADS;                                            // look-back: [LGW_LB][LG_STATES]
+    uint32_t* sh_exit = lbmaps + LGW_LB * LG_STATES;                                        // chain walk: exits, then the count prefix
+    uint16_t* plist = reinterpret_cast<uint16_t*>(sh_exit + LGW_THREADS);                   // pair list: [LGW_PAIR_CHUNK]
     __shared__ __align__(8) unsigned long long bar_storage;
     __shared__ uint32_t sh_map[LG_STATES], sh_merge[LG_STATES], warp_sums[LGW_WARPS];
     __shared__ uint32_t sh_ticket, sh_base, sh_skip, sh_rewalk;
@@ -350,17 +381,15 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                 else {
                     for (;;) {
                         if (q >= (uint32_t)LGW_TILE) { ex = (q - LGW_TILE) >> 1; break; }               // never met C0 in this tile
-                        if ((bitmap[q >> 6] >> ((q >> 1) & 31u)) & 1u) { m = q >> 1; break; }
+                        if (lgw_marked(bitmap, q)) { m = q >> 1; break; }
                         const uint32_t nq = q + leg_step(data[q]);
                         if (nq >= tile_rel) { d2 = true; break; }
                         q = nq;
                         pre++;
                     }
                     if (m != LG_NO_MERGE) {
-                        uint32_t before = 0;                    // blocks of C0 from the merge point on = total0 - (marks before it)
-                        for (uint32_t w = 0; w < (m >> 5); w++) before += __popc(bitmap[w]);
-                        before += __popc(bitmap[m >> 5] & ((1u << (m & 31u)) - 1u));
-                        count = pre + total0 - before;
+                        // blocks of C0 from the merge point on = total0 - (marks before it)
+                        count = pre + total0 - lgw_marks_before(bitmap, sh_exit, 2u * m);
                     } else {
                         count = pre;
                         if (d2 || last_tile) ex = LG_DEAD;
@@ -446,13 +475,16 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                 if (m == LG_NO_MERGE) {
                     if (lane == 0) sh_rewalk = 2u * entry;                         // blocks of one constant width: see below
                 } else {
-                    for (uint32_t w = lane; w < (m >> 5); w += 32) bitmap[w] = 0;  // C0's marks before the merge point go
+                    const uint32_t mseg = (2u * m) / (uint32_t)LGW_SEG, mpos = (2u * m - mseg * (uint32_t)LGW_SEG) >> 1;
+                    for (uint32_t w = lane; w < 2u * mseg; w += 32) bitmap[w] = 0;   // C0's marks before the merge point go
                     __syncwarp();
                     if (lane == 0) {
-                        bitmap[m >> 5] &= ~((1u << (m & 31u)) - 1u);
+                        if (mpos >= 32u) { bitmap[2u * mseg] = 0; bitmap[2u * mseg + 1] &= ~((1u << (mpos - 32u)) - 1u); }
+                        else bitmap[2u * mseg] &= ~((1u << mpos) - 1u);
                         uint32_t p = 2u * entry;
                         while (p < 2u * m) {
-                            bitmap[p >> 6] |= 1u << ((p >> 1) & 31u);
+                            const uint32_t sg = p / (uint32_t)LGW_SEG, ps = (p - sg * (uint32_t)LGW_SEG) >> 1;
+                            bitmap[2u * sg + (ps >> 5)] |= 1u << (ps & 31u);
                             p += leg_step(data[p]);
                         }
                     }
@@ -467,10 +499,10 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
             lgw_chain(data, bitmap, sh_exit, warp_sums, sh_rewalk, tile_rel, tid, t2);
         }
 
-        // ---- 5. decode: ordinal of the first block start in this thread's part of the stream, then the pairs led from
-        //      there.  Block starts with an even ordinal lead a pair (even-column block, then odd-column block, :480-481);
-        //      the partner's start is the next mark -- here or in the next thread's part, where it has an odd ordinal and
-        //      is dropped.
+        // ---- 5. pair list of the tile: every block with an even ordinal leads a pair (even-column block, then odd-column
+        //      block, RawData_Legacy.cpp:480-481); plist[q] = (tile-relative offset of the leader) / 2 for pair ordinal
+        //      p_first + q.  Ordinals come from prefix popcounts of the marks.  Consecutive lanes then decode consecutive
+        //      pairs: their reads of the staged tile are a few words apart (different banks), their stores adjacent.
         const uint32_t wv0 = bitmap[2 * tid], wv1 = bitmap[2 * tid + 1];
         const uint32_t c = __popc(wv0) + __popc(wv1);
         uint32_t incl = c;
@@ -479,30 +511,46 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= (uint32_t)d) incl += o;
         }
-        uint32_t before = 0;
+        uint32_t before = 0, total = incl;
         if (LGW_WARPS > 1) {
             if (lane == 31) warp_sums[warp] = incl;
             __syncthreads();
+            total = 0;
 #pragma unroll
-            for (int w = 0; w < LGW_WARPS; w++)
-                if ((uint32_t)w < warp) before += warp_sums[w];
+            for (int w = 0; w < LGW_WARPS; w++) {
+                const uint32_t v = warp_sums[w];
+                if ((uint32_t)w < warp) before += v;
+                total += v;
+            }
+        } else {
+            total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        const uint32_t ord0 = base + before + incl - c;
-        uint32_t P = (ord0 >> 1) + (ord0 & 1u);                                  // ordinal of the first pair led here
-        uint32_t y = P / ppr, xq = P - y * ppr;
-        const bool drop = (ord0 & 1u) != 0u;                                     // the first mark is a partner: not a leader
+        const uint32_t p_first = (base + 1u) >> 1;
+        uint32_t npairs = ((base + total + 1u) >> 1) - p_first;
+        npairs = min(npairs, need_pairs > p_first ? need_pairs - p_first : 0u);
+        const uint32_t ord0 = base + before + incl - c;          // ordinal of the first block start in this thread's segment
         const int width = F.width;
         uint16_t* __restrict__ dst = F.dst;
         const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
-        const unsigned epi = EPI ? F.epi_mode : 0u;       // EPI = false: the epilogue code is not even in the kernel
-        {
-            unsigned long long marks = (unsigned long long)wv0 | ((unsigned long long)wv1 << 32);
-            if (drop && marks) marks &= marks - 1;
-            while (marks && P < need_pairs) {
-                const uint32_t bpos = (uint32_t)__ffsll((long long)marks) - 1u;
-                marks &= marks - 1;                                                   // the leader ...
-                marks &= marks - 1;                                                   // ... and its partner, if it starts in this segment
-                const uint32_t oE = (uint32_t)LGW_SEG * tid + 2u * bpos;
+        const unsigned epi = EPI ? F.epi_mode : 0u;             // EPI = false: the epilogue code is not even in the kernel
+        for (uint32_t c0 = 0; c0 < npairs; c0 += LGW_PAIR_CHUNK) {
+            const uint32_t cn = min((uint32_t)LGW_PAIR_CHUNK, npairs - c0);
+            {
+                uint32_t ord = ord0;
+                unsigned long long marks = (unsigned long long)wv0 | ((unsigned long long)wv1 << 32);
+                while (marks) {
+                    const uint32_t b = (uint32_t)__ffsll((long long)marks) - 1u;
+                    marks &= marks - 1;
+                    const uint32_t q = (ord >> 1) - p_first - c0;       // wraps to a huge value for earlier passes' pairs
+                    if (!(ord & 1u) && q < cn) plist[q] = (uint16_t)(((uint32_t)LGW_SEG / 2u) * tid + b);
+                    ord++;
+                }
+            }
+            lgw_cta_sync();
+            uint32_t P = p_first + c0 + tid;
+            uint32_t y = P / ppr, xq = P - y * ppr;
+            for (uint32_t q = tid; q < cn; q += LGW_THREADS) {
+                const uint32_t oE = 2u * (uint32_t)plist[q];
                 const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
                 const uint32_t oO = oE + 2u + leg_len(bitsE);
                 const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
@@ -531,9 +579,10 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                         if (x + 2 * i + 1 < width) orow[2 * i + 1] = (uint16_t)(px[i] >> 16);
                     }
                 }
-                P++;
-                if (++xq == ppr) { xq = 0; y++; }
+                xq += LGW_THREADS;                                                            // the pair LGW_THREADS further on
+                while (xq >= ppr) { xq -= ppr; y++; }
             }
+            lgw_cta_sync();
         }
     }
     // the last CTA to leave resets the ticket counters for the next launch
