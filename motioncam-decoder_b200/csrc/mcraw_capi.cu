@@ -298,11 +298,12 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, const mcraw_levels* l
             if (d.len >= ((uint64_t)1 << 40)) return fail_arg(ctx, who() + ": legacy frame buffer too large");
             const uint64_t ntile = std::max<uint64_t>(1, (d.len + LGW_TILE - 1) / LGW_TILE);
             if (ntile > 0x7FFFFFFFull) return fail_arg(ctx, who() + ": legacy frame buffer too large");
-            // scratch layout (offsets for now): transfer maps | look-back status words of every tile
+            // scratch layout (offsets for now): exit maps (written only by tiles whose 17 exits differ) | two look-back
+            // status words per tile (count word, exit word)
             f.lg_tilemap = reinterpret_cast<uint32_t*>(scratch);
             scratch += ((size_t)ntile * LG_STATES * 4 + 15) & ~(size_t)15;
             f.lg_status = reinterpret_cast<unsigned long long*>(scratch);
-            scratch += ((size_t)ntile * 8 + 15) & ~(size_t)15;
+            scratch += (size_t)ntile * 16;
             scratch = (scratch + 127) & ~(size_t)127;
             max_ltiles = std::max<uint32_t>(max_ltiles, (uint32_t)ntile);
         }   // any other type: no work is queued, mcraw_batch_wait reports MCRAW_FRAME_BAD_TYPE

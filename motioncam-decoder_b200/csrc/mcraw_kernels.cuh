@@ -53,8 +53,8 @@ struct FrameDev {
     unsigned epi_range2[2];        // per row parity: white - black, packed the same way
     float epi_blackf[4];           // black level per CFA position (row parity * 2 + column parity)
     float epi_scalef[4];           // 1 / (white - black)
-    uint32_t* lg_tilemap;          // legacy scratch [tiles][17]   transfer map of every tile: exit | blocks << 5
-    unsigned long long* lg_status; // legacy scratch [tiles]       epoch-tagged look-back status of every tile (k_legacy_warp)
+    uint32_t* lg_tilemap;          // legacy scratch [tiles][17]   exit of every entry, for tiles whose exits differ (k_legacy_warp)
+    unsigned long long* lg_status; // legacy scratch [tiles][2]    epoch-tagged look-back words of every tile: count, exit
 };
 
 // Per-frame words written by the index kernels and read by the pixel kernels.  Every word is written on every path

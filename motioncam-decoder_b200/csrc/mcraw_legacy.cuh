@@ -5,34 +5,35 @@
 // (bits nibble, 12-bit reference) followed by 2*bits payload bytes (32 for nibbles 11..15): block k+1 starts
 // where block k ends, so the reference finds the blocks with 750 000 dependent steps per 4000x3000 frame.
 //
-// Here the chain is resolved in parallel, in ONE pass over the stream.  Two facts carry it:
-//   (1) all block lengths are even and <= 34 bytes, so the chain enters any fixed byte range at one of 17 even offsets;
-//   (2) two chains that ever share a block start are identical from there on, and with blocks of varying length chains
-//       started anywhere MERGE within a few blocks.  Nothing relies on (2) for correctness -- only for speed.
+// Here the chain is resolved in parallel, EXACTLY and in ONE pass over the stream.  What carries it: all block lengths
+// are even and <= 34 bytes, so a chain enters any fixed byte range at one of 17 even offsets -- the effect of a byte
+// range on the chain is a map  entry (17 values) -> exit (17 values), maps compose, and the map of a short range is
+// cheap to compute for ALL entries at once by going through its candidate block starts backwards.
 //
-// k_legacy_warp: one WARP per CTA, up to 32 CTAs per SM, persistent.  Warps take (frame, tile) tickets in a host-built
-// order (tile index major, frame minor: neighbouring tickets belong to different frames, so every frame's chain only has
-// to advance a few tiles per generation of warps).  A tile is 32 segments, one per lane.  Per tile:
+// k_legacy_warp: persistent CTAs of LGW_THREADS threads take (frame, tile) tickets in a host-built order (tile index
+// major, frame minor: neighbouring tickets belong to different frames).  A tile is one segment of LGW_SEG bytes per
+// thread.  Per tile:
 //   1. stage the tile (+ overrun) with ONE bulk copy (cp.async.bulk, TMA 1-D, mbarrier transaction count) -- the only
-//      time the stream is read;
-//   2. chain C0 (tile entry offset 0): every lane walks a GUESSED chain from the start of its segment and marks its block
-//      starts in a bitmap; then every lane re-walks from where its left neighbour's chain actually ends, only until it
-//      meets its own marks (self-synchronisation), repeated until no entry changes.  The other 16 possible entry offsets
-//      walk until they meet C0: the tile's transfer map  entry -> (exit offset, block count);
-//   3. publish the map (LOCAL), then DECOUPLED LOOK-BACK over the previous tiles of the frame: the nearest predecessor
-//      whose inclusive state (exit offset, blocks so far) is known, composed with the maps of the tiles in between
-//      (a window of status words per poll; one lane chases the concrete entry state through the staged maps);
-//      publish this tile's inclusive state (INCL) right away, so that successors can go on;
-//   4. patch the bitmap for the true entry (the few blocks before the merge point; a chain that never meets C0 --
-//      blocks of one constant width -- is re-walked from its entry);
-//   5. a prefix popcount gives every lane the ordinal of the first block start in ITS segment; it decodes the block PAIRS
-//      led from there (even-column block + odd-column block, :480-481) straight from shared memory: MSB-first bit
-//      extraction with rotates (:38-370), + reference mod 2^16, column interleave (:483-486) in registers, 16-byte
-//      stores, crop at width (:490).
-// No CTA-wide barrier anywhere: a warp never waits for another warp of its SM, only (bounded) for the status words of
-// earlier tickets, whose owners are resident and never wait for a later ticket -- so the waits always end; they are
-// bounded all the same (MCRAW_FRAME_INTERNAL instead of a hang).  Status words carry the launch epoch of the slot,
-// so nothing has to be zeroed between launches.
+//      time the stream is read; the tile of the ticket one grid further on is prefetched into L2;
+//   2. every thread: exit table of its segment.  For candidate block start c (even offsets, last to first)
+//      exit[c] = exit[c + length of the block whose header sits at c]; positions past the segment are their own exit.
+//      62 uniform steps, no guessing, no divergence; the first 17 entries are the segment's map;
+//   3. 17 lanes of every warp chase the 17 possible entries through the warp's 32 segment maps and leave, per segment,
+//      the entry each of them arrives with; composing the warps' maps gives the tile's map  entry -> exit;
+//   4. exits across tiles: nearly always the 17 exits of a tile are one value (chains started anywhere fall in step
+//      within a few hundred bytes), so the tile publishes "exit X whatever the entry" and its successor knows its entry
+//      after ONE hop -- no dependency chain across tiles.  Otherwise (runs of one constant block length) the tile
+//      publishes its map and, once it knows its own entry, its actual exit; successors compose the maps back to the
+//      nearest known exit;
+//   5. with its exact entry every thread walks its segment once: block starts (a bitmap in two registers) and their count;
+//      the tile's count goes through a plain DECOUPLED LOOK-BACK prefix sum over the tiles of the frame (aggregate /
+//      inclusive words): block ordinals give pair parity and the output position (:478-482);
+//   6. pair list from the bitmaps (even-ordinal block + the block behind it, :480-481), then consecutive threads decode
+//      consecutive pairs straight from shared memory: MSB-first bit extraction with rotates (:38-370), + reference
+//      mod 2^16, column interleave (:483-486) in registers, 16-byte stores, crop at width (:490).
+// Waits are only ever for the status words of EARLIER tickets, whose owners are resident or done and never wait for a
+// later ticket -- so they end; they are bounded all the same (MCRAW_FRAME_INTERNAL instead of a hang).  Status words
+// carry the launch epoch of the slot, so nothing has to be zeroed between launches.
 #pragma once
 #include "mcraw_kernels.cuh"
 
@@ -44,25 +45,29 @@ namespace mcraw {
 constexpr int LGW_WARPS = MCRAW_LGW_WARPS;     // warps per CTA
 constexpr int LGW_THREADS = 32 * LGW_WARPS;
 constexpr int LGW_SEG = 124;                   // bytes of the tile a thread owns: 62 candidate block starts, two words of marks.
-                                               // NOT a multiple of 128: threads at the same offset of their segments hit 32
-                                               // different shared-memory banks (the walks are byte loads at thread * LGW_SEG + d)
+                                               // 31 words: threads at the same offset of their segments hit 32 different banks
+constexpr int LGW_NC = LGW_SEG / 2;            // candidate block starts per segment
 constexpr int LGW_TILE = LGW_THREADS * LGW_SEG;   // bytes per tile (one CTA at a time): 15 872 for four warps
-constexpr int LGW_PRE = LGW_SEG;               // bytes a thread's guessed chain runs in front of its segment to fall in step
+constexpr int LGW_TAB = 84;                    // bytes of exit table per thread: LGW_NC candidates + 17 positions behind the segment
+                                               // (+ pad); 21 words, odd, for the same reason
+constexpr int LGW_ENT = 32;                    // table offset of the 17 entries a segment is reached with (one per warp entry):
+                                               // candidates 17.. of the table are dead once the segment's map is complete
 constexpr int LGW_PAIR_CHUNK = 1024;           // pairs listed and decoded per pass (a tile holds ~700 for typical images,
                                                // up to LGW_TILE / 4 when every block is 2 bytes: then several passes)
 constexpr int LG_STATES = 17;                  // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;               // exit code of a chain that ran into the end of the buffer
-constexpr uint32_t LG_NO_MERGE = 0xFFFFu;      // merge point of an entry whose chain never meets C0 inside the tile
 constexpr int LG_OVERRUN = 80;                 // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it (+ word reads)
 constexpr int LGW_DATA = LGW_TILE + LG_OVERRUN;
 constexpr int LGW_LB = 32;                     // look-back window: status words read per poll
-constexpr int LGW_SMEM = LGW_DATA + LGW_THREADS * 8 /*marks*/ + LGW_LB * LG_STATES * 4 + LGW_THREADS * 4 /*exits, prefix*/ + LGW_PAIR_CHUNK * 2;
-constexpr uint32_t LGW_ST_LOCAL = 1u, LGW_ST_INCL = 2u;
+constexpr int LGW_SMEM = LGW_DATA + LGW_THREADS * LGW_TAB;      // the pair list reuses the tables
+constexpr uint32_t LGW_ST_AGG = 1u, LGW_ST_INCL = 2u;          // count words: this tile's blocks / all blocks up to its end
+constexpr uint32_t LGW_EX_CONV = 1u, LGW_EX_MAP = 2u, LGW_EX_FINAL = 3u;   // exit words, see 4. above
 constexpr uint32_t LGW_ERR_BIT = 1u << 5;      // sticky: a wait gave up somewhere up the chain
 constexpr uint32_t LGW_SPIN_LIMIT = 1u << 18;  // polls of ~0.2 us: a wait that long means something is broken, not slow
-constexpr uint32_t LGW_NONE = 0xFFFFFFFFu;     // "no chain arrives here" (it ended at an undecodable block)
 static_assert(LGW_DATA % 16 == 0 && LGW_TILE % 16 == 0, "bulk copies work in 16-byte granules");
-static_assert(LGW_SEG % 2 == 0 && LGW_SEG / 2 <= 64 && LGW_SEG >= 34, "two words of marks per segment; a block never skips a segment");
+static_assert(LGW_SEG % 4 == 0 && LGW_NC <= 64 && LGW_SEG >= 34, "two words of marks per segment; a block never skips a segment");
+static_assert(LGW_NC + LG_STATES <= LGW_TAB && LGW_ENT >= LG_STATES && LGW_ENT + LG_STATES <= LGW_NC && LGW_TAB % 4 == 0, "exit table layout");
+static_assert(LGW_PAIR_CHUNK * 2 <= LGW_THREADS * LGW_TAB, "the pair list reuses the tables");
 
 struct LgWork { uint32_t frame, tile; };
 
@@ -99,9 +104,14 @@ __device__ __forceinline__ void lg_stage_tail(uint8_t* sm, const uint8_t* __rest
     }
 }
 
-// status word of a tile: blocks up to the end of the tile << 32 | epoch (24 bits) << 8 | state << 6 | error << 5 | exit offset / 2
+// status words of a tile (two per tile: [2 * tile] count word, [2 * tile + 1] exit word):
+//   value << 32 | epoch (24 bits) << 8 | state << 6 | error << 5 | exit offset / 2
 __device__ __forceinline__ unsigned long long lgw_pack(uint32_t count, uint32_t epoch, uint32_t st, uint32_t low6) {
     return ((unsigned long long)count << 32) | ((unsigned long long)(epoch & 0xFFFFFFu) << 8) | (st << 6) | low6;
+}
+__device__ __forceinline__ uint32_t lgw_state(const unsigned long long w, const uint32_t epoch) {
+    const uint32_t lo32 = (uint32_t)w;
+    return ((lo32 >> 8) & 0xFFFFFFu) == (epoch & 0xFFFFFFu) ? (lo32 >> 6) & 3u : 0u;
 }
 __device__ __forceinline__ void lgw_store_relaxed(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
@@ -115,124 +125,48 @@ __device__ __forceinline__ unsigned long long lgw_load_acquire(const unsigned lo
     return v;
 }
 
-__device__ __forceinline__ void lgw_cta_sync() {
-    if (LGW_WARPS == 1) __syncwarp(); else __syncthreads();
-}
-__device__ __forceinline__ bool lgw_cta_any(const bool v) {
-    if (LGW_WARPS == 1) return __any_sync(0xFFFFFFFFu, v) != 0;
-    return __syncthreads_or(v ? 1 : 0) != 0;
-}
-
 // One thread, its segment [seg0, seg0 + LGW_SEG) of the staged tile: walk from tile-relative byte offset p to the end of the
-// segment.  Block starts go into (m0, m1): one bit per even offset.  With MERGE the walk stops at the first position
-// already marked -- from there on the old marks are this chain's own -- and older marks before it are dropped.
-// rel: bytes from the tile start to the end of the buffer (a block is decoded only if it ends before the last byte,
-// RawData_Legacy.cpp:387,398).  Returns true if the chain ended at an undecodable block.
-template <bool MERGE>
-__device__ __forceinline__ bool lgw_walk_segment(const uint8_t* data, const uint32_t seg0, uint32_t& p, uint32_t& m0, uint32_t& m1, const uint32_t rel) {
-    const uint32_t old0 = m0, old1 = m1;
+// segment; block starts go into (m0, m1), one bit per even offset.  rel: bytes from the tile start to the end of the buffer
+// (a block is decoded only if it ends before the last byte, RawData_Legacy.cpp:387,398); the chain stops at the first
+// block that is not.
+__device__ __forceinline__ void lgw_walk_segment(const uint8_t* data, const uint32_t seg0, uint32_t p, uint32_t& m0, uint32_t& m1, const uint32_t rel) {
     uint32_t a0 = 0, a1 = 0;
-    bool dead = false;
     const uint32_t end = seg0 + (uint32_t)LGW_SEG;
     while (p < end) {
-        const uint32_t pos = (p - seg0) >> 1;                         // 0 .. 63
-        const uint32_t bit = 1u << (pos & 31u);
-        const bool hi = pos >= 32u;
-        if (MERGE && ((hi ? old1 : old0) & bit)) {                    // met the old chain: its marks from here on stay
-            if (hi) a1 |= old1 & ~(bit - 1u);
-            else { a0 |= old0 & ~(bit - 1u); a1 = old1; }
-            break;
-        }
+        const uint32_t pos = (p - seg0) >> 1;                         // 0 .. 61
         const uint32_t q = p + leg_step(data[p]);
-        if (q >= rel) { dead = true; break; }
-        if (hi) a1 |= bit; else a0 |= bit;
+        if (q >= rel) break;
+        if (pos >= 32u) a1 |= 1u << (pos - 32u); else a0 |= 1u << pos;
         p = q;
     }
     m0 = a0; m1 = a1;
-    return dead;
 }
 
-// CTA-wide: the exact chain that enters the tile at byte offset entry0 (even, <= 32), as a bitmap of block starts in
-// shared memory (thread t owns words 2t, 2t+1).  Thread 0 knows where its chain starts.  The others guess -- but not
-// blindly: a chain started anywhere falls in step with the true one within a few blocks, so the guess runs LGW_PRE bytes
-// in front of the segment first (no marks, five instructions a block) and nearly always enters the segment where the
-// true chain does.  Then every thread takes its left neighbour's real exit as its entry: if that is what it guessed,
-// nothing is left to do; otherwise it re-walks only until it meets its own marks (self-synchronisation).  Repeated
-// until no entry changes.  Returns (all threads) the chain's exit from the tile -- byte offset into the next tile, or
-// LGW_NONE if the chain died -- and its block count in `total`.
-__device__ __forceinline__ uint32_t lgw_chain(const uint8_t* data, uint32_t* bitmap, uint32_t* sh_exit, uint32_t* sh_sums,
-                                              const uint32_t entry0, const uint32_t tile_rel, const uint32_t tid, uint32_t& total) {
-    const uint32_t seg0 = tid * (uint32_t)LGW_SEG;
-    uint32_t p = entry0;
-    if (tid != 0) {
-        p = seg0 > (uint32_t)LGW_PRE + entry0 ? seg0 - (uint32_t)LGW_PRE : entry0;
-        while (p < seg0) p += leg_step(data[p]);
-    }
-    uint32_t entry = p, m0 = 0, m1 = 0;
-    bool dead = lgw_walk_segment<false>(data, seg0, p, m0, m1, tile_rel);
-    uint32_t exitv = dead ? LGW_NONE : p;                // tile-relative position in the next segment (steps are <= 34 bytes)
-    for (;;) {
-        sh_exit[tid] = exitv;
-        lgw_cta_sync();
-        const uint32_t e = tid == 0 ? entry0 : sh_exit[tid - 1];
-        const bool upd = e != entry;
-        if (upd) {
-            entry = e;
-            if (e == LGW_NONE) { m0 = 0; m1 = 0; exitv = LGW_NONE; }
-            else {
-                p = e;
-                dead = lgw_walk_segment<true>(data, seg0, p, m0, m1, tile_rel);
-                if (dead) exitv = LGW_NONE;
-                else if (p >= seg0 + (uint32_t)LGW_SEG) exitv = p;     // walked to the end without meeting the old chain
-                // else: merged -> the old exit stands
-            }
-        }
-        if (!lgw_cta_any(upd)) break;                    // (a CTA barrier: every read of sh_exit above is done)
-    }
-    bitmap[2 * tid] = m0;
-    bitmap[2 * tid + 1] = m1;
-    // exclusive prefix of the block counts per segment (kept in sh_exit for lgw_marks_before) and the total
-    const uint32_t c = __popc(m0) + __popc(m1);
-    uint32_t incl = c;
+// One thread: the exit table of its segment.  T[c], c = 0 .. LGW_NC - 1: where the chain that has a block start at byte
+// 2c of the segment enters the next segment (half offset 0 .. 16), or LG_DEAD if it ends at a block that cannot be decoded.
+// dw: the segment as words.  TAIL: the buffer may end inside or right behind the tile (rel as above, seg0 = the segment's
+// tile-relative offset); interior tiles skip that test.
+template <bool TAIL>
+__device__ __forceinline__ void lgw_exit_table(const uint32_t* __restrict__ dw, uint8_t* T, const uint32_t seg0, const uint32_t rel) {
+    // positions behind the segment are their own exit: T[LGW_NC + k] = k.  Written as words from T[LGW_NC - 2] on (the table
+    // is word-aligned and LGW_NC is even); the two candidates caught by the first word are written before they are read.
+    uint32_t* tw = reinterpret_cast<uint32_t*>(T + LGW_NC - 2);
+    tw[0] = 0x01000000u;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if ((tid & 31u) >= (uint32_t)d) incl += o;
-    }
-    const uint32_t ex = sh_exit[LGW_THREADS - 1];
-    uint32_t before = 0, all = incl;
-    if (LGW_WARPS > 1) {
-        if ((tid & 31u) == 31u) sh_sums[tid >> 5] = incl;
-        __syncthreads();
-        all = 0;
+    for (int k = 1; k < 5; k++) tw[k] = 0x03020100u + 0x04040404u * (uint32_t)k - 0x02020202u;
 #pragma unroll
-        for (int w = 0; w < LGW_WARPS; w++) {
-            const uint32_t v = sh_sums[w];
-            if ((uint32_t)w < (tid >> 5)) before += v;
-            all += v;
+    for (int w = LGW_SEG / 4 - 1; w >= 0; --w) {
+        const uint32_t v = dw[w];
+#pragma unroll
+        for (int hlf = 1; hlf >= 0; --hlf) {
+            const int c = 2 * w + hlf;
+            const uint32_t b = (v >> (16 * hlf + 4)) & 15u;
+            const uint32_t h = b > 10u ? 16u : b;                     // payload / 2
+            uint32_t x = T[c + 1 + h];
+            if (TAIL) { if (seg0 + 2u * (uint32_t)c + 2u + 2u * h >= rel) x = LG_DEAD; }
+            T[c] = (uint8_t)x;
         }
-    } else {
-        all = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        __syncwarp();                                    // every lane has read the last exit
     }
-    sh_exit[tid] = before + incl - c;
-    total = all;
-    lgw_cta_sync();
-    return ex == LGW_NONE ? LGW_NONE : ex - (uint32_t)LGW_TILE;
-}
-
-// marks are kept per segment: words 2s, 2s+1 hold the block starts of segment s, one bit per even offset from its start
-__device__ __forceinline__ bool lgw_marked(const uint32_t* bitmap, const uint32_t q) {
-    const uint32_t seg = q / (uint32_t)LGW_SEG, pos = (q - seg * (uint32_t)LGW_SEG) >> 1;
-    return (bitmap[2u * seg + (pos >> 5)] >> (pos & 31u)) & 1u;
-}
-// marked block starts in front of tile-relative position q (prefix: lgw_chain's per-segment counts)
-__device__ __forceinline__ uint32_t lgw_marks_before(const uint32_t* bitmap, const uint32_t* prefix, const uint32_t q) {
-    const uint32_t seg = q / (uint32_t)LGW_SEG, pos = (q - seg * (uint32_t)LGW_SEG) >> 1;
-    uint32_t n = prefix[seg];
-    if (pos >= 32u) n += __popc(bitmap[2u * seg]) + __popc(bitmap[2u * seg + 1] & ((1u << (pos - 32u)) - 1u));
-    else n += __popc(bitmap[2u * seg] & ((1u << pos) - 1u));
-    return n;
 }
 
 // OR the 16 samples of the block at byte offset o (header nibble `bits`) into px[], at bit ADJ of each word (0: even-column
@@ -306,13 +240,12 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                                                              uint32_t* __restrict__ counters, const uint32_t epoch) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
     uint8_t* data = lg_smem;
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(lg_smem + LGW_DATA);                     // marks: two words per segment
-    uint32_t* lbmaps = bitmap + 2 * LGW_THREADS;                                            // look-back: [LGW_LB][LG_STATES]
-    uint32_t* sh_exit = lbmaps + LGW_LB * LG_STATES;                                        // chain walk: exits, then the count prefix
-    uint16_t* plist = reinterpret_cast<uint16_t*>(sh_exit + LGW_THREADS);                   // pair list: [LGW_PAIR_CHUNK]
+    uint8_t* tables = lg_smem + LGW_DATA;                                                   // [LGW_THREADS][LGW_TAB]
+    uint16_t* plist = reinterpret_cast<uint16_t*>(tables);                                  // pair list: [LGW_PAIR_CHUNK], after the tables
     __shared__ __align__(8) unsigned long long bar_storage;
-    __shared__ uint32_t sh_map[LG_STATES], sh_merge[LG_STATES], warp_sums[LGW_WARPS];
-    __shared__ uint32_t sh_ticket, sh_base, sh_skip, sh_rewalk;
+    __shared__ uint8_t sh_wmap[LGW_WARPS][LG_STATES + 3];                                   // map of each warp's 32 segments
+    __shared__ uint32_t warp_sums[LGW_WARPS], sh_went[LGW_WARPS];
+    __shared__ uint32_t sh_ticket, sh_base, sh_skip, sh_err;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t bar = smem_u32(&bar_storage);
     if (tid == 0) {
@@ -320,10 +253,12 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const uint32_t* d32 = reinterpret_cast<const uint32_t*>(data);
+    const uint32_t seg0 = tid * (uint32_t)LGW_SEG;
+    uint8_t* T = tables + tid * (uint32_t)LGW_TAB;
     uint32_t bulk_uses = 0;                                  // bulk copies this CTA has waited for: the mbarrier's phase
 
     for (;;) {
-        lgw_cta_sync();                                       // every thread is done with the previous tile's shared memory
+        __syncthreads();                                      // every thread is done with the previous tile's shared memory
         // ---- 1. ticket; stage: ONE bulk copy for a tile that lies wholly inside the buffer
         if (tid == 0) {
             const uint32_t t = atomicAdd(&counters[2], 1u);
@@ -333,13 +268,23 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                 const FrameDev& F0 = frames[w0.frame];
                 const unsigned long long off0 = (unsigned long long)w0.tile * LGW_TILE;
                 if (off0 + (unsigned long long)LGW_DATA <= F0.len) {
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic accesses of the last tile before the async write
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)LGW_DATA) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                                  ::"r"(smem_u32(data)), "l"(F0.src + off0), "r"((uint32_t)LGW_DATA), "r"(bar) : "memory");
                 }
+                // the tile some CTA will take about one round of the grid from now: have it in L2 by then
+                const uint32_t tn = t + gridDim.x;
+                if (tn < nwork) {
+                    const LgWork w1 = work[tn];
+                    const FrameDev& F1 = frames[w1.frame];
+                    const unsigned long long off1 = (unsigned long long)w1.tile * LGW_TILE;
+                    if (off1 + (unsigned long long)LGW_DATA <= F1.len)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(F1.src + off1), "r"((uint32_t)LGW_DATA) : "memory");
+                }
             }
         }
-        lgw_cta_sync();
+        __syncthreads();
         const uint32_t ticket = sh_ticket;
         if (ticket >= nwork) break;
         const LgWork wk = work[ticket];
@@ -354,6 +299,7 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
         const uint32_t need_pairs = ppr * (uint32_t)F.height;                            // < 2^26: width * height <= 2^30 (prepare())
         const unsigned long long need = 2ull * need_pairs;                               // blocks of the image (:478-482)
         const bool fits = F.dst_cap >= (unsigned long long)F.width * (unsigned long long)F.height;
+        unsigned long long* const cntw = F.lg_status;                                    // [2 * tile]: count word, [2 * tile + 1]: exit word
         if (tile_off + (unsigned long long)LGW_DATA <= len) {
             for (;;) {
                 uint32_t ok;
@@ -365,78 +311,61 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
             bulk_uses++;
         } else {                                              // the tail of the buffer: 16-byte granules with zero fill
             lg_stage_tail(data, F.src, len, tile_off, LGW_DATA, (int)tid);
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");           // a later bulk copy overwrites these generic stores
-            lgw_cta_sync();
+            __syncthreads();
         }
 
-        // ---- 2. chain C0 (all threads), then the transfer map (warp 0)
-        uint32_t total0;
-        const uint32_t ex0 = lgw_chain(data, bitmap, sh_exit, warp_sums, 0u, tile_rel, tid, total0);
-        if (warp == 0) {
-            const uint32_t exit0 = (ex0 == LGW_NONE || last_tile) ? LG_DEAD : ex0 >> 1;
-            if (lane < LG_STATES) {
-                uint32_t q = 2u * lane, pre = 0, m = LG_NO_MERGE, ex = exit0, count;
-                bool d2 = false;
-                if (lane == 0) { m = 0; count = total0; }
-                else {
-                    for (;;) {
-                        if (q >= (uint32_t)LGW_TILE) { ex = (q - LGW_TILE) >> 1; break; }               // never met C0 in this tile
-                        if (lgw_marked(bitmap, q)) { m = q >> 1; break; }
-                        const uint32_t nq = q + leg_step(data[q]);
-                        if (nq >= tile_rel) { d2 = true; break; }
-                        q = nq;
-                        pre++;
-                    }
-                    if (m != LG_NO_MERGE) {
-                        // blocks of C0 from the merge point on = total0 - (marks before it)
-                        count = pre + total0 - lgw_marks_before(bitmap, sh_exit, 2u * m);
-                    } else {
-                        count = pre;
-                        if (d2 || last_tile) ex = LG_DEAD;
-                    }
-                }
-                const uint32_t mapv = ex | (count << 5);
-                sh_map[lane] = mapv;
-                sh_merge[lane] = m;
-                F.lg_tilemap[(size_t)tile * LG_STATES + lane] = mapv;
+        // ---- 2. exit table of this thread's segment
+        if (tile_rel > (uint32_t)LGW_TILE + 34u) lgw_exit_table<false>(d32 + tid * (uint32_t)(LGW_SEG / 4), T, seg0, tile_rel);
+        else lgw_exit_table<true>(d32 + tid * (uint32_t)(LGW_SEG / 4), T, seg0, tile_rel);
+        __syncthreads();
+        // ---- 3. the 17 entries of this warp's first segment, chased through its 32 segments
+        if (lane < (uint32_t)LG_STATES) {
+            uint32_t e = lane;
+            uint8_t* Ts = tables + (32u * warp) * (uint32_t)LGW_TAB;
+#pragma unroll 4
+            for (int s = 0; s < 32; s++) {
+                Ts[LGW_ENT + lane] = (uint8_t)e;              // what segment s is entered with when the warp is entered with `lane`
+                if (e != LG_DEAD) e = Ts[e];
+                Ts += LGW_TAB;
             }
-            __syncwarp();
-            // ---- 3. publish (release: the map entries the other lanes wrote are ordered before it by the warp barrier), look back
-            if (lane == 0) lgw_store_release(F.lg_status + tile, lgw_pack(0u, epoch, LGW_ST_LOCAL, 0u));
-            uint32_t entry = 0, base = 0, errbit = 0;
+            sh_wmap[warp][lane] = (uint8_t)e;
+        }
+        __syncthreads();
+        // ---- 4. warp 0: the tile's map, its exit word, this tile's entry
+        if (warp == 0) {
+            uint32_t x = lane < (uint32_t)LG_STATES ? lane : 0u;
+#pragma unroll
+            for (int w = 0; w < LGW_WARPS; w++)
+                if (x != LG_DEAD) x = sh_wmap[w][x];
+            if (last_tile) x = LG_DEAD;                       // nothing follows the last tile
+            const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, x, 0);
+            const bool conv = __all_sync(0xFFFFFFFFu, x == x0);
+            if (!conv) {
+                if (lane < (uint32_t)LG_STATES) F.lg_tilemap[(size_t)tile * LG_STATES + lane] = x;
+                __syncwarp();
+            }
+            // (release: the map entries the other lanes wrote are ordered before it by the warp barrier)
+            if (lane == 0) lgw_store_release(cntw + 2 * (size_t)tile + 1, lgw_pack(0u, epoch, conv ? LGW_EX_CONV : LGW_EX_MAP, x0));
+            uint32_t entry = 0, errbit = 0;
             if (tile > 0) {
                 const uint32_t jhi = tile - 1;
                 uint32_t spins = 0;
                 for (;;) {
                     const int j = (int)jhi - (int)lane;
                     unsigned long long sw = 0;
-                    if (lane < (uint32_t)LGW_LB && j >= 0) sw = lgw_load_acquire(F.lg_status + j);
-                    const uint32_t lo32 = (uint32_t)sw;
-                    const uint32_t st = ((lo32 >> 8) & 0xFFFFFFu) == (epoch & 0xFFFFFFu) ? (lo32 >> 6) & 3u : 0u;
-                    const unsigned incl = __ballot_sync(0xFFFFFFFFu, st == LGW_ST_INCL);
+                    if (j >= 0) sw = lgw_load_acquire(cntw + 2 * (size_t)j + 1);
+                    const uint32_t st = lgw_state(sw, epoch);
+                    const unsigned known = __ballot_sync(0xFFFFFFFFu, st == LGW_EX_CONV || st == LGW_EX_FINAL);
                     const unsigned any = __ballot_sync(0xFFFFFFFFu, st != 0u);
-                    if (incl) {
-                        const int d = __ffs(incl) - 1;            // nearest predecessor with a known inclusive state: tile jhi - d
+                    if (known) {
+                        const int d = __ffs(known) - 1;           // nearest predecessor whose exit is known: tile jhi - d
                         const unsigned between = (1u << d) - 1u;  // tiles jhi - d + 1 .. jhi must have published their maps
                         if ((any & between) == between) {
-                            uint32_t state = __shfl_sync(0xFFFFFFFFu, lo32 & 31u, d);
-                            uint32_t count = __shfl_sync(0xFFFFFFFFu, (uint32_t)(sw >> 32), d);
-                            errbit = __shfl_sync(0xFFFFFFFFu, lo32 & LGW_ERR_BIT, d);
-                            const uint32_t first = jhi - (uint32_t)d + 1u;                          // maps of tiles first .. jhi
-                            __syncwarp();                        // every lane's acquire load before any lane's map loads
-                            for (uint32_t idx = lane; idx < (uint32_t)d * LG_STATES; idx += 32)
-                                lbmaps[idx] = __ldcg(F.lg_tilemap + (size_t)first * LG_STATES + idx);
-                            __syncwarp();
-                            if (lane == 0) {
-                                for (int m = 0; m < d; m++) {
-                                    if (state == LG_DEAD) break;
-                                    const uint32_t v = lbmaps[m * LG_STATES + state];
-                                    count += v >> 5;
-                                    state = v & 31u;
-                                }
-                            }
-                            entry = __shfl_sync(0xFFFFFFFFu, state, 0);
-                            base = __shfl_sync(0xFFFFFFFFu, count, 0);
+                            uint32_t state = __shfl_sync(0xFFFFFFFFu, (uint32_t)sw & 31u, d);
+                            __syncwarp();                        // every lane's acquire load before any map load
+                            for (int m = d - 1; m >= 0 && state != LG_DEAD; m--)          // (rare: runs of one constant block length)
+                                state = __ldcg(F.lg_tilemap + (size_t)(jhi - (uint32_t)m) * LG_STATES + state);
+                            entry = state;
                             break;
                         }
                     }
@@ -444,66 +373,27 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                     __nanosleep(spins < 8 ? 40 : 200);
                 }
             }
-            uint32_t exitv = LG_DEAD, total = base;
-            if (entry != LG_DEAD) {
-                const uint32_t v = sh_map[entry];
-                exitv = v & 31u;
-                total = base + (v >> 5);
-            }
-            const bool skip = entry == LG_DEAD || !fits || (unsigned long long)base >= need;     // nothing of the image starts here
+            // the actual exit of a tile that published a map: successors stop composing here
+            const uint32_t x_act = entry == LG_DEAD ? LG_DEAD : __shfl_sync(0xFFFFFFFFu, x, entry & 31u);
+            if (!conv && lane == 0) lgw_store_relaxed(cntw + 2 * (size_t)tile + 1, lgw_pack(0u, epoch, LGW_EX_FINAL, x_act | errbit));
             if (lane == 0) {
-                lgw_store_relaxed(F.lg_status + tile, lgw_pack(total, epoch, LGW_ST_INCL, exitv | errbit));   // self-contained word
-                if (last_tile) {
-                    unsigned status = 0;
-                    if (!fits) status |= MCRAW_FRAME_GEOMETRY;
-                    if ((unsigned long long)total < need) status |= MCRAW_FRAME_TRUNCATED;     // reference: stale samples (:387,398)
-                    if (errbit) status |= MCRAW_FRAME_INTERNAL;
-                    Result r;
-                    r.written = status ? 0ull : (unsigned long long)F.width * (unsigned long long)F.height;   // :494
-                    r.status = status;
-                    r.pad = 0;
-                    results[wk.frame] = r;
+                uint32_t c = entry;
+#pragma unroll
+                for (int w = 0; w < LGW_WARPS; w++) {
+                    sh_went[w] = c;                                   // what warp w's first segment is entered with
+                    if (c != LG_DEAD) c = sh_wmap[w][c];
                 }
-                sh_base = base;
-                sh_skip = skip ? 1u : 0u;
-                sh_rewalk = 0;
-            }
-            // ---- 4. the bitmap for the true entry
-            if (!skip && entry != 0) {
-                const uint32_t m = sh_merge[entry];
-                __syncwarp();
-                if (m == LG_NO_MERGE) {
-                    if (lane == 0) sh_rewalk = 2u * entry;                         // blocks of one constant width: see below
-                } else {
-                    const uint32_t mseg = (2u * m) / (uint32_t)LGW_SEG, mpos = (2u * m - mseg * (uint32_t)LGW_SEG) >> 1;
-                    for (uint32_t w = lane; w < 2u * mseg; w += 32) bitmap[w] = 0;   // C0's marks before the merge point go
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (mpos >= 32u) { bitmap[2u * mseg] = 0; bitmap[2u * mseg + 1] &= ~((1u << (mpos - 32u)) - 1u); }
-                        else bitmap[2u * mseg] &= ~((1u << mpos) - 1u);
-                        uint32_t p = 2u * entry;
-                        while (p < 2u * m) {
-                            const uint32_t sg = p / (uint32_t)LGW_SEG, ps = (p - sg * (uint32_t)LGW_SEG) >> 1;
-                            bitmap[2u * sg + (ps >> 5)] |= 1u << (ps & 31u);
-                            p += leg_step(data[p]);
-                        }
-                    }
-                }
+                sh_err = errbit;
             }
         }
-        lgw_cta_sync();
-        if (sh_skip) continue;
-        const uint32_t base = sh_base;
-        if (sh_rewalk) {                                      // the entry's chain never meets C0 in this tile: walk it from its entry
-            uint32_t t2;
-            lgw_chain(data, bitmap, sh_exit, warp_sums, sh_rewalk, tile_rel, tid, t2);
+        __syncthreads();
+        // ---- 5. the exact chain: every thread walks its segment from the entry it is reached with
+        uint32_t wv0 = 0, wv1 = 0;
+        {
+            const uint32_t cw = sh_went[warp];
+            const uint32_t e = cw == LG_DEAD ? LG_DEAD : (uint32_t)T[LGW_ENT + cw];
+            if (e != LG_DEAD) lgw_walk_segment(data, seg0, seg0 + 2u * e, wv0, wv1, tile_rel);
         }
-
-        // ---- 5. pair list of the tile: every block with an even ordinal leads a pair (even-column block, then odd-column
-        //      block, RawData_Legacy.cpp:480-481); plist[q] = (tile-relative offset of the leader) / 2 for pair ordinal
-        //      p_first + q.  Ordinals come from prefix popcounts of the marks.  Consecutive lanes then decode consecutive
-        //      pairs: their reads of the staged tile are a few words apart (different banks), their stores adjacent.
-        const uint32_t wv0 = bitmap[2 * tid], wv1 = bitmap[2 * tid + 1];
         const uint32_t c = __popc(wv0) + __popc(wv1);
         uint32_t incl = c;
 #pragma unroll
@@ -512,6 +402,7 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
             if (lane >= (uint32_t)d) incl += o;
         }
         uint32_t before = 0, total = incl;
+        const uint32_t errbit0 = sh_err;
         if (LGW_WARPS > 1) {
             if (lane == 31) warp_sums[warp] = incl;
             __syncthreads();
@@ -525,6 +416,67 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
         } else {
             total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
+        // ---- blocks before this tile: decoupled look-back over the count words (warp 0)
+        if (warp == 0) {
+            uint32_t base = 0, errbit = errbit0;
+            if (tile > 0) {
+                if (lane == 0) lgw_store_release(cntw + 2 * (size_t)tile, lgw_pack(total, epoch, LGW_ST_AGG, errbit));
+                int jhi = (int)tile - 1;
+                uint32_t spins = 0;
+                for (;;) {
+                    const int j = jhi - (int)lane;
+                    unsigned long long sw = lgw_pack(0u, epoch, LGW_ST_INCL, 0u);        // in front of tile 0: nothing
+                    if (j >= 0) sw = lgw_load_acquire(cntw + 2 * (size_t)j);
+                    const uint32_t st = lgw_state(sw, epoch);
+                    const unsigned inclm = __ballot_sync(0xFFFFFFFFu, st == LGW_ST_INCL);
+                    const unsigned any = __ballot_sync(0xFFFFFFFFu, st != 0u);
+                    const int d = inclm ? __ffs(inclm) - 1 : 32;  // nearest predecessor with an inclusive count: tile jhi - d
+                    const unsigned upto = d >= 31 ? 0xFFFFFFFFu : (2u << d) - 1u;          // lanes 0 .. d (0 .. 31 if there is none)
+                    if ((any & upto) == upto) {
+                        uint32_t v = lane <= (uint32_t)d ? (uint32_t)(sw >> 32) : 0u;
+                        uint32_t eb = lane <= (uint32_t)d ? (uint32_t)sw & LGW_ERR_BIT : 0u;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                            eb |= __shfl_xor_sync(0xFFFFFFFFu, eb, o);
+                        }
+                        base += v;
+                        errbit |= eb;
+                        if (inclm) break;
+                        jhi -= 32;                                // 32 aggregates and no inclusive count yet: further back
+                        continue;
+                    }
+                    if (++spins > LGW_SPIN_LIMIT) { errbit = LGW_ERR_BIT; break; }        // never expected
+                    __nanosleep(spins < 8 ? 40 : 200);
+                }
+            }
+            const uint32_t all = base + total;
+            const bool skip = !fits || (unsigned long long)base >= need || total == 0u;   // nothing of the image starts here
+            if (lane == 0) {
+                lgw_store_relaxed(cntw + 2 * (size_t)tile, lgw_pack(all, epoch, LGW_ST_INCL, errbit));   // self-contained word
+                if (last_tile) {
+                    unsigned status = 0;
+                    if (!fits) status |= MCRAW_FRAME_GEOMETRY;
+                    if ((unsigned long long)all < need) status |= MCRAW_FRAME_TRUNCATED;       // reference: stale samples (:387,398)
+                    if (errbit) status |= MCRAW_FRAME_INTERNAL;
+                    Result r;
+                    r.written = status ? 0ull : (unsigned long long)F.width * (unsigned long long)F.height;   // :494
+                    r.status = status;
+                    r.pad = 0;
+                    results[wk.frame] = r;
+                }
+                sh_base = base;
+                sh_skip = skip ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        if (sh_skip) continue;
+        const uint32_t base = sh_base;
+
+        // ---- 6. pair list of the tile: every block with an even ordinal leads a pair (even-column block, then odd-column
+        //      block, RawData_Legacy.cpp:480-481); plist[q] = (tile-relative offset of the leader) / 2 for pair ordinal
+        //      p_first + q.  Consecutive threads then decode consecutive pairs: their reads of the staged tile are a few
+        //      words apart (different banks), their stores adjacent.
         const uint32_t p_first = (base + 1u) >> 1;
         uint32_t npairs = ((base + total + 1u) >> 1) - p_first;
         npairs = min(npairs, need_pairs > p_first ? need_pairs - p_first : 0u);
@@ -537,16 +489,19 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
             const uint32_t cn = min((uint32_t)LGW_PAIR_CHUNK, npairs - c0);
             {
                 uint32_t ord = ord0;
-                unsigned long long marks = (unsigned long long)wv0 | ((unsigned long long)wv1 << 32);
-                while (marks) {
-                    const uint32_t b = (uint32_t)__ffsll((long long)marks) - 1u;
-                    marks &= marks - 1;
-                    const uint32_t q = (ord >> 1) - p_first - c0;       // wraps to a huge value for earlier passes' pairs
-                    if (!(ord & 1u) && q < cn) plist[q] = (uint16_t)(((uint32_t)LGW_SEG / 2u) * tid + b);
-                    ord++;
+#pragma unroll
+                for (int hw = 0; hw < 2; hw++) {
+                    uint32_t marks = hw ? wv1 : wv0;
+                    while (marks) {
+                        const uint32_t b = (uint32_t)__ffs((int)marks) - 1u;
+                        marks &= marks - 1u;
+                        const uint32_t q = (ord >> 1) - p_first - c0;       // wraps to a huge value for earlier passes' pairs
+                        if (!(ord & 1u) && q < cn) plist[q] = (uint16_t)(((uint32_t)LGW_SEG / 2u) * tid + 32u * hw + b);
+                        ord++;
+                    }
                 }
             }
-            lgw_cta_sync();
+            __syncthreads();
             uint32_t P = p_first + c0 + tid;
             uint32_t y = P / ppr, xq = P - y * ppr;
             for (uint32_t q = tid; q < cn; q += LGW_THREADS) {
@@ -582,7 +537,7 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                 xq += LGW_THREADS;                                                            // the pair LGW_THREADS further on
                 while (xq >= ppr) { xq -= ppr; y++; }
             }
-            lgw_cta_sync();
+            __syncthreads();
         }
     }
     // the last CTA to leave resets the ticket counters for the next launch

@@ -52,6 +52,8 @@ def main():
     hdr = rows[hdr_i]
     si = hdr.index("# Samples")
     ii = hdr.index("Instructions Executed")
+    wi = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
+    wx = hdr.index("L1 Wavefronts Shared Excessive") if "L1 Wavefronts Shared Excessive" in hdr else None
     inst = [r for r in rows[hdr_i + 1:] if r and r[0].startswith("0x")]
     sass = sass_lines(so, kernel)
     if len(sass) != len(inst):
@@ -61,13 +63,17 @@ def main():
     for (addr, text, loc), r in zip(sass, inst):
         s = int(r[si] or 0)
         e = int(r[ii] or 0)
-        a = agg.setdefault(loc, [0, 0])
+        a = agg.setdefault(loc, [0, 0, 0, 0])
         a[0] += s
         a[1] += e
+        if wi is not None:
+            a[2] += int(r[wi] or 0)
+            a[3] += int(r[wx] or 0)
         total += s
     srcs = {}
-    print(f"total samples {total}")
-    for loc, (s, e) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    by = 2 if os.environ.get("NCU_LINES_SORT") == "smem" else 0
+    print(f"total samples {total}, shared-memory wavefronts {sum(a[2] for a in agg.values())} (excessive {sum(a[3] for a in agg.values())})")
+    for loc, (s, e, w, x) in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
         f, n = loc
         if f not in srcs:
             for root in (os.path.join(os.path.dirname(os.path.abspath(so)), "csrc"), "."):
@@ -78,7 +84,7 @@ def main():
             else:
                 srcs[f] = []
         code = srcs[f][n - 1].strip() if 0 < n <= len(srcs[f]) else ""
-        print(f"{100.0 * s / max(total, 1):6.2f}%  {s:7d} smp {e:10d} inst  {f}:{n}  {code[:110]}")
+        print(f"{100.0 * s / max(total, 1):6.2f}%  {s:7d} smp {e:10d} inst {w:10d} wf {x:9d} xs  {f}:{n}  {code[:100]}")
 
 
 if __name__ == "__main__":
