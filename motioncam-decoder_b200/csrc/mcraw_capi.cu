@@ -140,7 +140,8 @@ struct mcraw_ctx {
     std::vector<LgWork> tmp_lgwork;
     uint32_t sm_count = 0;
     bool meta_small_only = getenv("MCRAW_META_SMALL") != nullptr;   // A/B switch: never use the big-window shape of k_meta
-    uint32_t lgw_resident_ctas = 0; // CTAs (= warps) of k_legacy_warp the device holds at once
+    uint32_t lgw_resident_ctas = 0; // CTAs of k_legacy_warp<false> the device holds at once
+    uint32_t lgw_resident_ctas_epi = 0;   // the same for the variant with the epilogue (more registers)
     bool overlap = getenv("MCRAW_NO_OVERLAP") == nullptr;   // k_units as a programmatic dependent of k_meta
     uint32_t timing_every = 0;      // record kernel-timing events on every n-th chunk (0 = never)
     uint64_t chunk_seq = 0;
@@ -507,7 +508,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     if (any6) {
         // one pass over the stream: transfer maps, decoupled look-back and the pixel work in one persistent kernel
         s.lg_epoch += 1;
-        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(ctx->lgw_resident_ctas, s.lg_nwork));
+        const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(s.any_epi ? ctx->lgw_resident_ctas_epi : ctx->lgw_resident_ctas, s.lg_nwork));
         const LgWork* d_work = reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off);
         if (s.any_epi) k_legacy_warp<true><<<grid, LGW_THREADS, LGW_SMEM, st>>>(d_frames, d_results, d_work, s.lg_nwork, d_counter, s.lg_epoch);
         else k_legacy_warp<false><<<grid, LGW_THREADS, LGW_SMEM, st>>>(d_frames, d_results, d_work, s.lg_nwork, d_counter, s.lg_epoch);
@@ -602,11 +603,14 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
         ctx->sm_count = (uint32_t)prop.multiProcessorCount;
         ctx->chain_ctas = std::min(ctx->chain_ctas, ctx->resident_ctas / 2);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp<true>, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm < 1) {
+        int per_sm_epi = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp<false>, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm < 1 ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_epi, k_legacy_warp<true>, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm_epi < 1) {
             ctx->err = "k_legacy_warp does not fit on this device"; return bail(MCRAW_ERR_CUDA);
         }
-        if (const char* e = getenv("MCRAW_LGW_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        if (const char* e = getenv("MCRAW_LGW_CTAS_PER_SM")) { per_sm = std::max(1, std::min(per_sm, atoi(e))); per_sm_epi = std::min(per_sm_epi, per_sm); }
         ctx->lgw_resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
+        ctx->lgw_resident_ctas_epi = (uint32_t)per_sm_epi * (uint32_t)prop.multiProcessorCount;
     }
     for (auto& s : ctx->slots) {
         if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&s.e0) != cudaSuccess ||

@@ -52,14 +52,15 @@ constexpr int LGW_TAB = 84;                    // bytes of exit table per thread
                                                // (+ pad); 21 words, odd, for the same reason
 constexpr int LGW_ENT = 32;                    // table offset of the 17 entries a segment is reached with (one per warp entry):
                                                // candidates 17.. of the table are dead once the segment's map is complete
-constexpr int LGW_PAIR_CHUNK = 1024;           // pairs listed and decoded per pass (a tile holds ~700 for typical images,
-                                               // up to LGW_TILE / 4 when every block is 2 bytes: then several passes)
+constexpr int LGW_PAIR_CHUNK = LGW_WARPS >= 4 ? 1024 : 512;   // pairs listed and decoded per pass (a tile of four warps holds ~700 for
+                                               // typical images, up to LGW_TILE / 4 when every block is 2 bytes: then several passes)
+constexpr int LGW_OUT = 2048;                  // bytes of decoded pixels a warp hands to one bulk store: 32 pairs x 64 bytes
 constexpr int LG_STATES = 17;                  // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;               // exit code of a chain that ran into the end of the buffer
 constexpr int LG_OVERRUN = 80;                 // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it (+ word reads)
 constexpr int LGW_DATA = LGW_TILE + LG_OVERRUN;
 constexpr int LGW_LB = 32;                     // look-back window: status words read per poll
-constexpr int LGW_SMEM = LGW_DATA + LGW_THREADS * LGW_TAB;      // the pair list reuses the tables
+constexpr int LGW_SMEM = LGW_DATA + LGW_THREADS * LGW_TAB;      // the pair list and the output staging reuse the tables
 constexpr uint32_t LGW_ST_AGG = 1u, LGW_ST_INCL = 2u;          // count words: this tile's blocks / all blocks up to its end
 constexpr uint32_t LGW_EX_CONV = 1u, LGW_EX_MAP = 2u, LGW_EX_FINAL = 3u;   // exit words, see 4. above
 constexpr uint32_t LGW_ERR_BIT = 1u << 5;      // sticky: a wait gave up somewhere up the chain
@@ -67,7 +68,8 @@ constexpr uint32_t LGW_SPIN_LIMIT = 1u << 18;  // polls of ~0.2 us: a wait that 
 static_assert(LGW_DATA % 16 == 0 && LGW_TILE % 16 == 0, "bulk copies work in 16-byte granules");
 static_assert(LGW_SEG % 4 == 0 && LGW_NC <= 64 && LGW_SEG >= 34, "two words of marks per segment; a block never skips a segment");
 static_assert(LGW_NC + LG_STATES <= LGW_TAB && LGW_ENT >= LG_STATES && LGW_ENT + LG_STATES <= LGW_NC && LGW_TAB % 4 == 0, "exit table layout");
-static_assert(LGW_PAIR_CHUNK * 2 <= LGW_THREADS * LGW_TAB, "the pair list reuses the tables");
+static_assert(LGW_PAIR_CHUNK * 2 + LGW_WARPS * LGW_OUT <= LGW_THREADS * LGW_TAB && (LGW_PAIR_CHUNK * 2) % 16 == 0,
+              "the pair list and the warps' output staging reuse the tables");
 
 struct LgWork { uint32_t frame, tile; };
 
@@ -116,12 +118,9 @@ __device__ __forceinline__ uint32_t lgw_state(const unsigned long long w, const 
 __device__ __forceinline__ void lgw_store_relaxed(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void lgw_store_release(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long lgw_load_acquire(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long lgw_load_relaxed(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -145,7 +144,9 @@ __device__ __forceinline__ void lgw_walk_segment(const uint8_t* data, const uint
 // One thread: the exit table of its segment.  T[c], c = 0 .. LGW_NC - 1: where the chain that has a block start at byte
 // 2c of the segment enters the next segment (half offset 0 .. 16), or LG_DEAD if it ends at a block that cannot be decoded.
 // dw: the segment as words.  TAIL: the buffer may end inside or right behind the tile (rel as above, seg0 = the segment's
-// tile-relative offset); interior tiles skip that test.
+// tile-relative offset); interior tiles skip that test.  The two candidates of a word go together: both look-ups are
+// issued before either result is stored (the second one can only need the first one's result when its block is 2 bytes
+// long -- then it is taken from the register), which halves the chain of dependent shared-memory round trips.
 template <bool TAIL>
 __device__ __forceinline__ void lgw_exit_table(const uint32_t* __restrict__ dw, uint8_t* T, const uint32_t seg0, const uint32_t rel) {
     // positions behind the segment are their own exit: T[LGW_NC + k] = k.  Written as words from T[LGW_NC - 2] on (the table
@@ -157,15 +158,15 @@ __device__ __forceinline__ void lgw_exit_table(const uint32_t* __restrict__ dw, 
 #pragma unroll
     for (int w = LGW_SEG / 4 - 1; w >= 0; --w) {
         const uint32_t v = dw[w];
-#pragma unroll
-        for (int hlf = 1; hlf >= 0; --hlf) {
-            const int c = 2 * w + hlf;
-            const uint32_t b = (v >> (16 * hlf + 4)) & 15u;
-            const uint32_t h = b > 10u ? 16u : b;                     // payload / 2
-            uint32_t x = T[c + 1 + h];
-            if (TAIL) { if (seg0 + 2u * (uint32_t)c + 2u + 2u * h >= rel) x = LG_DEAD; }
-            T[c] = (uint8_t)x;
-        }
+        const int c0 = 2 * w, c1 = 2 * w + 1;
+        const uint32_t b1 = (v >> 20) & 15u, b0 = (v >> 4) & 15u;
+        const uint32_t h1 = b1 > 10u ? 16u : b1, h0 = b0 > 10u ? 16u : b0;                  // payload / 2
+        uint32_t x1 = T[c1 + 1 + h1];
+        uint32_t x0 = T[c0 + 1 + h0];                                 // = T[c1] (not yet written) when h0 == 0
+        if (TAIL) { if (seg0 + 2u * (uint32_t)c1 + 2u + 2u * h1 >= rel) x1 = LG_DEAD; }
+        if (h0 == 0u) x0 = x1;
+        if (TAIL) { if (seg0 + 2u * (uint32_t)c0 + 2u + 2u * h0 >= rel) x0 = LG_DEAD; }
+        *reinterpret_cast<uint16_t*>(T + c0) = (uint16_t)(x0 | (x1 << 8));
     }
 }
 
@@ -175,8 +176,12 @@ __device__ __forceinline__ void lgw_exit_table(const uint32_t* __restrict__ dw, 
 // big-endian words (PRMT with a runtime selector does alignment and byte order in one go) and every sample is one
 // rotate + one mask.  Three lane-uniform formulations instead of one code path per width: widths 0..8 (two 4-sample
 // windows per group), 9..10 (four 2-sample windows), and 16-bit big-endian samples (:360-370, nibbles 11..15, :395).
+// ROTATION: px[k] receives sample (k + 4 * rot) mod 16, rot = 0 .. 3 (rot1 = rot & 1, rot2 = rot & 2 as flags) -- the
+// lane's four 16-byte output pieces, rotated, which is what lets a warp write its 32 x 64 bytes into LINEAR shared memory
+// without bank conflicts (see the bulk store in the kernel).  The rotation is applied to the windows, not to the samples.
 template <int ADJ>
-__device__ __forceinline__ void lgw_block(const uint32_t* __restrict__ d32, const uint32_t o, const uint32_t bits, uint32_t (&px)[16]) {
+__device__ __forceinline__ void lgw_block(const uint32_t* __restrict__ d32, const uint32_t o, const uint32_t bits, uint32_t (&px)[16],
+                                          const bool rot1, const bool rot2, const uint32_t rot) {
     const uint32_t a = o + 2u;
     if (bits <= 8u) {
         const uint32_t w = bits;
@@ -184,58 +189,69 @@ __device__ __forceinline__ void lgw_block(const uint32_t* __restrict__ d32, cons
         uint32_t r[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) r[j] = (32u - ADJ - (uint32_t)(j + 1) * w) & 31u;
+        uint32_t win[4];                                                               // samples 4t .. 4t+3 sit at the top of win[t]
 #pragma unroll
         for (int g = 0; g < 2; g++) {
             const uint32_t ag = a + g * w;
             const uint32_t i = ag >> 2, sel = 0x0123u + 0x1111u * (ag & 3u);
             const uint32_t W0 = d32[i], W1 = d32[i + 1], W2 = d32[i + 2];
             const uint32_t G0 = __byte_perm(W0, W1, sel), G1 = __byte_perm(W1, W2, sel);
-            const uint32_t A1 = __funnelshift_lc(G1, G0, 4u * w);                      // the window of samples 4..7
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                px[8 * g + j] |= __funnelshift_r(G0, G0, r[j]) & mask;
-                px[8 * g + 4 + j] |= __funnelshift_r(A1, A1, r[j]) & mask;
-            }
+            win[2 * g] = G0;
+            win[2 * g + 1] = __funnelshift_lc(G1, G0, 4u * w);                         // the window of samples 4..7
         }
+        {
+            const uint32_t t0 = rot1 ? win[1] : win[0], t1 = rot1 ? win[2] : win[1], t2 = rot1 ? win[3] : win[2], t3 = rot1 ? win[0] : win[3];
+            win[0] = rot2 ? t2 : t0; win[1] = rot2 ? t3 : t1; win[2] = rot2 ? t0 : t2; win[3] = rot2 ? t1 : t3;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) px[4 * t + j] |= __funnelshift_r(win[t], win[t], r[j]) & mask;
     } else if (bits <= 10u) {
         const uint32_t w = bits;
         const uint32_t mask = ((1u << w) - 1u) << ADJ;
         const uint32_t r0 = (32u - ADJ - w) & 31u, r1 = (32u - ADJ - 2u * w) & 31u;
+        uint32_t win[8];                                                               // samples 2n, 2n+1 sit at the top of win[n]
 #pragma unroll
         for (int g = 0; g < 2; g++) {
             const uint32_t ag = a + g * w;
             const uint32_t i = ag >> 2, sel = 0x0123u + 0x1111u * (ag & 3u);
             const uint32_t W0 = d32[i], W1 = d32[i + 1], W2 = d32[i + 2], W3 = d32[i + 3];
             const uint32_t G0 = __byte_perm(W0, W1, sel), G1 = __byte_perm(W1, W2, sel), G2 = __byte_perm(W2, W3, sel);
-            uint32_t win[4];
-            win[0] = G0;                                                               // samples 2m, 2m+1 start at bit 2mw
-            win[1] = __funnelshift_l(G1, G0, 2u * w);
-            win[2] = __funnelshift_l(G2, G1, 4u * w - 32u);
-            win[3] = __funnelshift_l(G2, G1, 6u * w - 32u);
+            win[4 * g] = G0;                                                           // samples 2m, 2m+1 start at bit 2mw
+            win[4 * g + 1] = __funnelshift_l(G1, G0, 2u * w);
+            win[4 * g + 2] = __funnelshift_l(G2, G1, 4u * w - 32u);
+            win[4 * g + 3] = __funnelshift_l(G2, G1, 6u * w - 32u);
+        }
+        {
+            uint32_t t[8];
 #pragma unroll
-            for (int m = 0; m < 4; m++) {
-                px[8 * g + 2 * m] |= __funnelshift_r(win[m], win[m], r0) & mask;
-                px[8 * g + 2 * m + 1] |= __funnelshift_r(win[m], win[m], r1) & mask;
-            }
+            for (int n = 0; n < 8; n++) t[n] = rot1 ? win[(n + 2) & 7] : win[n];
+#pragma unroll
+            for (int n = 0; n < 8; n++) win[n] = rot2 ? t[(n + 4) & 7] : t[n];
+        }
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            px[2 * n] |= __funnelshift_r(win[n], win[n], r0) & mask;
+            px[2 * n + 1] |= __funnelshift_r(win[n], win[n], r1) & mask;
         }
     } else {
         const uint32_t i = a >> 2, k0 = a & 3u;                                        // the payload starts 2-byte aligned
         // sample k = bytes (2k, 2k+1), big-endian: byte index (k0 + 2 (k & 1)) of the word pair (k / 2, k / 2 + 1);
         // the selector puts (high byte, low byte) at result bytes (1, 0) for ADJ 0 and (3, 2) for ADJ 16
         const uint32_t selA = ((k0 + 1u) | (k0 << 4)) << (ADJ / 2), selB = ((k0 + 3u) | ((k0 + 2u) << 4)) << (ADJ / 2);
-        uint32_t lo = d32[i];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
-            const uint32_t hi = d32[i + m + 1];
+            const uint32_t ms = ((uint32_t)m + 2u * rot) & 7u;
+            const uint32_t lo = d32[i + ms], hi = d32[i + ms + 1u];
             px[2 * m] |= __byte_perm(lo, hi, selA) & (0xFFFFu << ADJ);
             px[2 * m + 1] |= __byte_perm(lo, hi, selB) & (0xFFFFu << ADJ);
-            lo = hi;
         }
     }
 }
 
 template <bool EPI>
-__global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __restrict__ frames, Result* __restrict__ results,
+__global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const FrameDev* __restrict__ frames, Result* __restrict__ results,
                                                              const LgWork* __restrict__ work, const uint32_t nwork,
                                                              uint32_t* __restrict__ counters, const uint32_t epoch) {
     extern __shared__ __align__(16) uint8_t lg_smem[];
@@ -256,6 +272,9 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
     const uint32_t seg0 = tid * (uint32_t)LGW_SEG;
     uint8_t* T = tables + tid * (uint32_t)LGW_TAB;
     uint32_t bulk_uses = 0;                                  // bulk copies this CTA has waited for: the mbarrier's phase
+    const uint32_t rot = (lane >> 1) & 3u;                   // rotation of this lane's output pieces (lgw_block)
+    const bool rot1 = (rot & 1u) != 0, rot2 = (rot & 2u) != 0;
+    const uint32_t out_s = smem_u32(tables) + 2u * (uint32_t)LGW_PAIR_CHUNK + (uint32_t)LGW_OUT * warp;   // this warp's output staging
 
     for (;;) {
         __syncthreads();                                      // every thread is done with the previous tile's shared memory
@@ -340,12 +359,15 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
             if (last_tile) x = LG_DEAD;                       // nothing follows the last tile
             const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, x, 0);
             const bool conv = __all_sync(0xFFFFFFFFu, x == x0);
+            // Status words are self-contained (value, epoch and state in one 64-bit store), so they travel as relaxed
+            // gpu-scope accesses; only a published MAP refers to other memory (the 17 map entries): fence, then the word
+            // on this side, the word, then a fence before the entries are read on the other.
             if (!conv) {
                 if (lane < (uint32_t)LG_STATES) F.lg_tilemap[(size_t)tile * LG_STATES + lane] = x;
+                __threadfence();
                 __syncwarp();
             }
-            // (release: the map entries the other lanes wrote are ordered before it by the warp barrier)
-            if (lane == 0) lgw_store_release(cntw + 2 * (size_t)tile + 1, lgw_pack(0u, epoch, conv ? LGW_EX_CONV : LGW_EX_MAP, x0));
+            if (lane == 0) lgw_store_relaxed(cntw + 2 * (size_t)tile + 1, lgw_pack(0u, epoch, conv ? LGW_EX_CONV : LGW_EX_MAP, x0));
             uint32_t entry = 0, errbit = 0;
             if (tile > 0) {
                 const uint32_t jhi = tile - 1;
@@ -353,7 +375,7 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                 for (;;) {
                     const int j = (int)jhi - (int)lane;
                     unsigned long long sw = 0;
-                    if (j >= 0) sw = lgw_load_acquire(cntw + 2 * (size_t)j + 1);
+                    if (j >= 0) sw = lgw_load_relaxed(cntw + 2 * (size_t)j + 1);
                     const uint32_t st = lgw_state(sw, epoch);
                     const unsigned known = __ballot_sync(0xFFFFFFFFu, st == LGW_EX_CONV || st == LGW_EX_FINAL);
                     const unsigned any = __ballot_sync(0xFFFFFFFFu, st != 0u);
@@ -362,7 +384,7 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                         const unsigned between = (1u << d) - 1u;  // tiles jhi - d + 1 .. jhi must have published their maps
                         if ((any & between) == between) {
                             uint32_t state = __shfl_sync(0xFFFFFFFFu, (uint32_t)sw & 31u, d);
-                            __syncwarp();                        // every lane's acquire load before any map load
+                            if (d > 0) __threadfence();          // the status loads before the map loads
                             for (int m = d - 1; m >= 0 && state != LG_DEAD; m--)          // (rare: runs of one constant block length)
                                 state = __ldcg(F.lg_tilemap + (size_t)(jhi - (uint32_t)m) * LG_STATES + state);
                             entry = state;
@@ -420,13 +442,13 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
         if (warp == 0) {
             uint32_t base = 0, errbit = errbit0;
             if (tile > 0) {
-                if (lane == 0) lgw_store_release(cntw + 2 * (size_t)tile, lgw_pack(total, epoch, LGW_ST_AGG, errbit));
+                if (lane == 0) lgw_store_relaxed(cntw + 2 * (size_t)tile, lgw_pack(total, epoch, LGW_ST_AGG, errbit));
                 int jhi = (int)tile - 1;
                 uint32_t spins = 0;
                 for (;;) {
                     const int j = jhi - (int)lane;
                     unsigned long long sw = lgw_pack(0u, epoch, LGW_ST_INCL, 0u);        // in front of tile 0: nothing
-                    if (j >= 0) sw = lgw_load_acquire(cntw + 2 * (size_t)j);
+                    if (j >= 0) sw = lgw_load_relaxed(cntw + 2 * (size_t)j);
                     const uint32_t st = lgw_state(sw, epoch);
                     const unsigned inclm = __ballot_sync(0xFFFFFFFFu, st == LGW_ST_INCL);
                     const unsigned any = __ballot_sync(0xFFFFFFFFu, st != 0u);
@@ -484,6 +506,7 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
         const int width = F.width;
         uint16_t* __restrict__ dst = F.dst;
         const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
+        const bool lin = vec && (width & 31) == 0;              // rows of whole pairs: consecutive pairs are consecutive memory
         const unsigned epi = EPI ? F.epi_mode : 0u;             // EPI = false: the epilogue code is not even in the kernel
         for (uint32_t c0 = 0; c0 < npairs; c0 += LGW_PAIR_CHUNK) {
             const uint32_t cn = min((uint32_t)LGW_PAIR_CHUNK, npairs - c0);
@@ -502,40 +525,87 @@ __global__ void __launch_bounds__(LGW_THREADS) k_legacy_warp(const FrameDev* __r
                 }
             }
             __syncthreads();
-            uint32_t P = p_first + c0 + tid;
-            uint32_t y = P / ppr, xq = P - y * ppr;
-            for (uint32_t q = tid; q < cn; q += LGW_THREADS) {
-                const uint32_t oE = 2u * (uint32_t)plist[q];
-                const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
-                const uint32_t oO = oE + 2u + leg_len(bitsE);
-                const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
-                uint32_t px[16];
+            if (lin) {
+                // Whole rows of pairs (width = 32 * pairs per row) and an aligned buffer: pair P occupies bytes [64 P, 64 P + 64)
+                // of the output, so the 32 pairs of a warp pass are 2 KiB in a row.  They go out as ONE bulk store (TMA, 1-D)
+                // from a linear staging buffer; lane l writes its piece (i + rot) mod 4 in round i, rot = (l / 2) mod 4, which
+                // spreads a quarter warp's 16-byte stores over all 32 banks.
+                for (uint32_t q0 = 32u * warp; q0 < cn; q0 += LGW_THREADS) {
+                    const uint32_t q = q0 + lane;
+                    uint32_t px[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) px[i] = 0;
-                lgw_block<0>(d32, oE, bitsE, px);
-                lgw_block<16>(d32, oO, bitsO, px);
-                const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
+                    for (int i = 0; i < 16; i++) px[i] = 0;
+                    if (q < cn) {
+                        const uint32_t oE = 2u * (uint32_t)plist[q];
+                        const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
+                        const uint32_t oO = oE + 2u + leg_len(bitsE);
+                        const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
+                        lgw_block<0>(d32, oE, bitsE, px, rot1, rot2, rot);
+                        lgw_block<16>(d32, oO, bitsO, px, rot1, rot2, rot);
+                        const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
 #pragma unroll
-                for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i], refs);                    // :483-486, + reference mod 2^16
-                if (epi) {                                                                    // optional black / white level epilogue
+                        for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i], refs);                // :483-486, + reference mod 2^16
+                        if (epi) {                                                                // optional black / white level epilogue
+                            const uint32_t y = (p_first + c0 + q) / ppr;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, F, (int)(y & 1u));
-                }
-                const int x = (int)(32u * xq);
-                uint16_t* orow = dst + (size_t)y * (size_t)width + x;
-                if (vec && x + 32 <= width) {
-                    uint4* o4 = reinterpret_cast<uint4*>(orow);
+                            for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, F, (int)(y & 1u));
+                        }
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the last store has read the buffer
+                    __syncwarp();
+                    if (q < cn) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) o4[i] = make_uint4(px[4 * i], px[4 * i + 1], px[4 * i + 2], px[4 * i + 3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {                                            // crop at width (:490)
-                        if (x + 2 * i < width) orow[2 * i] = (uint16_t)px[i];
-                        if (x + 2 * i + 1 < width) orow[2 * i + 1] = (uint16_t)(px[i] >> 16);
+                        for (int i = 0; i < 4; i++)
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n"
+                                         ::"r"(out_s + 64u * lane + 16u * (((uint32_t)i + rot) & 3u)), "r"(px[4 * i]), "r"(px[4 * i + 1]),
+                                           "r"(px[4 * i + 2]), "r"(px[4 * i + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");               // generic stores before the async read
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t nb = 64u * min(32u, cn - q0);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                                     ::"l"(reinterpret_cast<uint8_t*>(dst) + 64ull * (unsigned long long)(p_first + c0 + q0)), "r"(out_s), "r"(nb) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                     }
                 }
-                xq += LGW_THREADS;                                                            // the pair LGW_THREADS further on
-                while (xq >= ppr) { xq -= ppr; y++; }
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // before anyone reuses the tables
+            } else {
+                uint32_t P = p_first + c0 + tid;
+                uint32_t y = P / ppr, xq = P - y * ppr;
+                for (uint32_t q = tid; q < cn; q += LGW_THREADS) {
+                    const uint32_t oE = 2u * (uint32_t)plist[q];
+                    const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
+                    const uint32_t oO = oE + 2u + leg_len(bitsE);
+                    const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
+                    uint32_t px[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) px[i] = 0;
+                    lgw_block<0>(d32, oE, bitsE, px, false, false, 0u);
+                    lgw_block<16>(d32, oO, bitsO, px, false, false, 0u);
+                    const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i], refs);                    // :483-486, + reference mod 2^16
+                    if (epi) {                                                                    // optional black / white level epilogue
+#pragma unroll
+                        for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, F, (int)(y & 1u));
+                    }
+                    const int x = (int)(32u * xq);
+                    uint16_t* orow = dst + (size_t)y * (size_t)width + x;
+                    if (vec && x + 32 <= width) {
+                        uint4* o4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) o4[i] = make_uint4(px[4 * i], px[4 * i + 1], px[4 * i + 2], px[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {                                            // crop at width (:490)
+                            if (x + 2 * i < width) orow[2 * i] = (uint16_t)px[i];
+                            if (x + 2 * i + 1 < width) orow[2 * i + 1] = (uint16_t)(px[i] >> 16);
+                        }
+                    }
+                    xq += LGW_THREADS;                                                            // the pair LGW_THREADS further on
+                    while (xq >= ppr) { xq -= ppr; y++; }
+                }
             }
             __syncthreads();
         }
