@@ -297,7 +297,7 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, const mcraw_levels* l
         } else if (d.compression_type == MCRAW_COMPRESSION_LEGACY) {
             any6 = true;
             if (d.len >= ((uint64_t)1 << 40)) return fail_arg(ctx, who() + ": legacy frame buffer too large");
-            const uint64_t ntile = std::max<uint64_t>(1, (d.len + LGW_TILE - 1) / LGW_TILE);
+            const uint64_t ntile = lgw_ntiles(d.len);
             if (ntile > 0x7FFFFFFFull) return fail_arg(ctx, who() + ": legacy frame buffer too large");
             // scratch layout (offsets for now): exit maps (written only by tiles whose 17 exits differ) | two look-back
             // status words per tile (count word, exit word)
@@ -398,7 +398,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
             std::vector<std::pair<uint32_t, uint32_t>> lf;      // (frame, tiles)
             for (uint32_t i = 0; i < n; i++)
                 if (frames[i].type == MCRAW_COMPRESSION_LEGACY)
-                    lf.emplace_back(i, (uint32_t)std::max<uint64_t>(1, (frames[i].len + LGW_TILE - 1) / LGW_TILE));
+                    lf.emplace_back(i, (uint32_t)lgw_ntiles(frames[i].len));
             for (uint32_t t = 0; t < s.max_ltiles; t++)
                 for (const auto& fr : lf)
                     if (t < fr.second) lgwork.push_back(LgWork{fr.first, t});

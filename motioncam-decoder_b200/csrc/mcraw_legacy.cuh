@@ -47,7 +47,13 @@ constexpr int LGW_THREADS = 32 * LGW_WARPS;
 constexpr int LGW_SEG = 124;                   // bytes of the tile a thread owns: 62 candidate block starts, two words of marks.
                                                // 31 words: threads at the same offset of their segments hit 32 different banks
 constexpr int LGW_NC = LGW_SEG / 2;            // candidate block starts per segment
-constexpr int LGW_TILE = LGW_THREADS * LGW_SEG;   // bytes per tile (one CTA at a time): 15 872 for four warps
+constexpr int LGW_TILE = LGW_THREADS * LGW_SEG;   // bytes a CTA stages and indexes at a time (the WINDOW): 15 872 for four warps
+constexpr int LGW_RUN = 8;                     // the first LGW_RUN segments of a window are the RUN-UP: they belong to the tile before
+                                               // (for tile 0 they are its own); chains started at all 17 offsets of the window start
+                                               // have nearly always become one by the end of the run-up, and then the tile knows its
+                                               // entry without waiting for anybody
+constexpr int LGW_RUNB = LGW_RUN * LGW_SEG;
+constexpr int LGW_STRIDE = LGW_TILE - LGW_RUNB;   // window t starts at byte t * LGW_STRIDE; tile t owns window bytes [LGW_RUNB (0 for t = 0), LGW_TILE)
 constexpr int LGW_TAB = 84;                    // bytes of exit table per thread: LGW_NC candidates + 17 positions behind the segment
                                                // (+ pad); 21 words, odd, for the same reason
 constexpr int LGW_ENT = 32;                    // table offset of the 17 entries a segment is reached with (one per warp entry):
@@ -59,19 +65,28 @@ constexpr int LG_STATES = 17;                  // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;               // exit code of a chain that ran into the end of the buffer
 constexpr int LG_OVERRUN = 80;                 // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it (+ word reads)
 constexpr int LGW_DATA = LGW_TILE + LG_OVERRUN;
+#ifndef MCRAW_LGW_PF_DIV
+#define MCRAW_LGW_PF_DIV 1
+#endif
+constexpr int LGW_PF_DIV = MCRAW_LGW_PF_DIV;   // L2 prefetch distance: (resident CTAs) / LGW_PF_DIV tickets ahead
 constexpr int LGW_LB = 32;                     // look-back window: status words read per poll
 constexpr int LGW_SMEM = LGW_DATA + LGW_THREADS * LGW_TAB;      // the pair list and the output staging reuse the tables
 constexpr uint32_t LGW_ST_AGG = 1u, LGW_ST_INCL = 2u;          // count words: this tile's blocks / all blocks up to its end
 constexpr uint32_t LGW_EX_CONV = 1u, LGW_EX_MAP = 2u, LGW_EX_FINAL = 3u;   // exit words, see 4. above
 constexpr uint32_t LGW_ERR_BIT = 1u << 5;      // sticky: a wait gave up somewhere up the chain
 constexpr uint32_t LGW_SPIN_LIMIT = 1u << 18;  // polls of ~0.2 us: a wait that long means something is broken, not slow
-static_assert(LGW_DATA % 16 == 0 && LGW_TILE % 16 == 0, "bulk copies work in 16-byte granules");
+static_assert(LGW_DATA % 16 == 0 && LGW_TILE % 16 == 0 && LGW_STRIDE % 16 == 0, "bulk copies work in 16-byte granules");
+static_assert(LGW_RUN >= 1 && LGW_RUN < 32 && LGW_RUNB >= 34, "the run-up lies inside warp 0 and is at least one block long");
 static_assert(LGW_SEG % 4 == 0 && LGW_NC <= 64 && LGW_SEG >= 34, "two words of marks per segment; a block never skips a segment");
 static_assert(LGW_NC + LG_STATES <= LGW_TAB && LGW_ENT >= LG_STATES && LGW_ENT + LG_STATES <= LGW_NC && LGW_TAB % 4 == 0, "exit table layout");
 static_assert(LGW_PAIR_CHUNK * 2 + LGW_WARPS * LGW_OUT <= LGW_THREADS * LGW_TAB && (LGW_PAIR_CHUNK * 2) % 16 == 0,
               "the pair list and the warps' output staging reuse the tables");
 
 struct LgWork { uint32_t frame, tile; };
+// tiles of a frame buffer of len bytes
+__host__ __device__ inline unsigned long long lgw_ntiles(const unsigned long long len) {
+    return len > (unsigned long long)LGW_RUNB ? (len - LGW_RUNB + LGW_STRIDE - 1) / LGW_STRIDE : 1ull;
+}
 
 // payload bytes of a 16-sample block for header nibble b (RawData_Legacy.cpp:13-32, min(16, bits) at :395)
 __device__ __forceinline__ uint32_t leg_len(uint32_t b) { return b <= 10u ? 2u * b : 32u; }
@@ -170,32 +185,39 @@ __device__ __forceinline__ void lgw_exit_table(const uint32_t* __restrict__ dw, 
     }
 }
 
-// OR the 16 samples of the block at byte offset o (header nibble `bits`) into px[], at bit ADJ of each word (0: even-column
-// block, 16: odd-column block, RawData_Legacy.cpp:483-486).  d32: the staged tile as words.  The payload is a contiguous
-// MSB-first bit stream (:38-358), so 8 samples are exactly `bits` bytes: per group of 8 the bytes are fetched as
-// big-endian words (PRMT with a runtime selector does alignment and byte order in one go) and every sample is one
-// rotate + one mask.  Three lane-uniform formulations instead of one code path per width: widths 0..8 (two 4-sample
-// windows per group), 9..10 (four 2-sample windows), and 16-bit big-endian samples (:360-370, nibbles 11..15, :395).
+__device__ __forceinline__ uint32_t lg_prmt(const uint32_t a, const uint32_t b, const uint32_t sel) {   // selector nibbles must be 0 .. 7
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;\n" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// The 16 samples of the block at byte offset o (header nibble `bits`) go into the low (SECOND = false: even-column block)
+// or high (SECOND = true: odd-column block) halves of px[] (RawData_Legacy.cpp:483-486); returns the mask of a sample's
+// valid bits -- what lands above a sample inside its half is left for the caller to clear (one AND per word for both
+// blocks).  d32: the staged tile as words.  The payload is a contiguous MSB-first bit stream (:38-358), so 8 samples
+// are exactly `bits` bytes: per group of 8 the bytes are fetched as big-endian words (PRMT with a runtime selector does
+// alignment and byte order in one go) into windows with a few samples at the top, and a sample is the window shifted
+// right.  The arithmetic pipe is this kernel's bottleneck, so three of four shifts are multiplications
+// (mul.hi by a power of two, on the FMA pipe) and the halves are merged by PRMT.  Three lane-uniform formulations
+// instead of one code path per width: widths 0..8 (two 4-sample windows per group), 9..10 (four 2-sample windows),
+// and 16-bit big-endian samples (:360-370, nibbles 11..15, :395).
 // ROTATION: px[k] receives sample (k + 4 * rot) mod 16, rot = 0 .. 3 (rot1 = rot & 1, rot2 = rot & 2 as flags) -- the
 // lane's four 16-byte output pieces, rotated, which is what lets a warp write its 32 x 64 bytes into LINEAR shared memory
 // without bank conflicts (see the bulk store in the kernel).  The rotation is applied to the windows, not to the samples.
-template <int ADJ>
-__device__ __forceinline__ void lgw_block(const uint32_t* __restrict__ d32, const uint32_t o, const uint32_t bits, uint32_t (&px)[16],
-                                          const bool rot1, const bool rot2, const uint32_t rot) {
+template <bool SECOND>
+__device__ __forceinline__ uint32_t lgw_block(const uint32_t* __restrict__ d32, const uint32_t o, const uint32_t bits, uint32_t (&px)[16],
+                                              const bool rot1, const bool rot2, const uint32_t rot) {
     const uint32_t a = o + 2u;
+#define LGW_PUT(k, v) px[k] = SECOND ? lg_prmt(px[k], (v), 0x5410u) : (v)
     if (bits <= 8u) {
         const uint32_t w = bits;
-        const uint32_t mask = ((1u << w) - 1u) << ADJ;
-        uint32_t r[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) r[j] = (32u - ADJ - (uint32_t)(j + 1) * w) & 31u;
         uint32_t win[4];                                                               // samples 4t .. 4t+3 sit at the top of win[t]
 #pragma unroll
         for (int g = 0; g < 2; g++) {
             const uint32_t ag = a + g * w;
             const uint32_t i = ag >> 2, sel = 0x0123u + 0x1111u * (ag & 3u);
             const uint32_t W0 = d32[i], W1 = d32[i + 1], W2 = d32[i + 2];
-            const uint32_t G0 = __byte_perm(W0, W1, sel), G1 = __byte_perm(W1, W2, sel);
+            const uint32_t G0 = lg_prmt(W0, W1, sel), G1 = lg_prmt(W1, W2, sel);
             win[2 * g] = G0;
             win[2 * g + 1] = __funnelshift_lc(G1, G0, 4u * w);                         // the window of samples 4..7
         }
@@ -203,21 +225,25 @@ __device__ __forceinline__ void lgw_block(const uint32_t* __restrict__ d32, cons
             const uint32_t t0 = rot1 ? win[1] : win[0], t1 = rot1 ? win[2] : win[1], t2 = rot1 ? win[3] : win[2], t3 = rot1 ? win[0] : win[3];
             win[0] = rot2 ? t2 : t0; win[1] = rot2 ? t3 : t1; win[2] = rot2 ? t0 : t2; win[3] = rot2 ? t1 : t3;
         }
+        const uint32_t m1 = 1u << w, m2 = 1u << (2u * w), m3 = 1u << (3u * w);         // x >> (32 - k w) = mul.hi(x, 2^(k w)), k w <= 24
+        const uint32_t s4 = (32u - 4u * w) & 31u;                                       // w = 8: the window itself (w = 0: anything, mask 0)
 #pragma unroll
-        for (int t = 0; t < 4; t++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) px[4 * t + j] |= __funnelshift_r(win[t], win[t], r[j]) & mask;
+        for (int t = 0; t < 4; t++) {
+            LGW_PUT(4 * t, __umulhi(win[t], m1));
+            LGW_PUT(4 * t + 1, __umulhi(win[t], m2));
+            LGW_PUT(4 * t + 2, __umulhi(win[t], m3));
+            LGW_PUT(4 * t + 3, win[t] >> s4);
+        }
+        return m1 - 1u;
     } else if (bits <= 10u) {
         const uint32_t w = bits;
-        const uint32_t mask = ((1u << w) - 1u) << ADJ;
-        const uint32_t r0 = (32u - ADJ - w) & 31u, r1 = (32u - ADJ - 2u * w) & 31u;
         uint32_t win[8];                                                               // samples 2n, 2n+1 sit at the top of win[n]
 #pragma unroll
         for (int g = 0; g < 2; g++) {
             const uint32_t ag = a + g * w;
             const uint32_t i = ag >> 2, sel = 0x0123u + 0x1111u * (ag & 3u);
             const uint32_t W0 = d32[i], W1 = d32[i + 1], W2 = d32[i + 2], W3 = d32[i + 3];
-            const uint32_t G0 = __byte_perm(W0, W1, sel), G1 = __byte_perm(W1, W2, sel), G2 = __byte_perm(W2, W3, sel);
+            const uint32_t G0 = lg_prmt(W0, W1, sel), G1 = lg_prmt(W1, W2, sel), G2 = lg_prmt(W2, W3, sel);
             win[4 * g] = G0;                                                           // samples 2m, 2m+1 start at bit 2mw
             win[4 * g + 1] = __funnelshift_l(G1, G0, 2u * w);
             win[4 * g + 2] = __funnelshift_l(G2, G1, 4u * w - 32u);
@@ -230,24 +256,28 @@ __device__ __forceinline__ void lgw_block(const uint32_t* __restrict__ d32, cons
 #pragma unroll
             for (int n = 0; n < 8; n++) win[n] = rot2 ? t[(n + 4) & 7] : t[n];
         }
+        const uint32_t m1 = 1u << w, m2 = 1u << (2u * w);
 #pragma unroll
         for (int n = 0; n < 8; n++) {
-            px[2 * n] |= __funnelshift_r(win[n], win[n], r0) & mask;
-            px[2 * n + 1] |= __funnelshift_r(win[n], win[n], r1) & mask;
+            LGW_PUT(2 * n, __umulhi(win[n], m1));
+            LGW_PUT(2 * n + 1, __umulhi(win[n], m2));
         }
+        return m1 - 1u;
     } else {
         const uint32_t i = a >> 2, k0 = a & 3u;                                        // the payload starts 2-byte aligned
         // sample k = bytes (2k, 2k+1), big-endian: byte index (k0 + 2 (k & 1)) of the word pair (k / 2, k / 2 + 1);
-        // the selector puts (high byte, low byte) at result bytes (1, 0) for ADJ 0 and (3, 2) for ADJ 16
-        const uint32_t selA = ((k0 + 1u) | (k0 << 4)) << (ADJ / 2), selB = ((k0 + 3u) | ((k0 + 2u) << 4)) << (ADJ / 2);
+        // the selector puts (high byte, low byte) at result bytes (1, 0)
+        const uint32_t selA = (k0 + 1u) | (k0 << 4), selB = (k0 + 3u) | ((k0 + 2u) << 4);
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             const uint32_t ms = ((uint32_t)m + 2u * rot) & 7u;
             const uint32_t lo = d32[i + ms], hi = d32[i + ms + 1u];
-            px[2 * m] |= __byte_perm(lo, hi, selA) & (0xFFFFu << ADJ);
-            px[2 * m + 1] |= __byte_perm(lo, hi, selB) & (0xFFFFu << ADJ);
+            LGW_PUT(2 * m, lg_prmt(lo, hi, selA));
+            LGW_PUT(2 * m + 1, lg_prmt(lo, hi, selB));
         }
+        return 0xFFFFu;
     }
+#undef LGW_PUT
 }
 
 template <bool EPI>
@@ -260,8 +290,8 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
     uint16_t* plist = reinterpret_cast<uint16_t*>(tables);                                  // pair list: [LGW_PAIR_CHUNK], after the tables
     __shared__ __align__(8) unsigned long long bar_storage;
     __shared__ uint8_t sh_wmap[LGW_WARPS][LG_STATES + 3];                                   // map of each warp's 32 segments
-    __shared__ uint32_t warp_sums[LGW_WARPS], sh_went[LGW_WARPS];
-    __shared__ uint32_t sh_ticket, sh_base, sh_skip, sh_err;
+    __shared__ uint32_t warp_sums[LGW_WARPS];
+    __shared__ uint32_t sh_ticket, sh_base, sh_skip, sh_err, sh_runconv, sh_cw0;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t bar = smem_u32(&bar_storage);
     if (tid == 0) {
@@ -285,7 +315,7 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
             if (t < nwork) {
                 const LgWork w0 = work[t];
                 const FrameDev& F0 = frames[w0.frame];
-                const unsigned long long off0 = (unsigned long long)w0.tile * LGW_TILE;
+                const unsigned long long off0 = (unsigned long long)w0.tile * LGW_STRIDE;
                 if (off0 + (unsigned long long)LGW_DATA <= F0.len) {
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic accesses of the last tile before the async write
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)LGW_DATA) : "memory");
@@ -293,11 +323,11 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                                  ::"r"(smem_u32(data)), "l"(F0.src + off0), "r"((uint32_t)LGW_DATA), "r"(bar) : "memory");
                 }
                 // the tile some CTA will take about one round of the grid from now: have it in L2 by then
-                const uint32_t tn = t + gridDim.x;
+                const uint32_t tn = t + gridDim.x / (uint32_t)LGW_PF_DIV;
                 if (tn < nwork) {
                     const LgWork w1 = work[tn];
                     const FrameDev& F1 = frames[w1.frame];
-                    const unsigned long long off1 = (unsigned long long)w1.tile * LGW_TILE;
+                    const unsigned long long off1 = (unsigned long long)w1.tile * LGW_STRIDE;
                     if (off1 + (unsigned long long)LGW_DATA <= F1.len)
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(F1.src + off1), "r"((uint32_t)LGW_DATA) : "memory");
                 }
@@ -309,9 +339,9 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
         const LgWork wk = work[ticket];
         const FrameDev& F = frames[wk.frame];
         const unsigned long long len = F.len;
-        const uint32_t ntile = (uint32_t)max((len + LGW_TILE - 1) / LGW_TILE, 1ull);
+        const uint32_t ntile = (uint32_t)lgw_ntiles(len);
         const uint32_t tile = wk.tile;
-        const unsigned long long tile_off = (unsigned long long)tile * LGW_TILE;
+        const unsigned long long tile_off = (unsigned long long)tile * LGW_STRIDE;   // where the window starts
         const uint32_t tile_rel = (uint32_t)min(len > tile_off ? len - tile_off : 0ull, (unsigned long long)(1u << 30));
         const bool last_tile = tile + 1 == ntile;
         const uint32_t ppr = ((uint32_t)F.width + 31u) / 32u;                            // pairs per row (RawData_Legacy.cpp:34-36)
@@ -336,41 +366,54 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
         // ---- 2. exit table of this thread's segment
         if (tile_rel > (uint32_t)LGW_TILE + 34u) lgw_exit_table<false>(d32 + tid * (uint32_t)(LGW_SEG / 4), T, seg0, tile_rel);
         else lgw_exit_table<true>(d32 + tid * (uint32_t)(LGW_SEG / 4), T, seg0, tile_rel);
-        __syncthreads();
+        __syncwarp();                                         // the chase stays inside the warp's own 32 tables
         // ---- 3. the 17 entries of this warp's first segment, chased through its 32 segments
+        uint32_t eR = LG_DEAD;                                // warp 0: what the first segment behind the run-up is entered with
         if (lane < (uint32_t)LG_STATES) {
             uint32_t e = lane;
             uint8_t* Ts = tables + (32u * warp) * (uint32_t)LGW_TAB;
 #pragma unroll 4
             for (int s = 0; s < 32; s++) {
+                if (s == LGW_RUN) eR = e;
                 Ts[LGW_ENT + lane] = (uint8_t)e;              // what segment s is entered with when the warp is entered with `lane`
                 if (e != LG_DEAD) e = Ts[e];
                 Ts += LGW_TAB;
             }
             sh_wmap[warp][lane] = (uint8_t)e;
         }
+        if (warp == 0) {                                      // have all 17 chains become one inside the run-up?
+            const uint32_t e0 = __shfl_sync(0xFFFFFFFFu, eR, 0);
+            const bool one = __all_sync(0xFFFFFFFFu, lane >= (uint32_t)LG_STATES || eR == e0);
+            if (lane == 0) { sh_runconv = (tile == 0u || one) ? 1u : 0u; sh_err = 0u; }
+        }
         __syncthreads();
-        // ---- 4. warp 0: the tile's map, its exit word, this tile's entry
+        // ---- 4. warp 0: the tile's exit word.  Tile 0 starts with a block; every other tile whose run-up merged all chains
+        //      knows its entry already (any of the 17 chains is the true one from there on).  Only a tile whose run-up did not
+        //      (runs of one constant block length) has to look back for the exit of the tile before it.
+        const bool runconv = sh_runconv != 0u;
         if (warp == 0) {
             uint32_t x = lane < (uint32_t)LG_STATES ? lane : 0u;
 #pragma unroll
             for (int w = 0; w < LGW_WARPS; w++)
-                if (x != LG_DEAD) x = sh_wmap[w][x];
+                if (x != LG_DEAD) x = sh_wmap[w][x];          // where the chain that enters the window with `lane` leaves it
             if (last_tile) x = LG_DEAD;                       // nothing follows the last tile
             const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, x, 0);
-            const bool conv = __all_sync(0xFFFFFFFFu, x == x0);
+            const bool conv = tile == 0u || __all_sync(0xFFFFFFFFu, x == x0);   // tile 0: chain 0 is the chain
             // Status words are self-contained (value, epoch and state in one 64-bit store), so they travel as relaxed
             // gpu-scope accesses; only a published MAP refers to other memory (the 17 map entries): fence, then the word
             // on this side, the word, then a fence before the entries are read on the other.
-            if (!conv) {
-                if (lane < (uint32_t)LG_STATES) F.lg_tilemap[(size_t)tile * LG_STATES + lane] = x;
+            if (!conv) {                                      // map: entry of the TILE (behind the run-up) -> exit
+                uint32_t* const tm = F.lg_tilemap + (size_t)tile * LG_STATES;
+                if (lane < (uint32_t)LG_STATES) tm[lane] = LG_DEAD;           // entries no chain arrives with are never asked for
+                __syncwarp();
+                if (lane < (uint32_t)LG_STATES && eR != LG_DEAD) tm[eR] = x;  // chains that share eR share x
                 __threadfence();
                 __syncwarp();
             }
             if (lane == 0) lgw_store_relaxed(cntw + 2 * (size_t)tile + 1, lgw_pack(0u, epoch, conv ? LGW_EX_CONV : LGW_EX_MAP, x0));
-            uint32_t entry = 0, errbit = 0;
-            if (tile > 0) {
-                const uint32_t jhi = tile - 1;
+            if (!runconv) {
+                uint32_t entry = LG_DEAD, errbit = 0;
+                const uint32_t jhi = tile - 1;                // (tile 0 never gets here)
                 uint32_t spins = 0;
                 for (;;) {
                     const int j = (int)jhi - (int)lane;
@@ -384,6 +427,7 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                         const unsigned between = (1u << d) - 1u;  // tiles jhi - d + 1 .. jhi must have published their maps
                         if ((any & between) == between) {
                             uint32_t state = __shfl_sync(0xFFFFFFFFu, (uint32_t)sw & 31u, d);
+                            errbit = __shfl_sync(0xFFFFFFFFu, (uint32_t)sw & LGW_ERR_BIT, d);
                             if (d > 0) __threadfence();          // the status loads before the map loads
                             for (int m = d - 1; m >= 0 && state != LG_DEAD; m--)          // (rare: runs of one constant block length)
                                 state = __ldcg(F.lg_tilemap + (size_t)(jhi - (uint32_t)m) * LG_STATES + state);
@@ -394,26 +438,25 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                     if (++spins > LGW_SPIN_LIMIT) { entry = LG_DEAD; errbit = LGW_ERR_BIT; break; }   // never expected
                     __nanosleep(spins < 8 ? 40 : 200);
                 }
-            }
-            // the actual exit of a tile that published a map: successors stop composing here
-            const uint32_t x_act = entry == LG_DEAD ? LG_DEAD : __shfl_sync(0xFFFFFFFFu, x, entry & 31u);
-            if (!conv && lane == 0) lgw_store_relaxed(cntw + 2 * (size_t)tile + 1, lgw_pack(0u, epoch, LGW_EX_FINAL, x_act | errbit));
-            if (lane == 0) {
-                uint32_t c = entry;
-#pragma unroll
-                for (int w = 0; w < LGW_WARPS; w++) {
-                    sh_went[w] = c;                                   // what warp w's first segment is entered with
-                    if (c != LG_DEAD) c = sh_wmap[w][c];
-                }
-                sh_err = errbit;
+                // the chain of this window that arrives behind the run-up with `entry` (the true chain is one of the 17)
+                const unsigned match = __ballot_sync(0xFFFFFFFFu, lane < (uint32_t)LG_STATES && eR == entry && entry != LG_DEAD);
+                const uint32_t cw0 = match ? (uint32_t)__ffs((int)match) - 1u : LG_DEAD;
+                // the actual exit of a tile that published a map: successors stop composing here
+                const uint32_t x_act = cw0 == LG_DEAD ? LG_DEAD : __shfl_sync(0xFFFFFFFFu, x, cw0);
+                if (!conv && lane == 0) lgw_store_relaxed(cntw + 2 * (size_t)tile + 1, lgw_pack(0u, epoch, LGW_EX_FINAL, x_act | errbit));
+                if (lane == 0) { sh_cw0 = cw0; sh_err = errbit; }
             }
         }
-        __syncthreads();
+        if (!runconv) __syncthreads();                        // (uniform)
         // ---- 5. the exact chain: every thread walks its segment from the entry it is reached with
         uint32_t wv0 = 0, wv1 = 0;
         {
-            const uint32_t cw = sh_went[warp];
-            const uint32_t e = cw == LG_DEAD ? LG_DEAD : (uint32_t)T[LGW_ENT + cw];
+            uint32_t cw = runconv ? 0u : sh_cw0;             // what the window is entered with (any chain, if they merged in the run-up)
+#pragma unroll
+            for (int w = 0; w < LGW_WARPS - 1; w++)
+                if ((uint32_t)w < warp && cw != LG_DEAD) cw = sh_wmap[w][cw];     // ... and this thread's warp
+            const bool owned = tile == 0u || tid >= (uint32_t)LGW_RUN;            // run-up segments belong to the tile before
+            const uint32_t e = (cw == LG_DEAD || !owned) ? LG_DEAD : (uint32_t)T[LGW_ENT + cw];
             if (e != LG_DEAD) lgw_walk_segment(data, seg0, seg0 + 2u * e, wv0, wv1, tile_rel);
         }
         const uint32_t c = __popc(wv0) + __popc(wv1);
@@ -508,19 +551,29 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
         const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
         const bool lin = vec && (width & 31) == 0;              // rows of whole pairs: consecutive pairs are consecutive memory
         const unsigned epi = EPI ? F.epi_mode : 0u;             // EPI = false: the epilogue code is not even in the kernel
+        // the pair leaders among this thread's block starts: marks whose ordinal is even.  x = inclusive prefix parity of the
+        // marks (bit i: parity of the number of marks at or below i), so the k-th mark (k = 0, 1, ..) has x = (k + 1) & 1
+        uint32_t lead0, lead1;
+        {
+            uint32_t x0 = wv0, x1 = wv1;
+#pragma unroll
+            for (int sh = 1; sh < 32; sh <<= 1) { x0 ^= x0 << sh; x1 ^= x1 << sh; }
+            const uint32_t odd0 = 0u - (ord0 & 1u), odd1 = 0u - ((ord0 + __popc(wv0)) & 1u);   // all ones: the first mark has an odd ordinal
+            lead0 = wv0 & (x0 ^ odd0);
+            lead1 = wv1 & (x1 ^ odd1);
+        }
         for (uint32_t c0 = 0; c0 < npairs; c0 += LGW_PAIR_CHUNK) {
             const uint32_t cn = min((uint32_t)LGW_PAIR_CHUNK, npairs - c0);
             {
-                uint32_t ord = ord0;
+                uint32_t q = ((ord0 + 1u) >> 1) - p_first - c0;              // this thread's first pair; wraps to a huge value for earlier passes' pairs
 #pragma unroll
                 for (int hw = 0; hw < 2; hw++) {
-                    uint32_t marks = hw ? wv1 : wv0;
+                    uint32_t marks = hw ? lead1 : lead0;
                     while (marks) {
                         const uint32_t b = (uint32_t)__ffs((int)marks) - 1u;
                         marks &= marks - 1u;
-                        const uint32_t q = (ord >> 1) - p_first - c0;       // wraps to a huge value for earlier passes' pairs
-                        if (!(ord & 1u) && q < cn) plist[q] = (uint16_t)(((uint32_t)LGW_SEG / 2u) * tid + 32u * hw + b);
-                        ord++;
+                        if (q < cn) plist[q] = (uint16_t)(((uint32_t)LGW_SEG / 2u) * tid + 32u * hw + b);
+                        q++;
                     }
                 }
             }
@@ -533,18 +586,17 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                 for (uint32_t q0 = 32u * warp; q0 < cn; q0 += LGW_THREADS) {
                     const uint32_t q = q0 + lane;
                     uint32_t px[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) px[i] = 0;
                     if (q < cn) {
                         const uint32_t oE = 2u * (uint32_t)plist[q];
                         const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
                         const uint32_t oO = oE + 2u + leg_len(bitsE);
                         const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
-                        lgw_block<0>(d32, oE, bitsE, px, rot1, rot2, rot);
-                        lgw_block<16>(d32, oO, bitsO, px, rot1, rot2, rot);
+                        const uint32_t mE = lgw_block<false>(d32, oE, bitsE, px, rot1, rot2, rot);
+                        const uint32_t mO = lgw_block<true>(d32, oO, bitsO, px, rot1, rot2, rot);
+                        const uint32_t cm = mE | (mO << 16);
                         const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
 #pragma unroll
-                        for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i], refs);                // :483-486, + reference mod 2^16
+                        for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i] & cm, refs);           // :483-486, + reference mod 2^16
                         if (epi) {                                                                // optional black / white level epilogue
                             const uint32_t y = (p_first + c0 + q) / ppr;
 #pragma unroll
@@ -579,13 +631,12 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                     const uint32_t oO = oE + 2u + leg_len(bitsE);
                     const uint32_t hO = leg_header(data, oO), bitsO = leg_hdr_bits(hO);
                     uint32_t px[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) px[i] = 0;
-                    lgw_block<0>(d32, oE, bitsE, px, false, false, 0u);
-                    lgw_block<16>(d32, oO, bitsO, px, false, false, 0u);
+                    const uint32_t mE = lgw_block<false>(d32, oE, bitsE, px, false, false, 0u);
+                    const uint32_t mO = lgw_block<true>(d32, oO, bitsO, px, false, false, 0u);
+                    const uint32_t cm = mE | (mO << 16);
                     const uint32_t refs = leg_hdr_ref(hE) | (leg_hdr_ref(hO) << 16);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i], refs);                    // :483-486, + reference mod 2^16
+                    for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i] & cm, refs);               // :483-486, + reference mod 2^16
                     if (epi) {                                                                    // optional black / white level epilogue
 #pragma unroll
                         for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, F, (int)(y & 1u));
