@@ -48,7 +48,10 @@ constexpr int LGW_SEG = 124;                   // bytes of the tile a thread own
                                                // 31 words: threads at the same offset of their segments hit 32 different banks
 constexpr int LGW_NC = LGW_SEG / 2;            // candidate block starts per segment
 constexpr int LGW_TILE = LGW_THREADS * LGW_SEG;   // bytes a CTA stages and indexes at a time (the WINDOW): 15 872 for four warps
-constexpr int LGW_RUN = 8;                     // the first LGW_RUN segments of a window are the RUN-UP: they belong to the tile before
+#ifndef MCRAW_LGW_RUN
+#define MCRAW_LGW_RUN 8
+#endif
+constexpr int LGW_RUN = MCRAW_LGW_RUN;                     // the first LGW_RUN segments of a window are the RUN-UP: they belong to the tile before
                                                // (for tile 0 they are its own); chains started at all 17 offsets of the window start
                                                // have nearly always become one by the end of the run-up, and then the tile knows its
                                                // entry without waiting for anybody
@@ -63,7 +66,7 @@ constexpr int LGW_PAIR_CHUNK = LGW_WARPS >= 4 ? 1024 : 512;   // pairs listed an
 constexpr int LGW_OUT = 2048;                  // bytes of decoded pixels a warp hands to one bulk store: 32 pairs x 64 bytes
 constexpr int LG_STATES = 17;                  // entry offsets 0, 2, ..., 32
 constexpr uint32_t LG_DEAD = 31;               // exit code of a chain that ran into the end of the buffer
-constexpr int LG_OVERRUN = 80;                 // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it (+ word reads)
+constexpr int LG_OVERRUN = 128;                // a pair led inside the tile ends at most 2 + 34 + 34 bytes past it (+ word reads); keeps what follows 64-byte aligned
 constexpr int LGW_DATA = LGW_TILE + LG_OVERRUN;
 #ifndef MCRAW_LGW_PF_DIV
 #define MCRAW_LGW_PF_DIV 1
@@ -75,7 +78,8 @@ constexpr uint32_t LGW_ST_AGG = 1u, LGW_ST_INCL = 2u;          // count words: t
 constexpr uint32_t LGW_EX_CONV = 1u, LGW_EX_MAP = 2u, LGW_EX_FINAL = 3u;   // exit words, see 4. above
 constexpr uint32_t LGW_ERR_BIT = 1u << 5;      // sticky: a wait gave up somewhere up the chain
 constexpr uint32_t LGW_SPIN_LIMIT = 1u << 18;  // polls of ~0.2 us: a wait that long means something is broken, not slow
-static_assert(LGW_DATA % 16 == 0 && LGW_TILE % 16 == 0 && LGW_STRIDE % 16 == 0, "bulk copies work in 16-byte granules");
+static_assert(LGW_DATA % 64 == 0 && LGW_TILE % 16 == 0 && LGW_STRIDE % 16 == 0 && (2 * LGW_PAIR_CHUNK) % 64 == 0 && LGW_OUT % 64 == 0,
+              "bulk copies work in 16-byte granules; the output staging slots are 64-byte aligned");
 static_assert(LGW_RUN >= 1 && LGW_RUN < 32 && LGW_RUNB >= 34, "the run-up lies inside warp 0 and is at least one block long");
 static_assert(LGW_SEG % 4 == 0 && LGW_NC <= 64 && LGW_SEG >= 34, "two words of marks per segment; a block never skips a segment");
 static_assert(LGW_NC + LG_STATES <= LGW_TAB && LGW_ENT >= LG_STATES && LGW_ENT + LG_STATES <= LGW_NC && LGW_TAB % 4 == 0, "exit table layout");
@@ -139,21 +143,39 @@ __device__ __forceinline__ unsigned long long lgw_load_relaxed(const unsigned lo
     return v;
 }
 
-// One thread, its segment [seg0, seg0 + LGW_SEG) of the staged tile: walk from tile-relative byte offset p to the end of the
-// segment; block starts go into (m0, m1), one bit per even offset.  rel: bytes from the tile start to the end of the buffer
-// (a block is decoded only if it ends before the last byte, RawData_Legacy.cpp:387,398); the chain stops at the first
-// block that is not.
-__device__ __forceinline__ void lgw_walk_segment(const uint8_t* data, const uint32_t seg0, uint32_t p, uint32_t& m0, uint32_t& m1, const uint32_t rel) {
-    uint32_t a0 = 0, a1 = 0;
-    const uint32_t end = seg0 + (uint32_t)LGW_SEG;
-    while (p < end) {
-        const uint32_t pos = (p - seg0) >> 1;                         // 0 .. 61
-        const uint32_t q = p + leg_step(data[p]);
-        if (q >= rel) break;
-        if (pos >= 32u) a1 |= 1u << (pos - 32u); else a0 |= 1u << pos;
-        p = q;
+// One thread, its segment [seg0, seg0 + LGW_SEG) of the staged tile: walk from half offset `pos` of the segment (byte
+// seg0 + 2 pos) to the end of the segment; block starts go into (m0, m1), one bit per even offset.  TAIL: the buffer may
+// end inside or right behind the window; rel: bytes from the window start to the end of the buffer (a block is decoded
+// only if it ends before the last byte, RawData_Legacy.cpp:387,398); the chain stops at the first block that is not.
+template <bool TAIL>
+__device__ __forceinline__ void lgw_walk_segment(const uint8_t* data, const uint32_t seg0, uint32_t pos, uint32_t& m0, uint32_t& m1, const uint32_t rel) {
+    unsigned long long m = 0;
+    const uint8_t* sp = data + seg0;
+    while (pos < (uint32_t)LGW_NC) {
+        const uint32_t b = (uint32_t)sp[2u * pos] >> 4;
+        const uint32_t h = b > 10u ? 16u : b;                         // payload / 2
+        if (TAIL) { if (seg0 + 2u * pos + 2u + 2u * h >= rel) break; }
+        m |= 1ull << pos;
+        pos += 1u + h;
     }
-    m0 = a0; m1 = a1;
+    m0 = (uint32_t)m; m1 = (uint32_t)(m >> 32);
+}
+
+// One lane, one of the 17 states a warp's first segment can be entered with: follow it through the warp's 32 segment maps
+// (Tw: the warp's tables) and leave, in every segment's table, the state that segment is entered with.  Returns the state
+// the warp is left with; eR: the state the first segment behind the run-up is entered with (only warp 0's is used).
+// All offsets are immediates: a store, an add and a load per segment.  TAIL: chains can end (LG_DEAD) inside the window.
+template <bool TAIL>
+__device__ __forceinline__ uint32_t lgw_chase(uint8_t* const Tw, const uint32_t lane, uint32_t& eR) {
+    uint32_t e = lane;
+    uint8_t* const Te = Tw + LGW_ENT + lane;
+#pragma unroll
+    for (int s = 0; s < 32; s++) {
+        if (s == LGW_RUN) eR = e;
+        Te[s * LGW_TAB] = (uint8_t)e;
+        if (!TAIL || e != LG_DEAD) e = Tw[s * LGW_TAB + e];
+    }
+    return e;
 }
 
 // One thread: the exit table of its segment.  T[c], c = 0 .. LGW_NC - 1: where the chain that has a block start at byte
@@ -201,9 +223,9 @@ __device__ __forceinline__ uint32_t lg_prmt(const uint32_t a, const uint32_t b, 
 // (mul.hi by a power of two, on the FMA pipe) and the halves are merged by PRMT.  Three lane-uniform formulations
 // instead of one code path per width: widths 0..8 (two 4-sample windows per group), 9..10 (four 2-sample windows),
 // and 16-bit big-endian samples (:360-370, nibbles 11..15, :395).
-// ROTATION: px[k] receives sample (k + 4 * rot) mod 16, rot = 0 .. 3 (rot1 = rot & 1, rot2 = rot & 2 as flags) -- the
-// lane's four 16-byte output pieces, rotated, which is what lets a warp write its 32 x 64 bytes into LINEAR shared memory
-// without bank conflicts (see the bulk store in the kernel).  The rotation is applied to the windows, not to the samples.
+// PIECE ORDER: px[k] receives sample k ^ (4 * rot), rot = 0 .. 3 (rot1 = rot & 1, rot2 = rot & 2 as flags) -- the
+// lane's four 16-byte output pieces, exchanged, which is what lets a warp write its 32 x 64 bytes into LINEAR shared memory
+// without bank conflicts (see the bulk store in the kernel).  The exchange is applied to the windows, not to the samples.
 template <bool SECOND>
 __device__ __forceinline__ uint32_t lgw_block(const uint32_t* __restrict__ d32, const uint32_t o, const uint32_t bits, uint32_t (&px)[16],
                                               const bool rot1, const bool rot2, const uint32_t rot) {
@@ -222,7 +244,7 @@ __device__ __forceinline__ uint32_t lgw_block(const uint32_t* __restrict__ d32, 
             win[2 * g + 1] = __funnelshift_lc(G1, G0, 4u * w);                         // the window of samples 4..7
         }
         {
-            const uint32_t t0 = rot1 ? win[1] : win[0], t1 = rot1 ? win[2] : win[1], t2 = rot1 ? win[3] : win[2], t3 = rot1 ? win[0] : win[3];
+            const uint32_t t0 = rot1 ? win[1] : win[0], t1 = rot1 ? win[0] : win[1], t2 = rot1 ? win[3] : win[2], t3 = rot1 ? win[2] : win[3];
             win[0] = rot2 ? t2 : t0; win[1] = rot2 ? t3 : t1; win[2] = rot2 ? t0 : t2; win[3] = rot2 ? t1 : t3;
         }
         const uint32_t m1 = 1u << w, m2 = 1u << (2u * w), m3 = 1u << (3u * w);         // x >> (32 - k w) = mul.hi(x, 2^(k w)), k w <= 24
@@ -252,9 +274,9 @@ __device__ __forceinline__ uint32_t lgw_block(const uint32_t* __restrict__ d32, 
         {
             uint32_t t[8];
 #pragma unroll
-            for (int n = 0; n < 8; n++) t[n] = rot1 ? win[(n + 2) & 7] : win[n];
+            for (int n = 0; n < 8; n++) t[n] = rot1 ? win[n ^ 2] : win[n];
 #pragma unroll
-            for (int n = 0; n < 8; n++) win[n] = rot2 ? t[(n + 4) & 7] : t[n];
+            for (int n = 0; n < 8; n++) win[n] = rot2 ? t[n ^ 4] : t[n];
         }
         const uint32_t m1 = 1u << w, m2 = 1u << (2u * w);
 #pragma unroll
@@ -270,7 +292,7 @@ __device__ __forceinline__ uint32_t lgw_block(const uint32_t* __restrict__ d32, 
         const uint32_t selA = (k0 + 1u) | (k0 << 4), selB = (k0 + 3u) | ((k0 + 2u) << 4);
 #pragma unroll
         for (int m = 0; m < 8; m++) {
-            const uint32_t ms = ((uint32_t)m + 2u * rot) & 7u;
+            const uint32_t ms = (uint32_t)m ^ (2u * rot);
             const uint32_t lo = d32[i + ms], hi = d32[i + ms + 1u];
             LGW_PUT(2 * m, lg_prmt(lo, hi, selA));
             LGW_PUT(2 * m + 1, lg_prmt(lo, hi, selB));
@@ -284,7 +306,7 @@ template <bool EPI>
 __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const FrameDev* __restrict__ frames, Result* __restrict__ results,
                                                              const LgWork* __restrict__ work, const uint32_t nwork,
                                                              uint32_t* __restrict__ counters, const uint32_t epoch) {
-    extern __shared__ __align__(16) uint8_t lg_smem[];
+    extern __shared__ __align__(128) uint8_t lg_smem[];
     uint8_t* data = lg_smem;
     uint8_t* tables = lg_smem + LGW_DATA;                                                   // [LGW_THREADS][LGW_TAB]
     uint16_t* plist = reinterpret_cast<uint16_t*>(tables);                                  // pair list: [LGW_PAIR_CHUNK], after the tables
@@ -302,15 +324,19 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
     const uint32_t seg0 = tid * (uint32_t)LGW_SEG;
     uint8_t* T = tables + tid * (uint32_t)LGW_TAB;
     uint32_t bulk_uses = 0;                                  // bulk copies this CTA has waited for: the mbarrier's phase
-    const uint32_t rot = (lane >> 1) & 3u;                   // rotation of this lane's output pieces (lgw_block)
+    const uint32_t rot = (lane >> 1) & 3u;                   // exchange of this lane's output pieces (lgw_block)
     const bool rot1 = (rot & 1u) != 0, rot2 = (rot & 2u) != 0;
     const uint32_t out_s = smem_u32(tables) + 2u * (uint32_t)LGW_PAIR_CHUNK + (uint32_t)LGW_OUT * warp;   // this warp's output staging
 
+    uint32_t next_ticket = 0;                                // thread 0: the ticket drawn during the last decode pass of the previous tile
+    bool have_next = false;                                  // (one pass early hides the atomic's round trip; earlier than that, tiles
+                                                             // that wait for this one's block count would wait longer)
     for (;;) {
         __syncthreads();                                      // every thread is done with the previous tile's shared memory
         // ---- 1. ticket; stage: ONE bulk copy for a tile that lies wholly inside the buffer
         if (tid == 0) {
-            const uint32_t t = atomicAdd(&counters[2], 1u);
+            const uint32_t t = have_next ? next_ticket : atomicAdd(&counters[2], 1u);
+            have_next = false;
             sh_ticket = t;
             if (t < nwork) {
                 const LgWork w0 = work[t];
@@ -322,20 +348,22 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                                  ::"r"(smem_u32(data)), "l"(F0.src + off0), "r"((uint32_t)LGW_DATA), "r"(bar) : "memory");
                 }
-                // the tile some CTA will take about one round of the grid from now: have it in L2 by then
-                const uint32_t tn = t + gridDim.x / (uint32_t)LGW_PF_DIV;
-                if (tn < nwork) {
-                    const LgWork w1 = work[tn];
-                    const FrameDev& F1 = frames[w1.frame];
-                    const unsigned long long off1 = (unsigned long long)w1.tile * LGW_STRIDE;
-                    if (off1 + (unsigned long long)LGW_DATA <= F1.len)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(F1.src + off1), "r"((uint32_t)LGW_DATA) : "memory");
-                }
             }
         }
         __syncthreads();
         const uint32_t ticket = sh_ticket;
         if (ticket >= nwork) break;
+        if (tid == 0) {
+            // the tile some CTA will take about one round of the grid from now: have it in L2 by then
+            const uint32_t tn = ticket + gridDim.x / (uint32_t)LGW_PF_DIV;
+            if (tn < nwork) {
+                const LgWork w1 = work[tn];
+                const FrameDev& F1 = frames[w1.frame];
+                const unsigned long long off1 = (unsigned long long)w1.tile * LGW_STRIDE;
+                if (off1 + (unsigned long long)LGW_DATA <= F1.len)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(F1.src + off1), "r"((uint32_t)LGW_DATA) : "memory");
+            }
+        }
         const LgWork wk = work[ticket];
         const FrameDev& F = frames[wk.frame];
         const unsigned long long len = F.len;
@@ -364,21 +392,15 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
         }
 
         // ---- 2. exit table of this thread's segment
-        if (tile_rel > (uint32_t)LGW_TILE + 34u) lgw_exit_table<false>(d32 + tid * (uint32_t)(LGW_SEG / 4), T, seg0, tile_rel);
+        const bool interior = tile_rel > (uint32_t)LGW_TILE + 34u;     // no block that starts in this window reaches the end of the buffer
+        if (interior) lgw_exit_table<false>(d32 + tid * (uint32_t)(LGW_SEG / 4), T, seg0, tile_rel);
         else lgw_exit_table<true>(d32 + tid * (uint32_t)(LGW_SEG / 4), T, seg0, tile_rel);
         __syncwarp();                                         // the chase stays inside the warp's own 32 tables
         // ---- 3. the 17 entries of this warp's first segment, chased through its 32 segments
         uint32_t eR = LG_DEAD;                                // warp 0: what the first segment behind the run-up is entered with
         if (lane < (uint32_t)LG_STATES) {
-            uint32_t e = lane;
-            uint8_t* Ts = tables + (32u * warp) * (uint32_t)LGW_TAB;
-#pragma unroll 4
-            for (int s = 0; s < 32; s++) {
-                if (s == LGW_RUN) eR = e;
-                Ts[LGW_ENT + lane] = (uint8_t)e;              // what segment s is entered with when the warp is entered with `lane`
-                if (e != LG_DEAD) e = Ts[e];
-                Ts += LGW_TAB;
-            }
+            uint8_t* const Tw = tables + (32u * warp) * (uint32_t)LGW_TAB;
+            const uint32_t e = interior ? lgw_chase<false>(Tw, lane, eR) : lgw_chase<true>(Tw, lane, eR);
             sh_wmap[warp][lane] = (uint8_t)e;
         }
         if (warp == 0) {                                      // have all 17 chains become one inside the run-up?
@@ -457,7 +479,10 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                 if ((uint32_t)w < warp && cw != LG_DEAD) cw = sh_wmap[w][cw];     // ... and this thread's warp
             const bool owned = tile == 0u || tid >= (uint32_t)LGW_RUN;            // run-up segments belong to the tile before
             const uint32_t e = (cw == LG_DEAD || !owned) ? LG_DEAD : (uint32_t)T[LGW_ENT + cw];
-            if (e != LG_DEAD) lgw_walk_segment(data, seg0, seg0 + 2u * e, wv0, wv1, tile_rel);
+            if (e != LG_DEAD) {
+                if (interior) lgw_walk_segment<false>(data, seg0, e, wv0, wv1, tile_rel);
+                else lgw_walk_segment<true>(data, seg0, e, wv0, wv1, tile_rel);
+            }
         }
         const uint32_t c = __popc(wv0) + __popc(wv1);
         uint32_t incl = c;
@@ -581,9 +606,16 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
             if (lin) {
                 // Whole rows of pairs (width = 32 * pairs per row) and an aligned buffer: pair P occupies bytes [64 P, 64 P + 64)
                 // of the output, so the 32 pairs of a warp pass are 2 KiB in a row.  They go out as ONE bulk store (TMA, 1-D)
-                // from a linear staging buffer; lane l writes its piece (i + rot) mod 4 in round i, rot = (l / 2) mod 4, which
+                // from a linear staging buffer; lane l writes its piece i ^ rot in round i, rot = (l / 2) mod 4, which
                 // spreads a quarter warp's 16-byte stores over all 32 banks.
-                for (uint32_t q0 = 32u * warp; q0 < cn; q0 += LGW_THREADS) {
+                const uint32_t is_l0 = lane == 0u ? 1u : 0u;
+                const uint32_t slot_x = (out_s + 64u * lane) | (16u * rot);               // piece i of this lane goes to slot_x ^ 16 i
+                unsigned long long gdst = reinterpret_cast<unsigned long long>(dst) + 64ull * (unsigned long long)(p_first + c0 + 32u * warp);
+                for (uint32_t q0 = 32u * warp; q0 < cn; q0 += LGW_THREADS, gdst += 64ull * LGW_THREADS) {
+                    if (tid == 0 && q0 + LGW_THREADS >= cn && c0 + LGW_PAIR_CHUNK >= npairs) {   // this tile's last pass
+                        next_ticket = atomicAdd(&counters[2], 1u);
+                        have_next = true;
+                    }
                     const uint32_t q = q0 + lane;
                     uint32_t px[16];
                     if (q < cn) {
@@ -603,29 +635,33 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                             for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, F, (int)(y & 1u));
                         }
                     }
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the last store has read the buffer
+                    // lane 0: the last store has read the buffer
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p cp.async.bulk.wait_group.read 0;\n}\n" ::"r"(is_l0) : "memory");
                     __syncwarp();
                     if (q < cn) {
 #pragma unroll
                         for (int i = 0; i < 4; i++)
                             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n"
-                                         ::"r"(out_s + 64u * lane + 16u * (((uint32_t)i + rot) & 3u)), "r"(px[4 * i]), "r"(px[4 * i + 1]),
-                                           "r"(px[4 * i + 2]), "r"(px[4 * i + 3]) : "memory");
+                                         ::"r"(slot_x ^ (16u * (uint32_t)i)), "r"(px[4 * i]), "r"(px[4 * i + 1]), "r"(px[4 * i + 2]), "r"(px[4 * i + 3]) : "memory");
                     }
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");               // generic stores before the async read
                     __syncwarp();
-                    if (lane == 0) {
+                    {
                         const uint32_t nb = 64u * min(32u, cn - q0);
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
-                                     ::"l"(reinterpret_cast<uint8_t*>(dst) + 64ull * (unsigned long long)(p_first + c0 + q0)), "r"(out_s), "r"(nb) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\n"
+                                     "@p cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                                     "@p cp.async.bulk.commit_group;\n}\n" ::"l"(gdst), "r"(out_s), "r"(nb), "r"(is_l0) : "memory");
                     }
                 }
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // before anyone reuses the tables
+                asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p cp.async.bulk.wait_group.read 0;\n}\n" ::"r"(is_l0) : "memory");   // before anyone reuses the tables
             } else {
                 uint32_t P = p_first + c0 + tid;
                 uint32_t y = P / ppr, xq = P - y * ppr;
                 for (uint32_t q = tid; q < cn; q += LGW_THREADS) {
+                    if (tid == 0 && q + LGW_THREADS >= cn && c0 + LGW_PAIR_CHUNK >= npairs) {     // this tile's last pass
+                        next_ticket = atomicAdd(&counters[2], 1u);
+                        have_next = true;
+                    }
                     const uint32_t oE = 2u * (uint32_t)plist[q];
                     const uint32_t hE = leg_header(data, oE), bitsE = leg_hdr_bits(hE);
                     const uint32_t oO = oE + 2u + leg_len(bitsE);
