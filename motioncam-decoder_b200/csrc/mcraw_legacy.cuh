@@ -101,9 +101,7 @@ __device__ __forceinline__ uint32_t leg_step(uint32_t hb) {
 }
 // The 2-byte header at byte offset o (even) of the staged tile, as the low 16 bits of the result (byte o first).
 __device__ __forceinline__ uint32_t leg_header(const uint8_t* data, uint32_t o) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(data);
-    const uint32_t i0 = o >> 2;
-    return (o & 2u) ? w[i0] >> 16 : w[i0];
+    return *reinterpret_cast<const uint16_t*>(data + o);
 }
 __device__ __forceinline__ uint32_t leg_hdr_bits(uint32_t h) { return (h >> 4) & 15u; }                          // RawData_Legacy.cpp:372-375
 __device__ __forceinline__ uint32_t leg_hdr_ref(uint32_t h) { return ((h & 15u) << 8) | ((h >> 8) & 0xFFu); }
@@ -608,7 +606,8 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                 // of the output, so the 32 pairs of a warp pass are 2 KiB in a row.  They go out as ONE bulk store (TMA, 1-D)
                 // from a linear staging buffer; lane l writes its piece i ^ rot in round i, rot = (l / 2) mod 4, which
                 // spreads a quarter warp's 16-byte stores over all 32 banks.
-                const uint32_t is_l0 = lane == 0u ? 1u : 0u;
+                uint32_t leader;                                                            // one lane of the warp owns its bulk stores
+                asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xFFFFFFFF;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(leader));
                 const uint32_t slot_x = (out_s + 64u * lane) | (16u * rot);               // piece i of this lane goes to slot_x ^ 16 i
                 unsigned long long gdst = reinterpret_cast<unsigned long long>(dst) + 64ull * (unsigned long long)(p_first + c0 + 32u * warp);
                 for (uint32_t q0 = 32u * warp; q0 < cn; q0 += LGW_THREADS, gdst += 64ull * LGW_THREADS) {
@@ -636,7 +635,7 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                         }
                     }
                     // lane 0: the last store has read the buffer
-                    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p cp.async.bulk.wait_group.read 0;\n}\n" ::"r"(is_l0) : "memory");
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
                     __syncwarp();
                     if (q < cn) {
 #pragma unroll
@@ -646,14 +645,13 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                     }
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");               // generic stores before the async read
                     __syncwarp();
-                    {
+                    if (leader) {
                         const uint32_t nb = 64u * min(32u, cn - q0);
-                        asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\n"
-                                     "@p cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
-                                     "@p cp.async.bulk.commit_group;\n}\n" ::"l"(gdst), "r"(out_s), "r"(nb), "r"(is_l0) : "memory");
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                                     "cp.async.bulk.commit_group;\n" ::"l"(gdst), "r"(out_s), "r"(nb) : "memory");
                     }
                 }
-                asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p cp.async.bulk.wait_group.read 0;\n}\n" ::"r"(is_l0) : "memory");   // before anyone reuses the tables
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // before anyone reuses the tables
             } else {
                 uint32_t P = p_first + c0 + tid;
                 uint32_t y = P / ppr, xq = P - y * ppr;
