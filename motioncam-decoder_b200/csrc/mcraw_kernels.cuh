@@ -628,13 +628,50 @@ __device__ __forceinline__ void emit_half(const uint32_t (&LE)[16], const uint32
 // `rowpar`: what the reference's consumer does with the container's blackLevel[4] / whiteLevel (example.cpp:66-67,89-91 hands
 // them to the DNG; a raw processor subtracts and scales).  mode 1: integers, min(max(v - black, 0), white - black);
 // mode 2: IEEE half, ((float)v - black) * (1 / (white - black)) clamped to [0, 1], fp32 arithmetic, round to nearest.
-__device__ __forceinline__ uint32_t epilogue_word(const uint32_t v, const unsigned mode, const FrameDev& F, const int rowpar) {
+// The frame's epilogue constants, fetched ONCE per work item / tile into registers: read through the FrameDev reference
+// they would be loaded again after every store (the compiler cannot rule out that the stores alias them).
+struct EpiRegs {
+    unsigned black2[2], range2[2];
+    float blackf[4], scalef[4];
+};
+__device__ __forceinline__ EpiRegs epilogue_regs(const FrameDev& F, const unsigned mode) {
+    EpiRegs E;
+#pragma unroll
+    for (int i = 0; i < 2; i++) { E.black2[i] = 0; E.range2[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { E.blackf[i] = 0.f; E.scalef[i] = 0.f; }
     if (mode == MCRAW_OUT_BLACK_SUB) {
-        const uint32_t b = F.epi_black2[rowpar];
-        return __vminu2(__vsub2(__vmaxu2(v, b), b), F.epi_range2[rowpar]);
+#pragma unroll
+        for (int i = 0; i < 2; i++) { E.black2[i] = F.epi_black2[i]; E.range2[i] = F.epi_range2[i]; }
+    } else if (mode != 0u) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { E.blackf[i] = F.epi_blackf[i]; E.scalef[i] = F.epi_scalef[i]; }
     }
-    const float x = __saturatef((__uint2float_rn(v & 0xFFFFu) - F.epi_blackf[2 * rowpar]) * F.epi_scalef[2 * rowpar]);
-    const float y = __saturatef((__uint2float_rn(v >> 16) - F.epi_blackf[2 * rowpar + 1]) * F.epi_scalef[2 * rowpar + 1]);
+    return E;
+}
+// ... and the constants of one row parity (a compile-time index in k_units, a select in the legacy kernel: never a
+// dynamically indexed array, which would live in local memory)
+struct EpiRow {
+    unsigned black2, range2;
+    float blackf0, blackf1, scalef0, scalef1;
+};
+__device__ __forceinline__ EpiRow epilogue_row(const EpiRegs& E, const bool odd) {
+    EpiRow R;
+    R.black2 = odd ? E.black2[1] : E.black2[0];
+    R.range2 = odd ? E.range2[1] : E.range2[0];
+    R.blackf0 = odd ? E.blackf[2] : E.blackf[0];
+    R.blackf1 = odd ? E.blackf[3] : E.blackf[1];
+    R.scalef0 = odd ? E.scalef[2] : E.scalef[0];
+    R.scalef1 = odd ? E.scalef[3] : E.scalef[1];
+    return R;
+}
+__device__ __forceinline__ uint32_t epilogue_word(const uint32_t v, const unsigned mode, const EpiRow& F) {
+    if (mode == MCRAW_OUT_BLACK_SUB) {
+        const uint32_t b = F.black2;
+        return __vminu2(__vsub2(__vmaxu2(v, b), b), F.range2);
+    }
+    const float x = __saturatef((__uint2float_rn(v & 0xFFFFu) - F.blackf0) * F.scalef0);
+    const float y = __saturatef((__uint2float_rn(v >> 16) - F.blackf1) * F.scalef1);
     const __half2 h = __floats2half2_rn(x, y);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
@@ -645,9 +682,10 @@ struct CopyOut {
     uint32_t nrows[4];   // rows of that tile that may be written (0 = tile not live for this lane)
 };
 
-template <bool VEC, int HALF>
+template <bool VEC, int HALF, unsigned MODE>   // MODE: the epilogue as a compile-time constant (one test per row pair instead of one per word)
 __device__ __forceinline__ void copy_half(const CopyOut& co, const uint32_t out_base, const uint32_t lane, const int width,
-                                          const FrameDev& F, const unsigned epi) {
+                                          const EpiRegs& F) {
+    constexpr unsigned epi = MODE;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t s = out_base + ((lane >> 3) + 4u * k) * KU_SLOT_PITCH + (lane & 7u) * 16u;
@@ -658,8 +696,9 @@ __device__ __forceinline__ void copy_half(const CopyOut& co, const uint32_t out_
                 uint4 v;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s + qq * KU_ROW_PITCH));
                 if (epi) {                                   // output row 4 ty + r: its parity is qq; the chunk starts at an even column
-                    v.x = epilogue_word(v.x, epi, F, qq); v.y = epilogue_word(v.y, epi, F, qq);
-                    v.z = epilogue_word(v.z, epi, F, qq); v.w = epilogue_word(v.w, epi, F, qq);
+                    const EpiRow R = epilogue_row(F, qq != 0);
+                    v.x = epilogue_word(v.x, epi, R); v.y = epilogue_word(v.y, epi, R);
+                    v.z = epilogue_word(v.z, epi, R); v.w = epilogue_word(v.w, epi, R);
                 }
                 uint16_t* orow = co.ptr[k] + (size_t)r * (size_t)width;
                 if (VEC) *reinterpret_cast<uint4*>(orow) = v;
@@ -678,16 +717,20 @@ __device__ __forceinline__ void copy_half(const CopyOut& co, const uint32_t out_
 template <bool VEC>
 __device__ __forceinline__ void emit_and_copy(const uint32_t (&LE)[16], const uint32_t (&HE)[16], const uint32_t (&LO)[16],
                                               const uint32_t (&HO)[16], const uint32_t refs, const bool with_h, const CopyOut& co,
-                                              const uint32_t out_base, const uint32_t lane, const int width, const FrameDev& F,
+                                              const uint32_t out_base, const uint32_t lane, const int width, const EpiRegs& F,
                                               const unsigned epi) {
     const uint32_t out_lane = out_base + (lane & 1u) * KU_ROW_PITCH + (lane >> 1) * KU_SLOT_PITCH;
     if (with_h) emit_half<true, 0>(LE, HE, LO, HO, refs, out_lane); else emit_half<false, 0>(LE, HE, LO, HO, refs, out_lane);
     __syncwarp();
-    copy_half<VEC, 0>(co, out_base, lane, width, F, epi);
+    if (epi == MCRAW_OUT_RAW) copy_half<VEC, 0, MCRAW_OUT_RAW>(co, out_base, lane, width, F);
+    else if (epi == MCRAW_OUT_BLACK_SUB) copy_half<VEC, 0, MCRAW_OUT_BLACK_SUB>(co, out_base, lane, width, F);
+    else copy_half<VEC, 0, MCRAW_OUT_NORM_F16>(co, out_base, lane, width, F);
     __syncwarp();
     if (with_h) emit_half<true, 1>(LE, HE, LO, HO, refs, out_lane); else emit_half<false, 1>(LE, HE, LO, HO, refs, out_lane);
     __syncwarp();
-    copy_half<VEC, 1>(co, out_base, lane, width, F, epi);
+    if (epi == MCRAW_OUT_RAW) copy_half<VEC, 1, MCRAW_OUT_RAW>(co, out_base, lane, width, F);
+    else if (epi == MCRAW_OUT_BLACK_SUB) copy_half<VEC, 1, MCRAW_OUT_BLACK_SUB>(co, out_base, lane, width, F);
+    else copy_half<VEC, 1, MCRAW_OUT_NORM_F16>(co, out_base, lane, width, F);
     __syncwarp();
 }
 
@@ -752,6 +795,7 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
     const uint32_t inv = F.inv_tiles_x;
     const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
     const unsigned epi = EPI ? F.epi_mode : 0u;         // EPI = false: the epilogue code is not even in the kernel
+    const EpiRegs ER = epilogue_regs(F, epi);
     uint16_t* __restrict__ dst = F.dst;
 
     // payload offsets of this warp's units (+ end): lane i holds unitoff[u0 + i]; and their metadata records
@@ -889,8 +933,8 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
         }
 
         const bool with_h = __any_sync(0xFFFFFFFFu, (bE > 8u) | (bO > 8u));
-        if (vec) emit_and_copy<true>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width, F, epi);
-        else emit_and_copy<false>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width, F, epi);
+        if (vec) emit_and_copy<true>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width, ER, epi);
+        else emit_and_copy<false>(LE, HE, LO, HO, refs, with_h, co, out_base, lane, width, ER, epi);
     }
 }
 

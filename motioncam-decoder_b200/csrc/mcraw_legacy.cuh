@@ -301,7 +301,7 @@ __device__ __forceinline__ uint32_t lgw_block(const uint32_t* __restrict__ d32, 
 }
 
 template <bool EPI>
-__global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const FrameDev* __restrict__ frames, Result* __restrict__ results,
+__global__ void __launch_bounds__(LGW_THREADS, EPI ? 5 : 8) k_legacy_warp(const FrameDev* __restrict__ frames, Result* __restrict__ results,
                                                              const LgWork* __restrict__ work, const uint32_t nwork,
                                                              uint32_t* __restrict__ counters, const uint32_t epoch) {
     extern __shared__ __align__(128) uint8_t lg_smem[];
@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
         const bool vec = (F.flags & FLAG_VEC_STORE) != 0;
         const bool lin = vec && (width & 31) == 0;              // rows of whole pairs: consecutive pairs are consecutive memory
         const unsigned epi = EPI ? F.epi_mode : 0u;             // EPI = false: the epilogue code is not even in the kernel
+        const EpiRegs ER = epilogue_regs(F, epi);
         // the pair leaders among this thread's block starts: marks whose ordinal is even.  x = inclusive prefix parity of the
         // marks (bit i: parity of the number of marks at or below i), so the k-th mark (k = 0, 1, ..) has x = (k + 1) & 1
         uint32_t lead0, lead1;
@@ -630,8 +631,9 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
                         for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i] & cm, refs);           // :483-486, + reference mod 2^16
                         if (epi) {                                                                // optional black / white level epilogue
                             const uint32_t y = (p_first + c0 + q) / ppr;
+                            const EpiRow R = epilogue_row(ER, (y & 1u) != 0u);
 #pragma unroll
-                            for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, F, (int)(y & 1u));
+                            for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, R);
                         }
                     }
                     // lane 0: the last store has read the buffer
@@ -672,8 +674,9 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 6 : 8) k_legacy_warp(const 
 #pragma unroll
                     for (int i = 0; i < 16; i++) px[i] = __vadd2(px[i] & cm, refs);               // :483-486, + reference mod 2^16
                     if (epi) {                                                                    // optional black / white level epilogue
+                        const EpiRow R = epilogue_row(ER, (y & 1u) != 0u);
 #pragma unroll
-                        for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, F, (int)(y & 1u));
+                        for (int i = 0; i < 16; i++) px[i] = epilogue_word(px[i], epi, R);
                     }
                     const int x = (int)(32u * xq);
                     uint16_t* orow = dst + (size_t)y * (size_t)width + x;
