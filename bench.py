@@ -440,7 +440,7 @@ def run_leg(env, wl, steps, warmup, headline):
         pass
     step_gbs = (comp_step + out_step) * steps / (ms * 1e-3) / 1e9 if mine else 0.0
     res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                       "traffic": traffic, "kernel": "k_units" if ct == 7 else "k_legacy_fused",
+                       "traffic": traffic, "kernel": "k_units" if ct == 7 else "k_legacy_warp",
                        "algorithmic_bytes_per_launch": alg_main, "kernel_ms_per_launch": main_ms, "timed_launches": chunks,
                        "index_kernels_ms_per_launch": meta_ms, "peak_source": peak_src,
                        "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak, "bytes_per_step": comp_step + out_step,

@@ -96,7 +96,9 @@ def test_legacy_full_size_properties(ctx):
 
 def test_legacy_whole_frame_one_width(ctx):
     """Worst case of the index: every block of the frame has the same non-zero width, so chains entered at different
-    offsets never meet (the tile maps fall back to walking, k_legacy_decode to its slow path)."""
+    offsets never meet -- no run-up merges them, every tile of k_legacy_warp publishes its map and takes the look-back
+    path for its entry.  Small frames (a few tiles) and a batch of larger ones (tens of tiles per frame, several frames
+    in flight, so the maps are composed across tiles that are worked at the same time)."""
     from motioncam_decoder_b200 import capi, testvec as tv
     for hb in (4, 10):
         img = tv.gen_uniform(1024, 96, 0, (1 << hb) - 1, seed=77 + hb)
@@ -107,3 +109,20 @@ def test_legacy_whole_frame_one_width(ctx):
         assert status[0] == 0 and written[0] == n_or == 1024 * 96
         assert np.array_equal(batch.fetch(0), want) and np.array_equal(want, img)
         batch.free()
+    frames, wants = [], []
+    for k, hb in enumerate((3, 4, 7, 10, 4)):
+        w, h = 2048, 512 + 64 * k
+        img = tv.gen_uniform(w, h, 0, (1 << hb) - 1, seed=300 + k)
+        s = tv.encode_legacy(img, policy=tv.POLICY_FORCE, policy_arg=hb, seed=k)
+        n_or, want = ol.oracle_decode_legacy(s, w, h)
+        assert n_or == w * h and np.array_equal(want, img)
+        frames.append((s, w, h, capi.COMPRESSION_LEGACY))
+        wants.append(want)
+    batch = capi.DeviceBatch(ctx, frames)
+    for _ in range(3):                                   # the plan (and its epoch-tagged status words) is reused
+        batch.fill_outputs()
+        written, status = batch.decode()
+        for i, (s, w, h, _ct) in enumerate(frames):
+            assert status[i] == 0 and written[i] == w * h, i
+            assert np.array_equal(batch.fetch(i), wants[i]), i
+    batch.free()

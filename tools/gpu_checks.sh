@@ -24,8 +24,8 @@ if want launches; then   # per-launch durations (cold cache, serialised): shares
         python bench.py --workload c4 --steps 2 --warmup 3 > gpurun_out/launches_c4.log 2>&1
 fi
 if want ncu; then        # one full capture per kernel; read with ncu -i ... --page raw --csv and tools/ncu_lines.py
-    for k in k_units k_meta k_legacy_decode; do
-        wl=c2; [ $k = k_legacy_decode ] && wl=c4
+    for k in k_units k_meta k_legacy_warp; do
+        wl=c2; [ $k = k_legacy_warp ] && wl=c4
         ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -f -o gpurun_out/ncu_$k \
             python bench.py --workload $wl --steps 2 --warmup 3 > gpurun_out/ncu_$k.log 2>&1
     done
