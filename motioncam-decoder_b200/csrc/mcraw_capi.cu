@@ -94,6 +94,7 @@ struct Slot {
     std::vector<mcraw_levels> plan_levels;   // empty: raw output
     bool plan_valid = false, any7 = false, any6 = false, any_epi = false;
     uint32_t max_ltiles = 0, nitems = 0;
+    uint32_t split_nw = 0;          // > 0: this plan's metadata chains are resolved by k_meta_split with that many windows per stream
     size_t items_off = 0, plan_bytes = 0;
     uint32_t flag_uses = 0;         // k_meta launches on this plan since its counters were zeroed
     cudaStream_t stream = nullptr;  // the stream the chunk was enqueued on
@@ -140,6 +141,8 @@ struct mcraw_ctx {
     std::vector<LgWork> tmp_lgwork;
     uint32_t sm_count = 0;
     bool meta_small_only = getenv("MCRAW_META_SMALL") != nullptr;   // A/B switch: never use the big-window shape of k_meta
+    uint32_t split_resident_ctas = 0;   // CTAs of k_meta_split the device holds at once (all of a launch must be resident)
+    bool meta_split = !(getenv("MCRAW_META_SPLIT") && atoi(getenv("MCRAW_META_SPLIT")) == 0);   // A/B switch
     uint32_t lgw_resident_ctas = 0; // CTAs of k_legacy_warp<false> the device holds at once
     uint32_t lgw_resident_ctas_epi = 0;   // the same for the variant with the epilogue (more registers)
     bool overlap = getenv("MCRAW_NO_OVERLAP") == nullptr;   // k_units as a programmatic dependent of k_meta
@@ -240,9 +243,9 @@ int harvest(mcraw_ctx* ctx, Slot& s) {
 
 // Validate descriptors and build the device-side frame records; tilemeta holds an OFFSET until rebased.
 int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, const mcraw_levels* levels, uint32_t n, uint32_t first_index, std::vector<FrameDev>& out,
-            size_t& scratch, uint32_t& max_tile_rows, uint32_t& max_units, uint32_t& max_ltiles, bool& any7, bool& any6) {
+            size_t& scratch, uint32_t& max_tile_rows, uint32_t& max_units, uint32_t& max_ltiles, bool& any7, bool& any6, uint32_t& split_nw) {
     out.resize(n);
-    scratch = 0; max_tile_rows = 0; max_units = 0; max_ltiles = 0; any7 = any6 = false;
+    scratch = 0; max_tile_rows = 0; max_units = 0; max_ltiles = 0; any7 = any6 = false; split_nw = 0;
     for (uint32_t i = 0; i < n; i++) {
         const mcraw_frame_desc& d = descs[i];
         auto who = [&] { return "frame " + std::to_string(first_index + i); };   // only built on the error paths
@@ -309,6 +312,25 @@ int prepare(mcraw_ctx* ctx, const mcraw_frame_desc* descs, const mcraw_levels* l
             max_ltiles = std::max<uint32_t>(max_ltiles, (uint32_t)ntile);
         }   // any other type: no work is queued, mcraw_batch_wait reports MCRAW_FRAME_BAD_TYPE
         out[i] = f;
+    }
+    // A handful of big current-format frames: one stream's chain is the critical path, so it is cut into windows worked by
+    // several CTAs at once (k_meta_split).  A stream of u units is at most 4 + 130 u bytes long and starts anywhere in the
+    // buffer; every CTA of the launch has to be resident (they wait for each other), hence the bound.
+    if (any7 && ctx->meta_split) {
+        uint64_t nw = 0;
+        for (uint32_t i = 0; i < n; i++)
+            if (out[i].type == MCRAW_COMPRESSION_CURRENT) {
+                const uint64_t extent = std::min<uint64_t>(32 + 130ull * out[i].nunits, out[i].len + 16);
+                nw = std::max<uint64_t>(nw, (extent + KS::C - 1) / KS::C + 1);
+            }
+        if (nw >= 3 && nw <= (uint64_t)KS::MAXW && 2ull * n * nw <= ctx->split_resident_ctas) {
+            split_nw = (uint32_t)nw;
+            for (uint32_t i = 0; i < n; i++)
+                if (out[i].type == MCRAW_COMPRESSION_CURRENT) {
+                    out[i].sp_scratch = reinterpret_cast<void*>(scratch);
+                    scratch += (2 * ks_stream_scratch(split_nw) + 127) & ~(size_t)127;
+                }
+        }
     }
     return MCRAW_OK;
 }
@@ -384,7 +406,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         std::vector<FrameDev>& frames = ctx->tmp_frames;     // reused across calls: no allocation in steady state
         std::vector<WorkItem>& items = ctx->tmp_items;
         size_t scratch; uint32_t max_tile_rows, max_units;
-        rc = prepare(ctx, descs, levels, n, result_offset, frames, scratch, max_tile_rows, max_units, s.max_ltiles, s.any7, s.any6);
+        rc = prepare(ctx, descs, levels, n, result_offset, frames, scratch, max_tile_rows, max_units, s.max_ltiles, s.any7, s.any6, s.split_nw);
         if (rc) return rc;
         items.clear();
         if (s.any7) build_items(frames, ctx->resident_ctas, items);
@@ -415,6 +437,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
             if (f.type == MCRAW_COMPRESSION_CURRENT) {
                 f.unitoff = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.unitoff));
                 f.metarec = reinterpret_cast<uint4*>(s.d_scratch + reinterpret_cast<size_t>(f.metarec));
+                if (s.split_nw) f.sp_scratch = s.d_scratch + reinterpret_cast<size_t>(f.sp_scratch);
             } else if (f.type == MCRAW_COMPRESSION_LEGACY) {
                 f.lg_tilemap = reinterpret_cast<uint32_t*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_tilemap));
                 f.lg_status = reinterpret_cast<unsigned long long*>(s.d_scratch + reinterpret_cast<size_t>(f.lg_status));
@@ -462,7 +485,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         s.flag_uses = 0;
         s.plan_valid = true;
         // k_legacy_warp: the tiles' status words are tagged with the launch epoch of the plan, which starts over here
-        if (any6 && s.plan_scratch) CU_TRY(ctx, cudaMemsetAsync(s.d_scratch, 0, s.plan_scratch, st));
+        if ((any6 || s.split_nw) && s.plan_scratch) CU_TRY(ctx, cudaMemsetAsync(s.d_scratch, 0, s.plan_scratch, st));
         s.lg_epoch = 0;
     }
     if (any7) {
@@ -477,7 +500,11 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = chain ? 1 : 0;
-        if (few) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Few>, d_frames, d_states));
+        if (s.split_nw) {
+            // the launch epoch of the plan tags the windows' flags (the scratch was zeroed when the plan was uploaded)
+            cfg.gridDim = dim3(2 * n * s.split_nw); cfg.blockDim = dim3(KS::THREADS); cfg.dynamicSmemBytes = KS::SMEM;
+            CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta_split, d_frames, d_states, s.split_nw, s.flag_uses + 1u));
+        } else if (few) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Few>, d_frames, d_states));
         else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Batch>, d_frames, d_states));
         ctx->launches += 1;
     }
@@ -589,6 +616,7 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     if (const char* e = getenv("MCRAW_CHAIN")) ctx->chain_ctas = (uint32_t)std::max(0, atoi(e));
     if (cudaFuncSetAttribute(k_meta<K1Batch>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Batch::K1_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_meta<K1Few>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Few::K1_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_meta_split, cudaFuncAttributeMaxDynamicSharedMemorySize, KS::SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_units<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_units<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_legacy_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LGW_SMEM) != cudaSuccess ||
@@ -603,6 +631,9 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         ctx->resident_ctas = (uint32_t)per_sm * (uint32_t)prop.multiProcessorCount;
         ctx->sm_count = (uint32_t)prop.multiProcessorCount;
         ctx->chain_ctas = std::min(ctx->chain_ctas, ctx->resident_ctas / 2);
+        int per_sm_split = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_split, k_meta_split, KS::THREADS, KS::SMEM) != cudaSuccess) per_sm_split = 0;
+        ctx->split_resident_ctas = (uint32_t)std::max(0, per_sm_split) * (uint32_t)prop.multiProcessorCount;
         int per_sm_epi = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp<false>, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm < 1 ||
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_epi, k_legacy_warp<true>, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm_epi < 1) {

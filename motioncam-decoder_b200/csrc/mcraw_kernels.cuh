@@ -53,6 +53,7 @@ struct FrameDev {
     unsigned epi_range2[2];        // per row parity: white - black, packed the same way
     float epi_blackf[4];           // black level per CFA position (row parity * 2 + column parity)
     float epi_scalef[4];           // 1 / (white - black)
+    void* sp_scratch;              // k_meta_split scratch: two streams x (maps, flags), see ks_stream_scratch
     uint32_t* lg_tilemap;          // legacy scratch [tiles][17]   exit of every entry, for tiles whose exits differ (k_legacy_warp)
     unsigned long long* lg_status; // legacy scratch [tiles][2]    epoch-tagged look-back words of every tile: count, exit
 };
@@ -544,6 +545,439 @@ __global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 
             if (!err && (unsigned long long)carry > len) err = MCRAW_FRAME_TRUNCATED;   // RawData.cpp:419
             unitoff[need_mb] = carry;
         }
+        S.status[stream] = err;
+    }
+    meta_publish(S);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// k_meta_split: the chain of ONE stream resolved by several CTAs at once (a handful of big frames: k_meta's windows are
+// serial, 16 of them for the refs stream of a 4080x3072 frame).  CTA (frame, stream, w) owns window w = stream bytes
+// [W0 + w C, W0 + (w + 1) C).  A block that starts inside a window belongs to it (it ends at most 130 bytes behind it: the
+// window is staged with that margin), so a chain enters window w + 1 at one of 66 even offsets, and the effect of a window
+// on the chain is a map  entry -> (exit, blocks walked).  Phases:
+//   1. stage, next pointers for every candidate, doubled twice (as k_meta); 66 lanes walk the 66 entries through the
+//      window -> the window's map, published with a flag;
+//   2. wait for the maps of the windows before (all CTAs of a launch are resident: the host only picks this kernel when
+//      they fit), compose them in shared memory -> this window's true entry and the number of blocks before it;
+//   3. the true chain: anchors + per-thread positions + unit records (+ bits stream: decode, unit payload lengths) exactly
+//      as k_meta does per round; the payload offsets of a window's units are first written relative to the window;
+//   4. bits stream: the windows' payload totals are exchanged the same way and every window shifts its units' offsets;
+//      the last window collects the error bits and publishes the stream (meta_done) for the frame.
+// Chains that merge or not makes no difference here: maps are composed, never guessed.  Flags carry the launch epoch of the
+// plan (nothing is zeroed between launches).
+// --------------------------------------------------------------------------------------------------------
+struct KS {
+    static constexpr int C = 16384;              // window bytes
+    static constexpr int EXT = 160;              // staged behind the window: <= 130 bytes of a straddling block + group-fetch slack
+#ifndef MCRAW_KS_THREADS
+#define MCRAW_KS_THREADS 512
+#endif
+    static constexpr int THREADS = MCRAW_KS_THREADS;
+    static constexpr int NE = 66;                // entry states: even offsets 0 .. 130
+    static constexpr int MAXW = 32;              // windows per stream
+    static constexpr int STAGE_BYTES = C + EXT;
+    static constexpr int NXT_BYTES = C + EXT + 16;                          // u16 per even offset, byte offset == window offset
+    static constexpr uint32_t SENT = C + EXT;                               // dead chain (a block that does not fit the frame)
+    static constexpr int SMEM = STAGE_BYTES + 4 * NXT_BYTES + 4 * MAXW * NE;   // stage, next pointers after 1 / 4 / 16 / 64 blocks, maps
+    static constexpr int STAGE_PER_THREAD = (STAGE_BYTES / 16 + THREADS - 1) / THREADS;
+    static_assert(C % (16 * THREADS) == 0 && SENT < 65535 && STAGE_BYTES % 16 == 0, "window shape");
+};
+// scratch of one (frame, stream): maps [nw][NE] u32 (exit offset behind the window | blocks << 16; 0xFFFF = dead), then
+// three flag words per window (u64: epoch << 32 | payload): map ready, payload total, done + error bits
+__host__ __device__ inline size_t ks_stream_scratch(uint32_t nw) { return (size_t)nw * (KS::NE * 4 + 3 * 8); }
+
+__device__ __forceinline__ void ks_flag_store(unsigned long long* p, uint32_t epoch, uint32_t payload) {
+    const unsigned long long v = ((unsigned long long)epoch << 32) | payload;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ks_flag_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// all threads: wait until flags[0 .. n) carry `epoch` (n <= THREADS); returns false if it gave up (never expected)
+__device__ __forceinline__ bool ks_wait_flags(const unsigned long long* flags, uint32_t n, uint32_t epoch, uint32_t tid, uint32_t& payload) {
+    payload = 0;
+    for (uint32_t spins = 0;; spins++) {
+        bool ok = true;
+        if (tid < n) {
+            const unsigned long long v = ks_flag_load(flags + tid);
+            ok = (uint32_t)(v >> 32) == epoch;
+            payload = (uint32_t)v;
+        }
+        if (__syncthreads_and(ok)) break;
+        if (spins > (1u << 20)) return false;
+        __nanosleep(100);
+    }
+    __threadfence();                                           // the flags before what they announce
+    return true;
+}
+
+// dst = src o src o src o src for the candidates inside the window (positions behind it are fixed points of every table):
+// src o src first (kept in dst), then squared in place
+__device__ __forceinline__ void ks_quadruple(const uint32_t src_s, const uint32_t dst_s, const int tid) {
+    constexpr int K = KS::C / 16 / KS::THREADS;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const uint32_t v = tid + k * KS::THREADS;
+        const uint4 d = lds128(src_s + 16u * v);
+        const uint32_t wd[4] = {d.x, d.y, d.z, d.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = lds_u16(src_s + (wd[i] & 0xFFFFu)) | (lds_u16(src_s + (wd[i] >> 16)) << 16);
+        sts128(dst_s + 16u * v, o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    uint32_t o[K][4];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const uint32_t v = tid + k * KS::THREADS;
+        const uint4 d = lds128(dst_s + 16u * v);
+        const uint32_t wd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[k][i] = lds_u16(dst_s + (wd[i] & 0xFFFFu)) | (lds_u16(dst_s + (wd[i] >> 16)) << 16);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) sts128(dst_s + 16u * (tid + k * KS::THREADS), o[k][0], o[k][1], o[k][2], o[k][3]);
+    __syncthreads();
+}
+
+// grid = frames * 2 * nw, block = KS::THREADS, dynamic smem = KS::SMEM
+__global__ void __launch_bounds__(KS::THREADS, 1) k_meta_split(const FrameDev* __restrict__ frames, FrameState* __restrict__ states,
+                                                               const uint32_t nw, const uint32_t epoch) {
+    constexpr int C = KS::C, THREADS = KS::THREADS, NE = KS::NE;
+    constexpr uint32_t SENT = KS::SENT;
+    extern __shared__ __align__(16) uint8_t k1_smem[];
+    uint8_t* stage = k1_smem;
+    const uint32_t stage_s = smem_u32(stage);
+    const uint32_t nxt1_s = stage_s + KS::STAGE_BYTES;
+    const uint32_t nxt4_s = nxt1_s + KS::NXT_BYTES;
+    const uint32_t nxt16_s = nxt4_s + KS::NXT_BYTES;
+    const uint32_t nxt64_s = nxt16_s + KS::NXT_BYTES;
+    uint32_t* cmap = reinterpret_cast<uint32_t*>(k1_smem + KS::STAGE_BYTES + 4 * KS::NXT_BYTES);   // [w][NE] maps of the windows before this one
+    __shared__ uint32_t warp_sums[THREADS / 32];
+    __shared__ uint32_t sh_err, sh_bad, sh_entry, sh_cb;
+    __shared__ uint32_t sh_hdr[4];
+
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+#ifdef MCRAW_KS_DEBUG
+    long long dbg_t[8]; int dbg_n = 0;
+#define KS_STAMP() do { if (threadIdx.x == 0 && dbg_n < 8) dbg_t[dbg_n++] = clock64(); } while (0)
+#else
+#define KS_STAMP() do { } while (0)
+#endif
+    KS_STAMP();
+    const uint32_t w = blockIdx.x % nw;
+    const uint32_t fs = blockIdx.x / nw;
+    const int f = (int)(fs >> 1);
+    const int stream = (int)(fs & 1u);   // 0 = bits, 1 = refs
+    const FrameDev& F = frames[f];
+    FrameState& S = states[f];
+    if (F.type != MCRAW_COMPRESSION_CURRENT) return;
+    const int tid = threadIdx.x;
+    const uint8_t* __restrict__ src = F.src;
+    const unsigned long long len = F.len;
+    uint8_t* const sbase = reinterpret_cast<uint8_t*>(F.sp_scratch) + (size_t)stream * ks_stream_scratch(nw);
+    uint32_t* const gmap = reinterpret_cast<uint32_t*>(sbase);
+    unsigned long long* const flag1 = reinterpret_cast<unsigned long long*>(sbase + (size_t)nw * NE * 4);
+    unsigned long long* const flag2 = flag1 + nw;
+    unsigned long long* const flag3 = flag2 + nw;
+
+    if (tid == 0) {                                            // the frame header, as k_meta reads it (every window does)
+        uint32_t err = 0;
+        uint32_t ew = 0, eh = 0, boff = 0, roff = 0;
+        if (len < 16) err = MCRAW_FRAME_BAD_HEADER;
+        else {
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));                // RawData.cpp:500-524
+            ew = h.x; eh = h.y; boff = h.z; roff = h.w;
+            if (boff > len || roff > len) err |= MCRAW_FRAME_BAD_HEADER;            // :547
+            if (ew % 64u) err |= MCRAW_FRAME_BAD_HEADER;                            // :550
+            if (F.width <= 0 || ew < (uint32_t)F.width) err |= MCRAW_FRAME_BAD_HEADER;  // :553
+            if (ew == 0 || eh == 0) err |= MCRAW_FRAME_BAD_HEADER;
+            if (!err) {
+                if (ew / 64u != F.tiles_x) err |= MCRAW_FRAME_GEOMETRY;
+                if ((eh + 3u) / 4u > F.tile_rows) err |= MCRAW_FRAME_GEOMETRY;
+            }
+        }
+        const uint32_t tr = err ? 0u : (eh + 3u) / 4u;
+        const unsigned long long pos0 = stream ? roff : boff;
+        if (!err) {
+            const uint32_t nb = (ew / 64u) * tr * 4u;
+            if (pos0 + 4 > len) err = MCRAW_FRAME_TRUNCATED;
+            else if (ld_u32le(src + pos0) < nb) err = MCRAW_FRAME_BAD_META_COUNT;   // RawData.cpp:470-476
+        }
+        sh_hdr[0] = ew; sh_hdr[1] = eh; sh_hdr[2] = boff; sh_hdr[3] = roff;
+        sh_err = err;
+        sh_bad = 0;
+        if (stream == 0 && w == 0) {
+            unsigned long long fit = F.dst_cap / (unsigned long long)(F.width > 0 ? F.width : 1);
+            if (fit > 4ull * tr) fit = 4ull * tr;
+            S.tile_rows_dev = tr;
+            S.rows_fit = (uint32_t)fit;
+        }
+    }
+    __syncthreads();
+    const uint32_t hdr_err = sh_err;
+    const uint32_t tiles_x = sh_hdr[0] / 64u;
+    const uint32_t tile_rows = (sh_hdr[1] + 3u) / 4u;
+    const uint32_t ntiles = tiles_x * tile_rows;
+    const uint32_t need_mb = hdr_err ? 0u : (ntiles * 4u + 63u) / 64u;      // = number of units
+    const unsigned long long pos0 = (unsigned long long)sh_hdr[2 + stream] + 4;
+    const unsigned long long par = pos0 & 1ull;
+    const unsigned long long W0 = ((pos0 - par) & ~15ull) + par;
+    const unsigned long long base = W0 + (unsigned long long)w * C;
+    uint32_t* __restrict__ unitoff = F.unitoff;
+    uint32_t done = 0, first = 0, local_carry = 0;            // blocks finished up to here, blocks before this window, payload bytes / 8 of this window's units
+    bool dead = false;                                         // the chain ran into the end of the frame inside this window
+
+    if (!hdr_err) {
+        // ---- 1a. stage [base, base + C + EXT) (zero past len); an odd stream offset is staged byte by byte
+        {
+            uint4 q[KS::STAGE_PER_THREAD];
+#pragma unroll
+            for (int k = 0; k < KS::STAGE_PER_THREAD; k++) {
+                const int v = tid + k * THREADS;
+                const unsigned long long o = base + (unsigned long long)v * 16;
+                q[k] = make_uint4(0, 0, 0, 0);
+                if (v < KS::STAGE_BYTES / 16) {
+                    if (!par && o + 16 <= len) q[k] = __ldg(reinterpret_cast<const uint4*>(src + o));
+                    else if (o < len) {
+                        uint32_t t4[4] = {0, 0, 0, 0};
+                        for (int e = 0; e < 16; e++)
+                            if (o + e < len) t4[e >> 2] |= (uint32_t)src[o + e] << (8 * (e & 3));
+                        q[k] = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KS::STAGE_PER_THREAD; k++) {
+                const int v = tid + k * THREADS;
+                if (v < KS::STAGE_BYTES / 16) *reinterpret_cast<uint4*>(stage + v * 16) = q[k];
+            }
+        }
+        __syncthreads();
+        KS_STAMP();
+        // ---- 1b. nxt1[p] = p + 2 + payload length for every candidate p < C whose block fits the frame (RawData.cpp:419), else
+        //      SENT; positions behind the window (where a block that starts inside can end) and SENT loop on themselves
+        const unsigned long long room = len > base ? len - base : 0ull;
+#pragma unroll
+        for (int k = 0; k < C / 16 / THREADS; k++) {
+            const uint32_t v = tid + k * THREADS;
+            const uint4 d = lds128(stage_s + 16u * v);
+            const uint32_t wd[4] = {d.x, d.y, d.z, d.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t pr[2];
+#pragma unroll
+                for (int hlf = 0; hlf < 2; hlf++) {
+                    const uint32_t p = 16u * v + 4u * i + 2u * hlf;
+                    const uint32_t hb = (wd[i] >> (16 * hlf + 4)) & 15u;
+                    uint32_t q = p + 2u + 8u * cur_len8_nib(hb);
+                    if ((unsigned long long)q > room) q = SENT;
+                    pr[hlf] = q;
+                }
+                o[i] = pr[0] | (pr[1] << 16);
+            }
+            sts128(nxt1_s + 16u * v, o[0], o[1], o[2], o[3]);
+        }
+        for (uint32_t v = C / 16 + tid; v < (uint32_t)KS::NXT_BYTES / 16; v += THREADS) {
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const uint32_t p = 16u * v + 4u * i; o[i] = p | ((p + 2u) << 16); }
+            sts128(nxt1_s + 16u * v, o[0], o[1], o[2], o[3]);
+            sts128(nxt4_s + 16u * v, o[0], o[1], o[2], o[3]);
+            sts128(nxt16_s + 16u * v, o[0], o[1], o[2], o[3]);
+            sts128(nxt64_s + 16u * v, o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
+        // ---- 1c. pointer doubling: next position after 4, 16 and 64 blocks.  A dense window (2- to 12-byte blocks: the bits
+        //      stream of a smooth image) holds well over a thousand blocks; with these tables no walk through it is longer than
+        //      a few dozen dependent loads, and every thread finds its own block without a serial pass
+        ks_quadruple(nxt1_s, nxt4_s, tid);
+        ks_quadruple(nxt4_s, nxt16_s, tid);
+        ks_quadruple(nxt16_s, nxt64_s, tid);
+        KS_STAMP();
+        // ---- 1d. the window's map: entry 2 t -> (where the chain leaves the window, blocks it walked inside)
+        if (tid < NE && w + 1 < nw) {                          // (nobody reads the last window's map)
+            uint32_t p = 2u * (uint32_t)tid, cnt = 0;
+            for (;;) { const uint32_t q = lds_u16(nxt64_s + p); if (q >= (uint32_t)C) break; p = q; cnt += 64; }
+            for (;;) { const uint32_t q = lds_u16(nxt16_s + p); if (q >= (uint32_t)C) break; p = q; cnt += 16; }
+            for (;;) { const uint32_t q = lds_u16(nxt4_s + p); if (q >= (uint32_t)C) break; p = q; cnt += 4; }
+            while (p < (uint32_t)C) {                              // (a block that does not fit the frame is not counted)
+                p = lds_u16(nxt1_s + p);
+                if (p != SENT) cnt++;
+            }
+            gmap[(size_t)w * NE + tid] = (p == SENT ? 0xFFFFu : p - (uint32_t)C) | (cnt << 16);
+        }
+        __syncthreads();
+        if (tid == 0 && w + 1 < nw) { __threadfence(); ks_flag_store(flag1 + w, epoch, 0u); }
+
+        KS_STAMP();
+        // ---- 2. this window's entry and the blocks before it
+        uint32_t dummy;
+        bool ok = true;
+        if (w > 0) ok = ks_wait_flags(flag1, w, epoch, (uint32_t)tid, dummy);
+        for (uint32_t i = tid; i < w * NE; i += THREADS) cmap[i] = __ldcg(gmap + i);
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t e = (uint32_t)(pos0 - W0), cb = 0;
+            for (uint32_t k = 0; k < w && e != 0xFFFFu; k++) {
+                const uint32_t m = cmap[k * NE + (e >> 1)];
+                cb += m >> 16;
+                e = m & 0xFFFFu;
+            }
+            sh_entry = e; sh_cb = cb;
+            if (!ok) sh_err = MCRAW_FRAME_INTERNAL;
+        }
+        __syncthreads();
+        first = sh_cb;
+        done = first;
+        uint32_t pstart = sh_entry;                            // 0xFFFF: the chain died in an earlier window
+        if (pstart == 0xFFFFu) { dead = true; pstart = SENT; }
+
+        // ---- 3. the true chain through this window, THREADS blocks per round: thread t owns blocks t, t + THREADS, ... of the
+        //      window's chain and reaches them by itself (t = 64 a + 16 b + 4 c + d hops through the four tables, then
+        //      THREADS / 64 long hops per round); positions behind the window and SENT are fixed points
+        uint32_t mypos = pstart;
+        {
+            const uint32_t t = (uint32_t)tid;
+            for (uint32_t k = 0; k < (t >> 6); k++) mypos = lds_u16(nxt64_s + mypos);
+            for (uint32_t k = 0; k < ((t >> 4) & 3u); k++) mypos = lds_u16(nxt16_s + mypos);
+            for (uint32_t k = 0; k < ((t >> 2) & 3u); k++) mypos = lds_u16(nxt4_s + mypos);
+            for (uint32_t k = 0; k < (t & 3u); k++) mypos = lds_u16(nxt1_s + mypos);
+        }
+        while (done < need_mb && pstart < (uint32_t)C && !sh_err) {
+            const uint32_t limit = min((uint32_t)THREADS, need_mb - done);
+            const uint32_t my_start = mypos;
+            bool valid = false, hit_end = false;
+            if ((uint32_t)tid < limit) {
+                const uint32_t p = my_start;
+                const uint32_t e = lds_u16(nxt1_s + p);
+                valid = p < (uint32_t)C && e != SENT;
+                hit_end = p == SENT || (p < (uint32_t)C && e == SENT);          // a block that does not fit the frame
+            }
+            const uint32_t cnt = (uint32_t)__syncthreads_count(valid);         // validity is monotone along the chain
+            if (__syncthreads_or(hit_end)) dead = true;
+            uint32_t unit_len8 = 0;
+            const uint32_t unit = done + (uint32_t)tid;
+            if ((uint32_t)tid < cnt) {
+                const uint32_t p = my_start;
+                const uint32_t hdr = (uint32_t)stage[p] | ((uint32_t)stage[p + 1] << 8);
+                uint32_t* rec = reinterpret_cast<uint32_t*>(F.metarec + unit);
+                rec[stream] = (uint32_t)(base + p);
+                rec[2 + stream] = hdr;
+                if (stream == 0) {
+                    const uint32_t b = stage[p] >> 4;                                      // RawData.cpp:106-110
+                    const uint32_t ref = ((uint32_t)(stage[p] & 0x0F) << 8) | stage[p + 1];
+                    uint32_t L[16], H[16];
+                    StageFetch G{reinterpret_cast<const uint32_t*>(stage), p + 2u};
+                    decode_block(b, G, L, H);
+                    uint32_t bad = (ref > 16u) ? 1u : 0u;
+                    const uint32_t refb = MC_REP(ref & 0x1F);
+                    uint32_t acc[2] = {0, 0};
+#pragma unroll
+                    for (int m = 0; m < 16; m++) {
+                        const uint32_t tile = unit * 16u + m;
+                        uint32_t v = (L[m] & MC_REP(0x1F)) + refb;
+                        uint32_t badm = H[m] | (L[m] & MC_REP(0xE0));
+                        badm |= (v + MC_REP(0x6F)) & MC_REP(0x80);
+                        if (tile >= ntiles) { v = 0; badm = 0; }
+                        bad |= badm;
+                        acc[m >> 3] += mcraw_len8x4(v & MC_REP(0x1F));
+                    }
+                    if (bad) sh_bad = 1;
+                    const uint32_t s2 = (acc[0] & 0x00FF00FFu) + ((acc[0] >> 8) & 0x00FF00FFu) +
+                                        (acc[1] & 0x00FF00FFu) + ((acc[1] >> 8) & 0x00FF00FFu);
+                    unit_len8 = (s2 & 0xFFFFu) + (s2 >> 16);
+                }
+            }
+            if (stream == 0) {
+                uint32_t incl = unit_len8;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if ((tid & 31) >= d) incl += o;
+                }
+                if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
+                __syncthreads();
+                uint32_t wbase = 0, all = 0;
+#pragma unroll
+                for (int ww = 0; ww < THREADS / 32; ww++) {
+                    const uint32_t sv = warp_sums[ww];
+                    if (ww < (tid >> 5)) wbase += sv;
+                    all += sv;
+                }
+                if ((uint32_t)tid < cnt) unitoff[unit] = 8u * (local_carry + wbase + incl - unit_len8);   // relative to the window for now
+                local_carry += all;
+                if (sh_bad) { if (tid == 0) sh_err = MCRAW_FRAME_BAD_BITS; }
+            }
+            done += cnt;
+#pragma unroll
+            for (int k = 0; k < THREADS / 64; k++) mypos = lds_u16(nxt64_s + mypos);   // this thread's block of the next round
+            __syncthreads();
+            if (cnt < limit) break;                                // the window (or the chain) is exhausted
+        }
+        if (dead && done < need_mb && !sh_err) { if (tid == 0) sh_err = MCRAW_FRAME_TRUNCATED; }
+        __syncthreads();
+
+        KS_STAMP();
+        KS_STAMP();
+        // ---- 4. bits stream: absolute payload offsets = METADATA_OFFSET + the totals of the windows before + the local ones
+        if (stream == 0) {
+            if (tid == 0) ks_flag_store(flag2 + w, epoch, local_carry);   // (a plain number: nothing to fence)
+            uint32_t mine = 0;
+            bool ok2 = true;
+            if (w > 0) ok2 = ks_wait_flags(flag2, w, epoch, (uint32_t)tid, mine);
+            if ((uint32_t)tid >= w) mine = 0;
+            // sum of the totals before this window (w <= 32 values, one per thread)
+            uint32_t sum = mine;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+            if ((tid & 31) == 0) warp_sums[tid >> 5] = sum;
+            __syncthreads();
+            uint32_t before = 0;
+#pragma unroll
+            for (int ww = 0; ww < THREADS / 32; ww++) before += warp_sums[ww];
+            const uint32_t carry_abs = 16u + 8u * before;                                  // METADATA_OFFSET (RawData.cpp:25,562)
+            for (uint32_t u = first + tid; u < done; u += THREADS) unitoff[u] += carry_abs;
+            if (tid == 0) {
+                if (!ok2) sh_err = MCRAW_FRAME_INTERNAL;
+                if (done >= need_mb && first < need_mb) {                                  // the window that holds the last unit
+                    const unsigned long long endoff = (unsigned long long)carry_abs + 8ull * local_carry;
+                    unitoff[need_mb] = (uint32_t)endoff;
+                    if (!sh_err && endoff > len) sh_err = MCRAW_FRAME_TRUNCATED;            // RawData.cpp:419
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- done: every window says so (with its error bits); the last one answers for the stream
+    __syncthreads();
+    KS_STAMP();
+#ifdef MCRAW_KS_DEBUG
+    if (tid == 0 && epoch == 3u)
+        printf("ks f%d s%d w%2u first %5u done %5u | stage %6lld nxt %6lld map %6lld wait+compose %6lld chain %6lld offsets %6lld (cycles)\n", f, stream, w, first, done,
+               dbg_t[1] - dbg_t[0], dbg_t[2] - dbg_t[1], dbg_t[3] - dbg_t[2], dbg_t[4] - dbg_t[3], dbg_t[5] - dbg_t[4], dbg_t[6] - dbg_t[5]);
+#endif
+    const uint32_t my_err = sh_err;
+    if (w + 1 < nw) {
+        if (tid == 0) { __threadfence(); ks_flag_store(flag3 + w, epoch, my_err); }
+        return;
+    }
+    uint32_t e3 = 0;
+    const bool ok3 = nw > 1 ? ks_wait_flags(flag3, nw - 1, epoch, (uint32_t)tid, e3) : true;
+    if ((uint32_t)tid >= nw - 1) e3 = 0;
+    const uint32_t any_err = (uint32_t)__syncthreads_or((int)e3);   // (non-zero if any window reported an error; the bits themselves below)
+    if (tid == 0) {
+        uint32_t err = my_err;
+        if (any_err)
+            for (uint32_t k = 0; k + 1 < nw; k++) err |= (uint32_t)ks_flag_load(flag3 + k);
+        if (!ok3) err |= MCRAW_FRAME_INTERNAL;
+        if (!err && done < need_mb) err = MCRAW_FRAME_TRUNCATED;  // the windows of this launch do not reach the end of the chain
         S.status[stream] = err;
     }
     meta_publish(S);
