@@ -552,8 +552,8 @@ __global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 
 
 // --------------------------------------------------------------------------------------------------------
 // k_meta_split: the chain of ONE stream resolved by several CTAs at once (a handful of big frames: k_meta's windows are
-// serial, 16 of them for the refs stream of a 4080x3072 frame).  CTA (frame, stream, w) owns window w = stream bytes
-// [W0 + w C, W0 + (w + 1) C).  A block that starts inside a window belongs to it (it ends at most 130 bytes behind it: the
+// serial, 6 rounds of 48 KiB for the refs stream of a 4080x3072 frame).  CTA (frame, stream, w) owns window w = stream bytes
+// [W0 + w C, W0 + (w + 1) C), C = 8 KiB.  A block that starts inside a window belongs to it (it ends at most 130 bytes behind it: the
 // window is staged with that margin), so a chain enters window w + 1 at one of 66 even offsets, and the effect of a window
 // on the chain is a map  entry -> (exit, blocks walked).  Phases:
 //   1. stage, next pointers for every candidate, doubled twice (as k_meta); 66 lanes walk the 66 entries through the
@@ -568,14 +568,17 @@ __global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 
 // plan (nothing is zeroed between launches).
 // --------------------------------------------------------------------------------------------------------
 struct KS {
-    static constexpr int C = 16384;              // window bytes
+#ifndef MCRAW_KS_WINDOW
+#define MCRAW_KS_WINDOW 8192
+#endif
+    static constexpr int C = MCRAW_KS_WINDOW;    // window bytes
     static constexpr int EXT = 160;              // staged behind the window: <= 130 bytes of a straddling block + group-fetch slack
 #ifndef MCRAW_KS_THREADS
 #define MCRAW_KS_THREADS 512
 #endif
     static constexpr int THREADS = MCRAW_KS_THREADS;
     static constexpr int NE = 66;                // entry states: even offsets 0 .. 130
-    static constexpr int MAXW = 32;              // windows per stream
+    static constexpr int MAXW = 32 * (16384 / C);   // windows per stream (512 KiB of stream)
     static constexpr int STAGE_BYTES = C + EXT;
     static constexpr int NXT_BYTES = C + EXT + 16;                          // u16 per even offset, byte offset == window offset
     static constexpr uint32_t SENT = C + EXT;                               // dead chain (a block that does not fit the frame)
