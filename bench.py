@@ -659,6 +659,8 @@ def main():
 
     cpu = None
     if env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:
+        from motioncam_decoder_b200 import numa
+        numa.unbind()                                           # the CPU baseline gets every host core back
         desc, w, h, ct = WORKLOADS[head_wl][:4]
         r = CpuReference(head_streams, w, h, ct).measure(3, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
