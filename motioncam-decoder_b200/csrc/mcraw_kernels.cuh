@@ -923,7 +923,8 @@ __global__ void __launch_bounds__(KS::THREADS, 1) k_meta_split(const FrameDev* _
             __syncthreads();
             if (cnt < limit) break;                                // the window (or the chain) is exhausted
         }
-        if (dead && done < need_mb && !sh_err) { if (tid == 0) sh_err = MCRAW_FRAME_TRUNCATED; }
+        __syncthreads();                                           // (every thread has read sh_err in the loop condition)
+        if (tid == 0 && dead && done < need_mb && !sh_err) sh_err = MCRAW_FRAME_TRUNCATED;
         __syncthreads();
 
         KS_STAMP();
