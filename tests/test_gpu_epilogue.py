@@ -24,7 +24,7 @@ LEVELS = [
 def _frames():
     from motioncam_decoder_b200 import capi, testvec as tv
     out = []
-    for k, (w, h, mx) in enumerate([(328, 12, 1023), (1928, 8, 4095), (64, 4, 65535), (100, 6, 16383)]):
+    for k, (w, h, mx) in enumerate([(328, 12, 1023), (1928, 8, 4095), (64, 4, 65535), (100, 6, 16383), (1024, 36, 4095)]):
         img = tv.gen_photon(w, h, mx, seed=90 + k) if mx < 65535 else tv.gen_uniform(w, h, 0, 65535, seed=90 + k)
         h4 = h - h % 4
         out.append((tv.encode_current(img[:h4], policy=tv.POLICY_ALIASES, seed=k), w, h4, capi.COMPRESSION_CURRENT, img[:h4]))
