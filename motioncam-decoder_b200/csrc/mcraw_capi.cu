@@ -142,7 +142,12 @@ struct mcraw_ctx {
     uint32_t sm_count = 0;
     bool meta_small_only = getenv("MCRAW_META_SMALL") != nullptr;   // A/B switch: never use the big-window shape of k_meta
     uint32_t split_resident_ctas = 0;   // CTAs of k_meta_split the device holds at once (all of a launch must be resident)
-    bool meta_split = !(getenv("MCRAW_META_SPLIT") && atoi(getenv("MCRAW_META_SPLIT")) == 0);   // A/B switch
+    uint32_t meta_resident_ctas = 0;    // CTAs of k_meta<K1Batch> the device holds at once (one wave)
+    bool meta_split = !(getenv("MCRAW_META_SPLIT") && atoi(getenv("MCRAW_META_SPLIT")) == 0) &&
+                      !(getenv("MCRAW_META_WARP") && atoi(getenv("MCRAW_META_WARP")) == 2);     // A/B switch
+    // batches go to k_meta_warp; A/B and test switch MCRAW_META_WARP: 0 = k_meta<K1Batch> instead, 2 = k_meta_warp for EVERY launch
+    // (also where a handful of frames would pick the big-window or the split kernel)
+    int meta_warp = getenv("MCRAW_META_WARP") ? atoi(getenv("MCRAW_META_WARP")) : 1;
     uint32_t lgw_resident_ctas = 0; // CTAs of k_legacy_warp<false> the device holds at once
     uint32_t lgw_resident_ctas_epi = 0;   // the same for the variant with the epilogue (more registers)
     bool overlap = getenv("MCRAW_NO_OVERLAP") == nullptr;   // k_units as a programmatic dependent of k_meta
@@ -492,7 +497,7 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         cudaLaunchConfig_t cfg;
         std::memset(&cfg, 0, sizeof cfg);
         // a handful of frames: one stream's chain is the critical path -> big windows, one CTA per SM (k_meta)
-        const bool few = 2 * n <= ctx->sm_count && !ctx->meta_small_only;
+        const bool few = 2 * n <= ctx->sm_count && !ctx->meta_small_only && ctx->meta_warp != 2;
         cfg.gridDim = dim3(2 * n); cfg.blockDim = dim3(few ? K1Few::K1_THREADS : K1Batch::K1_THREADS);
         cfg.dynamicSmemBytes = few ? K1Few::K1_SMEM : K1Batch::K1_SMEM; cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -505,7 +510,13 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
             cfg.gridDim = dim3(2 * n * s.split_nw); cfg.blockDim = dim3(KS::THREADS); cfg.dynamicSmemBytes = KS::SMEM;
             CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta_split, d_frames, d_states, s.split_nw, s.flag_uses + 1u));
         } else if (few) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Few>, d_frames, d_states));
-        else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Batch>, d_frames, d_states));
+        else if (ctx->meta_warp == 2 || (ctx->meta_warp == 1 && (chain || 2 * n > 2 * ctx->meta_resident_ctas))) {
+            // a batch whose index work hides behind the pixel kernel of the batch before (chained), or one of more than two
+            // waves of k_meta CTAs: one warp per (frame, stream) -- a third of k_meta's instructions and a tenth of its SM
+            // time, all streams at once; slower per stream, so a lone smaller batch stays with k_meta (k_meta_warp)
+            cfg.gridDim = dim3((2 * n + KW::WARPS - 1) / KW::WARPS); cfg.blockDim = dim3(KW::THREADS); cfg.dynamicSmemBytes = KW::SMEM;
+            CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta_warp, d_frames, d_states, 2u * n));
+        } else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Batch>, d_frames, d_states));
         ctx->launches += 1;
     }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
@@ -634,6 +645,9 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
         int per_sm_split = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_split, k_meta_split, KS::THREADS, KS::SMEM) != cudaSuccess) per_sm_split = 0;
         ctx->split_resident_ctas = (uint32_t)std::max(0, per_sm_split) * (uint32_t)prop.multiProcessorCount;
+        int per_sm_meta = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_meta, k_meta<K1Batch>, K1Batch::K1_THREADS, K1Batch::K1_SMEM) != cudaSuccess) per_sm_meta = 0;
+        ctx->meta_resident_ctas = (uint32_t)std::max(1, per_sm_meta) * (uint32_t)prop.multiProcessorCount;
         int per_sm_epi = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_legacy_warp<false>, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm < 1 ||
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_epi, k_legacy_warp<true>, LGW_THREADS, LGW_SMEM) != cudaSuccess || per_sm_epi < 1) {

@@ -272,6 +272,36 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
+// One block of the bits stream, staged at byte p of `stage` (p even): its 64 values are the header bits of the 64 pixel blocks
+// of unit `unit` (value = unpacked + header reference, mod 2^16, RawData.cpp:491-492).  Returns the payload length of
+// the unit / 8 (the sum of the 64 block lengths, :27-45); bad != 0 when a value of a live tile exceeds 16 (the reference
+// would index its length table out of bounds) -- padding values behind the last tile are ignored.
+__device__ __forceinline__ uint32_t bits_block_len8(const uint8_t* stage, const uint32_t p, const uint32_t unit, const uint32_t ntiles,
+                                                    uint32_t& bad) {
+    const uint32_t b = stage[p] >> 4;                                                  // RawData.cpp:106-110
+    const uint32_t ref = ((uint32_t)(stage[p] & 0x0F) << 8) | stage[p + 1];
+    uint32_t L[16], H[16];
+    StageFetch G{reinterpret_cast<const uint32_t*>(stage), p + 2u};
+    decode_block(b, G, L, H);
+    // word m of L/H holds samples 4m..4m+3 = the four blocks of tile 16*unit + m
+    bad = (ref > 16u) ? 1u : 0u;
+    const uint32_t refb = MC_REP(ref & 0x1F);
+    uint32_t acc[2] = {0, 0};                                                          // byte-wise sums of 8 words each: <= 128 per byte
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        const uint32_t tile = unit * 16u + m;
+        uint32_t v = (L[m] & MC_REP(0x1F)) + refb;                                     // bytes <= 31 + 16: no carries
+        uint32_t badm = H[m] | (L[m] & MC_REP(0xE0));
+        badm |= (v + MC_REP(0x6F)) & MC_REP(0x80);                                     // a byte > 16 (reference: OOB table read)
+        if (tile >= ntiles) { v = 0; badm = 0; }                                       // padding values are ignored
+        bad |= badm;
+        acc[m >> 3] += mcraw_len8x4(v & MC_REP(0x1F));                                 // four block lengths at once
+    }
+    const uint32_t s2 = (acc[0] & 0x00FF00FFu) + ((acc[0] >> 8) & 0x00FF00FFu) +
+                        (acc[1] & 0x00FF00FFu) + ((acc[1] >> 8) & 0x00FF00FFu);
+    return (s2 & 0xFFFFu) + (s2 >> 16);
+}
+
 // grid = 2 * frames, block = Shape::K1_THREADS, dynamic smem = Shape::K1_SMEM
 // Publish everything this CTA wrote for (frame, stream): the barrier orders every thread's writes before thread 0, whose
 // fence (cumulative) and counter bump form the release; k_units may be running already (programmatic dependent launch)
@@ -489,29 +519,9 @@ __global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 
             rec[stream] = (uint32_t)(base + p);
             rec[2 + stream] = hdr;
             if (stream == 0) {
-                const uint32_t b = stage[p] >> 4;                                      // RawData.cpp:106-110
-                const uint32_t ref = ((uint32_t)(stage[p] & 0x0F) << 8) | stage[p + 1];
-                uint32_t L[16], H[16];
-                StageFetch G{reinterpret_cast<const uint32_t*>(stage), p + 2u};
-                decode_block(b, G, L, H);
-                // word m of L/H holds samples 4m..4m+3 = the four blocks of tile 16*unit + m
-                uint32_t bad = (ref > 16u) ? 1u : 0u;
-                const uint32_t refb = MC_REP(ref & 0x1F);
-                uint32_t acc[2] = {0, 0};                                              // byte-wise sums of 8 words each: <= 128 per byte
-#pragma unroll
-                for (int m = 0; m < 16; m++) {
-                    const uint32_t tile = unit * 16u + m;
-                    uint32_t v = (L[m] & MC_REP(0x1F)) + refb;                         // bytes <= 31 + 16: no carries
-                    uint32_t badm = H[m] | (L[m] & MC_REP(0xE0));
-                    badm |= (v + MC_REP(0x6F)) & MC_REP(0x80);                         // a byte > 16 (reference: OOB table read)
-                    if (tile >= ntiles) { v = 0; badm = 0; }                           // padding values are ignored
-                    bad |= badm;
-                    acc[m >> 3] += mcraw_len8x4(v & MC_REP(0x1F));                     // four block lengths at once
-                }
+                uint32_t bad;
+                unit_len8 = bits_block_len8(stage, p, unit, ntiles, bad);
                 if (bad) sh_bad = 1;
-                const uint32_t s2 = (acc[0] & 0x00FF00FFu) + ((acc[0] >> 8) & 0x00FF00FFu) +
-                                    (acc[1] & 0x00FF00FFu) + ((acc[1] >> 8) & 0x00FF00FFu);
-                unit_len8 = (s2 & 0xFFFFu) + (s2 >> 16);
             }
         }
         if (stream == 0) {
@@ -548,6 +558,226 @@ __global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 
         S.status[stream] = err;
     }
     meta_publish(S);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// k_meta_warp: the index work of a BATCH, one WARP per (frame, metadata stream).  k_meta spends a CTA of 256 threads and
+// 50 KB of shared memory on a stream and computes next pointers for every candidate offset three times over (pointer
+// doubling buys latency with work: 15 M warp instructions per C2 batch, a tenth of the SM time of the pixel kernel it is
+// supposed to hide behind).  A batch has hundreds of streams, so latency per stream is not what counts: here a warp walks
+// its stream through 2 KiB windows at fixed addresses (window j = stream bytes [S0 + j W, S0 + (j + 1) W + 144): a block
+// that starts inside a window ends at most 130 bytes behind it), double-buffered by bulk copies (TMA 1-D, one mbarrier per
+// buffer).  Per window: next pointers for its 1024 even offsets (once), then rounds of up to 32 hops of the chain taken
+// by all lanes together -- lane k keeps the start of block k -- followed by the parallel part exactly as in k_meta: the
+// unit's record, and for the bits stream the 64 values of the block -> payload length of the unit -> prefix sums (warp
+// scan + carry) -> unitoff.  Same results word for word as k_meta (RawData.cpp:463-498,562,576-579).
+// grid = ceil(2 * frames / 4), block = 128, dynamic smem = KW::SMEM
+// --------------------------------------------------------------------------------------------------------
+struct KW {
+    static constexpr int WARPS = 4, THREADS = 32 * WARPS;
+    static constexpr int W = 2048;                   // stream bytes a window owns (chain positions p < W)
+    static constexpr int MARGIN = 144;               // 130 bytes of the last block + the group fetch's look-ahead, 16-multiple
+    static constexpr int STAGE = W + MARGIN;
+    static constexpr int WARP_SMEM = 2 * STAGE + W + 32;   // two window buffers, u16 next pointer per even offset (byte offset == stream offset), two mbarriers
+    static constexpr int SMEM = WARPS * WARP_SMEM;
+    static constexpr uint32_t NONE = 0xFFFFu;        // next pointer of a block that does not fit the frame
+    static_assert(STAGE % 16 == 0 && WARP_SMEM % 16 == 0 && W % 512 == 0, "window shape");
+    static_assert(SMEM + 4096 < 0xFFFF, "next pointers are 16-bit shared-memory addresses");
+};
+
+__global__ void __launch_bounds__(KW::THREADS, 6) k_meta_warp(const FrameDev* __restrict__ frames, FrameState* __restrict__ states,
+                                                              const uint32_t npairs) {
+    extern __shared__ __align__(128) uint8_t kw_smem[];
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t pair = blockIdx.x * KW::WARPS + wid;
+    if (pair >= npairs) return;
+    const uint32_t f = pair >> 1, stream = pair & 1u;            // 0 = bits, 1 = refs
+    const FrameDev& F = frames[f];
+    FrameState& S = states[f];
+    if (F.type != MCRAW_COMPRESSION_CURRENT) return;
+    uint8_t* const sm = kw_smem + wid * KW::WARP_SMEM;
+    const uint32_t sm_s = smem_u32(sm);
+    const uint32_t nxt_s = sm_s + 2u * KW::STAGE;
+    const uint32_t bar_s = nxt_s + KW::W;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_s) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_s + 8u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+
+    const uint8_t* __restrict__ src = F.src;
+    const unsigned long long len = F.len;
+    // ---- frame header (RawData.cpp:500-524,547-560): every lane reads the same 16 bytes
+    uint32_t err = 0, ew = 0, eh = 0, boff = 0, roff = 0;
+    if (len < 16) err = MCRAW_FRAME_BAD_HEADER;
+    else {
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));
+        ew = h.x; eh = h.y; boff = h.z; roff = h.w;
+        if (boff > len || roff > len) err |= MCRAW_FRAME_BAD_HEADER;
+        if (ew % 64u) err |= MCRAW_FRAME_BAD_HEADER;
+        if (F.width <= 0 || ew < (uint32_t)F.width) err |= MCRAW_FRAME_BAD_HEADER;
+        if (ew == 0 || eh == 0) err |= MCRAW_FRAME_BAD_HEADER;
+        if (!err) {
+            if (ew / 64u != F.tiles_x) err |= MCRAW_FRAME_GEOMETRY;
+            if ((eh + 3u) / 4u > F.tile_rows) err |= MCRAW_FRAME_GEOMETRY;
+        }
+    }
+    const uint32_t tile_rows = err ? 0u : (eh + 3u) / 4u;
+    if (stream == 0 && lane == 0) {
+        unsigned long long fit = F.dst_cap / (unsigned long long)(F.width > 0 ? F.width : 1);
+        if (fit > 4ull * tile_rows) fit = 4ull * tile_rows;        // the reference emits 4 rows per tile row (:598-608)
+        S.tile_rows_dev = tile_rows;
+        S.rows_fit = (uint32_t)fit;
+    }
+    const unsigned long long pos0 = stream ? roff : boff;          // the stream starts with its 32-bit value count
+    if (!err && pos0 + 4 > len) err = MCRAW_FRAME_TRUNCATED;
+    const uint32_t ntiles = (ew / 64u) * tile_rows;
+    const uint32_t need_mb = (ntiles * 4u + 63u) / 64u;            // = number of units
+    const unsigned long long par = pos0 & 1ull;                    // block lengths are even: the chain keeps the parity of its start
+    const unsigned long long S0 = ((pos0 - par) & ~15ull) + par;   // window 0 starts here (16-byte aligned for even streams)
+
+    // a window that lies inside the buffer and starts 16-byte aligned arrives by one bulk copy, any other by plain loads
+    auto bulk_able = [&](const uint32_t j) { return !par && S0 + (unsigned long long)j * KW::W + KW::STAGE <= len; };
+    auto issue_bulk = [&](const uint32_t j) {
+        if (lane == 0) {
+            const uint32_t bar = bar_s + 8u * (j & 1u);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)KW::STAGE) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(sm_s + (j & 1u) * KW::STAGE), "l"(src + S0 + (unsigned long long)j * KW::W), "r"((uint32_t)KW::STAGE), "r"(bar) : "memory");
+        }
+    };
+    uint32_t phase0 = 0, phase1 = 0;                               // uses of the two mbarriers
+    auto wait_bulk = [&](const uint32_t j) {
+        const uint32_t bar = bar_s + 8u * (j & 1u);
+        const uint32_t ph = (j & 1u) ? phase1 : phase0;
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(bar), "r"(ph & 1u) : "memory");
+        }
+        if (j & 1u) phase1++; else phase0++;
+    };
+    auto stage_plain = [&](const uint32_t j) {
+        const unsigned long long base = S0 + (unsigned long long)j * KW::W;
+        for (uint32_t c = lane; c < (uint32_t)KW::STAGE / 16u; c += 32u) {
+            const unsigned long long o = base + 16ull * c;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (!par && o + 16 <= len) q = __ldg(reinterpret_cast<const uint4*>(src + o));
+            else if (o < len) {
+                uint32_t t4[4] = {0, 0, 0, 0};
+                for (int e = 0; e < 16; e++)
+                    if (o + e < len) t4[e >> 2] |= (uint32_t)src[o + e] << (8 * (e & 3));
+                q = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+            }
+            sts128(sm_s + (j & 1u) * KW::STAGE + 16u * c, q.x, q.y, q.z, q.w);
+        }
+        __syncwarp();
+    };
+
+    uint32_t done = 0;                    // meta blocks (= units) finished
+    uint32_t carry = 16;                  // running payload offset, METADATA_OFFSET (RawData.cpp:25,562)
+    int pending = -1;                     // window whose bulk copy is in flight
+    if (!err) {
+        if (bulk_able(0)) { issue_bulk(0); pending = 0; }
+        uint32_t p = (uint32_t)(pos0 - S0) + 4u;                   // chain position relative to the window (even, < W)
+        uint32_t* __restrict__ unitoff = F.unitoff;
+        uint4* __restrict__ metarec = F.metarec;
+        for (uint32_t j = 0;; j++) {
+            if (pending == (int)j) wait_bulk(j); else stage_plain(j);
+            pending = -1;
+            __syncwarp();
+            if (bulk_able(j + 1u)) { issue_bulk(j + 1u); pending = (int)(j + 1u); }   // buffer (j + 1) & 1 was read for the last time a window ago
+            const uint8_t* stage = sm + (j & 1u) * KW::STAGE;
+            const uint32_t stage_s = sm_s + (j & 1u) * KW::STAGE;
+            const unsigned long long base = S0 + (unsigned long long)j * KW::W;
+            if (j == 0) {                                          // RawData.cpp:470-476
+                const uint32_t c = (uint32_t)(pos0 - S0);
+                const uint32_t count = lds_u16(stage_s + c) | (lds_u16(stage_s + c + 2u) << 16);
+                if (count < ntiles * 4u) { err = MCRAW_FRAME_BAD_META_COUNT; break; }
+            }
+            // ---- next pointer of every even offset of the window: p + 2 + payload length of the header at p (:419), stored as
+            //      the shared-memory ADDRESS of that offset's own entry (a CTA's window is < 64 KiB, so it fits 16 bits and a hop of
+            //      the chain is one dependent load and nothing else); NONE when the block does not fit the frame
+            const unsigned long long room = len > base ? len - base : 0ull;
+            const uint32_t lim = (uint32_t)(room < 0xFFF0ull ? room : 0xFFF0ull);
+#pragma unroll
+            for (int k = 0; k < KW::W / 16 / 32; k++) {
+                const uint32_t v = lane + 32u * k;
+                const uint4 d = lds128(stage_s + 16u * v);
+                const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t pr[2];
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; hlf++) {
+                        const uint32_t q = 16u * v + 4u * i + 2u * hlf + 2u + 8u * cur_len8_nib((w[i] >> (16 * hlf + 4)) & 15u);
+                        pr[hlf] = q > lim ? KW::NONE : nxt_s + q;
+                    }
+                    o[i] = pr[0] | (pr[1] << 16);
+                }
+                sts128(nxt_s + 16u * v, o[0], o[1], o[2], o[3]);
+            }
+            __syncwarp();
+            // ---- rounds of up to 32 blocks
+            bool stop = false;
+            const uint32_t a_end = nxt_s + (uint32_t)KW::W;          // entries at or behind it belong to the next window
+            uint32_t a = nxt_s + p;
+            while (a < a_end) {
+                const uint32_t want = min(32u, need_mb - done);
+                uint32_t my_a = 0, cnt = 0;
+#pragma unroll 4
+                for (; cnt < want; cnt++) {                        // the same hop in every lane (one broadcast load each)
+                    if (a >= a_end) break;                         // (NONE ends the walk here as well)
+                    if (lane == cnt) my_a = a;
+                    a = lds_u16(a);
+                }
+                if (a == KW::NONE) { err = MCRAW_FRAME_TRUNCATED; stop = true; break; }   // the chain ran into the end of the frame
+                uint32_t unit_len8 = 0, bad = 0;
+                const uint32_t unit = done + lane;
+                if (lane < cnt) {
+                    const uint32_t my_start = my_a - nxt_s;
+                    uint32_t* rec = reinterpret_cast<uint32_t*>(metarec + unit);
+                    rec[stream] = (uint32_t)(base + my_start);
+                    rec[2 + stream] = lds_u16(stage_s + my_start);
+                    if (stream == 0) unit_len8 = bits_block_len8(stage, my_start, unit, ntiles, bad);
+                }
+                if (stream == 0) {
+                    uint32_t incl = unit_len8;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= (uint32_t)d) incl += o;
+                    }
+                    if (lane < cnt) unitoff[unit] = carry + 8u * (incl - unit_len8);
+                    carry += 8u * __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    if (__any_sync(0xFFFFFFFFu, bad != 0u)) { err = MCRAW_FRAME_BAD_BITS; stop = true; break; }
+                }
+                done += cnt;
+                if (done >= need_mb) { stop = true; break; }
+            }
+            p = a - nxt_s;
+            if (stop) break;
+            p -= (uint32_t)KW::W;
+            __syncwarp();
+        }
+        if (pending >= 0) wait_bulk((uint32_t)pending);            // nothing may still be landing in shared memory when the warp leaves
+    }
+    if (lane == 0) {
+        if (stream == 0) {
+            if (!err && (unsigned long long)carry > len) err = MCRAW_FRAME_TRUNCATED;   // RawData.cpp:419
+            if (!(err & (MCRAW_FRAME_BAD_HEADER | MCRAW_FRAME_GEOMETRY))) F.unitoff[need_mb] = carry;
+        }
+        S.status[stream] = err;
+    }
+    // publish: the warp barrier orders every lane's writes before lane 0, whose fence (cumulative) and counter bump form the release
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        atomicAdd(&S.meta_done, 1u);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -873,28 +1103,9 @@ __global__ void __launch_bounds__(KS::THREADS, 1) k_meta_split(const FrameDev* _
                 rec[stream] = (uint32_t)(base + p);
                 rec[2 + stream] = hdr;
                 if (stream == 0) {
-                    const uint32_t b = stage[p] >> 4;                                      // RawData.cpp:106-110
-                    const uint32_t ref = ((uint32_t)(stage[p] & 0x0F) << 8) | stage[p + 1];
-                    uint32_t L[16], H[16];
-                    StageFetch G{reinterpret_cast<const uint32_t*>(stage), p + 2u};
-                    decode_block(b, G, L, H);
-                    uint32_t bad = (ref > 16u) ? 1u : 0u;
-                    const uint32_t refb = MC_REP(ref & 0x1F);
-                    uint32_t acc[2] = {0, 0};
-#pragma unroll
-                    for (int m = 0; m < 16; m++) {
-                        const uint32_t tile = unit * 16u + m;
-                        uint32_t v = (L[m] & MC_REP(0x1F)) + refb;
-                        uint32_t badm = H[m] | (L[m] & MC_REP(0xE0));
-                        badm |= (v + MC_REP(0x6F)) & MC_REP(0x80);
-                        if (tile >= ntiles) { v = 0; badm = 0; }
-                        bad |= badm;
-                        acc[m >> 3] += mcraw_len8x4(v & MC_REP(0x1F));
-                    }
+                    uint32_t bad;
+                    unit_len8 = bits_block_len8(stage, p, unit, ntiles, bad);
                     if (bad) sh_bad = 1;
-                    const uint32_t s2 = (acc[0] & 0x00FF00FFu) + ((acc[0] >> 8) & 0x00FF00FFu) +
-                                        (acc[1] & 0x00FF00FFu) + ((acc[1] >> 8) & 0x00FF00FFu);
-                    unit_len8 = (s2 & 0xFFFFu) + (s2 >> 16);
                 }
             }
             if (stream == 0) {
