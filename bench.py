@@ -43,7 +43,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "decoded_mpix_per_s"
 UNIT = "Mpix/s"
-KSLOTS = 6   # plan slots of a context (mcraw_capi.cu kSlots): c1 cycles over this many copies so that every call is a plan hit
+KSLOTS = 8   # plan slots of a context (mcraw_capi.cu kSlots): c1 cycles over this many copies so that every call is a plan hit
 
 WORKLOADS = {
     # name: (description, width, height, compression_type, generator, maxval, frames, distinct, strong-scaled over ranks)
@@ -77,7 +77,7 @@ def workload_config(wl, streams, world):
             "compressed_bytes_per_frame": comp, "compressed_bytes_per_pixel": comp / (w * h),
             "algorithmic_bytes_per_pixel": comp / (w * h) + 2.0,
             "l2": "every frame has its own input and output buffer; a step touches far more than the 126 MB L2 "
-                  "(c1: six copies of the frame are cycled), no flush needed",
+                  "(c1: eight copies of the frame are cycled), no flush needed",
             "scaling": "strong (clip split over the ranks)" if strong else "weak (clip per rank)",
             "parallelism": f"frame-parallel, {world} rank(s), no collective"}
 
@@ -321,6 +321,37 @@ def h2d_ceiling(env, chunk_bytes=96 << 20, reps=8):
     return chunk_bytes * reps / (ms * 1e-3) / 1e9
 
 
+def duplex_ceiling(env, in_bytes=96 << 20, out_bytes=200 << 20, reps=6):
+    """Both directions of the link at once, nothing else on the GPU: pinned host -> device in 96 MB chunks on one stream while
+    device -> pinned host runs on another (about two output bytes per input byte, the C2 mix), all ranks together.  The
+    ceiling of the host-out legs: what the platform gives each direction while the other one is busy."""
+    torch = env.torch
+    hin = torch.empty(in_bytes, dtype=torch.uint8, pin_memory=True)
+    din = torch.empty(in_bytes, dtype=torch.uint8, device="cuda")
+    hout = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+    dout = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for timed in (False, True):
+        torch.cuda.synchronize()
+        env.barrier()
+        with torch.cuda.stream(s_in):
+            ev[0].record(s_in)
+            for _ in range(reps if timed else 1):
+                din.copy_(hin, non_blocking=True)
+            ev[1].record(s_in)
+        with torch.cuda.stream(s_out):
+            ev[2].record(s_out)
+            for _ in range(reps if timed else 1):
+                hout.copy_(dout, non_blocking=True)
+            ev[3].record(s_out)
+        torch.cuda.synchronize()
+    env.barrier()
+    return {"h2d_gbs": in_bytes * reps / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9,
+            "d2h_gbs": out_bytes * reps / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9,
+            "how": f"{reps} x {in_bytes >> 20} MB H2D and {reps} x {out_bytes >> 20} MB D2H, pinned, on two streams at the same time"}
+
+
 def run_leg(env, wl, steps, warmup, headline):
     """All measurements of one workload on this rank.  Returns the dict that goes into the JSON line."""
     torch, capi, ctx = env.torch, env.capi, env.ctx
@@ -332,7 +363,7 @@ def run_leg(env, wl, steps, warmup, headline):
         mine = list(shard.shard_contiguous(frames_total, env.world, env.rank))      # global frame indices of this rank
     else:
         mine = list(range(frames_total))
-    copies = KSLOTS if frames_total == 1 else 1       # c1: cycle over six copies of the frame (> L2, every call a plan hit)
+    copies = KSLOTS if frames_total == 1 else 1       # c1: cycle over that many copies of the frame (> L2, every call a plan hit)
     nf = len(mine) * copies
     gidx = [mine[i % len(mine)] for i in range(nf)] if mine else []
     npix = w * h
@@ -640,19 +671,26 @@ def main():
     head_wl = args.workload or "c2"
     head, head_streams = run_leg(env, head_wl, args.steps, args.warmup, headline=True)
     peak_h2d = h2d_ceiling(env)
-    for key in ("e2e", "e2e_host_out"):
-        if head.get(key):
-            head[key]["h2d_peak_gbs"] = peak_h2d
-            head[key]["frac_of_h2d"] = head[key]["h2d_gbs"] / peak_h2d
+    duplex = duplex_ceiling(env)
+
+    def ceilings(leg):
+        for key in ("e2e", "e2e_host_out"):
+            if leg.get(key):
+                leg[key]["h2d_peak_gbs"] = peak_h2d
+                leg[key]["frac_of_h2d"] = leg[key]["h2d_gbs"] / peak_h2d
+        ho = leg.get("e2e_host_out")
+        if ho:                                                   # host-out: the device -> host direction is the busy one
+            ho["d2h_gbs"] = ho["d2h_bytes_per_step"] / (ho["ms_per_step"] * 1e-3) / 1e9
+            ho["duplex_peak"] = duplex
+            ho["frac_of_duplex_d2h"] = ho["d2h_gbs"] / duplex["d2h_gbs"]
+
+    ceilings(head)
     extras = {}
     if not args.workload:
         for wl in ("c1", "c3", "c4"):
             leg, st = run_leg(env, wl, max(3, min(args.steps, 20)), args.warmup, headline=False)
             leg["config"] = workload_config(wl, st, env.world)
-            for key in ("e2e", "e2e_host_out"):
-                if leg.get(key):
-                    leg[key]["h2d_peak_gbs"] = peak_h2d
-                    leg[key]["frac_of_h2d"] = leg[key]["h2d_gbs"] / peak_h2d
+            ceilings(leg)
             extras[wl] = leg
         extras["c5"] = run_file_leg(env)
     sampler.stop_flag = True

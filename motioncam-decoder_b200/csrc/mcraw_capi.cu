@@ -65,7 +65,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSlots = 6;              // chunks (sub-batches) that may be in flight per context (each owns its scratch)
+constexpr int kSlots = 8;              // chunks (sub-batches) that may be in flight per context (each owns its scratch)
 constexpr uint32_t kMaxGridY = 32768;  // frames per launch
 constexpr int kStage = 3;              // device staging buffers of the host-input pipeline
 constexpr size_t kStageBytes = 96u << 20;   // per-chunk overhead (cross-stream events) favours large chunks: 48 MB -> 51.6 GB/s, 96 MB -> 52.7 GB/s
@@ -143,6 +143,8 @@ struct mcraw_ctx {
     bool meta_small_only = getenv("MCRAW_META_SMALL") != nullptr;   // A/B switch: never use the big-window shape of k_meta
     uint32_t split_resident_ctas = 0;   // CTAs of k_meta_split the device holds at once (all of a launch must be resident)
     uint32_t meta_resident_ctas = 0;    // CTAs of k_meta<K1Batch> the device holds at once (one wave)
+    size_t hostout_first_bytes = getenv("MCRAW_HOSTOUT_FIRST_MB") ? (size_t)std::max(0, atoi(getenv("MCRAW_HOSTOUT_FIRST_MB"))) << 20
+                                                                   : (size_t)32 << 20;   // first chunk of a host-out batch (measured on C2: 0 / 8 / 16 / 32 / 48 MB -> 23.8 / 23.3 / 23.2 / 21.8 / 22.3 ms per 240 frames)
     bool meta_split = !(getenv("MCRAW_META_SPLIT") && atoi(getenv("MCRAW_META_SPLIT")) == 0) &&
                       !(getenv("MCRAW_META_WARP") && atoi(getenv("MCRAW_META_WARP")) == 2);     // A/B switch
     // batches go to k_meta_warp; A/B and test switch MCRAW_META_WARP: 0 = k_meta<K1Batch> instead, 2 = k_meta_warp for EVERY launch
@@ -392,7 +394,25 @@ void build_items(const std::vector<FrameDev>& frames, uint32_t resident_ctas, st
 int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st,
                   const mcraw_levels* levels = nullptr) {
     if (n == 0) return MCRAW_OK;
-    ctx->cur = (ctx->cur + 1) % kSlots;
+    // Which slot: one that was built for exactly these descriptors and whose last use has finished (a caller that cycles
+    // through a few distinct chunks -- a ring of buffers cut into chunks -- finds every plan again, whatever the number of
+    // chunks per round); else the next one in turn.  The scan starts behind the current slot, so a caller that presents
+    // the same batch again and again still rotates through the slots (consecutive batches in different slots: the chain).
+    auto matches = [&](const Slot& c) {
+        if (!c.plan_valid || c.plan_descs.size() != n || c.flag_uses >= (1u << 30) || c.lg_epoch >= 0xFFFFF0u) return false;
+        if (levels ? !(c.plan_levels.size() == n && std::memcmp(c.plan_levels.data(), levels, sizeof(mcraw_levels) * n) == 0) : !c.plan_levels.empty()) return false;
+        return std::memcmp(c.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
+    };
+    int pick = (ctx->cur + 1) % kSlots;
+    if (!matches(ctx->slots[pick])) {                           // (the next slot in turn matches: nothing to look for)
+        for (int k = 2; k <= kSlots; k++) {
+            const int idx = (ctx->cur + k) % kSlots;
+            const Slot& c = ctx->slots[idx];
+            if (matches(c) && (!c.in_flight || cudaEventQuery(c.done) == cudaSuccess)) { pick = idx; break; }
+        }
+        (void)cudaGetLastError();                               // cudaErrorNotReady of a query is not an error
+    }
+    ctx->cur = pick;
     Slot& s = ctx->slots[ctx->cur];
     int rc = harvest(ctx, s);
     if (rc) return rc;
@@ -788,6 +808,10 @@ static int append_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* 
     std::vector<mcraw_frame_desc> chunk;
     uint32_t i = 0;
     int copy_rr = ctx->copy_rr;
+    // Host output: the device -> host direction carries about twice the bytes and is the one to keep busy, and nothing
+    // goes back before the first chunk has been copied in and decoded -- so the chunks start small and double
+    // (MCRAW_HOSTOUT_FIRST_MB, 0 = full-size chunks from the start).
+    size_t cap = host_dst && ctx->hostout_first_bytes ? std::min(kStageBytes, ctx->hostout_first_bytes) : kStageBytes;
     while (i < n) {
         // ---- pick the frames of this chunk: as many as fit one staging buffer (at least one)
         size_t bytes = 0;
@@ -795,7 +819,7 @@ static int append_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* 
         while (j < n && j - i < kMaxGridY) {
             if (!descs[j].src) return fail_arg(ctx, "frame " + std::to_string(first + j) + ": null src");
             size_t need = (descs[j].len + 255) & ~(size_t)255;
-            if (j > i && bytes + need > kStageBytes) break;
+            if (j > i && bytes + need > cap) break;
             bytes += need;
             j++;
         }
@@ -848,21 +872,45 @@ static int append_host(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint16_t* 
             // pixels of this chunk go back while the next chunk is copied in and decoded (PCIe is full duplex); frames that
             // lie back to back on both sides travel in one copy
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, g.freed, 0));
+            for (uint32_t k = i; k < j; k++)
+                if (!host_dst[k] || !descs[k].dst) return fail_arg(ctx, "frame " + std::to_string(k) + ": null dst");
             for (uint32_t k = i; k < j;) {
-                size_t elems = 0;
-                uint32_t m = k;
-                for (; m < j; m++) {
-                    if (!host_dst[m] || !descs[m].dst) return fail_arg(ctx, "frame " + std::to_string(m) + ": null dst");
-                    if (m > k && (descs[m].dst != descs[k].dst + elems || host_dst[m] != host_dst[k] + elems)) break;
-                    elems += (size_t)descs[m].width * (size_t)descs[m].height;
+                // frames of one size at a constant pitch on both sides (a ring of output buffers) travel as ONE 2-D copy: a copy
+                // per 4 MB frame leaves gaps on the link (240 of them per C2 batch); back to back they are one plain copy
+                const size_t fbytes = 2 * (size_t)descs[k].width * (size_t)descs[k].height;
+                uint32_t m = k + 1;
+                ptrdiff_t dpitch = 0, hpitch = 0;
+                if (m < j) {
+                    dpitch = reinterpret_cast<const uint8_t*>(descs[m].dst) - reinterpret_cast<const uint8_t*>(descs[k].dst);
+                    hpitch = reinterpret_cast<const uint8_t*>(host_dst[m]) - reinterpret_cast<const uint8_t*>(host_dst[k]);
                 }
-                CU_TRY(ctx, cudaMemcpyAsync(host_dst[k], descs[k].dst, elems * 2, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                if (m < j && dpitch >= (ptrdiff_t)fbytes && hpitch >= (ptrdiff_t)fbytes && dpitch < ((ptrdiff_t)1 << 30) && hpitch < ((ptrdiff_t)1 << 30)) {
+                    for (; m < j; m++) {
+                        if (2 * (size_t)descs[m].width * (size_t)descs[m].height != fbytes) break;
+                        if (reinterpret_cast<const uint8_t*>(descs[m].dst) - reinterpret_cast<const uint8_t*>(descs[m - 1].dst) != dpitch) break;
+                        if (reinterpret_cast<const uint8_t*>(host_dst[m]) - reinterpret_cast<const uint8_t*>(host_dst[m - 1]) != hpitch) break;
+                    }
+                } else m = k + 1;
+                const size_t rows = m - k;
+                if (rows > 1 && dpitch == (ptrdiff_t)fbytes && hpitch == (ptrdiff_t)fbytes)
+                    CU_TRY(ctx, cudaMemcpyAsync(host_dst[k], descs[k].dst, fbytes * rows, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                else if (rows > 1) {
+                    // (a run that spans separate allocations is refused by the runtime: frame by frame then)
+                    if (cudaMemcpy2DAsync(host_dst[k], (size_t)hpitch, descs[k].dst, (size_t)dpitch, fbytes, rows, cudaMemcpyDeviceToHost,
+                                          ctx->d2h_stream) != cudaSuccess) {
+                        (void)cudaGetLastError();
+                        for (uint32_t q = k; q < m; q++)
+                            CU_TRY(ctx, cudaMemcpyAsync(host_dst[q], descs[q].dst, fbytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    }
+                } else
+                    CU_TRY(ctx, cudaMemcpyAsync(host_dst[k], descs[k].dst, fbytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
                 k = m;
             }
             CU_TRY(ctx, cudaEventRecord(ctx->d2h_done, ctx->d2h_stream));
             ctx->d2h_pending = true;
         }
         i = j;
+        cap = std::min(kStageBytes, 2 * cap);
     }
     ctx->copy_rr = copy_rr;
     return MCRAW_OK;

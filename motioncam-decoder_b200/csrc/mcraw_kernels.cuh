@@ -1369,6 +1369,13 @@ __device__ __forceinline__ void emit_and_copy(const uint32_t (&LE)[16], const ui
                                               const uint32_t out_base, const uint32_t lane, const int width, const EpiRegs& F,
                                               const unsigned epi) {
     const uint32_t out_lane = out_base + (lane & 1u) * KU_ROW_PITCH + (lane >> 1) * KU_SLOT_PITCH;
+#ifdef MCRAW_KU_EXP_NOEMIT        // experiment (wrong pixels): staging and copy-out only -- the memory system's share
+    sts128(out_lane, LE[0], LO[0], refs, HE[0] | HO[0]);
+    __syncwarp();
+    if (epi == MCRAW_OUT_RAW) { copy_half<VEC, 0, MCRAW_OUT_RAW>(co, out_base, lane, width, F); __syncwarp(); copy_half<VEC, 1, MCRAW_OUT_RAW>(co, out_base, lane, width, F); }
+    __syncwarp();
+    return;
+#endif
     if (with_h) emit_half<true, 0>(LE, HE, LO, HO, refs, out_lane); else emit_half<false, 0>(LE, HE, LO, HO, refs, out_lane);
     __syncwarp();
     if (epi == MCRAW_OUT_RAW) copy_half<VEC, 0, MCRAW_OUT_RAW>(co, out_base, lane, width, F);
@@ -1568,8 +1575,14 @@ __device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& 
 
         // ---- decode the even-column and the odd-column block of the pair
         uint32_t LE[16], HE[16], LO[16], HO[16];
+#ifdef MCRAW_KU_EXP_NODECODE      // experiment (wrong pixels): what the kernel costs without the block decode
+#pragma unroll
+        for (int q = 0; q < 16; q++) { LE[q] = aE + q; LO[q] = bE + q; HE[q] = 0; HO[q] = 0; }
+        { const uint2 t = lds64(in_base + 8u * lane); LE[0] ^= t.x; LO[0] ^= t.y; }
+#else
         const uint32_t lenE = decode_block(bE, SwzFetch{in_base, aE}, LE, HE);
         decode_block(bO, SwzFetch{in_base, aE + lenE}, LO, HO);
+#endif
         __syncwarp();
 
         // ---- the input buffer is free again: start fetching the next unit behind the emit / copy-out phases
