@@ -43,7 +43,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "decoded_mpix_per_s"
 UNIT = "Mpix/s"
-KSLOTS = 8   # plan slots of a context (mcraw_capi.cu kSlots): c1 cycles over this many copies so that every call is a plan hit
+KSLOTS = 6   # plan slots of a context (mcraw_capi.cu kSlots): c1 cycles over this many copies so that every call is a plan hit
 
 WORKLOADS = {
     # name: (description, width, height, compression_type, generator, maxval, frames, distinct, strong-scaled over ranks)
@@ -77,7 +77,7 @@ def workload_config(wl, streams, world):
             "compressed_bytes_per_frame": comp, "compressed_bytes_per_pixel": comp / (w * h),
             "algorithmic_bytes_per_pixel": comp / (w * h) + 2.0,
             "l2": "every frame has its own input and output buffer; a step touches far more than the 126 MB L2 "
-                  "(c1: eight copies of the frame are cycled), no flush needed",
+                  "(c1: six copies of the frame are cycled), no flush needed",
             "scaling": "strong (clip split over the ranks)" if strong else "weak (clip per rank)",
             "parallelism": f"frame-parallel, {world} rank(s), no collective"}
 

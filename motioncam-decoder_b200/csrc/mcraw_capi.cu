@@ -65,7 +65,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSlots = 8;              // chunks (sub-batches) that may be in flight per context (each owns its scratch)
+constexpr int kSlots = 6;              // chunks (sub-batches) that may be in flight per context (each owns its scratch)
 constexpr uint32_t kMaxGridY = 32768;  // frames per launch
 constexpr int kStage = 3;              // device staging buffers of the host-input pipeline
 constexpr size_t kStageBytes = 96u << 20;   // per-chunk overhead (cross-stream events) favours large chunks: 48 MB -> 51.6 GB/s, 96 MB -> 52.7 GB/s
@@ -394,24 +394,11 @@ void build_items(const std::vector<FrameDev>& frames, uint32_t resident_ctas, st
 int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uint32_t result_offset, cudaStream_t st,
                   const mcraw_levels* levels = nullptr) {
     if (n == 0) return MCRAW_OK;
-    // Which slot: one that was built for exactly these descriptors and whose last use has finished (a caller that cycles
-    // through a few distinct chunks -- a ring of buffers cut into chunks -- finds every plan again, whatever the number of
-    // chunks per round); else the next one in turn.  The scan starts behind the current slot, so a caller that presents
-    // the same batch again and again still rotates through the slots (consecutive batches in different slots: the chain).
-    auto matches = [&](const Slot& c) {
-        if (!c.plan_valid || c.plan_descs.size() != n || c.flag_uses >= (1u << 30) || c.lg_epoch >= 0xFFFFF0u) return false;
-        if (levels ? !(c.plan_levels.size() == n && std::memcmp(c.plan_levels.data(), levels, sizeof(mcraw_levels) * n) == 0) : !c.plan_levels.empty()) return false;
-        return std::memcmp(c.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
-    };
-    int pick = (ctx->cur + 1) % kSlots;
-    if (!matches(ctx->slots[pick])) {                           // (the next slot in turn matches: nothing to look for)
-        for (int k = 2; k <= kSlots; k++) {
-            const int idx = (ctx->cur + k) % kSlots;
-            const Slot& c = ctx->slots[idx];
-            if (matches(c) && (!c.in_flight || cudaEventQuery(c.done) == cudaSuccess)) { pick = idx; break; }
-        }
-        (void)cudaGetLastError();                               // cudaErrorNotReady of a query is not an error
-    }
+    // Slots are taken in turn: a caller that presents the same batch again and again has every slot built for it after one
+    // round, and consecutive batches always sit in different slots (the chain).  (Looking a plan up by content instead --
+    // measured -- leaves stale slots unconverted for as long as finished matching ones turn up, and the conversions, which
+    // may have to grow a slot's buffers behind a device-wide synchronisation, then land anywhere in a steady-state loop.)
+    const int pick = (ctx->cur + 1) % kSlots;
     ctx->cur = pick;
     Slot& s = ctx->slots[ctx->cur];
     int rc = harvest(ctx, s);
