@@ -480,22 +480,38 @@ def run_leg(env, wl, steps, warmup, headline):
                                       "frac_of_8000": step_gbs / 8000.0, "note": "this rank's bytes / this rank's time"}}
     ctx.set_kernel_timing(0)
 
-    # ---- cold plan: every call presents descriptors the context has not seen (validation, work list, upload, memset inside)
+    # ---- cold plans: every call presents descriptors the context has not seen (validation, work list, plan upload inside).
+    #      Two flavours: consecutive batches write ALTERNATING output areas (a double-buffered consumer: the new batch may be
+    #      chained to the one before, its plan goes up beside the decode stream), and all batches write the SAME buffers (no
+    #      chain: a batch with other descriptors may not overlap one that still writes there).
     if headline and mine and copies == 1:
-        cold = [capi.Context.make_descs([it[:6] + (it[6] + 8 * (k + 1),) for it in items]) for k in range(KSLOTS + 1)]
-        for d, n in cold:
-            ctx.decode_batch(d, n, env.sh)
-        ctx.batch_wait(per_step)
-        env.barrier()
-        ev0.record(env.stream)
-        csteps = 2 * len(cold)
-        for i in range(csteps):
-            d, n = cold[i % len(cold)]
-            ctx.decode_batch(d, n, env.sh)
-        ev1.record(env.stream)
-        ctx.batch_wait(per_step)
-        env.barrier()
-        res["cold_plan_ms_per_step"] = env.max_over_ranks(ev0.elapsed_time(ev1)) / csteps
+        def cold_loop(plans):
+            for d, n in plans:
+                ctx.decode_batch(d, n, env.sh)
+            ctx.batch_wait(per_step)
+            env.barrier()
+            ev0.record(env.stream)
+            csteps = 3 * len(plans)
+            for i in range(csteps):
+                d, n = plans[i % len(plans)]
+                ctx.decode_batch(d, n, env.sh)
+            ev1.record(env.stream)
+            written, status = ctx.batch_wait(per_step)
+            assert all(v == npix for v in written) and not any(status)
+            env.barrier()
+            return env.max_over_ranks(ev0.elapsed_time(ev1)) / csteps
+
+        dst2 = torch.empty_like(dst)
+        shift = dst2.data_ptr() - dst.data_ptr()
+        alt = [capi.Context.make_descs([it[:5] + (it[5] + (shift if k % 2 else 0), it[6] + 8 * (k + 1)) for it in items]) for k in range(KSLOTS + 2)]
+        poison()
+        dst2.fill_(0xA5)
+        res["cold_plan_ms_per_step"] = cold_loop(alt)
+        verify(dst_ptrs, gidx, "cold plans, first output area")
+        verify([p_ + shift for p_ in dst_ptrs], gidx, "cold plans, second output area")
+        del dst2
+        same = [capi.Context.make_descs([it[:6] + (it[6] + 8 * (k + 1),) for it in items]) for k in range(KSLOTS + 1)]
+        res["cold_plan_same_outputs_ms_per_step"] = cold_loop(same)
 
     # ---- end to end: pinned host inputs -> H2D on side streams -> decode -> results to host, every step.
     #      One pinned ring holds the clip back to back (256-byte aligned frames), as a container reader would fill it;
@@ -716,6 +732,7 @@ def main():
             "e2e": head["e2e"], "e2e_host_out": head["e2e_host_out"],
             "pixels_verified": head["pixels_verified"], "verified_frames_total": head["verified_frames_total"],
             "cold_plan_ms_per_step": head.get("cold_plan_ms_per_step"),
+            "cold_plan_same_outputs_ms_per_step": head.get("cold_plan_same_outputs_ms_per_step"),
             "chain": os.environ.get("MCRAW_CHAIN", "default (24 CTAs held back for the next batch's index kernel)"),
             "gpu_launches": head["gpu_launches"],
             "clocks": clocks,

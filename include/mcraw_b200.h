@@ -86,7 +86,9 @@ int mcraw_ctx_device(const mcraw_ctx* ctx);
  * Back-to-back calls on one stream overlap where that cannot be observed: when a call presents the descriptors of the
  * previous call again, or writes a disjoint range of output addresses, its index kernel is launched as a programmatic
  * dependent of the previous call's pixel kernel and resolves the metadata while those pixels still stream
- * (MCRAW_CHAIN=0 in the environment switches this off). */
+ * (MCRAW_CHAIN=0 in the environment switches this off).  That holds for NEW descriptors as well: their plan (device-side
+ * copies of the descriptors, work list) is uploaded on a stream of the context's own and the kernels wait for it
+ * themselves, so `stream` carries nothing but the two kernels of the call (MCRAW_PLAN_SIDE=0: upload on `stream`). */
 int mcraw_decode_batch(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, void* stream);
 
 /* For callers that upload compressed frames themselves: the value to put into mcraw_frame_desc.encoded_width for a

@@ -70,7 +70,7 @@ constexpr uint32_t kMaxGridY = 32768;  // frames per launch
 constexpr int kStage = 3;              // device staging buffers of the host-input pipeline
 constexpr size_t kStageBytes = 96u << 20;   // per-chunk overhead (cross-stream events) favours large chunks: 48 MB -> 51.6 GB/s, 96 MB -> 52.7 GB/s
 constexpr int kCopyStreams = 2;
-constexpr int kHostParts = 4;          // pieces (and threads) of the host-side copies of the single-frame call
+constexpr int kHostParts = 16;         // at most that many pieces (and threads) of the host-side copies of the single-frame call
 
 struct Slot {
     // one pinned / device buffer pair per chunk: [FrameDev x n | WorkItem x items]
@@ -96,7 +96,9 @@ struct Slot {
     uint32_t max_ltiles = 0, nitems = 0;
     uint32_t split_nw = 0;          // > 0: this plan's metadata chains are resolved by k_meta_split with that many windows per stream
     size_t items_off = 0, plan_bytes = 0;
-    uint32_t flag_uses = 0;         // k_meta launches on this plan since its counters were zeroed
+    uint32_t flag_uses = 0;         // index-kernel launches of this SLOT (whatever the plan): the epoch the per-frame done words carry
+    uint32_t plan_epoch = 0;        // plan uploads of this slot: the value of the ready word behind the plan (plan_wait in the kernels)
+    size_t ready_off = 0;           // offset of that word in h_up / d_up
     cudaStream_t stream = nullptr;  // the stream the chunk was enqueued on
     uintptr_t dst_lo = 0, dst_hi = 0;   // address range spanned by the plan's output buffers
     uint32_t lg_nwork = 0;          // (frame, tile) tickets of the legacy frames of the plan
@@ -119,6 +121,7 @@ struct mcraw_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_streams[kCopyStreams] = {nullptr, nullptr};
     cudaStream_t d2h_stream = nullptr;      // mcraw_decode_batch_host_out: device -> host copies of decoded chunks
+    cudaStream_t plan_stream = nullptr;     // uploads of new plans (descriptors + work lists): beside the decode stream, not on it
     cudaEvent_t d2h_done = nullptr;
     bool d2h_pending = false;
     // CHAIN: back-to-back batches on one stream are linked by programmatic dependent launches all the way -- k_meta of
@@ -143,6 +146,8 @@ struct mcraw_ctx {
     bool meta_small_only = getenv("MCRAW_META_SMALL") != nullptr;   // A/B switch: never use the big-window shape of k_meta
     uint32_t split_resident_ctas = 0;   // CTAs of k_meta_split the device holds at once (all of a launch must be resident)
     uint32_t meta_resident_ctas = 0;    // CTAs of k_meta<K1Batch> the device holds at once (one wave)
+    bool plan_side = !(getenv("MCRAW_PLAN_SIDE") && atoi(getenv("MCRAW_PLAN_SIDE")) == 0);   // A/B switch: 0 = new plans are uploaded on the decode stream
+    int host_parts = std::max(1, std::min(kHostParts, getenv("MCRAW_HOST_PARTS") ? atoi(getenv("MCRAW_HOST_PARTS")) : 4));   // mcraw_decode_host
     size_t hostout_first_bytes = getenv("MCRAW_HOSTOUT_FIRST_MB") ? (size_t)std::max(0, atoi(getenv("MCRAW_HOSTOUT_FIRST_MB"))) << 20
                                                                    : (size_t)32 << 20;   // first chunk of a host-out batch (measured on C2: 0 / 8 / 16 / 32 / 48 MB -> 23.8 / 23.3 / 23.2 / 21.8 / 22.3 ms per 240 frames)
     bool meta_split = !(getenv("MCRAW_META_SPLIT") && atoi(getenv("MCRAW_META_SPLIT")) == 0) &&
@@ -203,6 +208,8 @@ int slot_reserve(mcraw_ctx* ctx, Slot& s, uint32_t n, size_t up_bytes, size_t sc
         s.h_results = nullptr; s.d_dyn = nullptr; s.cap_frames = 0;
         CU_TRY(ctx, cudaMallocHost(&s.h_results, sizeof(Result) * cap));
         CU_TRY(ctx, cudaMalloc(&s.d_dyn, 16 + sizeof(FrameState) * cap));
+        // queue counters (the kernels leave them at zero) and done words (epochs: zero is older than any launch)
+        CU_TRY(ctx, cudaMemset(s.d_dyn, 0, 16 + sizeof(FrameState) * cap));
         s.cap_frames = cap;
     }
     if (up_bytes > s.up_bytes) {
@@ -407,11 +414,11 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     // A slot remembers the descriptors it was last built for: a caller that decodes into a ring of buffers presents the
     // same descriptors again and again, and then the device-side tables of the slot are still valid -- nothing to
     // validate, build or upload.
-    // (flag_uses bound: the per-frame meta_done counters k_units compares with 2 * flag_uses are 32 bits wide and only
-    // zeroed when a plan is uploaded, so a plan that has been reused 2^30 times is uploaded afresh.)
+    // (flag_uses bound: the per-frame done words carry the slot's launch count as their epoch, 32 bits wide; a slot that
+    // has launched 2^32 - 16 times has its words zeroed and starts over -- as a plan that is uploaded afresh.)
     const bool same_levels = levels ? (s.plan_levels.size() == n && std::memcmp(s.plan_levels.data(), levels, sizeof(mcraw_levels) * n) == 0)
                                     : s.plan_levels.empty();
-    const bool hit = s.plan_valid && same_levels && s.flag_uses < (1u << 30) && s.lg_epoch < 0xFFFFF0u && s.plan_descs.size() == n &&
+    const bool hit = s.plan_valid && same_levels && s.flag_uses < 0xFFFFFFF0u && s.lg_epoch < 0xFFFFF0u && s.plan_descs.size() == n &&
                      std::memcmp(s.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
     if (!hit) {
         s.plan_valid = false;
@@ -441,7 +448,8 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         s.lg_nwork = (uint32_t)lgwork.size();
         s.plan_bytes = (s.lg_work_off + sizeof(LgWork) * lgwork.size() + 15) & ~(size_t)15;
         s.plan_scratch = scratch;
-        rc = slot_reserve(ctx, s, n, s.plan_bytes, scratch);
+        s.ready_off = s.plan_bytes;                                  // the plan's ready word travels behind it
+        rc = slot_reserve(ctx, s, n, s.plan_bytes + 16, scratch);
         if (rc) return rc;
         FrameDev* h_frames = reinterpret_cast<FrameDev*>(s.h_up);
         for (uint32_t i = 0; i < n; i++) {
@@ -474,13 +482,20 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     Result* d_results = s.h_results;   // pinned host memory: the kernels write the 16-byte per-frame results straight to the host
     const FrameDev* d_frames = reinterpret_cast<const FrameDev*>(s.d_up);
     const WorkItem* d_items = reinterpret_cast<const WorkItem*>(s.d_up + s.items_off);
+    const uint32_t* d_ready = reinterpret_cast<const uint32_t*>(s.d_up + s.ready_off);
     const bool any7 = s.any7, any6 = s.any6;
     s.n = n; s.result_offset = result_offset; s.batch_id = ctx->batch_id;
 
     // descriptor + work list upload and the index kernels between e0 and e1, the pixel kernels between e1 and e2
     const bool timed = ctx->timing_every && (ctx->chunk_seq++ % ctx->timing_every) == 0;
+    // A NEW plan of current-format frames goes up on the plan stream, beside the decode stream: the kernels wait for its
+    // ready word themselves (plan_wait), the per-frame done words carry epochs and the queue counters reset themselves, so
+    // the decode stream holds nothing but the two kernels -- a batch of new descriptors chains like a repeated one.
+    // Plans with legacy frames or k_meta_split scratch (status words / flags zeroed per plan) keep the in-stream upload.
+    const bool wrap = s.flag_uses >= 0xFFFFFFF0u;
+    const bool side = !hit && any7 && !any6 && !s.split_nw && !wrap && ctx->plan_side;
     bool chain = false;
-    if (ctx->overlap && ctx->chain_ctas && hit && any7 && !any6 && !timed && ctx->prev_slot >= 0 && ctx->prev_slot != ctx->cur) {
+    if (ctx->overlap && ctx->chain_ctas && (hit || side) && any7 && !any6 && !timed && ctx->prev_slot >= 0 && ctx->prev_slot != ctx->cur) {
         const Slot& p = ctx->slots[ctx->prev_slot];
         // the previous chunk ended with k_units on this stream, and whatever it still writes cannot collide with this chunk
         if (p.plan_valid && p.any7 && !p.any6 && p.stream == st && !p.timed) {
@@ -491,10 +506,15 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
     s.stream = st;
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e0, st));
     if (!hit) {
-        CU_TRY(ctx, cudaMemcpyAsync(s.d_up, s.h_up, s.plan_bytes, cudaMemcpyHostToDevice, st));
-        // the queue counters and the per-frame meta_done counters start from zero for a new plan
-        CU_TRY(ctx, cudaMemsetAsync(s.d_dyn, 0, 16 + sizeof(FrameState) * n, st));
-        s.flag_uses = 0;
+        s.plan_epoch += 1;
+        std::memcpy(s.h_up + s.ready_off, &s.plan_epoch, sizeof s.plan_epoch);
+        cudaStream_t up = side ? ctx->plan_stream : st;
+        CU_TRY(ctx, cudaMemcpyAsync(s.d_up, s.h_up, s.plan_bytes, cudaMemcpyHostToDevice, up));
+        CU_TRY(ctx, cudaMemcpyAsync(s.d_up + s.ready_off, s.h_up + s.ready_off, 4, cudaMemcpyHostToDevice, up));   // behind the plan, in stream order
+        if (wrap) {                                        // the epochs start over: every done word of the slot back to zero
+            CU_TRY(ctx, cudaMemsetAsync(s.d_dyn, 0, 16 + sizeof(FrameState) * s.cap_frames, st));
+            s.flag_uses = 0;
+        }
         s.plan_valid = true;
         // k_legacy_warp: the tiles' status words are tagged with the launch epoch of the plan, which starts over here
         if ((any6 || s.split_nw) && s.plan_scratch) CU_TRY(ctx, cudaMemsetAsync(s.d_scratch, 0, s.plan_scratch, st));
@@ -516,14 +536,14 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
             // the launch epoch of the plan tags the windows' flags (the scratch was zeroed when the plan was uploaded)
             cfg.gridDim = dim3(2 * n * s.split_nw); cfg.blockDim = dim3(KS::THREADS); cfg.dynamicSmemBytes = KS::SMEM;
             CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta_split, d_frames, d_states, s.split_nw, s.flag_uses + 1u));
-        } else if (few) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Few>, d_frames, d_states));
+        } else if (few) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Few>, d_frames, d_states, s.flag_uses + 1u, d_ready, s.plan_epoch));
         else if (ctx->meta_warp == 2 || (ctx->meta_warp == 1 && (chain || 2 * n > 2 * ctx->meta_resident_ctas))) {
             // a batch whose index work hides behind the pixel kernel of the batch before (chained), or one of more than two
             // waves of k_meta CTAs: one warp per (frame, stream) -- a third of k_meta's instructions and a tenth of its SM
             // time, all streams at once; slower per stream, so a lone smaller batch stays with k_meta (k_meta_warp)
             cfg.gridDim = dim3((2 * n + KW::WARPS - 1) / KW::WARPS); cfg.blockDim = dim3(KW::THREADS); cfg.dynamicSmemBytes = KW::SMEM;
-            CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta_warp, d_frames, d_states, 2u * n));
-        } else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Batch>, d_frames, d_states));
+            CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta_warp, d_frames, d_states, 2u * n, s.flag_uses + 1u, d_ready, s.plan_epoch));
+        } else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_meta<K1Batch>, d_frames, d_states, s.flag_uses + 1u, d_ready, s.plan_epoch));
         ctx->launches += 1;
     }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e1, st));
@@ -545,9 +565,9 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
         if (s.any_epi) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units<true>, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems,
-                                                      d_counter, pdl ? 2u * s.flag_uses : 0u));
+                                                      d_counter, pdl ? s.flag_uses : 0u, d_ready, s.plan_epoch));
         else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_units<false>, d_frames, (const FrameState*)d_states, d_results, d_items, s.nitems,
-                                            d_counter, pdl ? 2u * s.flag_uses : 0u));
+                                            d_counter, pdl ? s.flag_uses : 0u, d_ready, s.plan_epoch));
         ctx->launches += 1;
     }
     if (any6) {
@@ -631,6 +651,7 @@ int mcraw_ctx_create(int device, mcraw_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
     for (auto& cs : ctx->copy_streams)
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
+    if (cudaStreamCreateWithFlags(&ctx->plan_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(MCRAW_ERR_CUDA); }
     if (const char* e = getenv("MCRAW_CHAIN")) ctx->chain_ctas = (uint32_t)std::max(0, atoi(e));
     if (cudaFuncSetAttribute(k_meta<K1Batch>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Batch::K1_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_meta<K1Few>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Few::K1_SMEM) != cudaSuccess ||
@@ -707,6 +728,7 @@ void mcraw_ctx_destroy(mcraw_ctx* ctx) {
     if (ctx->d_out) cudaFree(ctx->d_out);
     for (auto& cs : ctx->copy_streams) if (cs) cudaStreamDestroy(cs);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->plan_stream) cudaStreamDestroy(ctx->plan_stream);
     if (ctx->d2h_done) cudaEventDestroy(ctx->d2h_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -938,7 +960,7 @@ size_t mcraw_decode_host(mcraw_ctx* ctx, uint16_t* output, int width, int height
     // The caller's buffers are pageable: the bytes go through pinned staging, and for a 25 MB frame the two host copies
     // cost more than PCIe and the kernels together.  So large copies are cut into kHostParts pieces handled by as many
     // threads, and on the way back every piece is copied out as soon as ITS device-to-host transfer has landed.
-    const int in_parts = len >= (2u << 20) ? kHostParts : 1, out_parts = out_bytes >= (2u << 20) ? kHostParts : 1;
+    const int in_parts = len >= (2u << 20) ? ctx->host_parts : 1, out_parts = out_bytes >= (2u << 20) ? ctx->host_parts : 1;
     parallel_parts(in_parts, [&](int k) {
         const size_t a = len * k / in_parts, b = len * (k + 1) / in_parts;
         std::memcpy(reinterpret_cast<uint8_t*>(ctx->h_in) + a, input + a, b - a);

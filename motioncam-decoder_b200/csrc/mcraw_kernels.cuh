@@ -64,8 +64,45 @@ struct FrameState {
     unsigned status[2];            // MCRAW_FRAME_* bits
     unsigned tile_rows_dev;        // ceil(encodedHeight/4) from the frame header
     unsigned rows_fit;             // rows emitted: min(4*tile_rows_dev, dst_cap / width)
-    unsigned meta_done;            // + 1 per metadata stream published by k_meta (k_units waits for 2 * uses of the slot's plan)
+    unsigned done[2];              // per metadata stream: the launch epoch of the slot (mcraw_capi.cu: Slot::flag_uses) once the index
+                                   // kernel has published the stream for this launch; k_units waits until both carry its own epoch.
+                                   // Stale values are older epochs, so nothing is zeroed between launches or plans (8-byte aligned pair)
 };
+static_assert(sizeof(FrameState) == 24, "done[] is read as one 64-bit word: FrameState arrays must keep it 8-byte aligned");
+
+// The plan of a launch (FrameDev[] + work lists) may arrive by a copy on ANOTHER stream while the kernels are already
+// resident (mcraw_capi.cu, enqueue_chunk): the copy ends with the plan's epoch in a ready word, which one thread per warp /
+// CTA polls before it touches the plan.  Plan data is then read with ld.global.cg (L2): the same addresses held the
+// slot's previous plan, of which nothing may come back from L1.
+__device__ __forceinline__ void plan_wait(const uint32_t* ready, const uint32_t epoch) {
+    uint32_t v;
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(ready) : "memory");
+        if (v == epoch) break;
+        __nanosleep(128);
+    }
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(ready) : "memory");
+}
+template <class T>
+__device__ __forceinline__ T* ldcg_ptr(T* const* p) {
+    return reinterpret_cast<T*>(__ldcg(reinterpret_cast<const unsigned long long*>(p)));
+}
+// what the index kernels need of a frame's descriptor
+struct FrameIdx {
+    const uint8_t* src;
+    unsigned long long len, dst_cap;
+    int width, type;
+    unsigned tiles_x, tile_rows;
+    uint32_t* unitoff;
+    uint4* metarec;
+};
+__device__ __forceinline__ FrameIdx frame_idx_cg(const FrameDev* p) {
+    FrameIdx f;
+    f.src = ldcg_ptr(&p->src); f.len = __ldcg(&p->len); f.dst_cap = __ldcg(&p->dst_cap);
+    f.width = __ldcg(&p->width); f.type = __ldcg(&p->type); f.tiles_x = __ldcg(&p->tiles_x); f.tile_rows = __ldcg(&p->tile_rows);
+    f.unitoff = ldcg_ptr(&p->unitoff); f.metarec = ldcg_ptr(&p->metarec);
+    return f;
+}
 
 struct Result {
     unsigned long long written;    // uint16 elements, 0 = failed
@@ -304,18 +341,20 @@ __device__ __forceinline__ uint32_t bits_block_len8(const uint8_t* stage, const 
 
 // grid = 2 * frames, block = Shape::K1_THREADS, dynamic smem = Shape::K1_SMEM
 // Publish everything this CTA wrote for (frame, stream): the barrier orders every thread's writes before thread 0, whose
-// fence (cumulative) and counter bump form the release; k_units may be running already (programmatic dependent launch)
-// and polls the counter, ending the poll with an acquire load.
-__device__ __forceinline__ void meta_publish(FrameState& S) {
+// fence (cumulative) and store of the launch epoch form the release; k_units may be running already (programmatic
+// dependent launch) and polls the frame's two words, ending the poll with an acquire load.
+__device__ __forceinline__ void meta_done_store(FrameState& S, const uint32_t stream, const uint32_t epoch) {
+    __threadfence();
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(&S.done[stream]), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void meta_publish(FrameState& S, const uint32_t stream, const uint32_t epoch) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(&S.meta_done, 1u);
-    }
+    if (threadIdx.x == 0) meta_done_store(S, stream, epoch);
 }
 
 template <class Shape>
-__global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 3 : 1) k_meta(const FrameDev* __restrict__ frames, FrameState* __restrict__ states) {
+__global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 3 : 1) k_meta(const FrameDev* frames, FrameState* __restrict__ states,
+                                                                                               const uint32_t epoch, const uint32_t* plan_ready, const uint32_t plan_epoch) {
     constexpr int K1_THREADS = Shape::K1_THREADS, K1_CHUNK = Shape::K1_CHUNK, K1_MB = Shape::K1_MB, K1_NXT_BYTES = Shape::K1_NXT_BYTES;
     constexpr int K1_STAGE = Shape::K1_STAGE_PER_THREAD;
     extern __shared__ __align__(16) uint8_t k1_smem[];
@@ -333,10 +372,12 @@ __global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int f = blockIdx.x >> 1;
     const int stream = blockIdx.x & 1;   // 0 = bits, 1 = refs
-    const FrameDev& F = frames[f];
+    const int tid = threadIdx.x;
+    if (tid == 0) plan_wait(plan_ready, plan_epoch);
+    __syncthreads();
+    const FrameIdx F = frame_idx_cg(frames + f);
     FrameState& S = states[f];
     if (F.type != MCRAW_COMPRESSION_CURRENT) return;
-    const int tid = threadIdx.x;
     const uint8_t* __restrict__ src = F.src;
     const unsigned long long len = F.len;
 
@@ -376,7 +417,7 @@ __global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 
     __syncthreads();
     if (sh_err) {
         if (tid == 0) S.status[stream] = sh_err;
-        meta_publish(S);
+        meta_publish(S, (uint32_t)stream, epoch);
         return;
     }
     const uint32_t tiles_x = sh_hdr[0] / 64u;
@@ -557,7 +598,7 @@ __global__ void __launch_bounds__(Shape::K1_THREADS, Shape::K1_THREADS == 256 ? 
         }
         S.status[stream] = err;
     }
-    meta_publish(S);
+    meta_publish(S, (uint32_t)stream, epoch);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -585,15 +626,18 @@ struct KW {
     static_assert(SMEM + 4096 < 0xFFFF, "next pointers are 16-bit shared-memory addresses");
 };
 
-__global__ void __launch_bounds__(KW::THREADS, 6) k_meta_warp(const FrameDev* __restrict__ frames, FrameState* __restrict__ states,
-                                                              const uint32_t npairs) {
+__global__ void __launch_bounds__(KW::THREADS, 6) k_meta_warp(const FrameDev* frames, FrameState* __restrict__ states,
+                                                              const uint32_t npairs, const uint32_t epoch, const uint32_t* plan_ready,
+                                                              const uint32_t plan_epoch) {
     extern __shared__ __align__(128) uint8_t kw_smem[];
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t pair = blockIdx.x * KW::WARPS + wid;
     if (pair >= npairs) return;
     const uint32_t f = pair >> 1, stream = pair & 1u;            // 0 = bits, 1 = refs
-    const FrameDev& F = frames[f];
+    if (lane == 0) plan_wait(plan_ready, plan_epoch);
+    __syncwarp();
+    const FrameIdx F = frame_idx_cg(frames + f);
     FrameState& S = states[f];
     if (F.type != MCRAW_COMPRESSION_CURRENT) return;
     uint8_t* const sm = kw_smem + wid * KW::WARP_SMEM;
@@ -772,12 +816,9 @@ __global__ void __launch_bounds__(KW::THREADS, 6) k_meta_warp(const FrameDev* __
         }
         S.status[stream] = err;
     }
-    // publish: the warp barrier orders every lane's writes before lane 0, whose fence (cumulative) and counter bump form the release
+    // publish: the warp barrier orders every lane's writes before lane 0, whose fence (cumulative) and epoch store form the release
     __syncwarp();
-    if (lane == 0) {
-        __threadfence();
-        atomicAdd(&S.meta_done, 1u);
-    }
+    if (lane == 0) meta_done_store(S, stream, epoch);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1195,7 +1236,7 @@ __global__ void __launch_bounds__(KS::THREADS, 1) k_meta_split(const FrameDev* _
         if (!err && done < need_mb) err = MCRAW_FRAME_TRUNCATED;  // the windows of this launch do not reach the end of the chain
         S.status[stream] = err;
     }
-    meta_publish(S);
+    meta_publish(S, (uint32_t)stream, epoch);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1283,7 +1324,8 @@ struct EpiRegs {
     unsigned black2[2], range2[2];
     float blackf[4], scalef[4];
 };
-__device__ __forceinline__ EpiRegs epilogue_regs(const FrameDev& F, const unsigned mode) {
+template <class Frame>
+__device__ __forceinline__ EpiRegs epilogue_regs(const Frame& F, const unsigned mode) {
     EpiRegs E;
 #pragma unroll
     for (int i = 0; i < 2; i++) { E.black2[i] = 0; E.range2[i] = 0; }
@@ -1422,13 +1464,46 @@ __device__ __forceinline__ uint32_t meta_values(const uint32_t blk, const uint32
     return __vadd2(v, ref | (ref << 16));
 }
 
+// what the pixel kernel needs of a frame's descriptor (read through L2, see plan_wait)
+struct FramePix {
+    const uint8_t* src;
+    unsigned long long len;
+    uint16_t* dst;
+    int width;
+    unsigned tiles_x, flags, inv_tiles_x, epi_mode;
+    uint32_t* unitoff;
+    uint4* metarec;
+    unsigned epi_black2[2], epi_range2[2];
+    float epi_blackf[4], epi_scalef[4];
+};
 template <bool EPI>
-__device__ __forceinline__ void units_task(const FrameDev& F, const FrameState& S, Result* __restrict__ result,
+__device__ __forceinline__ FramePix frame_pix_cg(const FrameDev* p) {
+    FramePix f;
+    f.src = ldcg_ptr(&p->src); f.len = __ldcg(&p->len); f.dst = ldcg_ptr(&p->dst);
+    f.width = __ldcg(&p->width); f.tiles_x = __ldcg(&p->tiles_x); f.flags = __ldcg(&p->flags); f.inv_tiles_x = __ldcg(&p->inv_tiles_x);
+    f.unitoff = ldcg_ptr(&p->unitoff); f.metarec = ldcg_ptr(&p->metarec);
+    f.epi_mode = EPI ? __ldcg(&p->epi_mode) : 0u;
+#pragma unroll
+    for (int i = 0; i < 2; i++) { f.epi_black2[i] = 0; f.epi_range2[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { f.epi_blackf[i] = 0.f; f.epi_scalef[i] = 0.f; }
+    if (EPI && f.epi_mode != 0u) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) { f.epi_black2[i] = __ldcg(&p->epi_black2[i]); f.epi_range2[i] = __ldcg(&p->epi_range2[i]); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { f.epi_blackf[i] = __ldcg(&p->epi_blackf[i]); f.epi_scalef[i] = __ldcg(&p->epi_scalef[i]); }
+    }
+    return f;
+}
+
+template <bool EPI>
+__device__ __forceinline__ void units_task(const FrameDev* Fd, const FrameState& S, Result* __restrict__ result,
                                            const uint32_t u0, const uint32_t upw, uint8_t* smem_warp, const uint32_t* s_terms,
                                            uint32_t& bulk_phase) {
     const uint32_t lane = threadIdx.x & 31;
     const unsigned status = __ldcg(&S.status[0]) | __ldcg(&S.status[1]);
     const uint32_t rows_fit = __ldcg(&S.rows_fit);
+    const FramePix F = frame_pix_cg<EPI>(Fd);
     const int width = F.width;
     if (u0 == 0 && lane == 0) {
         Result r;
@@ -1617,14 +1692,15 @@ constexpr int KD_THREADS = 32 * KU_WARPS;
 
 // counters[0]: next item; counters[1]: warps that have left the kernel (the last one resets both for the next launch).
 // flag_target != 0: launched as a programmatic dependent of k_meta, i.e. possibly while k_meta's last wave is still
-// running -- before touching a frame, lane 0 polls the frame's meta_done counter (relaxed loads served by L2) and closes
-// the wait with one acquire load; the other lanes wait at the warp barrier.  The per-unit records are then read with
+// running -- before touching a frame, lane 0 polls the frame's two done words for this launch's epoch (relaxed loads served
+// by L2) and closes the wait with one acquire load; the other lanes wait at the warp barrier.  The per-unit records are then read with
 // ld.global.cg (L2), so they see everything k_meta released before bumping the counter.
 // Three CTAs per SM (168 registers): the fourth buys 2 % of bandwidth and leaves no room for this logic without spills.
 template <bool EPI>
 __global__ void __launch_bounds__(KD_THREADS, 3)
-k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ states, Result* __restrict__ results,
-        const WorkItem* __restrict__ items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target) {
+k_units(const FrameDev* frames, const FrameState* __restrict__ states, Result* __restrict__ results,
+        const WorkItem* items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target,
+        const uint32_t* plan_ready, const uint32_t plan_epoch) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint32_t s_terms[MCRAW_META_ROWS * 8 * 3];
     // The NEXT batch's k_meta may be launched as a programmatic dependent of this kernel (mcraw_capi.cu, "chain"): it touches
@@ -1643,28 +1719,37 @@ k_units(const FrameDev* __restrict__ frames, const FrameState* __restrict__ stat
     __syncwarp();
 #endif
     uint32_t it = 0;
-    if (lane == 0) it = atomicAdd(&counters[0], 1u);
+    if (lane == 0) {
+        plan_wait(plan_ready, plan_epoch);                 // the work list and the descriptors are in place
+        it = atomicAdd(&counters[0], 1u);
+    }
+    __syncwarp();
     it = __shfl_sync(0xFFFFFFFFu, it, 0);
     while (it < nitems) {
-        const WorkItem w = items[it];
+        WorkItem w;
+        {
+            const unsigned long long raw = __ldcg(reinterpret_cast<const unsigned long long*>(items + it));
+            w.frame = (uint32_t)raw; w.what = (uint32_t)(raw >> 32);
+        }
         uint32_t nxt = 0;
         if (lane == 0) {
             nxt = atomicAdd(&counters[0], 1u);             // take the next item early
             if (flag_target) {
-                const unsigned* flag = &states[w.frame].meta_done;
-                unsigned v;
+                const unsigned* flag = &states[w.frame].done[0];   // both streams' words as one 64-bit load
+                unsigned long long v;
+                const unsigned long long want = ((unsigned long long)flag_target << 32) | flag_target;
                 for (;;) {
-                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
-                    if (v >= flag_target) break;
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(flag) : "memory");
+                    if (v == want) break;
                     __nanosleep(256);
                 }
-                // the counter is monotone: one acquire load now pairs with k_meta's release (relaxed polls keep the L1
-                // invalidations of an acquire out of the wait loop); the warp barrier below extends the order to the other lanes
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+                // a word that carries this launch's epoch stays: one acquire load now pairs with the index kernel's releases (relaxed
+                // polls keep the L1 invalidations of an acquire out of the wait loop); the warp barrier below extends the order to the other lanes
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(flag) : "memory");
             }
         }
         __syncwarp();
-        units_task<EPI>(frames[w.frame], states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 31u) + 1u, smem_warp, s_terms,
+        units_task<EPI>(frames + w.frame, states[w.frame], results + w.frame, w.what & 0x07FFFFFFu, ((w.what >> 27) & 31u) + 1u, smem_warp, s_terms,
                    bulk_phase);
         __syncwarp();
         it = __shfl_sync(0xFFFFFFFFu, nxt, 0);

@@ -20,4 +20,4 @@ for k, w in (d.get("workloads") or {}).items():
     except Exception:
         print(k, {a: b for a, b in w.items() if not isinstance(b, dict)})
 print("clocks", d.get("clocks"), "frac_of_h2d", (d.get("e2e") or {}).get("frac_of_h2d"), "pixels_verified", d.get("pixels_verified"),
-      "cold_plan_ms", d.get("cold_plan_ms_per_step"))
+      "cold_plan_ms", d.get("cold_plan_ms_per_step"), "cold_same_outputs_ms", d.get("cold_plan_same_outputs_ms_per_step"))
