@@ -417,7 +417,7 @@ def run_leg(env, wl, steps, warmup, headline):
     res = {"frames_per_step_this_rank": per_step}
     # kernel-timing events on a SAMPLE of the timed region's batches (four of a hundred, two of twenty): a sampled batch runs its
     # two kernels one after the other between events, and it and the batch behind it leave the chain of programmatic launches
-    ctx.set_kernel_timing(max(4, steps // 4 if steps > 40 else steps // 2))
+    ctx.set_kernel_timing(steps // 4 if steps > 40 else max(2, steps // 2))     # any window of `steps` batches holds at least one sample
     if mine:
         # set-up, not warm-up: the context's plan slots are allocated on first use; touch all of them now
         poison()
