@@ -1176,7 +1176,13 @@ __global__ void __launch_bounds__(KS::THREADS, 1) k_meta_split(const FrameDev* _
             if (cnt < limit) break;                                // the window (or the chain) is exhausted
         }
         __syncthreads();                                           // (every thread has read sh_err in the loop condition)
-        if (tid == 0 && dead && done < need_mb && !sh_err) sh_err = MCRAW_FRAME_TRUNCATED;
+        {
+            // every thread reads the flag, a barrier, then one thread may set it: the compiler is free to hoist the load of a
+            // predicated read-modify-write to all threads, which racecheck (rightly) reports against thread 0's store
+            const uint32_t err_now = sh_err;
+            __syncthreads();
+            if (tid == 0 && dead && done < need_mb && !err_now) sh_err = MCRAW_FRAME_TRUNCATED;
+        }
         __syncthreads();
 
         KS_STAMP();
