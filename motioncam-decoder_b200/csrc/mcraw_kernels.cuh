@@ -1702,8 +1702,11 @@ constexpr int KD_THREADS = 32 * KU_WARPS;
 // by L2) and closes the wait with one acquire load; the other lanes wait at the warp barrier.  The per-unit records are then read with
 // ld.global.cg (L2), so they see everything k_meta released before bumping the counter.
 // Three CTAs per SM (168 registers): the fourth buys 2 % of bandwidth and leaves no room for this logic without spills.
+#ifndef MCRAW_KU_EPI_CTAS
+#define MCRAW_KU_EPI_CTAS 0      // experiment: CTAs per SM the epilogue variant of k_units is compiled for (0 = like the raw one)
+#endif
 template <bool EPI>
-__global__ void __launch_bounds__(KD_THREADS, 3)
+__global__ void __launch_bounds__(KD_THREADS, (EPI && MCRAW_KU_EPI_CTAS) ? MCRAW_KU_EPI_CTAS : 3)
 k_units(const FrameDev* frames, const FrameState* __restrict__ states, Result* __restrict__ results,
         const WorkItem* items, const uint32_t nitems, uint32_t* __restrict__ counters, const uint32_t flag_target,
         const uint32_t* plan_ready, const uint32_t plan_epoch) {
