@@ -127,7 +127,7 @@ struct mcraw_ctx {
     // CHAIN: back-to-back batches on one stream are linked by programmatic dependent launches all the way -- k_meta of
     // batch i+1 is a programmatic dependent of k_units of batch i, so it resolves the next batch's metadata in the room
     // k_units leaves (chain_ctas of its resident CTAs held back) while batch i still streams pixels; the kernels only meet
-    // through the per-frame meta_done counters.  Stream order is kept for everything the caller can observe: the link is
+    // through the per-frame done words (epochs).  Stream order is kept for everything the caller can observe: the link is
     // only made when batch i+1 presents the descriptors of batch i again or writes a disjoint range of output addresses,
     // and anything else enqueued on the stream in between ends the overlap by itself (a programmatic edge only relaxes
     // kernel -> kernel).  MCRAW_CHAIN=<CTAs> overrides the hold-back (0 = no chaining); 24 measured best on B200.

@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(KW::THREADS, 6) k_meta_warp(const FrameDev* fr
 //   3. the true chain: anchors + per-thread positions + unit records (+ bits stream: decode, unit payload lengths) exactly
 //      as k_meta does per round; the payload offsets of a window's units are first written relative to the window;
 //   4. bits stream: the windows' payload totals are exchanged the same way and every window shifts its units' offsets;
-//      the last window collects the error bits and publishes the stream (meta_done) for the frame.
+//      the last window collects the error bits and publishes the stream (its done word) for the frame.
 // Chains that merge or not makes no difference here: maps are composed, never guessed.  Flags carry the launch epoch of the
 // plan (nothing is zeroed between launches).
 // --------------------------------------------------------------------------------------------------------
