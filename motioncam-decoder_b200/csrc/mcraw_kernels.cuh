@@ -1249,7 +1249,10 @@ __global__ void __launch_bounds__(KS::THREADS, 1) k_meta_split(const FrameDev* _
 // k_units
 // --------------------------------------------------------------------------------------------------------
 constexpr int KU_WARPS = 4;                       // warps per CTA
-constexpr int KU_UPW = 24;                        // consecutive units handled by one warp (software pipelined)
+#ifndef MCRAW_KU_UPW
+#define MCRAW_KU_UPW 24
+#endif
+constexpr int KU_UPW = MCRAW_KU_UPW;              // consecutive units handled by one warp (software pipelined); <= 31: a warp keeps the unit offsets (+ end) in its lanes
 constexpr int KU_IN_BYTES = 16 * 512 + 256;       // worst case unit payload (16-bit blocks) + alignment slack, 128-multiple
 constexpr int KU_SLOT_PITCH = 144;                // bytes per tile slot in an output row: 128 + 16 (bank skew)
 constexpr int KU_ROW_PITCH = 16 * KU_SLOT_PITCH + 64;   // 2368: (pitch/16) % 8 == 4 -> the two pair rows hit disjoint banks
@@ -1271,6 +1274,7 @@ constexpr int KU_BAR_BYTES = 0;
 constexpr int KU_WARP_SMEM = ((KU_IN_BYTES + KU_OUT_BYTES + KU_META_BYTES + KU_BAR_BYTES + 127) / 128) * 128;
 constexpr int KU_SMEM = KU_WARPS * KU_WARP_SMEM;
 static_assert(KU_IN_BYTES % 128 == 0 && KU_WARP_SMEM % 128 == 0, "swizzle rows are 128 bytes");
+static_assert(KU_UPW >= 1 && KU_UPW <= 31, "lane i holds unitoff[u0 + i], i = 0 .. units");
 static_assert((KU_ROW_PITCH / 16) % 8 == 4, "row pitch must skew pair rows by four 16-byte bank groups");
 
 // 128-byte rows, 16-byte chunks XOR-ed with the row index: lanes reading at a 128-byte stride stay (nearly) conflict free
