@@ -575,8 +575,27 @@ int enqueue_chunk(mcraw_ctx* ctx, const mcraw_frame_desc* descs, uint32_t n, uin
         s.lg_epoch += 1;
         const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(s.any_epi ? ctx->lgw_resident_ctas_epi : ctx->lgw_resident_ctas, s.lg_nwork));
         const LgWork* d_work = reinterpret_cast<const LgWork*>(s.d_up + s.lg_work_off);
-        if (s.any_epi) k_legacy_warp<true><<<grid, LGW_THREADS, LGW_SMEM, st>>>(d_frames, d_results, d_work, s.lg_nwork, d_counter, s.lg_epoch);
-        else k_legacy_warp<false><<<grid, LGW_THREADS, LGW_SMEM, st>>>(d_frames, d_results, d_work, s.lg_nwork, d_counter, s.lg_epoch);
+        // Chained like the current-format kernels: a batch of legacy frames that follows a batch of legacy frames on the same
+        // stream, with a plan that is already on the device (nothing but the kernel goes onto the stream) and outputs that
+        // are the same or disjoint, is a programmatic dependent of the kernel before -- no bubble while that one's last tiles finish.
+        bool chain6 = false;
+        if (ctx->overlap && ctx->chain_ctas && hit && !any7 && !timed && ctx->prev_slot >= 0 && ctx->prev_slot != ctx->cur) {
+            const Slot& p = ctx->slots[ctx->prev_slot];
+            if (p.plan_valid && p.any6 && !p.any7 && p.stream == st && !p.timed) {
+                const bool same = p.plan_descs.size() == n && std::memcmp(p.plan_descs.data(), descs, sizeof(mcraw_frame_desc) * n) == 0;
+                chain6 = same || p.dst_hi <= s.dst_lo || s.dst_hi <= p.dst_lo;
+            }
+        }
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LGW_THREADS); cfg.dynamicSmemBytes = LGW_SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = chain6 ? 1 : 0;
+        if (s.any_epi) CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_legacy_warp<true>, d_frames, d_results, d_work, s.lg_nwork, d_counter, s.lg_epoch));
+        else CU_TRY(ctx, cudaLaunchKernelEx(&cfg, k_legacy_warp<false>, d_frames, d_results, d_work, s.lg_nwork, d_counter, s.lg_epoch));
         ctx->launches += 1;
     }
     if (timed) CU_TRY(ctx, cudaEventRecord(s.e2, st));

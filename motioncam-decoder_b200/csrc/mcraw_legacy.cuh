@@ -305,6 +305,10 @@ __global__ void __launch_bounds__(LGW_THREADS, EPI ? 5 : 8) k_legacy_warp(const 
                                                              const LgWork* __restrict__ work, const uint32_t nwork,
                                                              uint32_t* __restrict__ counters, const uint32_t epoch) {
     extern __shared__ __align__(128) uint8_t lg_smem[];
+    // The NEXT batch's kernel may be launched as a programmatic dependent of this one (mcraw_capi.cu, "chain": its own slot's
+    // tickets, status words and counters; outputs that are the same or disjoint): its CTAs move in as this grid's CTAs run out
+    // of tickets, instead of waiting for the last of them.
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     uint8_t* data = lg_smem;
     uint8_t* tables = lg_smem + LGW_DATA;                                                   // [LGW_THREADS][LGW_TAB]
     uint16_t* plist = reinterpret_cast<uint16_t*>(tables);                                  // pair list: [LGW_PAIR_CHUNK], after the tables

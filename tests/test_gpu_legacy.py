@@ -126,3 +126,38 @@ def test_legacy_whole_frame_one_width(ctx):
             assert status[i] == 0 and written[i] == w * h, i
             assert np.array_equal(batch.fetch(i), wants[i]), i
     batch.free()
+
+
+def test_legacy_batches_back_to_back():
+    """Legacy batches enqueued back to back without waiting: once a slot holds a batch's plan, its kernel is launched as a
+    programmatic dependent of the legacy kernel before (same outputs, or disjoint ones) -- two grids of look-back status
+    words, tickets and counters side by side.  Every frame of both batches against its source image, round after round."""
+    from motioncam_decoder_b200 import capi, testvec as tv
+    ctx = capi.Context(0)
+    frames = []
+    for k, (w, h) in enumerate([(2048, 96), (1000, 64), (4000, 48), (640, 128), (2048, 96), (3008, 40)]):
+        img = tv.gen_photon(w, h, 1023 if k % 2 else 4095, seed=500 + k)
+        s = tv.encode_legacy(img, policy=tv.POLICY_ALIASES if k % 3 else tv.POLICY_MINIMAL, seed=k)
+        n, want = ol.oracle_decode_legacy(s, w, h)
+        assert n == w * h and np.array_equal(want, img)
+        frames.append((s, w, h, capi.COMPRESSION_LEGACY))
+    img7 = tv.gen_uniform(2048, 64, 0, 127, seed=77)                       # constant width: tiles that publish maps and look back
+    frames.append((tv.encode_legacy(img7, policy=tv.POLICY_FORCE, policy_arg=7, seed=3), 2048, 64, capi.COMPRESSION_LEGACY))
+    images = [ol.oracle_decode_legacy(s, w, h)[1] for (s, w, h, _) in frames]
+    a = capi.DeviceBatch(ctx, frames * 3)
+    b = capi.DeviceBatch(ctx, list(reversed(frames)) * 2)
+    for rnd in range(3):
+        a.fill_outputs(0xA5A5)
+        b.fill_outputs(0x5A5A)
+        for k in range(14):                                               # 6 slots: from the 7th enqueue on the plans are on the device
+            ctx.decode_batch(a.descs, a.n) if (k % 2 == 0 or rnd == 0) else ctx.decode_batch(b.descs, b.n)
+        ctx.decode_batch(b.descs, b.n)
+        written, status = ctx.batch_wait(b.n)
+        assert not any(status) and all(wr == f[1] * f[2] for wr, f in zip(written, b.frames)), rnd
+        for i in range(a.n):
+            assert np.array_equal(a.fetch(i), images[i % len(frames)]), (rnd, "a", i)
+        for i in range(b.n):
+            assert np.array_equal(b.fetch(i), images[len(frames) - 1 - i % len(frames)]), (rnd, "b", i)
+    a.free()
+    b.free()
+    ctx.close()
