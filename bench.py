@@ -471,6 +471,8 @@ def run_leg(env, wl, steps, warmup, headline):
             traffic = json.load(f).get(wl, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
+    if per_step != frames_total:          # a strong-scaled leg: the capture was one launch over the WHOLE clip
+        traffic = None
     step_gbs = (comp_step + out_step) * steps / (ms * 1e-3) / 1e9 if mine else 0.0
     res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                        "traffic": traffic, "kernel": "k_units" if ct == 7 else "k_legacy_warp",
